@@ -1,0 +1,940 @@
+// extern "C" surface of libddlo_gicp_b200.so (declared in include/ddlo_gicp.h).
+// Host-side bookkeeping only: handles, reference counts, uploads/downloads and the state rules of
+// NanoGICP (nano_gicp_impl.hpp:98-196).  All arithmetic happens in the kernels of index.cu,
+// knn_cov.cu and gicp.cu; there is no CPU implementation of any of it in this library.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "gicp.cuh"
+
+namespace ddlo {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+int build_index(ddlo_cloud* c);
+int launch_knn_queries(ddlo_cloud* c, const float4* d_queries, int nq, int k, int* d_idx, float* d_d2);
+int launch_covariances(ddlo_cloud* c, int k, int method, double* d_covs);
+
+// raw strided host points -> float4 (x, y, z, 1)
+__global__ void __launch_bounds__(256) k_repack(const unsigned char* __restrict__ raw, int n, int stride, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+  out[i] = make_float4(p[0], p[1], p[2], 1.0f);
+}
+
+// Eigen::Matrix4d per point <-> 6 doubles per point
+__global__ void __launch_bounds__(256) k_cov_pack(const double* __restrict__ m16, int n, double* __restrict__ c6) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* m = m16 + (size_t)i * 16;  // column-major: (r,c) at m[4c + r]
+  double* o = c6 + (size_t)i * 6;
+  o[0] = m[0];
+  o[1] = 0.5 * (m[4] + m[1]);
+  o[2] = 0.5 * (m[8] + m[2]);
+  o[3] = m[5];
+  o[4] = 0.5 * (m[9] + m[6]);
+  o[5] = m[10];
+}
+__global__ void __launch_bounds__(256) k_cov_unpack(const double* __restrict__ c6, int n, double* __restrict__ m16) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* s = c6 + (size_t)i * 6;
+  double* m = m16 + (size_t)i * 16;
+  m[0] = s[0], m[1] = s[1], m[2] = s[2], m[3] = 0.0;
+  m[4] = s[1], m[5] = s[3], m[6] = s[4], m[7] = 0.0;
+  m[8] = s[2], m[9] = s[4], m[10] = s[5], m[11] = 0.0;
+  m[12] = 0.0, m[13] = 0.0, m[14] = 0.0, m[15] = 0.0;
+}
+__global__ void __launch_bounds__(256) k_sqrt_f2d(const float* __restrict__ in, int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = sqrt((double)in[i]);
+}
+__global__ void __launch_bounds__(256) k_fill(float4* p, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+static int use_device(const ddlo_runtime* rt) {
+  DDLO_CUDA(cudaSetDevice(rt->device));
+  return DDLO_OK;
+}
+
+static int ensure_pinned(ddlo_runtime* rt, size_t bytes) {
+  if (rt->h_pinned_bytes >= bytes) return DDLO_OK;
+  if (rt->h_pinned) {
+    DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+    DDLO_CUDA(cudaFreeHost(rt->h_pinned));
+    rt->h_pinned = nullptr;
+    rt->h_pinned_bytes = 0;
+  }
+  const size_t want = std::max<size_t>(bytes, 1u << 16);
+  DDLO_CUDA(cudaMallocHost(&rt->h_pinned, want));
+  rt->h_pinned_bytes = want;
+  return DDLO_OK;
+}
+
+static void cloud_free(ddlo_cloud* c) {
+  cudaSetDevice(c->rt->device);
+  cudaStream_t st = c->rt->stream;
+  if (c->pts) cudaFreeAsync(c->pts, st);
+  if (c->spts) cudaFreeAsync(c->spts, st);
+  if (c->boxes) cudaFreeAsync(c->boxes, st);
+  delete c;
+}
+static void covs_free(ddlo_covs* v) {
+  cudaSetDevice(v->rt->device);
+  if (v->c) cudaFreeAsync(v->c, v->rt->stream);
+  delete v;
+}
+
+}  // namespace ddlo
+
+using namespace ddlo;
+
+struct ddlo_gicp {
+  ddlo_runtime* rt = nullptr;
+  ddlo_params p{};
+  ddlo_cloud* src = nullptr;
+  ddlo_cloud* tgt = nullptr;
+  ddlo_covs* src_cov = nullptr;
+  ddlo_covs* tgt_cov = nullptr;
+  // per-source-point workspace (correspondences_, sq_distances_, mahalanobis_)
+  int ws_n = 0;
+  int* corr = nullptr;
+  float* sqd = nullptr;
+  double* mahal = nullptr;
+  int corr_n = 0;  // number of valid entries (0 after swap/clear: correspondences_.clear())
+  double* partials = nullptr;
+  int partial_stride = 0;
+  AlignOut* d_out = nullptr;
+  float last_T[16];
+  bool has_last_T = false;
+};
+
+static void set_cloud(ddlo_cloud*& slot, ddlo_cloud* c) {
+  if (c) c->refs.fetch_add(1);
+  if (slot && slot->refs.fetch_sub(1) == 1) cloud_free(slot);
+  slot = c;
+}
+static void set_covs(ddlo_covs*& slot, ddlo_covs* v) {
+  if (v) v->refs.fetch_add(1);
+  if (slot && slot->refs.fetch_sub(1) == 1) covs_free(slot);
+  slot = v;
+}
+
+extern "C" {
+
+int ddlo_abi_version(void) { return DDLO_ABI_VERSION; }
+const char* ddlo_last_error(void) { return g_err.c_str(); }
+
+int ddlo_device_count(int* count) {
+  if (!count) return fail(DDLO_E_INVALID, "count is null");
+  DDLO_CUDA(cudaGetDeviceCount(count));
+  return DDLO_OK;
+}
+
+// ---- runtime --------------------------------------------------------------------------------------
+int ddlo_runtime_create(int device, ddlo_runtime** out) {
+  if (!out) return fail(DDLO_E_INVALID, "out is null");
+  *out = nullptr;
+  int count = 0;
+  DDLO_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(DDLO_E_CUDA, "no such CUDA device (this library has no CPU fallback)");
+  DDLO_CUDA(cudaSetDevice(device));
+  ddlo_runtime* rt = new (std::nothrow) ddlo_runtime();
+  if (!rt) return fail(DDLO_E_INVALID, "out of host memory");
+  rt->device = device;
+  DDLO_CUDA(cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking));
+  DDLO_CUDA(cudaEventCreate(&rt->ev0));
+  DDLO_CUDA(cudaEventCreate(&rt->ev1));
+  DDLO_CUDA(cudaDeviceGetAttribute(&rt->num_sms, cudaDevAttrMultiProcessorCount, device));
+  cudaMemPool_t pool;
+  DDLO_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t keep = ~0ull;  // keep freed blocks cached: handle churn must not hit cudaMalloc
+  DDLO_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  DDLO_CUDA(cudaMalloc(&rt->d_scratch, 1u << 20));
+  rt->d_scratch_bytes = 1u << 20;
+  DDLO_TRY(ensure_pinned(rt, 1u << 16));
+  int per_sm = 0;
+  DDLO_TRY(gicp_max_coop_blocks(device, &per_sm));
+  rt->max_coop_blocks_align = per_sm * rt->num_sms;
+  if (rt->max_coop_blocks_align <= 0) return fail(DDLO_E_CUDA, "align kernel does not fit on this device");
+  *out = rt;
+  return DDLO_OK;
+}
+
+int ddlo_runtime_destroy(ddlo_runtime* rt) {
+  if (!rt) return DDLO_OK;
+  cudaSetDevice(rt->device);
+  cudaStreamSynchronize(rt->stream);
+  if (rt->d_scratch) cudaFree(rt->d_scratch);
+  if (rt->flush_buf) cudaFree(rt->flush_buf);
+  if (rt->h_pinned) cudaFreeHost(rt->h_pinned);
+  cudaEventDestroy(rt->ev0);
+  cudaEventDestroy(rt->ev1);
+  cudaStreamDestroy(rt->stream);
+  delete rt;
+  return DDLO_OK;
+}
+
+int ddlo_runtime_synchronize(ddlo_runtime* rt) {
+  if (!rt) return fail(DDLO_E_INVALID, "runtime is null");
+  DDLO_TRY(use_device(rt));
+  DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+  return DDLO_OK;
+}
+
+int ddlo_runtime_timer_begin(ddlo_runtime* rt) {
+  if (!rt) return fail(DDLO_E_INVALID, "runtime is null");
+  DDLO_TRY(use_device(rt));
+  DDLO_CUDA(cudaEventRecord(rt->ev0, rt->stream));
+  return DDLO_OK;
+}
+
+int ddlo_runtime_timer_end(ddlo_runtime* rt, float* elapsed_ms) {
+  if (!rt || !elapsed_ms) return fail(DDLO_E_INVALID, "null argument");
+  DDLO_TRY(use_device(rt));
+  DDLO_CUDA(cudaEventRecord(rt->ev1, rt->stream));
+  DDLO_CUDA(cudaEventSynchronize(rt->ev1));
+  DDLO_CUDA(cudaEventElapsedTime(elapsed_ms, rt->ev0, rt->ev1));
+  return DDLO_OK;
+}
+
+int ddlo_runtime_launch_count(ddlo_runtime* rt, long long* count) {
+  if (!rt || !count) return fail(DDLO_E_INVALID, "null argument");
+  *count = rt->launches;
+  return DDLO_OK;
+}
+
+int ddlo_runtime_flush_l2(ddlo_runtime* rt, size_t bytes) {
+  if (!rt) return fail(DDLO_E_INVALID, "runtime is null");
+  DDLO_TRY(use_device(rt));
+  if (rt->flush_bytes < bytes) {
+    if (rt->flush_buf) {
+      DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+      DDLO_CUDA(cudaFree(rt->flush_buf));
+      rt->flush_buf = nullptr;
+      rt->flush_bytes = 0;
+    }
+    DDLO_CUDA(cudaMalloc(&rt->flush_buf, bytes));
+    rt->flush_bytes = bytes;
+  }
+  k_fill<<<rt->num_sms * 8, 256, 0, rt->stream>>>(static_cast<float4*>(rt->flush_buf), bytes / 16);
+  DDLO_CUDA(cudaGetLastError());
+  return DDLO_OK;
+}
+
+// ---- clouds ---------------------------------------------------------------------------------------
+static int cloud_new(ddlo_runtime* rt, int n, ddlo_cloud** out) {
+  ddlo_cloud* c = new (std::nothrow) ddlo_cloud();
+  if (!c) return fail(DDLO_E_INVALID, "out of host memory");
+  c->rt = rt;
+  c->n = n;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&c->pts), std::max<size_t>(1, (size_t)n) * sizeof(float4), rt->stream);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(DDLO_E_CUDA, std::string("cudaMallocAsync(cloud): ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return DDLO_OK;
+}
+
+int ddlo_cloud_create(ddlo_runtime* rt, const float* xyz, int n, int stride_bytes, ddlo_cloud** out) {
+  if (!rt || !out || (n > 0 && !xyz)) return fail(DDLO_E_INVALID, "null argument");
+  if (n < 0 || stride_bytes < 12 || (stride_bytes & 3)) return fail(DDLO_E_INVALID, "bad n or stride");
+  *out = nullptr;
+  DDLO_TRY(use_device(rt));
+  ddlo_cloud* c = nullptr;
+  DDLO_TRY(cloud_new(rt, n, &c));
+  if (n > 0) {
+    const size_t raw_bytes = (size_t)(n - 1) * stride_bytes + 12;
+    unsigned char* d_raw = nullptr;
+    DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_raw), raw_bytes, rt->stream));
+    DDLO_CUDA(cudaMemcpyAsync(d_raw, xyz, raw_bytes, cudaMemcpyHostToDevice, rt->stream));
+    k_repack<<<(n + 255) / 256, 256, 0, rt->stream>>>(d_raw, n, stride_bytes, c->pts);
+    rt->launches += 1;
+    DDLO_CUDA(cudaGetLastError());
+    DDLO_CUDA(cudaFreeAsync(d_raw, rt->stream));
+  }
+  *out = c;
+  return DDLO_OK;
+}
+
+int ddlo_cloud_create_from_device(ddlo_runtime* rt, const void* d_xyzw, int n, ddlo_cloud** out) {
+  if (!rt || !out || (n > 0 && !d_xyzw)) return fail(DDLO_E_INVALID, "null argument");
+  if (n < 0) return fail(DDLO_E_INVALID, "bad n");
+  *out = nullptr;
+  DDLO_TRY(use_device(rt));
+  ddlo_cloud* c = nullptr;
+  DDLO_TRY(cloud_new(rt, n, &c));
+  if (n > 0) {
+    k_repack<<<(n + 255) / 256, 256, 0, rt->stream>>>(static_cast<const unsigned char*>(d_xyzw), n, 16, c->pts);
+    rt->launches += 1;
+    DDLO_CUDA(cudaGetLastError());
+  }
+  *out = c;
+  return DDLO_OK;
+}
+
+int ddlo_cloud_retain(ddlo_cloud* c) {
+  if (!c) return fail(DDLO_E_INVALID, "cloud is null");
+  c->refs.fetch_add(1);
+  return DDLO_OK;
+}
+int ddlo_cloud_release(ddlo_cloud* c) {
+  if (!c) return DDLO_OK;
+  if (c->refs.fetch_sub(1) == 1) cloud_free(c);
+  return DDLO_OK;
+}
+int ddlo_cloud_size(const ddlo_cloud* c, int* n) {
+  if (!c || !n) return fail(DDLO_E_INVALID, "null argument");
+  *n = c->n;
+  return DDLO_OK;
+}
+int ddlo_cloud_download(ddlo_cloud* c, float* xyzw_out) {
+  if (!c || !xyzw_out) return fail(DDLO_E_INVALID, "null argument");
+  DDLO_TRY(use_device(c->rt));
+  DDLO_CUDA(cudaMemcpyAsync(xyzw_out, c->pts, (size_t)c->n * sizeof(float4), cudaMemcpyDeviceToHost, c->rt->stream));
+  DDLO_CUDA(cudaStreamSynchronize(c->rt->stream));
+  return DDLO_OK;
+}
+int ddlo_cloud_build_index(ddlo_cloud* c) {
+  if (!c) return fail(DDLO_E_INVALID, "cloud is null");
+  DDLO_TRY(use_device(c->rt));
+  return build_index(c);
+}
+int ddlo_cloud_has_index(const ddlo_cloud* c, int* has) {
+  if (!c || !has) return fail(DDLO_E_INVALID, "null argument");
+  *has = c->has_index ? 1 : 0;
+  return DDLO_OK;
+}
+
+int ddlo_cloud_knn(ddlo_cloud* c, const float* queries, int nq, int qstride_bytes, int k, int* idx, float* sqdist, int* counts) {
+  if (!c || (nq > 0 && (!queries || !idx || !sqdist))) return fail(DDLO_E_INVALID, "null argument");
+  if (nq < 0 || k < 1 || qstride_bytes < 12 || (qstride_bytes & 3)) return fail(DDLO_E_INVALID, "bad nq, k or stride");
+  if (c->n <= 0) return fail(DDLO_E_EMPTY, "kNN on an empty cloud");
+  ddlo_runtime* rt = c->rt;
+  DDLO_TRY(use_device(rt));
+  DDLO_TRY(build_index(c));
+  if (nq == 0) return DDLO_OK;
+  cudaStream_t st = rt->stream;
+  const size_t raw_bytes = (size_t)(nq - 1) * qstride_bytes + 12;
+  unsigned char* d_raw = nullptr;
+  float4* d_q = nullptr;
+  int* d_idx = nullptr;
+  float* d_d2 = nullptr;
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_raw), raw_bytes, st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_q), (size_t)nq * sizeof(float4), st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_idx), (size_t)nq * k * sizeof(int), st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_d2), (size_t)nq * k * sizeof(float), st));
+  DDLO_CUDA(cudaMemcpyAsync(d_raw, queries, raw_bytes, cudaMemcpyHostToDevice, st));
+  k_repack<<<(nq + 255) / 256, 256, 0, st>>>(d_raw, nq, qstride_bytes, d_q);
+  rt->launches += 1;
+  int rc = launch_knn_queries(c, d_q, nq, k, d_idx, d_d2);
+  if (rc == DDLO_OK) {
+    DDLO_CUDA(cudaMemcpyAsync(idx, d_idx, (size_t)nq * k * sizeof(int), cudaMemcpyDeviceToHost, st));
+    DDLO_CUDA(cudaMemcpyAsync(sqdist, d_d2, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  cudaFreeAsync(d_raw, st);
+  cudaFreeAsync(d_q, st);
+  cudaFreeAsync(d_idx, st);
+  cudaFreeAsync(d_d2, st);
+  DDLO_CUDA(cudaStreamSynchronize(st));
+  if (rc != DDLO_OK) return rc;
+  if (counts)
+    for (int i = 0; i < nq; ++i) counts[i] = std::min(k, c->n);
+  return DDLO_OK;
+}
+
+int ddlo_cloud_transform(ddlo_cloud* c, const float* T16, ddlo_cloud** out) {
+  if (!c || !T16 || !out) return fail(DDLO_E_INVALID, "null argument");
+  *out = nullptr;
+  DDLO_TRY(use_device(c->rt));
+  ddlo_cloud* r = nullptr;
+  DDLO_TRY(cloud_new(c->rt, c->n, &r));
+  if (c->n > 0) {
+    int rc = launch_transform_cloud(c->rt, c->pts, c->n, T16, r->pts);
+    if (rc != DDLO_OK) {
+      cloud_free(r);
+      return rc;
+    }
+  }
+  *out = r;
+  return DDLO_OK;
+}
+
+int ddlo_cloud_concat(ddlo_runtime* rt, ddlo_cloud* const* parts, int m, ddlo_cloud** out) {
+  if (!rt || !out || (m > 0 && !parts)) return fail(DDLO_E_INVALID, "null argument");
+  *out = nullptr;
+  DDLO_TRY(use_device(rt));
+  long long total = 0;
+  for (int i = 0; i < m; ++i) {
+    if (!parts[i] || parts[i]->rt != rt) return fail(DDLO_E_INVALID, "concat: null part or part of another runtime");
+    total += parts[i]->n;
+  }
+  if (total > std::numeric_limits<int>::max()) return fail(DDLO_E_UNSUPPORTED, "concat: too many points");
+  ddlo_cloud* r = nullptr;
+  DDLO_TRY(cloud_new(rt, (int)total, &r));
+  size_t off = 0;
+  for (int i = 0; i < m; ++i) {
+    if (parts[i]->n == 0) continue;
+    DDLO_CUDA(cudaMemcpyAsync(r->pts + off, parts[i]->pts, (size_t)parts[i]->n * sizeof(float4), cudaMemcpyDeviceToDevice, rt->stream));
+    off += parts[i]->n;
+  }
+  *out = r;
+  return DDLO_OK;
+}
+
+// ---- covariances ------------------------------------------------------------------------------------
+static int covs_new(ddlo_runtime* rt, int n, ddlo_covs** out) {
+  ddlo_covs* v = new (std::nothrow) ddlo_covs();
+  if (!v) return fail(DDLO_E_INVALID, "out of host memory");
+  v->rt = rt;
+  v->n = n;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&v->c), std::max<size_t>(1, (size_t)n) * kCovStride * sizeof(double), rt->stream);
+  if (e != cudaSuccess) {
+    delete v;
+    return fail(DDLO_E_CUDA, std::string("cudaMallocAsync(covs): ") + cudaGetErrorString(e));
+  }
+  *out = v;
+  return DDLO_OK;
+}
+
+int ddlo_covs_compute(ddlo_cloud* c, int k, int regularization_method, ddlo_covs** out) {
+  if (!c || !out) return fail(DDLO_E_INVALID, "null argument");
+  *out = nullptr;
+  if (c->n <= 0) return fail(DDLO_E_EMPTY, "covariances of an empty cloud");
+  if (k < 1) return fail(DDLO_E_INVALID, "k must be >= 1");
+  if (c->n < k) return fail(DDLO_E_TOO_FEW, "cloud has fewer points than k_correspondences");
+  if (regularization_method < DDLO_REG_NONE || regularization_method > DDLO_REG_FROBENIUS)
+    return fail(DDLO_E_INVALID, "unknown regularization method");
+  DDLO_TRY(use_device(c->rt));
+  DDLO_TRY(build_index(c));
+  ddlo_covs* v = nullptr;
+  DDLO_TRY(covs_new(c->rt, c->n, &v));
+  int rc = launch_covariances(c, k, regularization_method, v->c);
+  if (rc != DDLO_OK) {
+    covs_free(v);
+    return rc;
+  }
+  *out = v;
+  return DDLO_OK;
+}
+
+int ddlo_covs_from_host(ddlo_runtime* rt, const double* mat4x4, int n, ddlo_covs** out) {
+  if (!rt || !out || (n > 0 && !mat4x4)) return fail(DDLO_E_INVALID, "null argument");
+  if (n < 0) return fail(DDLO_E_INVALID, "bad n");
+  *out = nullptr;
+  DDLO_TRY(use_device(rt));
+  ddlo_covs* v = nullptr;
+  DDLO_TRY(covs_new(rt, n, &v));
+  if (n > 0) {
+    double* d_m = nullptr;
+    DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_m), (size_t)n * 16 * sizeof(double), rt->stream));
+    DDLO_CUDA(cudaMemcpyAsync(d_m, mat4x4, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, rt->stream));
+    k_cov_pack<<<(n + 255) / 256, 256, 0, rt->stream>>>(d_m, n, v->c);
+    rt->launches += 1;
+    DDLO_CUDA(cudaGetLastError());
+    DDLO_CUDA(cudaFreeAsync(d_m, rt->stream));
+  }
+  *out = v;
+  return DDLO_OK;
+}
+
+int ddlo_covs_to_host(ddlo_covs* v, double* mat4x4_out) {
+  if (!v || (v->n > 0 && !mat4x4_out)) return fail(DDLO_E_INVALID, "null argument");
+  if (v->n == 0) return DDLO_OK;
+  ddlo_runtime* rt = v->rt;
+  DDLO_TRY(use_device(rt));
+  double* d_m = nullptr;
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_m), (size_t)v->n * 16 * sizeof(double), rt->stream));
+  k_cov_unpack<<<(v->n + 255) / 256, 256, 0, rt->stream>>>(v->c, v->n, d_m);
+  rt->launches += 1;
+  DDLO_CUDA(cudaGetLastError());
+  DDLO_CUDA(cudaMemcpyAsync(mat4x4_out, d_m, (size_t)v->n * 16 * sizeof(double), cudaMemcpyDeviceToHost, rt->stream));
+  DDLO_CUDA(cudaFreeAsync(d_m, rt->stream));
+  DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+  return DDLO_OK;
+}
+
+int ddlo_covs_size(const ddlo_covs* v, int* n) {
+  if (!v || !n) return fail(DDLO_E_INVALID, "null argument");
+  *n = v->n;
+  return DDLO_OK;
+}
+int ddlo_covs_retain(ddlo_covs* v) {
+  if (!v) return fail(DDLO_E_INVALID, "covs is null");
+  v->refs.fetch_add(1);
+  return DDLO_OK;
+}
+int ddlo_covs_release(ddlo_covs* v) {
+  if (!v) return DDLO_OK;
+  if (v->refs.fetch_sub(1) == 1) covs_free(v);
+  return DDLO_OK;
+}
+
+int ddlo_covs_concat(ddlo_runtime* rt, ddlo_covs* const* parts, int m, ddlo_covs** out) {
+  if (!rt || !out || (m > 0 && !parts)) return fail(DDLO_E_INVALID, "null argument");
+  *out = nullptr;
+  DDLO_TRY(use_device(rt));
+  long long total = 0;
+  for (int i = 0; i < m; ++i) {
+    if (!parts[i] || parts[i]->rt != rt) return fail(DDLO_E_INVALID, "concat: null part or part of another runtime");
+    total += parts[i]->n;
+  }
+  if (total > std::numeric_limits<int>::max()) return fail(DDLO_E_UNSUPPORTED, "concat: too many points");
+  ddlo_covs* r = nullptr;
+  DDLO_TRY(covs_new(rt, (int)total, &r));
+  size_t off = 0;
+  for (int i = 0; i < m; ++i) {
+    if (parts[i]->n == 0) continue;
+    DDLO_CUDA(cudaMemcpyAsync(r->c + off * kCovStride, parts[i]->c, (size_t)parts[i]->n * kCovStride * sizeof(double),
+                              cudaMemcpyDeviceToDevice, rt->stream));
+    off += parts[i]->n;
+  }
+  *out = r;
+  return DDLO_OK;
+}
+
+// ---- engine ---------------------------------------------------------------------------------------------
+int ddlo_params_default(ddlo_params* p) {
+  if (!p) return fail(DDLO_E_INVALID, "params is null");
+  std::memset(p, 0, sizeof(*p));
+  p->k_correspondences = 20;
+  p->regularization_method = DDLO_REG_PLANE;
+  p->max_iterations = 64;
+  p->optimizer = DDLO_OPT_LEVENBERG_MARQUARDT;
+  p->lm_max_iterations = 10;
+  p->max_correspondence_distance = (double)std::numeric_limits<float>::max();
+  p->transformation_epsilon = 5e-4;
+  p->rotation_epsilon = 2e-3;
+  p->lm_init_lambda_factor = 1e-9;
+  return DDLO_OK;
+}
+
+int ddlo_gicp_create(ddlo_runtime* rt, ddlo_gicp** out) {
+  if (!rt || !out) return fail(DDLO_E_INVALID, "null argument");
+  *out = nullptr;
+  DDLO_TRY(use_device(rt));
+  ddlo_gicp* g = new (std::nothrow) ddlo_gicp();
+  if (!g) return fail(DDLO_E_INVALID, "out of host memory");
+  g->rt = rt;
+  ddlo_params_default(&g->p);
+  g->partial_stride = std::max(rt->max_coop_blocks_align, 1024);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&g->partials), (size_t)2 * kNumSums * g->partial_stride * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->d_out), sizeof(AlignOut));
+  if (e != cudaSuccess) {
+    delete g;
+    return fail(DDLO_E_CUDA, std::string("cudaMalloc(engine): ") + cudaGetErrorString(e));
+  }
+  *out = g;
+  return DDLO_OK;
+}
+
+int ddlo_gicp_destroy(ddlo_gicp* g) {
+  if (!g) return DDLO_OK;
+  cudaSetDevice(g->rt->device);
+  cudaStreamSynchronize(g->rt->stream);
+  set_cloud(g->src, nullptr);
+  set_cloud(g->tgt, nullptr);
+  set_covs(g->src_cov, nullptr);
+  set_covs(g->tgt_cov, nullptr);
+  if (g->corr) cudaFree(g->corr);
+  if (g->sqd) cudaFree(g->sqd);
+  if (g->mahal) cudaFree(g->mahal);
+  if (g->partials) cudaFree(g->partials);
+  if (g->d_out) cudaFree(g->d_out);
+  delete g;
+  return DDLO_OK;
+}
+
+int ddlo_gicp_set_params(ddlo_gicp* g, const ddlo_params* p) {
+  if (!g || !p) return fail(DDLO_E_INVALID, "null argument");
+  if (p->k_correspondences < 1) return fail(DDLO_E_INVALID, "k_correspondences must be >= 1");
+  if (p->regularization_method < DDLO_REG_NONE || p->regularization_method > DDLO_REG_FROBENIUS)
+    return fail(DDLO_E_INVALID, "unknown regularization method");
+  if (p->optimizer != DDLO_OPT_GAUSS_NEWTON && p->optimizer != DDLO_OPT_LEVENBERG_MARQUARDT)
+    return fail(DDLO_E_INVALID, "unknown optimizer");
+  if (p->max_iterations < 0 || p->lm_max_iterations < 0) return fail(DDLO_E_INVALID, "negative iteration limit");
+  g->p = *p;
+  return DDLO_OK;
+}
+int ddlo_gicp_get_params(const ddlo_gicp* g, ddlo_params* p) {
+  if (!g || !p) return fail(DDLO_E_INVALID, "null argument");
+  *p = g->p;
+  return DDLO_OK;
+}
+
+int ddlo_gicp_set_input_source(ddlo_gicp* g, ddlo_cloud* c, int build) {
+  if (!g || !c) return fail(DDLO_E_INVALID, "null argument");
+  if (c->rt != g->rt) return fail(DDLO_E_INVALID, "cloud belongs to another runtime");
+  if (g->src == c) return DDLO_OK;  // if (input_ == cloud) return;
+  DDLO_TRY(use_device(g->rt));
+  set_cloud(g->src, c);
+  if (build) {
+    if (c->n > 0) DDLO_TRY(build_index(c));
+    set_covs(g->src_cov, nullptr);
+  }
+  return DDLO_OK;
+}
+
+int ddlo_gicp_set_input_target(ddlo_gicp* g, ddlo_cloud* c) {
+  if (!g || !c) return fail(DDLO_E_INVALID, "null argument");
+  if (c->rt != g->rt) return fail(DDLO_E_INVALID, "cloud belongs to another runtime");
+  if (g->tgt == c) return DDLO_OK;
+  DDLO_TRY(use_device(g->rt));
+  set_cloud(g->tgt, c);
+  if (c->n > 0) DDLO_TRY(build_index(c));
+  set_covs(g->tgt_cov, nullptr);
+  return DDLO_OK;
+}
+
+int ddlo_gicp_clear_source(ddlo_gicp* g) {
+  if (!g) return fail(DDLO_E_INVALID, "engine is null");
+  set_cloud(g->src, nullptr);
+  set_covs(g->src_cov, nullptr);
+  return DDLO_OK;
+}
+int ddlo_gicp_clear_target(ddlo_gicp* g) {
+  if (!g) return fail(DDLO_E_INVALID, "engine is null");
+  set_cloud(g->tgt, nullptr);
+  set_covs(g->tgt_cov, nullptr);
+  return DDLO_OK;
+}
+
+int ddlo_gicp_set_source_covariances(ddlo_gicp* g, ddlo_covs* v) {
+  if (!g) return fail(DDLO_E_INVALID, "engine is null");
+  if (v && v->rt != g->rt) return fail(DDLO_E_INVALID, "covariances belong to another runtime");
+  set_covs(g->src_cov, v);
+  return DDLO_OK;
+}
+int ddlo_gicp_set_target_covariances(ddlo_gicp* g, ddlo_covs* v) {
+  if (!g) return fail(DDLO_E_INVALID, "engine is null");
+  if (v && v->rt != g->rt) return fail(DDLO_E_INVALID, "covariances belong to another runtime");
+  set_covs(g->tgt_cov, v);
+  return DDLO_OK;
+}
+int ddlo_gicp_get_source_covariances(ddlo_gicp* g, ddlo_covs** out) {
+  if (!g || !out) return fail(DDLO_E_INVALID, "null argument");
+  *out = g->src_cov;
+  if (*out) (*out)->refs.fetch_add(1);
+  return DDLO_OK;
+}
+int ddlo_gicp_get_target_covariances(ddlo_gicp* g, ddlo_covs** out) {
+  if (!g || !out) return fail(DDLO_E_INVALID, "null argument");
+  *out = g->tgt_cov;
+  if (*out) (*out)->refs.fetch_add(1);
+  return DDLO_OK;
+}
+int ddlo_gicp_get_input_source(ddlo_gicp* g, ddlo_cloud** out) {
+  if (!g || !out) return fail(DDLO_E_INVALID, "null argument");
+  *out = g->src;
+  if (*out) (*out)->refs.fetch_add(1);
+  return DDLO_OK;
+}
+int ddlo_gicp_get_input_target(ddlo_gicp* g, ddlo_cloud** out) {
+  if (!g || !out) return fail(DDLO_E_INVALID, "null argument");
+  *out = g->tgt;
+  if (*out) (*out)->refs.fetch_add(1);
+  return DDLO_OK;
+}
+
+static int calc_covs(ddlo_gicp* g, ddlo_cloud* c, ddlo_covs*& slot) {
+  if (!c) return fail(DDLO_E_NOT_READY, "calculate covariances: no cloud set");
+  ddlo_covs* v = nullptr;
+  DDLO_TRY(ddlo_covs_compute(c, g->p.k_correspondences, g->p.regularization_method, &v));
+  set_covs(slot, v);
+  ddlo_covs_release(v);
+  return DDLO_OK;
+}
+int ddlo_gicp_calculate_source_covariances(ddlo_gicp* g) {
+  if (!g) return fail(DDLO_E_INVALID, "engine is null");
+  return calc_covs(g, g->src, g->src_cov);
+}
+int ddlo_gicp_calculate_target_covariances(ddlo_gicp* g) {
+  if (!g) return fail(DDLO_E_INVALID, "engine is null");
+  return calc_covs(g, g->tgt, g->tgt_cov);
+}
+
+int ddlo_gicp_swap_source_and_target(ddlo_gicp* g) {
+  if (!g) return fail(DDLO_E_INVALID, "engine is null");
+  std::swap(g->src, g->tgt);          // input_.swap(target_) and the kd-trees with them
+  std::swap(g->src_cov, g->tgt_cov);  // source_covs_.swap(target_covs_)
+  g->corr_n = 0;                      // correspondences_.clear(); sq_distances_.clear();
+  return DDLO_OK;
+}
+
+static int ensure_workspace(ddlo_gicp* g, int ns) {
+  if (g->ws_n >= ns) return DDLO_OK;
+  DDLO_CUDA(cudaStreamSynchronize(g->rt->stream));
+  if (g->corr) cudaFree(g->corr);
+  if (g->sqd) cudaFree(g->sqd);
+  if (g->mahal) cudaFree(g->mahal);
+  g->corr = nullptr, g->sqd = nullptr, g->mahal = nullptr, g->ws_n = 0;
+  const size_t cap = (size_t)ns + ns / 4 + 256;
+  DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->corr), cap * sizeof(int)));
+  DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->sqd), cap * sizeof(float)));
+  DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->mahal), cap * kCovStride * sizeof(double)));
+  g->ws_n = (int)cap;
+  return DDLO_OK;
+}
+
+// everything align/linearize need, or the reason they can not run
+static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, GicpArgs* a) {
+  if (!g->src || !g->tgt) return fail(DDLO_E_NOT_READY, "input source and target must both be set");
+  if (g->src->n <= 0 || g->tgt->n <= 0) return fail(DDLO_E_EMPTY, "source or target cloud is empty");
+  DDLO_TRY(use_device(g->rt));
+  DDLO_TRY(build_index(g->tgt));
+  if (!g->src_cov || g->src_cov->n != g->src->n) {
+    if (!compute_missing_covs) return fail(g->src_cov ? DDLO_E_SIZE : DDLO_E_NOT_READY, "source covariances missing or of the wrong size");
+    DDLO_TRY(calc_covs(g, g->src, g->src_cov));
+    if (covs_computed) *covs_computed = 1;
+  }
+  if (!g->tgt_cov || g->tgt_cov->n != g->tgt->n) {
+    if (!compute_missing_covs) return fail(g->tgt_cov ? DDLO_E_SIZE : DDLO_E_NOT_READY, "target covariances missing or of the wrong size");
+    DDLO_TRY(calc_covs(g, g->tgt, g->tgt_cov));
+    if (covs_computed) *covs_computed = 1;
+  }
+  DDLO_TRY(ensure_workspace(g, g->src->n));
+  a->tgt = g->tgt->view;
+  a->src_pts = g->src->pts;
+  a->src_cov = g->src_cov->c;
+  a->tgt_pts = g->tgt->pts;
+  a->tgt_cov = g->tgt_cov->c;
+  a->ns = g->src->n;
+  a->corr = g->corr;
+  a->sqd = g->sqd;
+  a->mahal = g->mahal;
+  a->partials = g->partials;
+  a->partial_stride = g->partial_stride;
+  a->max_iterations = g->p.max_iterations;
+  a->optimizer = g->p.optimizer;
+  a->lm_max_iterations = g->p.lm_max_iterations;
+  a->thr2 = g->p.max_correspondence_distance * g->p.max_correspondence_distance;
+  a->trans_eps = g->p.transformation_epsilon;
+  a->rot_eps = g->p.rotation_epsilon;
+  a->lm_init_lambda_factor = g->p.lm_init_lambda_factor;
+  a->out = g->d_out;
+  return DDLO_OK;
+}
+
+static int align_blocks(const ddlo_gicp* g) {
+  const int want = (g->src->n + kAlignThreads - 1) / kAlignThreads;
+  return std::max(1, std::min(want, g->rt->max_coop_blocks_align));
+}
+
+static int enqueue_align(ddlo_gicp* g, const float* guess16, int* covs_computed) {
+  GicpArgs a;
+  DDLO_TRY(prepare(g, true, covs_computed, &a));
+  static const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  std::memcpy(a.guess, guess16 ? guess16 : I16, sizeof(a.guess));
+  std::memset(a.T_step, 0, sizeof(a.T_step));
+  DDLO_TRY(launch_align(g->rt, a, align_blocks(g)));
+  g->corr_n = g->p.max_iterations > 0 ? g->src->n : g->corr_n;
+  return DDLO_OK;
+}
+
+static void fill_result(const AlignOut* o, int covs_computed, ddlo_align_result* r) {
+  std::memcpy(r->final_transformation, o->final_transformation, sizeof(r->final_transformation));
+  std::memcpy(r->final_hessian, o->final_hessian, sizeof(r->final_hessian));
+  r->flags = o->flags | (covs_computed ? DDLO_FLAG_COVS_COMPUTED : 0);
+  r->nr_iterations = o->nr_iterations;
+  r->n_linearize = o->n_linearize;
+  r->n_compute_error = o->n_compute_error;
+  r->final_error = o->final_error;
+  r->lm_lambda = o->lm_lambda;
+}
+
+int ddlo_gicp_align(ddlo_gicp* g, const float* guess16, ddlo_align_result* result) {
+  if (!g || !result) return fail(DDLO_E_INVALID, "null argument");
+  int covs_computed = 0;
+  DDLO_TRY(enqueue_align(g, guess16, &covs_computed));
+  ddlo_runtime* rt = g->rt;
+  DDLO_TRY(ensure_pinned(rt, sizeof(AlignOut)));
+  DDLO_CUDA(cudaMemcpyAsync(rt->h_pinned, g->d_out, sizeof(AlignOut), cudaMemcpyDeviceToHost, rt->stream));
+  DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+  fill_result(static_cast<const AlignOut*>(rt->h_pinned), covs_computed, result);
+  std::memcpy(g->last_T, result->final_transformation, sizeof(g->last_T));
+  g->has_last_T = true;
+  return DDLO_OK;
+}
+
+int ddlo_gicp_align_batch(ddlo_gicp* const* engines, int m, const float* guesses16, ddlo_align_result* results) {
+  if (m < 0 || (m > 0 && (!engines || !results))) return fail(DDLO_E_INVALID, "null argument");
+  if (m == 0) return DDLO_OK;
+  ddlo_runtime* rt = engines[0] ? engines[0]->rt : nullptr;
+  if (!rt) return fail(DDLO_E_INVALID, "null engine");
+  for (int i = 0; i < m; ++i)
+    if (!engines[i] || engines[i]->rt != rt) return fail(DDLO_E_INVALID, "batch engines must share one runtime");
+  DDLO_TRY(ensure_pinned(rt, sizeof(AlignOut) * (size_t)m));
+  std::vector<int> covs_computed(m, 0);
+  AlignOut* h = static_cast<AlignOut*>(rt->h_pinned);
+  for (int i = 0; i < m; ++i) {
+    DDLO_TRY(enqueue_align(engines[i], guesses16 ? guesses16 + 16 * (size_t)i : nullptr, &covs_computed[i]));
+    DDLO_CUDA(cudaMemcpyAsync(h + i, engines[i]->d_out, sizeof(AlignOut), cudaMemcpyDeviceToHost, rt->stream));
+  }
+  DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+  for (int i = 0; i < m; ++i) {
+    fill_result(h + i, covs_computed[i], results + i);
+    std::memcpy(engines[i]->last_T, results[i].final_transformation, sizeof(engines[i]->last_T));
+    engines[i]->has_last_T = true;
+  }
+  return DDLO_OK;
+}
+
+int ddlo_gicp_aligned_cloud(ddlo_gicp* g, ddlo_cloud** out) {
+  if (!g || !out) return fail(DDLO_E_INVALID, "null argument");
+  if (!g->src || !g->has_last_T) return fail(DDLO_E_NOT_READY, "aligned cloud requested before align");
+  return ddlo_cloud_transform(g->src, g->last_T, out);
+}
+
+static int read_out(ddlo_gicp* g, AlignOut* host) {
+  ddlo_runtime* rt = g->rt;
+  DDLO_TRY(ensure_pinned(rt, sizeof(AlignOut)));
+  DDLO_CUDA(cudaMemcpyAsync(rt->h_pinned, g->d_out, sizeof(AlignOut), cudaMemcpyDeviceToHost, rt->stream));
+  DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+  std::memcpy(host, rt->h_pinned, sizeof(AlignOut));
+  return DDLO_OK;
+}
+
+int ddlo_gicp_linearize(ddlo_gicp* g, const double* T16, double* H36, double* b6, double* error) {
+  if (!g || !T16) return fail(DDLO_E_INVALID, "null argument");
+  GicpArgs a;
+  DDLO_TRY(prepare(g, false, nullptr, &a));
+  std::memset(a.guess, 0, sizeof(a.guess));
+  std::memcpy(a.T_step, T16, sizeof(a.T_step));
+  const int blocks = std::min(std::max(1, (a.ns + kAlignThreads - 1) / kAlignThreads), g->partial_stride);
+  DDLO_TRY(launch_linearize_step(g->rt, a, blocks));
+  g->corr_n = a.ns;
+  AlignOut o;
+  DDLO_TRY(read_out(g, &o));
+  const double* t = o.sums;
+  if (H36) {
+    double H[36];
+    // same unpacking as the device (row-major == column-major for a symmetric matrix)
+    H[0] = t[0], H[1] = t[1], H[2] = t[2], H[7] = t[3], H[8] = t[4], H[14] = t[5];
+    H[6] = t[1], H[12] = t[2], H[13] = t[4];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        H[6 * r + 3 + c] = t[6 + 3 * r + c];
+        H[6 * (3 + c) + r] = t[6 + 3 * r + c];
+      }
+    H[21] = t[15], H[22] = t[16], H[23] = t[17], H[28] = t[18], H[29] = t[19], H[35] = t[20];
+    H[27] = t[16], H[33] = t[17], H[34] = t[19];
+    std::memcpy(H36, H, sizeof(H));
+  }
+  if (b6)
+    for (int r = 0; r < 6; ++r) b6[r] = t[21 + r];
+  if (error) *error = t[27];
+  return DDLO_OK;
+}
+
+int ddlo_gicp_compute_error(ddlo_gicp* g, const double* T16, double* error) {
+  if (!g || !T16 || !error) return fail(DDLO_E_INVALID, "null argument");
+  if (!g->src || g->corr_n != g->src->n) return fail(DDLO_E_NOT_READY, "compute_error needs the correspondences of a previous linearize");
+  GicpArgs a;
+  DDLO_TRY(prepare(g, false, nullptr, &a));
+  std::memset(a.guess, 0, sizeof(a.guess));
+  std::memcpy(a.T_step, T16, sizeof(a.T_step));
+  const int blocks = std::min(std::max(1, (a.ns + kAlignThreads - 1) / kAlignThreads), g->partial_stride);
+  DDLO_TRY(launch_error_step(g->rt, a, blocks));
+  AlignOut o;
+  DDLO_TRY(read_out(g, &o));
+  *error = o.sums[0];
+  return DDLO_OK;
+}
+
+int ddlo_gicp_get_correspondences(ddlo_gicp* g, int* correspondences, float* sq_distances, int capacity) {
+  if (!g) return fail(DDLO_E_INVALID, "engine is null");
+  if (!g->src || g->corr_n != g->src->n) return fail(DDLO_E_NOT_READY, "no correspondences: run align or linearize first");
+  if (capacity < g->corr_n) return fail(DDLO_E_SIZE, "output capacity is smaller than the source cloud");
+  ddlo_runtime* rt = g->rt;
+  DDLO_TRY(use_device(rt));
+  if (correspondences) DDLO_CUDA(cudaMemcpyAsync(correspondences, g->corr, (size_t)g->corr_n * sizeof(int), cudaMemcpyDeviceToHost, rt->stream));
+  if (sq_distances) DDLO_CUDA(cudaMemcpyAsync(sq_distances, g->sqd, (size_t)g->corr_n * sizeof(float), cudaMemcpyDeviceToHost, rt->stream));
+  DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+  return DDLO_OK;
+}
+
+int ddlo_gicp_get_mahalanobis(ddlo_gicp* g, double* mat4x4_out, int capacity) {
+  if (!g || !mat4x4_out) return fail(DDLO_E_INVALID, "null argument");
+  if (!g->src || g->corr_n != g->src->n) return fail(DDLO_E_NOT_READY, "no Mahalanobis matrices: run align or linearize first");
+  if (capacity < g->corr_n) return fail(DDLO_E_SIZE, "output capacity is smaller than the source cloud");
+  ddlo_runtime* rt = g->rt;
+  DDLO_TRY(use_device(rt));
+  const int n = g->corr_n;
+  double* d_m = nullptr;
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_m), (size_t)n * 16 * sizeof(double), rt->stream));
+  k_cov_unpack<<<(n + 255) / 256, 256, 0, rt->stream>>>(g->mahal, n, d_m);
+  rt->launches += 1;
+  DDLO_CUDA(cudaGetLastError());
+  DDLO_CUDA(cudaMemcpyAsync(mat4x4_out, d_m, (size_t)n * 16 * sizeof(double), cudaMemcpyDeviceToHost, rt->stream));
+  DDLO_CUDA(cudaFreeAsync(d_m, rt->stream));
+  DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+  return DDLO_OK;
+}
+
+int ddlo_gicp_get_residuals(ddlo_gicp* g, double* out, int capacity) {
+  if (!g || !out) return fail(DDLO_E_INVALID, "null argument");
+  if (!g->src || g->corr_n != g->src->n) return fail(DDLO_E_NOT_READY, "no residuals: run align first");
+  if (capacity < g->corr_n) return fail(DDLO_E_SIZE, "output capacity is smaller than the source cloud");
+  ddlo_runtime* rt = g->rt;
+  DDLO_TRY(use_device(rt));
+  const int n = g->corr_n;
+  double* d_r = nullptr;
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_r), (size_t)n * sizeof(double), rt->stream));
+  k_sqrt_f2d<<<(n + 255) / 256, 256, 0, rt->stream>>>(g->sqd, n, d_r);
+  rt->launches += 1;
+  DDLO_CUDA(cudaGetLastError());
+  DDLO_CUDA(cudaMemcpyAsync(out, d_r, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, rt->stream));
+  DDLO_CUDA(cudaFreeAsync(d_r, rt->stream));
+  DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+  return DDLO_OK;
+}
+
+int ddlo_gicp_get_residual_vectors(ddlo_gicp* g, const float* T16, float* out_xyz, int capacity) {
+  if (!g || !T16 || !out_xyz) return fail(DDLO_E_INVALID, "null argument");
+  if (!g->src || !g->tgt || g->corr_n != g->src->n) return fail(DDLO_E_NOT_READY, "no residuals: run align first");
+  if (capacity < g->corr_n) return fail(DDLO_E_SIZE, "output capacity is smaller than the source cloud");
+  ddlo_runtime* rt = g->rt;
+  DDLO_TRY(use_device(rt));
+  const int n = g->corr_n;
+  float* d_r = nullptr;
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_r), (size_t)n * 3 * sizeof(float), rt->stream));
+  DDLO_TRY(launch_residual_vectors(rt, g->src->pts, g->tgt->pts, g->corr, n, T16, d_r));
+  DDLO_CUDA(cudaMemcpyAsync(out_xyz, d_r, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, rt->stream));
+  DDLO_CUDA(cudaFreeAsync(d_r, rt->stream));
+  DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+  return DDLO_OK;
+}
+
+// ---- host-callable copies of the device math (CPU tests of the exact code the kernels run) --------------
+void ddlo_math_sym3_eig(const double* sym6, double* w3, double* V9) {
+  Sym3 s{sym6[0], sym6[1], sym6[2], sym6[3], sym6[4], sym6[5]};
+  sym3_eig(s, w3, V9);
+}
+void ddlo_math_regularize(const double* sym6, int method, double* out6) {
+  Sym3 s{sym6[0], sym6[1], sym6[2], sym6[3], sym6[4], sym6[5]};
+  Sym3 r = regularize_cov(s, method);
+  out6[0] = r.xx, out6[1] = r.xy, out6[2] = r.xz, out6[3] = r.yy, out6[4] = r.yz, out6[5] = r.zz;
+}
+void ddlo_math_ldlt6_solve(const double* A36, const double* rhs6, double* x6) { ldlt6_solve(A36, rhs6, x6); }
+void ddlo_math_so3_exp(const double* omega3, double* R9) { so3_exp_matrix(omega3, R9); }
+void ddlo_math_sym3_inverse(const double* sym6, double* out6) {
+  Sym3 s{sym6[0], sym6[1], sym6[2], sym6[3], sym6[4], sym6[5]};
+  Sym3 r = sym3_inverse(s);
+  out6[0] = r.xx, out6[1] = r.xy, out6[2] = r.xz, out6[3] = r.yy, out6[4] = r.yz, out6[5] = r.zz;
+}
+
+}  // extern "C"

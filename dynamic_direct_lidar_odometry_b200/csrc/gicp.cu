@@ -1,0 +1,497 @@
+// The GICP cost function and the Levenberg-Marquardt / Gauss-Newton driver, on the device.
+//
+//   lin_point          NanoGICP::update_correspondences + the body of linearize
+//                                                    (nano_gicp_impl.hpp:235-275, 292-328)
+//   err_point          the body of compute_error     (nano_gicp_impl.hpp:349-368)
+//   k_align            LsqRegistration::computeTransformation, step_lm, step_gn, is_converged
+//                                                    (lsq_registration_impl.hpp:96-232)
+//
+// k_align is ONE cooperative launch per align(): every outer iteration does the fused
+// 1-NN + Mahalanobis + H/b pass over the source points, a grid-wide fp64 reduction
+// (warp shuffle -> block -> per-block partials in L2 -> fixed-order sum), then the 6x6 LM solve
+// and the trial-error passes, with grid.sync() between phases and no host involvement.  Every
+// block evaluates the (tiny) LM controller redundantly from the same reduced sums, which keeps the
+// control flow uniform across the grid without a broadcast step.  Reductions have a fixed order,
+// so results are bit-reproducible run to run.
+#include <cooperative_groups.h>
+
+#include "gicp.cuh"
+#include "knn.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ddlo {
+
+// accumulator layout: [0..5] H_rr upper, [6..14] H_rt row-major, [15..20] H_tt upper, [21..23] b_r,
+// [24..26] b_t, [27] sum of e^T M e
+struct LmShared {
+  Iso3 x0, xi, delta;
+  float Rf[9], tf[3];  // float cast of the transform used for the 1-NN queries (:240)
+  double H[36], b[6], d[6];
+  double y0, yi, lambda, nu, final_error;
+  double final_H[36];
+  int action, converged, step_ok, lm_failed, n_lin, n_err, nr_iter;
+};
+
+__device__ __forceinline__ void iso_to_float(const Iso3& T, float* Rf, float* tf) {
+  for (int i = 0; i < 9; ++i) Rf[i] = (float)T.r[i];
+  for (int i = 0; i < 3; ++i) tf[i] = (float)T.t[i];
+}
+
+// Eigen evaluates Transform * Vector4 coefficient-wise with a pairwise unrolled sum:
+// (r0*x + r1*y) + (r2*z + t*1).  In float this order is observable in the 1-NN query, so it is
+// spelled out with non-contracting intrinsics.
+__device__ __forceinline__ float xform_f(const float* r, float t, float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(r[0], x), __fmul_rn(r[1], y)), __fadd_rn(__fmul_rn(r[2], z), t));
+}
+__device__ __forceinline__ double xform_d(const double* r, double t, double x, double y, double z) {
+  return (r[0] * x + r[1] * y) + (r[2] * z + t);
+}
+
+__device__ __forceinline__ Sym3 load_sym3(const double* p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  return Sym3{a.x, a.y, b.x, b.y, c.x, c.y};
+}
+__device__ __forceinline__ Sym3 load_sym3_cg(const double* p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2);
+  return Sym3{a.x, a.y, b.x, b.y, c.x, c.y};
+}
+__device__ __forceinline__ void store_sym3(double* p, const Sym3& s) {
+  double2* q = reinterpret_cast<double2*>(p);
+  q[0] = make_double2(s.xx, s.xy);
+  q[1] = make_double2(s.xz, s.yy);
+  q[2] = make_double2(s.yz, s.zz);
+}
+
+__device__ __forceinline__ double quad_form(const Sym3& M, double ex, double ey, double ez, double& mx, double& my, double& mz) {
+  mx = M.xx * ex + M.xy * ey + M.xz * ez;
+  my = M.xy * ex + M.yy * ey + M.yz * ez;
+  mz = M.xz * ex + M.yz * ey + M.zz * ez;
+  return ex * mx + ey * my + ez * mz;
+}
+
+// one source point of update_correspondences + linearize
+__device__ __forceinline__ void lin_point(const GicpArgs& a, const LmShared& s, int i, double* acc) {
+  const float4 pa = __ldg(a.src_pts + i);
+  const float qx = xform_f(s.Rf + 0, s.tf[0], pa.x, pa.y, pa.z);
+  const float qy = xform_f(s.Rf + 3, s.tf[1], pa.x, pa.y, pa.z);
+  const float qz = xform_f(s.Rf + 6, s.tf[2], pa.x, pa.y, pa.z);
+  Best1 best;
+  knn_traverse(a.tgt, qx, qy, qz, best);
+  a.sqd[i] = best.d;
+  const int j = (best.idx >= 0 && (double)best.d < a.thr2) ? best.idx : -1;
+  a.corr[i] = j;
+  if (j < 0) return;
+
+  const float4 pb = __ldg(a.tgt.spts + best.pos);
+  const Sym3 CA = load_sym3(a.src_cov + (size_t)i * kCovStride);
+  const Sym3 CB = load_sym3(a.tgt_cov + (size_t)j * kCovStride);
+  Sym3 RCR = sym3_rotate(s.x0.r, CA);
+  RCR.xx += CB.xx, RCR.xy += CB.xy, RCR.xz += CB.xz, RCR.yy += CB.yy, RCR.yz += CB.yz, RCR.zz += CB.zz;
+  const Sym3 M = sym3_inverse(RCR);
+  store_sym3(a.mahal + (size_t)i * kCovStride, M);
+
+  const double x = xform_d(s.x0.r + 0, s.x0.t[0], (double)pa.x, (double)pa.y, (double)pa.z);
+  const double y = xform_d(s.x0.r + 3, s.x0.t[1], (double)pa.x, (double)pa.y, (double)pa.z);
+  const double z = xform_d(s.x0.r + 6, s.x0.t[2], (double)pa.x, (double)pa.y, (double)pa.z);
+  const double ex = (double)pb.x - x, ey = (double)pb.y - y, ez = (double)pb.z - z;
+  double mex, mey, mez;
+  acc[27] += quad_form(M, ex, ey, ez, mex, mey, mez);
+
+  // G = S^T M with S = skew(T p_A);  J = [S | -I]
+  const double g00 = z * M.xy - y * M.xz, g01 = z * M.yy - y * M.yz, g02 = z * M.yz - y * M.zz;
+  const double g10 = x * M.xz - z * M.xx, g11 = x * M.yz - z * M.xy, g12 = x * M.zz - z * M.xz;
+  const double g20 = y * M.xx - x * M.xy, g21 = y * M.xy - x * M.yy, g22 = y * M.xz - x * M.yz;
+  // H_rr = G S (symmetric)
+  acc[0] += z * g01 - y * g02;
+  acc[1] += x * g02 - z * g00;
+  acc[2] += y * g00 - x * g01;
+  acc[3] += x * g12 - z * g10;
+  acc[4] += y * g10 - x * g11;
+  acc[5] += y * g20 - x * g21;
+  // H_rt = -G
+  acc[6] -= g00, acc[7] -= g01, acc[8] -= g02;
+  acc[9] -= g10, acc[10] -= g11, acc[11] -= g12;
+  acc[12] -= g20, acc[13] -= g21, acc[14] -= g22;
+  // H_tt = M
+  acc[15] += M.xx, acc[16] += M.xy, acc[17] += M.xz, acc[18] += M.yy, acc[19] += M.yz, acc[20] += M.zz;
+  // b_r = G e, b_t = -M e
+  acc[21] += g00 * ex + g01 * ey + g02 * ez;
+  acc[22] += g10 * ex + g11 * ey + g12 * ez;
+  acc[23] += g20 * ex + g21 * ey + g22 * ez;
+  acc[24] -= mex, acc[25] -= mey, acc[26] -= mez;
+}
+
+// one source point of compute_error: stored correspondence and Mahalanobis matrix, new transform
+__device__ __forceinline__ double err_point(const GicpArgs& a, const Iso3& T, int i) {
+  const int j = __ldcg(a.corr + i);
+  if (j < 0) return 0.0;
+  const float4 pa = __ldg(a.src_pts + i);
+  const float4 pb = __ldg(a.tgt_pts + j);
+  const Sym3 M = load_sym3_cg(a.mahal + (size_t)i * kCovStride);
+  const double x = xform_d(T.r + 0, T.t[0], (double)pa.x, (double)pa.y, (double)pa.z);
+  const double y = xform_d(T.r + 3, T.t[1], (double)pa.x, (double)pa.y, (double)pa.z);
+  const double z = xform_d(T.r + 6, T.t[2], (double)pa.x, (double)pa.y, (double)pa.z);
+  const double ex = (double)pb.x - x, ey = (double)pb.y - y, ez = (double)pb.z - z;
+  double mx, my, mz;
+  return quad_form(M, ex, ey, ez, mx, my, mz);
+}
+
+// ---- reductions -------------------------------------------------------------------------------
+// block: warp shuffle tree, then a fixed-order sum over the warps; result -> dst[c * stride + block]
+template <int NCOMP>
+__device__ __forceinline__ void block_reduce_store(const double* acc, double* s_red /*[warps][NCOMP]*/, double* dst, int stride) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int c = 0; c < NCOMP; ++c) {
+    double v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[warp * NCOMP + c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NCOMP) {
+    double v = 0.0;
+    for (int w = 0; w < nwarp; ++w) v += s_red[w * NCOMP + threadIdx.x];
+    __stcg(dst + (size_t)threadIdx.x * stride + blockIdx.x, v);
+  }
+  __syncthreads();
+}
+
+// grid: every block sums all per-block partials in the same fixed order (L2 reads, L1 bypassed)
+template <int NCOMP>
+__device__ __forceinline__ void grid_sum(const double* src, int stride, int nblk, double* s_tot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int c = warp; c < NCOMP; c += nwarp) {
+    double v = 0.0;
+    for (int b = lane; b < nblk; b += 32) v += __ldcg(src + (size_t)c * stride + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_tot[c] = v;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void unpack_sums(const double* t, double* H /*row-major 6x6*/, double* b, double& err) {
+  // H_rr
+  H[0] = t[0], H[1] = t[1], H[2] = t[2], H[7] = t[3], H[8] = t[4], H[14] = t[5];
+  H[6] = t[1], H[12] = t[2], H[13] = t[4];
+  // H_rt and its transpose
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      H[6 * r + 3 + c] = t[6 + 3 * r + c];
+      H[6 * (3 + c) + r] = t[6 + 3 * r + c];
+    }
+  // H_tt
+  H[21] = t[15], H[22] = t[16], H[23] = t[17], H[28] = t[18], H[29] = t[19], H[35] = t[20];
+  H[27] = t[16], H[33] = t[17], H[34] = t[19];
+  for (int r = 0; r < 6; ++r) b[r] = t[21 + r];
+  err = t[27];
+}
+
+// lsq_registration_impl.hpp:129-139
+__device__ __forceinline__ bool is_converged(const Iso3& delta, double rot_eps, double trans_eps) {
+  double rmax = 0.0, tmax = 0.0;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) rmax = fmax(rmax, 1.0 / rot_eps * fabs(delta.r[3 * i + j] - (i == j ? 1.0 : 0.0)));
+    tmax = fmax(tmax, 1.0 / trans_eps * fabs(delta.t[i]));
+  }
+  return fmax(rmax, tmax) < 1;
+}
+
+__device__ __forceinline__ void iso_from_colmajor(const float* m, Iso3& T) {
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) T.r[3 * i + j] = (double)m[4 * j + i];
+    T.t[i] = (double)m[12 + i];
+  }
+}
+__device__ __forceinline__ void iso_from_colmajor(const double* m, Iso3& T) {
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) T.r[3 * i + j] = m[4 * j + i];
+    T.t[i] = m[12 + i];
+  }
+}
+
+// solve (H + lambda I) d = -b, delta = [exp(d_0..2) | d_3..5]
+__device__ __forceinline__ void lm_solve(LmShared& s, double lambda) {
+  double A[36], nb[6];
+  for (int i = 0; i < 36; ++i) A[i] = s.H[i];
+  for (int i = 0; i < 6; ++i) {
+    A[7 * i] += lambda;
+    nb[i] = -s.b[i];
+  }
+  ldlt6_solve(A, nb, s.d);
+  so3_exp_matrix(s.d, s.delta.r);
+  for (int i = 0; i < 3; ++i) s.delta.t[i] = s.d[3 + i];
+}
+
+__global__ void __launch_bounds__(kAlignThreads, 2) k_align(const GicpArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ LmShared s;
+  __shared__ double s_red[(kAlignThreads / 32) * kNumSums];
+  __shared__ double s_tot[kNumSums];
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  const int nblk = gridDim.x;
+  int seq = 0;  // reduction counter: partial buffers alternate so a fast block can not overwrite
+                // sums a slow block is still reading
+
+  if (threadIdx.x == 0) {
+    iso_from_colmajor(a.guess, s.x0);
+    s.lambda = -1.0;  // lm_lambda_ = -1 (:100)
+    s.converged = 0;
+    s.lm_failed = 0;
+    s.n_lin = s.n_err = 0;
+    s.nr_iter = 0;
+    s.final_error = 0.0;
+    for (int i = 0; i < 36; ++i) s.final_H[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity()
+  }
+  __syncthreads();
+
+  for (int it = 0; it < a.max_iterations; ++it) {
+    if (s.converged) break;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s.nr_iter = it;
+      iso_to_float(s.x0, s.Rf, s.tf);
+    }
+    __syncthreads();
+
+    // ---- linearize(x0): correspondences, Mahalanobis, H, b, error ---------------------------
+    {
+      double acc[kNumSums];
+#pragma unroll
+      for (int c = 0; c < kNumSums; ++c) acc[c] = 0.0;
+      for (int i = gtid; i < a.ns; i += gsize) lin_point(a, s, i, acc);
+      block_reduce_store<kNumSums>(acc, s_red, a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride, a.partial_stride);
+    }
+    grid.sync();
+    grid_sum<kNumSums>(a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride, a.partial_stride, nblk, s_tot);
+    ++seq;
+
+    if (threadIdx.x == 0) {
+      unpack_sums(s_tot, s.H, s.b, s.y0);
+      s.n_lin += 1;
+      s.step_ok = 0;
+      if (a.optimizer == DDLO_OPT_GAUSS_NEWTON) {
+        // step_gn (:156-173)
+        lm_solve(s, 0.0);
+        s.x0 = iso_mul(s.delta, s.x0);
+        for (int i = 0; i < 36; ++i) s.final_H[i] = s.H[i];
+        s.final_error = s.y0;
+        s.step_ok = 1;
+      } else {
+        if (s.lambda < 0.0) {
+          double mx = 0.0;
+          for (int i = 0; i < 6; ++i) mx = fmax(mx, fabs(s.H[7 * i]));
+          s.lambda = a.lm_init_lambda_factor * mx;
+        }
+        s.nu = 2.0;
+      }
+    }
+    __syncthreads();
+
+    if (a.optimizer != DDLO_OPT_GAUSS_NEWTON) {
+      // ---- step_lm trials (:188-229) ---------------------------------------------------------
+      for (int trial = 0; trial < a.lm_max_iterations; ++trial) {
+        if (threadIdx.x == 0) {
+          lm_solve(s, s.lambda);
+          s.xi = iso_mul(s.delta, s.x0);
+        }
+        __syncthreads();
+        {
+          double e = 0.0;
+          for (int i = gtid; i < a.ns; i += gsize) e += err_point(a, s.xi, i);
+          block_reduce_store<1>(&e, s_red, a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride, a.partial_stride);
+        }
+        grid.sync();
+        grid_sum<1>(a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride, a.partial_stride, nblk, s_tot);
+        ++seq;
+        if (threadIdx.x == 0) {
+          s.n_err += 1;
+          s.yi = s_tot[0];
+          double den = 0.0;
+          for (int r = 0; r < 6; ++r) den += s.d[r] * (s.lambda * s.d[r] - s.b[r]);
+          const double rho = (s.y0 - s.yi) / den;
+          if (rho < 0) {
+            if (is_converged(s.delta, a.rot_eps, a.trans_eps)) {
+              s.step_ok = 1;  // returns true with x0 unchanged (:215-218)
+              s.action = 1;
+            } else {
+              s.lambda = s.nu * s.lambda;
+              s.nu = 2 * s.nu;
+              s.action = 0;
+            }
+          } else {  // also taken when rho is NaN, like the reference's `if (rho < 0)`
+            s.x0 = s.xi;
+            const double q = 2 * rho - 1;
+            s.lambda = s.lambda * fmax(1.0 / 3.0, 1 - q * q * q);
+            for (int i = 0; i < 36; ++i) s.final_H[i] = s.H[i];
+            s.final_error = s.yi;
+            s.step_ok = 1;
+            s.action = 1;
+          }
+        }
+        __syncthreads();
+        if (s.action) break;
+      }
+    }
+    __syncthreads();
+    if (!s.step_ok) {  // "lm not converged!!" (:115-119)
+      if (threadIdx.x == 0) s.lm_failed = 1;
+      __syncthreads();
+      break;
+    }
+    if (threadIdx.x == 0) s.converged = is_converged(s.delta, a.rot_eps, a.trans_eps) ? 1 : 0;
+    __syncthreads();
+  }
+  __syncthreads();
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    AlignOut* o = a.out;
+    for (int i = 0; i < 16; ++i) o->final_transformation[i] = 0.0f;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) o->final_transformation[4 * j + i] = (float)s.x0.r[3 * i + j];
+      o->final_transformation[12 + i] = (float)s.x0.t[i];
+    }
+    o->final_transformation[15] = 1.0f;
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) o->final_hessian[6 * j + i] = s.final_H[6 * i + j];
+    o->flags = (s.converged ? DDLO_FLAG_CONVERGED : 0) | (s.lm_failed ? DDLO_FLAG_LM_FAILED : 0);
+    o->nr_iterations = s.nr_iter;
+    o->n_linearize = s.n_lin;
+    o->n_compute_error = s.n_err;
+    o->final_error = s.final_error;
+    o->lm_lambda = s.lambda;
+  }
+}
+
+// ---- stepwise hooks (parity tests compare H, b, error, correspondences with the oracle) ---------
+__global__ void __launch_bounds__(kAlignThreads, 2) k_linearize_step(const GicpArgs a) {
+  __shared__ LmShared s;
+  __shared__ double s_red[(kAlignThreads / 32) * kNumSums];
+  if (threadIdx.x == 0) {
+    iso_from_colmajor(a.T_step, s.x0);
+    iso_to_float(s.x0, s.Rf, s.tf);
+  }
+  __syncthreads();
+  double acc[kNumSums];
+#pragma unroll
+  for (int c = 0; c < kNumSums; ++c) acc[c] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x) lin_point(a, s, i, acc);
+  block_reduce_store<kNumSums>(acc, s_red, a.partials, a.partial_stride);
+}
+
+__global__ void __launch_bounds__(kAlignThreads, 2) k_error_step(const GicpArgs a) {
+  __shared__ Iso3 T;
+  __shared__ double s_red[(kAlignThreads / 32)];
+  if (threadIdx.x == 0) iso_from_colmajor(a.T_step, T);
+  __syncthreads();
+  double e = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x) e += err_point(a, T, i);
+  block_reduce_store<1>(&e, s_red, a.partials, a.partial_stride);
+}
+
+__global__ void __launch_bounds__(kAlignThreads) k_sum_partials(const double* partials, int stride, int nblk, int ncomp, AlignOut* out) {
+  __shared__ double s_tot[kNumSums];
+  if (ncomp == 1)
+    grid_sum<1>(partials, stride, nblk, s_tot);
+  else
+    grid_sum<kNumSums>(partials, stride, nblk, s_tot);
+  if (threadIdx.x < ncomp) out->sums[threadIdx.x] = s_tot[threadIdx.x];
+}
+
+// getResiduals(std::vector<Eigen::Vector3f>&, trans) (nano_gicp_impl.hpp:199-222): float B - trans*A
+__global__ void __launch_bounds__(256) k_residual_vectors(const float4* __restrict__ src, const float4* __restrict__ tgt,
+                                                          const int* __restrict__ corr, int n, const float* __restrict__ T /*Rf9,tf3*/,
+                                                          float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int j = corr[i];
+  float rx = 0.0f, ry = 0.0f, rz = 0.0f;
+  if (j >= 0) {
+    const float4 p = src[i], b = tgt[j];
+    rx = __fsub_rn(b.x, xform_f(T + 0, T[9], p.x, p.y, p.z));
+    ry = __fsub_rn(b.y, xform_f(T + 3, T[10], p.x, p.y, p.z));
+    rz = __fsub_rn(b.z, xform_f(T + 6, T[11], p.x, p.y, p.z));
+  }
+  out[3 * i + 0] = rx;
+  out[3 * i + 1] = ry;
+  out[3 * i + 2] = rz;
+}
+
+// pcl::transformPointCloud (float)
+__global__ void __launch_bounds__(256) k_transform_cloud(const float4* __restrict__ src, int n, const float* __restrict__ T,
+                                                         float4* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = src[i];
+  dst[i] = make_float4(xform_f(T + 0, T[9], p.x, p.y, p.z), xform_f(T + 3, T[10], p.x, p.y, p.z), xform_f(T + 6, T[11], p.x, p.y, p.z), 1.0f);
+}
+
+// ---- launchers ----------------------------------------------------------------------------------
+int gicp_max_coop_blocks(int device, int* blocks_per_sm) {
+  int per_sm = 0;
+  DDLO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align, kAlignThreads, 0));
+  int coop = 0;
+  DDLO_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+  if (!coop) return fail(DDLO_E_UNSUPPORTED, "device lacks cooperative launch");
+  *blocks_per_sm = per_sm;
+  return DDLO_OK;
+}
+
+int launch_align(ddlo_runtime* rt, const GicpArgs& args, int blocks) {
+  void* kargs[] = {const_cast<GicpArgs*>(&args)};
+  DDLO_CUDA(cudaLaunchCooperativeKernel((const void*)k_align, dim3(blocks), dim3(kAlignThreads), kargs, 0, rt->stream));
+  rt->launches += 1;
+  return DDLO_OK;
+}
+
+int launch_linearize_step(ddlo_runtime* rt, const GicpArgs& args, int blocks) {
+  k_linearize_step<<<blocks, kAlignThreads, 0, rt->stream>>>(args);
+  k_sum_partials<<<1, kAlignThreads, 0, rt->stream>>>(args.partials, args.partial_stride, blocks, kNumSums, args.out);
+  rt->launches += 2;
+  DDLO_CUDA(cudaGetLastError());
+  return DDLO_OK;
+}
+
+int launch_error_step(ddlo_runtime* rt, const GicpArgs& args, int blocks) {
+  k_error_step<<<blocks, kAlignThreads, 0, rt->stream>>>(args);
+  k_sum_partials<<<1, kAlignThreads, 0, rt->stream>>>(args.partials, args.partial_stride, blocks, 1, args.out);
+  rt->launches += 2;
+  DDLO_CUDA(cudaGetLastError());
+  return DDLO_OK;
+}
+
+static void pack_T(const float* T16, float* out12) {
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) out12[3 * i + j] = T16[4 * j + i];
+    out12[9 + i] = T16[12 + i];
+  }
+}
+
+int launch_residual_vectors(ddlo_runtime* rt, const float4* src, const float4* tgt, const int* corr, int n, const float* T16_host,
+                            float* d_out3) {
+  float h[12];
+  pack_T(T16_host, h);
+  float* dT = reinterpret_cast<float*>(rt->d_scratch);
+  DDLO_CUDA(cudaMemcpyAsync(dT, h, sizeof(h), cudaMemcpyHostToDevice, rt->stream));
+  k_residual_vectors<<<(n + 255) / 256, 256, 0, rt->stream>>>(src, tgt, corr, n, dT, d_out3);
+  rt->launches += 1;
+  DDLO_CUDA(cudaGetLastError());
+  return DDLO_OK;
+}
+
+int launch_transform_cloud(ddlo_runtime* rt, const float4* src, int n, const float* T16_host, float4* dst) {
+  float h[12];
+  pack_T(T16_host, h);
+  float* dT = reinterpret_cast<float*>(rt->d_scratch);
+  DDLO_CUDA(cudaMemcpyAsync(dT, h, sizeof(h), cudaMemcpyHostToDevice, rt->stream));
+  k_transform_cloud<<<(n + 255) / 256, 256, 0, rt->stream>>>(src, n, dT, dst);
+  rt->launches += 1;
+  DDLO_CUDA(cudaGetLastError());
+  return DDLO_OK;
+}
+
+}  // namespace ddlo

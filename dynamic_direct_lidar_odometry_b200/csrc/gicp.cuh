@@ -1,0 +1,54 @@
+// Device-side data of one NanoGICP engine and the launchers implemented in gicp.cu.
+#pragma once
+
+#include "common.cuh"
+#include "math.cuh"
+
+namespace ddlo {
+
+// what align() leaves behind for the host (one small D2H copy)
+struct AlignOut {
+  float final_transformation[16];  // column-major
+  double final_hessian[36];        // column-major (symmetric)
+  int flags;
+  int nr_iterations;
+  int n_linearize;
+  int n_compute_error;
+  double final_error;
+  double lm_lambda;
+  double sums[kNumSums];  // stepwise hooks: H upper / b / error of the last reduction
+};
+
+struct GicpArgs {
+  IndexView tgt;            // target kNN index (Morton-ordered points + box tree)
+  const float4* src_pts;    // ns, original order
+  const double* src_cov;    // ns * 6
+  const float4* tgt_pts;    // nt, original order (compute_error gathers matched points here)
+  const double* tgt_cov;    // nt * 6, original order
+  int ns;
+  int* corr;                // correspondences_   (ns)
+  float* sqd;               // sq_distances_      (ns)
+  double* mahal;            // mahalanobis_       (ns * 6)
+  double* partials;         // [2][kNumSums][partial_stride]
+  int partial_stride;
+  int max_iterations;
+  int optimizer;
+  int lm_max_iterations;
+  double thr2;              // corr_dist_threshold_^2
+  double trans_eps, rot_eps, lm_init_lambda_factor;
+  float guess[16];          // column-major Eigen::Matrix4f
+  double T_step[16];        // stepwise hooks: transform to evaluate at (column-major)
+  AlignOut* out;
+};
+
+int gicp_max_coop_blocks(int device, int* blocks_per_sm);
+int launch_align(ddlo_runtime* rt, const GicpArgs& args, int blocks);
+int launch_linearize_step(ddlo_runtime* rt, const GicpArgs& args, int blocks);
+int launch_error_step(ddlo_runtime* rt, const GicpArgs& args, int blocks);
+int launch_residual_vectors(ddlo_runtime* rt, const float4* src, const float4* tgt, const int* corr, int n, const float* T16_host,
+                            float* d_out3);
+int launch_transform_cloud(ddlo_runtime* rt, const float4* src, int n, const float* T16_host, float4* dst);
+
+constexpr int kAlignThreads = 256;
+
+}  // namespace ddlo

@@ -1,0 +1,417 @@
+"""Host-side mirror of the reference's `nano_gicp::NanoGICP` over the C ABI (include/ddlo_gicp.h).
+
+Same method names, argument meaning and state rules as
+/root/reference/dynamic_direct_lidar_odometry/include/nano_gicp/nano_gicp.hpp:80-136 and
+lsq_registration.hpp:86-101, so tests and benchmarks read like calls into the reference.  The C++
+equivalent for OdomNode is include/nano_gicp/nano_gicp.hpp in this package; this Python class exists
+because the test and benchmark harness of this repo is Python.  Everything numeric happens in
+libddlo_gicp_b200.so on the GPU.
+
+numpy convention: 4x4 / 6x6 matrices are ordinary `M[row, col]` arrays; they are transposed into the
+ABI's column-major (Eigen) layout here.  Covariances are (n, 4, 4) float64 (`Eigen::Matrix4d`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import binding as B
+from .binding import (FLAG_CONVERGED, FLAG_COVS_COMPUTED, FLAG_LM_FAILED, OPT_GAUSS_NEWTON, OPT_LEVENBERG_MARQUARDT, REG_FROBENIUS,
+                      REG_MIN_EIG, REG_NONE, REG_NORMALIZED_MIN_EIG, REG_PLANE, DdloError)
+
+__all__ = ["Runtime", "PointCloud", "Covariances", "NanoGICP", "AlignInfo", "DdloError", "REG_NONE", "REG_MIN_EIG",
+           "REG_NORMALIZED_MIN_EIG", "REG_PLANE", "REG_FROBENIUS", "OPT_GAUSS_NEWTON", "OPT_LEVENBERG_MARQUARDT"]
+
+
+def device_count() -> int:
+    n = C.c_int()
+    B.check(B.load().ddlo_device_count(C.byref(n)))
+    return n.value
+
+
+class Runtime:
+    """One device + one CUDA stream; all handles made from it are ordered on that stream."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        B.check(B.load().ddlo_runtime_create(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            B.load().ddlo_runtime_destroy(self._h)
+            self._h = None
+
+    def synchronize(self):
+        B.check(B.load().ddlo_runtime_synchronize(self._h))
+
+    def timer_begin(self):
+        B.check(B.load().ddlo_runtime_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        B.check(B.load().ddlo_runtime_timer_end(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_longlong()
+        B.check(B.load().ddlo_runtime_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def flush_l2(self, nbytes: int = 256 << 20):
+        B.check(B.load().ddlo_runtime_flush_l2(self._h, nbytes))
+
+
+class PointCloud:
+    """`pcl::PointCloud<PointXYZI>::Ptr` living on the device, plus its kNN index once built
+    (what `nanoflann::KdTreeFLANN::setInputCloud` creates in the reference)."""
+
+    def __init__(self, rt: Runtime, points=None, _handle=None):
+        self.rt = rt
+        if _handle is not None:
+            self._h = _handle
+            return
+        p = np.ascontiguousarray(points, dtype=np.float32)
+        if p.ndim != 2 or p.shape[1] < 3:
+            raise ValueError("points must be (n, >=3) float32")
+        self._h = C.c_void_p()
+        B.check(B.load().ddlo_cloud_create(rt._h, B.ptr(p), p.shape[0], p.strides[0] if p.shape[0] else 4 * p.shape[1], C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and getattr(self.rt, "_h", None):
+            B.load().ddlo_cloud_release(self._h)
+            self._h = None
+
+    def size(self) -> int:
+        n = C.c_int()
+        B.check(B.load().ddlo_cloud_size(self._h, C.byref(n)))
+        return n.value
+
+    __len__ = size
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.size(), 4), dtype=np.float32)
+        B.check(B.load().ddlo_cloud_download(self._h, B.ptr(out)))
+        return out
+
+    def build_index(self) -> "PointCloud":
+        B.check(B.load().ddlo_cloud_build_index(self._h))
+        return self
+
+    def has_index(self) -> bool:
+        v = C.c_int()
+        B.check(B.load().ddlo_cloud_has_index(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def nearestKSearch(self, queries, k: int):
+        """KdTreeFLANN::nearestKSearch for a batch: (idx (nq,k) int32, sqdist (nq,k) float32)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        idx = np.empty((q.shape[0], k), dtype=np.int32)
+        d2 = np.empty((q.shape[0], k), dtype=np.float32)
+        B.check(B.load().ddlo_cloud_knn(self._h, B.ptr(q), q.shape[0], q.strides[0] if q.shape[0] else 12, k, B.ptr(idx), B.ptr(d2), None))
+        return idx, d2
+
+    def transformed(self, T) -> "PointCloud":
+        t = np.ascontiguousarray(np.asarray(T, dtype=np.float32).T)
+        h = C.c_void_p()
+        B.check(B.load().ddlo_cloud_transform(self._h, B.ptr(t), C.byref(h)))
+        return PointCloud(self.rt, _handle=h)
+
+    @staticmethod
+    def concat(rt: Runtime, parts: Sequence["PointCloud"]) -> "PointCloud":
+        arr = (C.c_void_p * len(parts))(*[p._h for p in parts])
+        h = C.c_void_p()
+        B.check(B.load().ddlo_cloud_concat(rt._h, arr, len(parts), C.byref(h)))
+        return PointCloud(rt, _handle=h)
+
+
+class Covariances:
+    """`std::vector<Eigen::Matrix4d>` on the device; assignment shares the buffer (no copy)."""
+
+    def __init__(self, rt: Runtime, matrices=None, _handle=None):
+        self.rt = rt
+        if _handle is not None:
+            self._h = _handle
+            return
+        m = np.ascontiguousarray(matrices, dtype=np.float64)
+        if m.ndim != 3 or m.shape[1:] != (4, 4):
+            raise ValueError("covariances must be (n, 4, 4) float64")
+        self._h = C.c_void_p()
+        B.check(B.load().ddlo_covs_from_host(rt._h, B.ptr(m), m.shape[0], C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and getattr(self.rt, "_h", None):
+            B.load().ddlo_covs_release(self._h)
+            self._h = None
+
+    @staticmethod
+    def compute(cloud: PointCloud, k: int = 20, method: int = REG_PLANE) -> "Covariances":
+        h = C.c_void_p()
+        B.check(B.load().ddlo_covs_compute(cloud._h, k, method, C.byref(h)))
+        return Covariances(cloud.rt, _handle=h)
+
+    def size(self) -> int:
+        n = C.c_int()
+        B.check(B.load().ddlo_covs_size(self._h, C.byref(n)))
+        return n.value
+
+    __len__ = size
+
+    def to_host(self) -> np.ndarray:
+        out = np.empty((self.size(), 4, 4), dtype=np.float64)
+        B.check(B.load().ddlo_covs_to_host(self._h, B.ptr(out)))
+        return out
+
+    @staticmethod
+    def concat(rt: Runtime, parts: Sequence["Covariances"]) -> "Covariances":
+        arr = (C.c_void_p * len(parts))(*[p._h for p in parts])
+        h = C.c_void_p()
+        B.check(B.load().ddlo_covs_concat(rt._h, arr, len(parts), C.byref(h)))
+        return Covariances(rt, _handle=h)
+
+
+class AlignInfo:
+    def __init__(self, r: B.AlignResult):
+        self.T = np.array(r.final_transformation, dtype=np.float32).reshape(4, 4).T.copy()
+        self.hessian = np.array(r.final_hessian, dtype=np.float64).reshape(6, 6).T.copy()
+        self.flags = r.flags
+        self.converged = bool(r.flags & FLAG_CONVERGED)
+        self.lm_failed = bool(r.flags & FLAG_LM_FAILED)
+        self.covs_computed = bool(r.flags & FLAG_COVS_COMPUTED)
+        self.iterations = r.nr_iterations
+        self.n_linearize = r.n_linearize
+        self.n_compute_error = r.n_compute_error
+        self.final_error = r.final_error
+        self.lm_lambda = r.lm_lambda
+
+
+class NanoGICP:
+    """nano_gicp::NanoGICP<PointXYZI, PointXYZI> (nano_gicp.hpp:58-148)."""
+
+    def __init__(self, rt: Runtime):
+        self.rt = rt
+        self._g = C.c_void_p()
+        B.check(B.load().ddlo_gicp_create(rt._h, C.byref(self._g)))
+        self._p = B.Params()
+        B.check(B.load().ddlo_gicp_get_params(self._g, C.byref(self._p)))
+        self._src: Optional[PointCloud] = None
+        self._tgt: Optional[PointCloud] = None
+        self._last: Optional[AlignInfo] = None
+
+    def __del__(self):
+        if getattr(self, "_g", None) and getattr(self.rt, "_h", None):
+            B.load().ddlo_gicp_destroy(self._g)
+            self._g = None
+
+    def _push(self):
+        B.check(B.load().ddlo_gicp_set_params(self._g, C.byref(self._p)))
+
+    # -- knobs: nano_gicp.hpp:83-85, lsq_registration.hpp:89-91, pcl::Registration ---------------
+    def setNumThreads(self, n: int):  # OpenMP thread count: meaningless on the device, accepted for source compatibility
+        pass
+
+    def setCorrespondenceRandomness(self, k: int):
+        self._p.k_correspondences = k
+        self._push()
+
+    def setRegularizationMethod(self, method: int):
+        self._p.regularization_method = method
+        self._push()
+
+    def setMaxCorrespondenceDistance(self, d: float):
+        self._p.max_correspondence_distance = d
+        self._push()
+
+    def setMaximumIterations(self, n: int):
+        self._p.max_iterations = n
+        self._push()
+
+    def setTransformationEpsilon(self, eps: float):
+        self._p.transformation_epsilon = eps
+        self._push()
+
+    def setRotationEpsilon(self, eps: float):
+        self._p.rotation_epsilon = eps
+        self._push()
+
+    def setInitialLambdaFactor(self, f: float):
+        self._p.lm_init_lambda_factor = f
+        self._push()
+
+    def setLMMaxIterations(self, n: int):
+        self._p.lm_max_iterations = n
+        self._push()
+
+    def setOptimizer(self, t: int):
+        self._p.optimizer = t
+        self._push()
+
+    def setDebugPrint(self, flag: bool):
+        pass
+
+    # accepted and ignored, exactly like nano_gicp ignores them (odom.cc:96-98,104-112)
+    def setEuclideanFitnessEpsilon(self, eps): pass
+    def setRANSACIterations(self, n): pass
+    def setRANSACOutlierRejectionThreshold(self, t): pass
+    def setSearchMethodSource(self, tree, force_no_recompute=False): pass
+    def setSearchMethodTarget(self, tree, force_no_recompute=False): pass
+
+    # -- state plumbing: nano_gicp_impl.hpp:98-181 ---------------------------------------------------
+    def setInputSource(self, cloud: PointCloud):
+        B.check(B.load().ddlo_gicp_set_input_source(self._g, cloud._h, 1))
+        self._src = cloud
+
+    def registerInputSource(self, cloud: PointCloud):
+        B.check(B.load().ddlo_gicp_set_input_source(self._g, cloud._h, 0))
+        self._src = cloud
+
+    def setInputTarget(self, cloud: PointCloud):
+        B.check(B.load().ddlo_gicp_set_input_target(self._g, cloud._h))
+        self._tgt = cloud
+
+    def clearSource(self):
+        B.check(B.load().ddlo_gicp_clear_source(self._g))
+        self._src = None
+
+    def clearTarget(self):
+        B.check(B.load().ddlo_gicp_clear_target(self._g))
+        self._tgt = None
+
+    def setSourceCovariances(self, covs):
+        c = covs if isinstance(covs, Covariances) else Covariances(self.rt, covs)
+        B.check(B.load().ddlo_gicp_set_source_covariances(self._g, c._h))
+
+    def setTargetCovariances(self, covs):
+        c = covs if isinstance(covs, Covariances) else Covariances(self.rt, covs)
+        B.check(B.load().ddlo_gicp_set_target_covariances(self._g, c._h))
+
+    def _get_covs(self, fn) -> Optional[Covariances]:
+        h = C.c_void_p()
+        B.check(fn(self._g, C.byref(h)))
+        return Covariances(self.rt, _handle=h) if h.value else None
+
+    def getSourceCovariances(self) -> Optional[Covariances]:
+        return self._get_covs(B.load().ddlo_gicp_get_source_covariances)
+
+    def getTargetCovariances(self) -> Optional[Covariances]:
+        return self._get_covs(B.load().ddlo_gicp_get_target_covariances)
+
+    # the reference's public data members source_covs_ / target_covs_ (nano_gicp.hpp:135-136):
+    # reading gives the shared device vector, assigning None is `.clear()`
+    @property
+    def source_covs_(self): return self.getSourceCovariances()
+
+    @source_covs_.setter
+    def source_covs_(self, v):
+        B.check(B.load().ddlo_gicp_set_source_covariances(self._g, v._h if v is not None else None))
+
+    @property
+    def target_covs_(self): return self.getTargetCovariances()
+
+    @target_covs_.setter
+    def target_covs_(self, v):
+        B.check(B.load().ddlo_gicp_set_target_covariances(self._g, v._h if v is not None else None))
+
+    # source_kdtree_ / target_kdtree_ (nano_gicp.hpp:132-133): the index lives in the cloud handle, so
+    # `s2m.source_kdtree_ = s2s.source_kdtree_` (odom.cc:530) is sharing the cloud that carries it
+    @property
+    def source_kdtree_(self): return self._src
+
+    @source_kdtree_.setter
+    def source_kdtree_(self, cloud: PointCloud):
+        B.check(B.load().ddlo_gicp_set_input_source(self._g, cloud._h, 0))
+        self._src = cloud
+
+    @property
+    def target_kdtree_(self): return self._tgt
+
+    def calculateSourceCovariances(self) -> bool:
+        B.check(B.load().ddlo_gicp_calculate_source_covariances(self._g))
+        return True
+
+    def calculateTargetCovariances(self) -> bool:
+        B.check(B.load().ddlo_gicp_calculate_target_covariances(self._g))
+        return True
+
+    def swapSourceAndTarget(self):
+        B.check(B.load().ddlo_gicp_swap_source_and_target(self._g))
+        self._src, self._tgt = self._tgt, self._src
+
+    # -- registration --------------------------------------------------------------------------------------
+    def align(self, guess=None) -> AlignInfo:
+        r = B.AlignResult()
+        g = None if guess is None else np.ascontiguousarray(np.asarray(guess, dtype=np.float32).T)
+        B.check(B.load().ddlo_gicp_align(self._g, None if g is None else B.ptr(g), C.byref(r)))
+        self._last = AlignInfo(r)
+        return self._last
+
+    def getFinalTransformation(self) -> np.ndarray: return self._last.T
+    def hasConverged(self) -> bool: return self._last.converged
+    def getFinalHessian(self) -> np.ndarray: return self._last.hessian
+
+    def alignedCloud(self) -> PointCloud:
+        h = C.c_void_p()
+        B.check(B.load().ddlo_gicp_aligned_cloud(self._g, C.byref(h)))
+        return PointCloud(self.rt, _handle=h)
+
+    # -- cost-function hooks (protected in the reference, exposed for parity checks) -------------------------
+    def linearize(self, T):
+        t = np.ascontiguousarray(np.asarray(T, dtype=np.float64).T)
+        H = np.empty((6, 6), dtype=np.float64)
+        b = np.empty(6, dtype=np.float64)
+        e = C.c_double()
+        B.check(B.load().ddlo_gicp_linearize(self._g, B.ptr(t), B.ptr(H), B.ptr(b), C.byref(e)))
+        return e.value, H.T.copy(), b
+
+    def compute_error(self, T) -> float:
+        t = np.ascontiguousarray(np.asarray(T, dtype=np.float64).T)
+        e = C.c_double()
+        B.check(B.load().ddlo_gicp_compute_error(self._g, B.ptr(t), C.byref(e)))
+        return e.value
+
+    def correspondences(self):
+        n = self._src.size()
+        corr = np.empty(n, dtype=np.int32)
+        sqd = np.empty(n, dtype=np.float32)
+        B.check(B.load().ddlo_gicp_get_correspondences(self._g, B.ptr(corr), B.ptr(sqd), n))
+        return corr, sqd
+
+    def mahalanobis(self) -> np.ndarray:
+        n = self._src.size()
+        out = np.empty((n, 4, 4), dtype=np.float64)
+        B.check(B.load().ddlo_gicp_get_mahalanobis(self._g, B.ptr(out), n))
+        return out
+
+    def getResiduals(self, T=None) -> np.ndarray:
+        """getResiduals(std::vector<double>&, trans): sqrt(sq_distances_) of the last linearize."""
+        n = self._src.size()
+        out = np.empty(n, dtype=np.float64)
+        B.check(B.load().ddlo_gicp_get_residuals(self._g, B.ptr(out), n))
+        return out
+
+    def getResidualVectors(self, T) -> np.ndarray:
+        """getResiduals(std::vector<Eigen::Vector3f>&, trans)."""
+        n = self._src.size()
+        t = np.ascontiguousarray(np.asarray(T, dtype=np.float32).T)
+        out = np.empty((n, 3), dtype=np.float32)
+        B.check(B.load().ddlo_gicp_get_residual_vectors(self._g, B.ptr(t), B.ptr(out), n))
+        return out
+
+
+def align_batch(engines: Sequence[NanoGICP], guesses=None):
+    """ddlo_gicp_align_batch: independent registrations queued back to back, one host sync."""
+    m = len(engines)
+    arr = (C.c_void_p * m)(*[e._g for e in engines])
+    res = (B.AlignResult * m)()
+    g = None
+    if guesses is not None:
+        g = np.ascontiguousarray(np.transpose(np.asarray(guesses, dtype=np.float32), (0, 2, 1)))
+    B.check(B.load().ddlo_gicp_align_batch(arr, m, None if g is None else B.ptr(g), res))
+    out = [AlignInfo(r) for r in res]
+    for e, o in zip(engines, out):
+        e._last = o
+    return out

@@ -1,0 +1,198 @@
+/*
+ * ddlo_gicp.h — C ABI of the B200-native nano_gicp scan-registration path.
+ *
+ * This is the drop-in boundary for the reference's registration engine
+ *   R = /root/reference/dynamic_direct_lidar_odometry/include/nano_gicp
+ *   nano_gicp::NanoGICP<PointXYZI,PointXYZI>        R/nano_gicp.hpp:58-148
+ *   nano_gicp::LsqRegistration                      R/lsq_registration.hpp:60-128
+ *   nanoflann::KdTreeFLANN                          R/nanoflann.hpp:53-203
+ * Every entry point names the reference member it replaces.  The C++ class that keeps the
+ * reference's method names on top of this ABI is
+ *   dynamic_direct_lidar_odometry_b200/include/nano_gicp/nano_gicp.hpp
+ * and INTEGRATION.md shows how OdomNode (R/../src/odometry/odom.cc) binds to it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns an int status (DDLO_OK == 0,
+ *     negative = error, text via ddlo_last_error()); nothing throws across this boundary.
+ *   - 4x4 / 6x6 matrices are COLUMN-MAJOR, exactly the memory of Eigen::Matrix4f / Matrix4d /
+ *     Matrix<double,6,6>, so `final_transformation_.data()` etc. can be passed straight through.
+ *   - covariances cross the boundary as Eigen::Matrix4d per point (16 doubles, rows/cols 3 zero),
+ *     the element type of `source_covs_` / `target_covs_` (R/nano_gicp.hpp:135-136).
+ *   - handles are opaque, reference counted and bound to the device of the runtime that made them.
+ *     A runtime owns one CUDA stream; all work of its handles is ordered on that stream.
+ *   - there is no CPU fallback: without a CUDA device every call fails with DDLO_E_CUDA.
+ */
+#ifndef DDLO_GICP_H
+#define DDLO_GICP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDLO_ABI_VERSION 1
+
+/* status codes */
+enum {
+  DDLO_OK = 0,
+  DDLO_E_INVALID = -1,      /* null / malformed argument */
+  DDLO_E_CUDA = -2,         /* CUDA runtime error, or no device */
+  DDLO_E_EMPTY = -3,        /* empty cloud (nanoflann throws here, nanoflann_impl.hpp:1470) */
+  DDLO_E_TOO_FEW = -4,      /* fewer points than k (undefined behaviour in the reference) */
+  DDLO_E_NOT_READY = -5,    /* source/target/covariances/correspondences missing */
+  DDLO_E_SIZE = -6,         /* covariance count does not match the cloud */
+  DDLO_E_NONFINITE = -7,    /* NaN/Inf coordinate in an input cloud */
+  DDLO_E_UNSUPPORTED = -8
+};
+
+/* RegularizationMethod, same order as R/gicp/gicp_settings.hpp:47-54 */
+enum { DDLO_REG_NONE = 0, DDLO_REG_MIN_EIG = 1, DDLO_REG_NORMALIZED_MIN_EIG = 2, DDLO_REG_PLANE = 3, DDLO_REG_FROBENIUS = 4 };
+/* LSQ_OPTIMIZER_TYPE, same order as R/lsq_registration.hpp:54-58 */
+enum { DDLO_OPT_GAUSS_NEWTON = 0, DDLO_OPT_LEVENBERG_MARQUARDT = 1 };
+
+/* align() status bits (ddlo_align_result.flags) */
+enum {
+  DDLO_FLAG_CONVERGED = 1,      /* converged_ (lsq_registration_impl.hpp:121) */
+  DDLO_FLAG_LM_FAILED = 2,      /* step_lm ran out of trials: the reference prints "lm not converged!!" (:117) */
+  DDLO_FLAG_COVS_COMPUTED = 4   /* align had to compute missing covariances (nano_gicp_impl.hpp:186-193) */
+};
+
+typedef struct ddlo_runtime ddlo_runtime; /* device + stream + scratch */
+typedef struct ddlo_cloud ddlo_cloud;     /* pcl::PointCloud<PointXYZI> on the device, with an optional kNN index */
+typedef struct ddlo_covs ddlo_covs;       /* std::vector<Eigen::Matrix4d> on the device (6 doubles per point) */
+typedef struct ddlo_gicp ddlo_gicp;       /* one NanoGICP instance */
+
+/* Knobs of NanoGICP / LsqRegistration / pcl::Registration that the engine honours; defaults are the
+ * reference's (nano_gicp_impl.hpp:58-62, lsq_registration_impl.hpp:53-61). */
+typedef struct ddlo_params {
+  int k_correspondences;              /* setCorrespondenceRandomness        (20) */
+  int regularization_method;          /* setRegularizationMethod            (DDLO_REG_PLANE) */
+  int max_iterations;                 /* setMaximumIterations               (64) */
+  int optimizer;                      /* lsq_optimizer_type_                (DDLO_OPT_LEVENBERG_MARQUARDT) */
+  int lm_max_iterations;              /* lm_max_iterations_                 (10) */
+  int reserved_;
+  double max_correspondence_distance; /* setMaxCorrespondenceDistance       (FLT_MAX) */
+  double transformation_epsilon;      /* setTransformationEpsilon           (5e-4) */
+  double rotation_epsilon;            /* setRotationEpsilon                 (2e-3) */
+  double lm_init_lambda_factor;       /* setInitialLambdaFactor             (1e-9) */
+} ddlo_params;
+
+typedef struct ddlo_align_result {
+  float final_transformation[16]; /* getFinalTransformation(), column-major */
+  double final_hessian[36];       /* getFinalHessian(), column-major */
+  int flags;                      /* DDLO_FLAG_* */
+  int nr_iterations;              /* nr_iterations_ (index of the last outer iteration) */
+  int n_linearize;                /* linearize() calls executed   (for the traffic model) */
+  int n_compute_error;            /* compute_error() calls executed */
+  double final_error;             /* last accepted sum of e^T M e */
+  double lm_lambda;               /* lm_lambda_ on exit */
+} ddlo_align_result;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int ddlo_abi_version(void);
+const char* ddlo_last_error(void); /* thread-local text of the last failure */
+int ddlo_device_count(int* count);
+
+/* ---- runtime --------------------------------------------------------------------------------- */
+int ddlo_runtime_create(int device, ddlo_runtime** out);
+int ddlo_runtime_destroy(ddlo_runtime* rt);
+int ddlo_runtime_synchronize(ddlo_runtime* rt);
+/* CUDA-event timer on the runtime's stream (bench.py times kernels with these) */
+int ddlo_runtime_timer_begin(ddlo_runtime* rt);
+int ddlo_runtime_timer_end(ddlo_runtime* rt, float* elapsed_ms); /* synchronises */
+/* number of this library's kernels launched on this runtime since creation */
+int ddlo_runtime_launch_count(ddlo_runtime* rt, long long* count);
+/* write `bytes` of device scratch (L2 flush between timed iterations) */
+int ddlo_runtime_flush_l2(ddlo_runtime* rt, size_t bytes);
+
+/* ---- clouds: pcl::PointCloud + nanoflann::KdTreeFLANN ------------------------------------------ */
+/* Upload n points from HOST memory; point i starts at (const char*)xyz + i*stride_bytes and holds
+ * x,y,z as float (a pcl::PointXYZI array is stride 32).  data[3] is taken as 1.0f. */
+int ddlo_cloud_create(ddlo_runtime* rt, const float* xyz, int n, int stride_bytes, ddlo_cloud** out);
+/* Same from DEVICE memory (float4 per point, w ignored); copies. */
+int ddlo_cloud_create_from_device(ddlo_runtime* rt, const void* d_xyzw, int n, ddlo_cloud** out);
+int ddlo_cloud_retain(ddlo_cloud* c);
+int ddlo_cloud_release(ddlo_cloud* c);
+int ddlo_cloud_size(const ddlo_cloud* c, int* n);
+int ddlo_cloud_download(ddlo_cloud* c, float* xyzw_out /* n*4 */);
+/* KdTreeFLANN::setInputCloud -> buildIndex (nanoflann.hpp:137-143). Idempotent. */
+int ddlo_cloud_build_index(ddlo_cloud* c);
+int ddlo_cloud_has_index(const ddlo_cloud* c, int* has);
+/* KdTreeFLANN::nearestKSearch (nanoflann.hpp:146-156) for nq HOST queries (x,y,z float, stride in
+ * bytes).  Output, HOST: idx[nq*k] (int32, -1 padded), sqdist[nq*k] (float, +inf padded), ascending
+ * by (sqdist, idx) — ties are broken by index.  counts (optional) receives min(k, n) per query. */
+int ddlo_cloud_knn(ddlo_cloud* c, const float* queries, int nq, int qstride_bytes, int k, int* idx, float* sqdist, int* counts);
+/* rigidly transformed copy (pcl::transformPointCloud, float arithmetic), T column-major 4x4 float */
+int ddlo_cloud_transform(ddlo_cloud* c, const float* T16, ddlo_cloud** out);
+/* concatenation of m clouds (device-side `*submap_cloud_ += *keyframe`, odom.cc:1298-1313) */
+int ddlo_cloud_concat(ddlo_runtime* rt, ddlo_cloud* const* parts, int m, ddlo_cloud** out);
+
+/* ---- covariances: std::vector<Eigen::Matrix4d> ---------------------------------------------------- */
+/* NanoGICP::calculate_covariances (nano_gicp_impl.hpp:374-441); builds the index if missing. */
+int ddlo_covs_compute(ddlo_cloud* c, int k, int regularization_method, ddlo_covs** out);
+int ddlo_covs_from_host(ddlo_runtime* rt, const double* mat4x4, int n, ddlo_covs** out);
+int ddlo_covs_to_host(ddlo_covs* v, double* mat4x4_out /* n*16 */);
+int ddlo_covs_size(const ddlo_covs* v, int* n);
+int ddlo_covs_retain(ddlo_covs* v);
+int ddlo_covs_release(ddlo_covs* v);
+int ddlo_covs_concat(ddlo_runtime* rt, ddlo_covs* const* parts, int m, ddlo_covs** out);
+
+/* ---- the engine: NanoGICP ---------------------------------------------------------------------------- */
+int ddlo_gicp_create(ddlo_runtime* rt, ddlo_gicp** out);
+int ddlo_gicp_destroy(ddlo_gicp* g);
+int ddlo_params_default(ddlo_params* p);
+int ddlo_gicp_set_params(ddlo_gicp* g, const ddlo_params* p);
+int ddlo_gicp_get_params(const ddlo_gicp* g, ddlo_params* p);
+
+/* setInputSource (nano_gicp_impl.hpp:133-143): no-op for the same handle; else store, build the
+ * index, drop source covariances.  build_index = 0 gives registerInputSource (:123-130). */
+int ddlo_gicp_set_input_source(ddlo_gicp* g, ddlo_cloud* c, int build_index);
+/* setInputTarget (:146-155) */
+int ddlo_gicp_set_input_target(ddlo_gicp* g, ddlo_cloud* c);
+/* clearSource / clearTarget (:109-120) */
+int ddlo_gicp_clear_source(ddlo_gicp* g);
+int ddlo_gicp_clear_target(ddlo_gicp* g);
+/* setSourceCovariances / setTargetCovariances (:158-169); v == NULL is `source_covs_.clear()`. The
+ * handle is shared, not copied: `s2m.source_covs_ = s2s.source_covs_` (odom.cc:765) costs nothing. */
+int ddlo_gicp_set_source_covariances(ddlo_gicp* g, ddlo_covs* v);
+int ddlo_gicp_set_target_covariances(ddlo_gicp* g, ddlo_covs* v);
+/* getSourceCovariances / getTargetCovariances (nano_gicp.hpp:106-114): *out is retained, may be NULL */
+int ddlo_gicp_get_source_covariances(ddlo_gicp* g, ddlo_covs** out);
+int ddlo_gicp_get_target_covariances(ddlo_gicp* g, ddlo_covs** out);
+int ddlo_gicp_get_input_source(ddlo_gicp* g, ddlo_cloud** out);
+int ddlo_gicp_get_input_target(ddlo_gicp* g, ddlo_cloud** out);
+/* calculateSourceCovariances / calculateTargetCovariances (:172-181) */
+int ddlo_gicp_calculate_source_covariances(ddlo_gicp* g);
+int ddlo_gicp_calculate_target_covariances(ddlo_gicp* g);
+/* swapSourceAndTarget (:98-106) */
+int ddlo_gicp_swap_source_and_target(ddlo_gicp* g);
+
+/* pcl::Registration::align -> NanoGICP::computeTransformation -> LsqRegistration::
+ * computeTransformation (nano_gicp_impl.hpp:184-196, lsq_registration_impl.hpp:96-232).  The whole
+ * LM / GN loop runs on the device; the host sees one launch and one small read-back.
+ * guess16 == NULL means identity. */
+int ddlo_gicp_align(ddlo_gicp* g, const float* guess16, ddlo_align_result* result);
+/* the `output` cloud of align(): the source moved by the final transformation (:125) */
+int ddlo_gicp_aligned_cloud(ddlo_gicp* g, ddlo_cloud** out);
+
+/* Cost-function hooks (protected in the reference; exported so parity tests can compare H, b and
+ * the error with the oracle).  T16 is a column-major 4x4 double (Eigen::Isometry3d::matrix()). */
+int ddlo_gicp_linearize(ddlo_gicp* g, const double* T16, double* H36, double* b6, double* error);          /* :278-342 */
+int ddlo_gicp_compute_error(ddlo_gicp* g, const double* T16, double* error);                                /* :345-371 */
+int ddlo_gicp_get_correspondences(ddlo_gicp* g, int* correspondences, float* sq_distances, int capacity);   /* :235-275 */
+int ddlo_gicp_get_mahalanobis(ddlo_gicp* g, double* mat4x4_out, int capacity);
+/* getResiduals(std::vector<double>&, trans) (:225-232): sqrt(sq_distances_) of the last linearize */
+int ddlo_gicp_get_residuals(ddlo_gicp* g, double* out, int capacity);
+/* getResiduals(std::vector<Eigen::Vector3f>&, trans) (:199-222) */
+int ddlo_gicp_get_residual_vectors(ddlo_gicp* g, const float* T16, float* out_xyz, int capacity);
+
+/* Batched registrations (BASELINE.json config C5): m independent engines of one runtime, aligned
+ * back to back on the device with a single host synchronisation at the end. */
+int ddlo_gicp_align_batch(ddlo_gicp* const* engines, int m, const float* guesses16 /* m*16 or NULL */, ddlo_align_result* results);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDLO_GICP_H */

@@ -1,0 +1,1026 @@
+// ORACLE / TEST INFRASTRUCTURE ONLY.
+//
+// CPU restatement of the reference's nano_gicp scan-registration path.  It exists so that tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs have something to
+// compare the CUDA path with.  Nothing in dynamic_direct_lidar_odometry_b200/ may import, link,
+// load or call it, and it is not a fallback: the product fails loudly without its CUDA library.
+//
+// PARITY PIN STATUS
+//   * kNN layer: PINNED.  The reference's own vendored nanoflann compiles standalone
+//     (oracle/ref_nanoflann_shim.cpp -> oracle/_ref/libnanoflann_ref.so) and tests/ check this
+//     file's canonical kNN against it (bit-identical d^2 everywhere, identical indices wherever
+//     the k+1 smallest distances are distinct).
+//   * GICP / LM layer: PARITY UNPINNED by the reference itself.  The reference ships no tests,
+//     golden vectors or fixtures, and nano_gicp_impl.hpp / lsq_registration_impl.hpp need Eigen,
+//     PCL and Boost, none of which exist in this image, so they cannot be compiled here.  The
+//     restatement below follows those files line by line (citations at each function) and its
+//     linear algebra is cross-checked against numpy in tests/test_oracle_math.py.
+//
+// Reference files restated (R = /root/reference/dynamic_direct_lidar_odometry/include/nano_gicp):
+//   R/impl/nano_gicp_impl.hpp:98-106,133-196,199-441   NanoGICP state, covariances, linearize
+//   R/impl/lsq_registration_impl.hpp:50-64,96-232      LM / GN driver, convergence test
+//   R/gicp/so3.hpp:63-74,101-124                       skew, SO(3) exponential (quaternion)
+//   R/gicp/gicp_settings.hpp:47-54                     regularisation enum
+//   R/impl/nanoflann_impl.hpp:161-243,508-517,1495-1566   distance expression and result-set rules
+// Third-party arithmetic the reference takes from Eigen 3.3.x (absent here) is restated from the
+// published algorithms: JacobiSVD of a symmetric 3x3 -> cyclic Jacobi eigen-decomposition,
+// fixed-size inverse -> cofactor inverse, LDLT -> symmetric-pivoting LDL^T, Quaternion::
+// toRotationMatrix, Transform*Transform and Transform*Vector4 products.
+//
+// Build: g++ -O2 -fopenmp -ffp-contract=off (the reference builds -O2 with no -march, so no FMA
+// contraction happens there either; R/../CMakeLists.txt:5,16-20).
+#include <dlfcn.h>
+#include <omp.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <numeric>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// float32 squared distance exactly as nanoflann's L2_Simple_Adaptor::evalMetric evaluates it
+// (nanoflann_impl.hpp:508-517): result = 0; result += diff*diff for x, y, z, all in float.
+// ---------------------------------------------------------------------------------------------
+inline float sqdist3(const float* a, const float* b) {
+  float r = 0.0f;
+  for (int i = 0; i < 3; ++i) {
+    const float diff = a[i] - b[i];
+    r += diff * diff;
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Canonical exact kNN.  BASELINE.json asks for "bit-exact, ties broken by index": the result is
+// the k lexicographically smallest (d^2, index) pairs, ascending.  nanoflann itself keeps the
+// first-VISITED of equal distances (NANOFLANN_FIRST_MATCH is never defined, nanoflann_impl.hpp:
+// 209-219) so its order among exact ties depends on tree traversal; away from ties both agree.
+// ---------------------------------------------------------------------------------------------
+struct TopK {
+  int k, count;
+  int* idx;
+  float* d;
+  TopK(int k_, int* idx_, float* d_) : k(k_), count(0), idx(idx_), d(d_) {}
+  inline bool full() const { return count == k; }
+  inline bool admits(float dist, int index) const {
+    if (count < k) return true;
+    return dist < d[k - 1] || (dist == d[k - 1] && index < idx[k - 1]);
+  }
+  inline void add(float dist, int index) {
+    int i = count < k ? count : k - 1;
+    while (i > 0 && (d[i - 1] > dist || (d[i - 1] == dist && idx[i - 1] > index))) {
+      d[i] = d[i - 1];
+      idx[i] = idx[i - 1];
+      --i;
+    }
+    d[i] = dist;
+    idx[i] = index;
+    if (count < k) ++count;
+  }
+};
+
+struct KdNode {
+  float lo[3], hi[3];
+  int left = -1, right = -1;  // children (internal) ...
+  int begin = 0, end = 0;     // ... or [begin,end) into vind (leaf)
+};
+
+struct CanonTree {
+  const float* p = nullptr;  // n * 4 floats
+  int n = 0;
+  std::vector<int> vind;
+  std::vector<KdNode> nodes;
+
+  int build_rec(int begin, int end) {
+    KdNode nd;
+    for (int a = 0; a < 3; ++a) nd.lo[a] = nd.hi[a] = p[4 * (size_t)vind[begin] + a];
+    for (int i = begin + 1; i < end; ++i)
+      for (int a = 0; a < 3; ++a) {
+        const float v = p[4 * (size_t)vind[i] + a];
+        nd.lo[a] = std::min(nd.lo[a], v);
+        nd.hi[a] = std::max(nd.hi[a], v);
+      }
+    const int me = (int)nodes.size();
+    nodes.push_back(nd);
+    if (end - begin <= 16) {
+      nodes[me].begin = begin;
+      nodes[me].end = end;
+      return me;
+    }
+    int axis = 0;
+    float span = nd.hi[0] - nd.lo[0];
+    for (int a = 1; a < 3; ++a)
+      if (nd.hi[a] - nd.lo[a] > span) {
+        span = nd.hi[a] - nd.lo[a];
+        axis = a;
+      }
+    const int mid = begin + (end - begin) / 2;
+    std::nth_element(vind.begin() + begin, vind.begin() + mid, vind.begin() + end, [&](int a, int b) {
+      const float va = p[4 * (size_t)a + axis], vb = p[4 * (size_t)b + axis];
+      return va < vb || (va == vb && a < b);
+    });
+    const int l = build_rec(begin, mid);
+    const int r = build_rec(mid, end);
+    nodes[me].left = l;
+    nodes[me].right = r;
+    return me;
+  }
+
+  void build(const float* pts, int n_) {
+    p = pts;
+    n = n_;
+    vind.resize(n);
+    std::iota(vind.begin(), vind.end(), 0);
+    nodes.clear();
+    nodes.reserve(n / 4 + 16);
+    if (n > 0) build_rec(0, n);
+  }
+
+  // Lower bound of sqdist3(q, x) over every x inside the node's box, evaluated with the same
+  // float expression tree as sqdist3.  Because IEEE subtraction, multiplication and addition are
+  // monotone under round-to-nearest, bound <= sqdist3(q, x) holds in *float* arithmetic, so
+  // pruning on `bound > worst` can never discard a candidate the brute-force scan would admit.
+  inline float box_bound(const KdNode& nd, const float* q) const {
+    float r = 0.0f;
+    for (int a = 0; a < 3; ++a) {
+      float diff = 0.0f;
+      if (q[a] < nd.lo[a]) diff = q[a] - nd.lo[a];
+      else if (q[a] > nd.hi[a]) diff = q[a] - nd.hi[a];
+      r += diff * diff;
+    }
+    return r;
+  }
+
+  void search(int node, const float* q, TopK& rs) const {
+    const KdNode& nd = nodes[node];
+    if (nd.left < 0) {
+      for (int i = nd.begin; i < nd.end; ++i) {
+        const int id = vind[i];
+        const float d = sqdist3(q, p + 4 * (size_t)id);
+        if (rs.admits(d, id)) rs.add(d, id);
+      }
+      return;
+    }
+    const float bl = box_bound(nodes[nd.left], q), br = box_bound(nodes[nd.right], q);
+    const int first = bl <= br ? nd.left : nd.right, second = bl <= br ? nd.right : nd.left;
+    const float bf = bl <= br ? bl : br, bs = bl <= br ? br : bl;
+    if (!rs.full() || bf <= rs.d[rs.k - 1]) search(first, q, rs);
+    if (!rs.full() || bs <= rs.d[rs.k - 1]) search(second, q, rs);
+  }
+
+  int knn(const float* q, int k, int* idx, float* d) const {
+    TopK rs(k, idx, d);
+    if (n > 0) search(0, q, rs);
+    for (int i = rs.count; i < k; ++i) {
+      idx[i] = -1;
+      d[i] = std::numeric_limits<float>::infinity();
+    }
+    return rs.count;
+  }
+};
+
+// reference nanoflann, loaded from oracle/_ref/libnanoflann_ref.so when present
+struct RefApi {
+  void* lib = nullptr;
+  void* (*build)(const float*, int, int) = nullptr;
+  void (*free_)(void*) = nullptr;
+  int (*knn)(void*, const float*, int, int*, float*) = nullptr;
+} g_ref;
+
+enum Backend { BACKEND_CANONICAL = 0, BACKEND_NANOFLANN_REF = 1 };
+
+struct Cloud {
+  std::vector<float> xyzw;  // n*4, w forced to 1 (pcl::PointXYZI data[3])
+  int n = 0;
+  int backend = -1;  // -1: no tree built
+  CanonTree canon;
+  void* ref = nullptr;
+  ~Cloud() {
+    if (ref && g_ref.free_) g_ref.free_(ref);
+  }
+  bool build(int be) {
+    if (ref && g_ref.free_) {
+      g_ref.free_(ref);
+      ref = nullptr;
+    }
+    backend = -1;
+    if (be == BACKEND_NANOFLANN_REF) {
+      if (!g_ref.build) return false;
+      ref = g_ref.build(xyzw.data(), n, 4);
+      backend = be;
+      return true;
+    }
+    canon.build(xyzw.data(), n);
+    backend = BACKEND_CANONICAL;
+    return true;
+  }
+  inline int knn(const float* q, int k, int* idx, float* d) const {
+    if (backend == BACKEND_NANOFLANN_REF) {
+      const int c = g_ref.knn(ref, q, k, idx, d);
+      for (int i = c; i < k; ++i) {
+        idx[i] = -1;
+        d[i] = std::numeric_limits<float>::infinity();
+      }
+      return c;
+    }
+    return canon.knn(q, k, idx, d);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// small dense linear algebra (restating what the reference takes from Eigen)
+// ---------------------------------------------------------------------------------------------
+struct M3 {
+  double m[3][3];
+};
+
+inline M3 mul(const M3& a, const M3& b) {
+  M3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j];
+  return r;
+}
+inline M3 transpose(const M3& a) {
+  M3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[j][i];
+  return r;
+}
+inline M3 inverse(const M3& a) {  // cofactor inverse (Eigen's fixed-size 3x3 path)
+  M3 c;
+  c.m[0][0] = a.m[1][1] * a.m[2][2] - a.m[1][2] * a.m[2][1];
+  c.m[0][1] = a.m[0][2] * a.m[2][1] - a.m[0][1] * a.m[2][2];
+  c.m[0][2] = a.m[0][1] * a.m[1][2] - a.m[0][2] * a.m[1][1];
+  c.m[1][0] = a.m[1][2] * a.m[2][0] - a.m[1][0] * a.m[2][2];
+  c.m[1][1] = a.m[0][0] * a.m[2][2] - a.m[0][2] * a.m[2][0];
+  c.m[1][2] = a.m[0][2] * a.m[1][0] - a.m[0][0] * a.m[1][2];
+  c.m[2][0] = a.m[1][0] * a.m[2][1] - a.m[1][1] * a.m[2][0];
+  c.m[2][1] = a.m[0][1] * a.m[2][0] - a.m[0][0] * a.m[2][1];
+  c.m[2][2] = a.m[0][0] * a.m[1][1] - a.m[0][1] * a.m[1][0];
+  const double det = a.m[0][0] * c.m[0][0] + a.m[0][1] * c.m[1][0] + a.m[0][2] * c.m[2][0];
+  const double inv = 1.0 / det;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) c.m[i][j] *= inv;
+  return c;
+}
+
+// Symmetric 3x3 eigen-decomposition by cyclic Jacobi rotations; eigenvalues descending, columns
+// of V the eigenvectors.  For a symmetric positive semi-definite input this is what
+// Eigen::JacobiSVD (nano_gicp_impl.hpp:415) returns: singular values = eigenvalues, U = V.
+void sym_eig3(const M3& a_in, double w[3], M3& V) {
+  double a[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      a[i][j] = 0.5 * (a_in.m[i][j] + a_in.m[j][i]);
+      V.m[i][j] = i == j ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    const double off = std::fabs(a[0][1]) + std::fabs(a[0][2]) + std::fabs(a[1][2]);
+    const double diag = std::fabs(a[0][0]) + std::fabs(a[1][1]) + std::fabs(a[2][2]);
+    if (off <= 1e-300 || off <= 1e-22 * diag) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (a[p][q] == 0.0) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {  // A <- A * G
+          const double akp = a[k][p], akq = a[k][q];
+          a[k][p] = c * akp - s * akq;
+          a[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {  // A <- G^T * A
+          const double apk = a[p][k], aqk = a[q][k];
+          a[p][k] = c * apk - s * aqk;
+          a[q][k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = V.m[k][p], vkq = V.m[k][q];
+          V.m[k][p] = c * vkp - s * vkq;
+          V.m[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  w[0] = a[0][0];
+  w[1] = a[1][1];
+  w[2] = a[2][2];
+  for (int i = 0; i < 2; ++i)  // sort descending, permuting eigenvector columns alongside
+    for (int j = i + 1; j < 3; ++j)
+      if (w[j] > w[i]) {
+        std::swap(w[i], w[j]);
+        for (int k = 0; k < 3; ++k) std::swap(V.m[k][i], V.m[k][j]);
+      }
+}
+
+// Solve A x = rhs for symmetric 6x6 A with an LDL^T factorisation using symmetric (diagonal)
+// pivoting, the algorithm behind Eigen::LDLT (lsq_registration_impl.hpp:162,190).
+void ldlt6_solve(const double A_in[6][6], const double rhs[6], double x[6]) {
+  double A[6][6];
+  int perm[6];
+  for (int i = 0; i < 6; ++i) {
+    perm[i] = i;
+    for (int j = 0; j < 6; ++j) A[i][j] = A_in[i][j];
+  }
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double big = std::fabs(A[k][k]);
+    for (int i = k + 1; i < 6; ++i)
+      if (std::fabs(A[i][i]) > big) {
+        big = std::fabs(A[i][i]);
+        piv = i;
+      }
+    if (piv != k) {
+      for (int j = 0; j < 6; ++j) std::swap(A[k][j], A[piv][j]);
+      for (int i = 0; i < 6; ++i) std::swap(A[i][k], A[i][piv]);
+      std::swap(perm[k], perm[piv]);
+    }
+    const double d = A[k][k];
+    if (d == 0.0) continue;
+    for (int i = k + 1; i < 6; ++i) A[i][k] /= d;  // column of L
+    for (int i = k + 1; i < 6; ++i)
+      for (int j = k + 1; j <= i; ++j) {
+        A[i][j] -= A[i][k] * d * A[j][k];
+        A[j][i] = A[i][j];
+      }
+  }
+  double y[6];
+  for (int i = 0; i < 6; ++i) y[i] = rhs[perm[i]];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
+  for (int i = 0; i < 6; ++i) y[i] = A[i][i] != 0.0 ? y[i] / A[i][i] : 0.0;
+  for (int i = 5; i >= 0; --i)
+    for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
+  for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+}
+
+// Rigid transform kept as R (3x3) and t, like Eigen::Isometry3d's affine part.
+struct Iso {
+  double R[3][3];
+  double t[3];
+};
+
+inline Iso iso_from_colmajor16(const double* m) {
+  Iso T;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) T.R[i][j] = m[j * 4 + i];
+    T.t[i] = m[12 + i];
+  }
+  return T;
+}
+
+// Transform*Transform for Isometry mode: linear = L1*L2, translation = L1*t2 + t1.
+inline Iso iso_mul(const Iso& a, const Iso& b) {
+  Iso r;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) r.R[i][j] = a.R[i][0] * b.R[0][j] + a.R[i][1] * b.R[1][j] + a.R[i][2] * b.R[2][j];
+    r.t[i] = a.R[i][0] * b.t[0] + a.R[i][1] * b.t[1] + a.R[i][2] * b.t[2] + a.t[i];
+  }
+  return r;
+}
+
+// Transform * homogeneous 4-vector (w = 1).  Eigen evaluates the 3x4 * 4x1 product coefficient
+// by coefficient with a fully unrolled pairwise reduction: (a0 + a1) + (a2 + a3).
+inline void iso_apply(const Iso& T, const double p[3], double out[3]) {
+  for (int i = 0; i < 3; ++i) out[i] = (T.R[i][0] * p[0] + T.R[i][1] * p[1]) + (T.R[i][2] * p[2] + T.t[i]);
+}
+inline void iso_apply_f(const float R[3][3], const float t[3], const float p[3], float out[3]) {
+  for (int i = 0; i < 3; ++i) out[i] = (R[i][0] * p[0] + R[i][1] * p[1]) + (R[i][2] * p[2] + t[i]);
+}
+
+// so3.hpp:101-124 followed by Eigen::Quaterniond::toRotationMatrix()
+void so3_exp_matrix(const double omega[3], double R[3][3]) {
+  const double theta_sq = omega[0] * omega[0] + omega[1] * omega[1] + omega[2] * omega[2];
+  double imag_factor, real_factor;
+  if (theta_sq < 1e-10) {
+    const double theta_quad = theta_sq * theta_sq;
+    imag_factor = 0.5 - 1.0 / 48.0 * theta_sq + 1.0 / 3840.0 * theta_quad;
+    real_factor = 1.0 - 1.0 / 8.0 * theta_sq + 1.0 / 384.0 * theta_quad;
+  } else {
+    const double theta = std::sqrt(theta_sq);
+    const double half_theta = 0.5 * theta;
+    imag_factor = std::sin(half_theta) / theta;
+    real_factor = std::cos(half_theta);
+  }
+  const double w = real_factor, x = imag_factor * omega[0], y = imag_factor * omega[1], z = imag_factor * omega[2];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0][0] = 1 - (tyy + tzz);
+  R[0][1] = txy - twz;
+  R[0][2] = txz + twy;
+  R[1][0] = txy + twz;
+  R[1][1] = 1 - (txx + tzz);
+  R[1][2] = tyz - twx;
+  R[2][0] = txz - twy;
+  R[2][1] = tyz + twx;
+  R[2][2] = 1 - (txx + tyy);
+}
+
+enum RegMethod { REG_NONE = 0, REG_MIN_EIG = 1, REG_NORMALIZED_MIN_EIG = 2, REG_PLANE = 3, REG_FROBENIUS = 4 };
+
+// nano_gicp_impl.hpp:374-441 for one point: kNN -> centred fp64 scatter / k -> regularise.
+// cov16 is a column-major 4x4 (Eigen::Matrix4d) with row/column 3 zero.
+void covariance_of_point(const Cloud& c, int i, int k, int method, double* cov16, int* kidx, float* kd) {
+  c.knn(&c.xyzw[4 * (size_t)i], k, kidx, kd);
+  double mean[3] = {0, 0, 0};
+  for (int j = 0; j < k; ++j)
+    for (int a = 0; a < 3; ++a) mean[a] += (double)c.xyzw[4 * (size_t)kidx[j] + a];
+  for (int a = 0; a < 3; ++a) mean[a] /= (double)k;
+  M3 cov;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) cov.m[a][b] = 0.0;
+  for (int j = 0; j < k; ++j) {
+    double d[3];
+    for (int a = 0; a < 3; ++a) d[a] = (double)c.xyzw[4 * (size_t)kidx[j] + a] - mean[a];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) cov.m[a][b] += d[a] * d[b];
+  }
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) cov.m[a][b] /= (double)k;
+
+  M3 out;
+  if (method == REG_NONE) {
+    out = cov;
+  } else if (method == REG_FROBENIUS) {
+    M3 C = cov;
+    for (int a = 0; a < 3; ++a) C.m[a][a] += 1e-3;
+    M3 Ci = inverse(C);
+    double nrm = 0.0;
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) nrm += Ci.m[a][b] * Ci.m[a][b];
+    nrm = std::sqrt(nrm);
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) Ci.m[a][b] /= nrm;
+    out = inverse(Ci);
+  } else {
+    double w[3];
+    M3 V;
+    sym_eig3(cov, w, V);
+    double values[3];
+    if (method == REG_PLANE) {
+      values[0] = 1.0;
+      values[1] = 1.0;
+      values[2] = 1e-3;
+    } else if (method == REG_MIN_EIG) {
+      for (int a = 0; a < 3; ++a) values[a] = std::max(w[a], 1e-3);
+    } else {  // NORMALIZED_MIN_EIG
+      const double wmax = std::max(w[0], std::max(w[1], w[2]));
+      for (int a = 0; a < 3; ++a) values[a] = std::max(w[a] / wmax, 1e-3);
+    }
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+        out.m[a][b] = V.m[a][0] * values[0] * V.m[b][0] + V.m[a][1] * values[1] * V.m[b][1] + V.m[a][2] * values[2] * V.m[b][2];
+  }
+  for (int q = 0; q < 16; ++q) cov16[q] = 0.0;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) cov16[b * 4 + a] = out.m[a][b];
+}
+
+bool covariances(const Cloud& c, int k, int method, std::vector<double>& out, int threads) {
+  if (c.backend < 0 || c.n < k || k < 1) return false;
+  out.assign((size_t)c.n * 16, 0.0);
+#pragma omp parallel num_threads(threads)
+  {
+    std::vector<int> kidx(k);
+    std::vector<float> kd(k);
+#pragma omp for schedule(guided, 8)
+    for (int i = 0; i < c.n; ++i) covariance_of_point(c, i, k, method, &out[(size_t)i * 16], kidx.data(), kd.data());
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The engine: NanoGICP + LsqRegistration state, same defaults (nano_gicp_impl.hpp:50-65,
+// lsq_registration_impl.hpp:50-64).
+// ---------------------------------------------------------------------------------------------
+struct Engine {
+  int num_threads = omp_get_max_threads();
+  int k_correspondences = 20;
+  double corr_dist_threshold = (double)std::numeric_limits<float>::max();
+  int reg_method = REG_PLANE;
+  int max_iterations = 64;
+  double rotation_epsilon = 2e-3;
+  double transformation_epsilon = 5e-4;
+  int optimizer = 1;  // 0 GaussNewton, 1 LevenbergMarquardt (the only one the reference can select)
+  int lm_max_iterations = 10;
+  double lm_init_lambda_factor = 1e-9;
+  double lm_lambda = -1.0;
+  int knn_backend = BACKEND_CANONICAL;
+
+  std::shared_ptr<Cloud> input, target;             // input_ / target_ (+ their kd-trees)
+  std::vector<double> source_covs, target_covs;     // n*16
+  std::vector<double> mahalanobis;                  // n*16
+  std::vector<int> correspondences;
+  std::vector<float> sq_distances;
+
+  double final_hessian[6][6];
+  float final_transformation[16];
+  bool converged = false;
+  int nr_iterations = 0;
+  int n_linearize = 0, n_compute_error = 0;  // bookkeeping for the algorithmic-bytes model
+  bool lm_failed = false;
+
+  Engine() {
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) final_hessian[i][j] = i == j ? 1.0 : 0.0;
+    for (int i = 0; i < 16; ++i) final_transformation[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  }
+
+  // nano_gicp_impl.hpp:235-275
+  void update_correspondences(const Iso& trans) {
+    const int n = input->n;
+    float Rf[3][3], tf[3];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) Rf[i][j] = (float)trans.R[i][j];
+      tf[i] = (float)trans.t[i];
+    }
+    correspondences.resize(n);
+    sq_distances.resize(n);
+    mahalanobis.resize((size_t)n * 16);
+    const double thr2 = corr_dist_threshold * corr_dist_threshold;
+#pragma omp parallel for num_threads(num_threads) schedule(guided, 8)
+    for (int i = 0; i < n; ++i) {
+      float q[3];
+      iso_apply_f(Rf, tf, &input->xyzw[4 * (size_t)i], q);
+      int ki;
+      float kd;
+      target->knn(q, 1, &ki, &kd);
+      sq_distances[i] = kd;
+      correspondences[i] = (double)kd < thr2 ? ki : -1;
+      if (correspondences[i] < 0) continue;
+      const double* cA = &source_covs[(size_t)i * 16];
+      const double* cB = &target_covs[(size_t)ki * 16];
+      M3 A, RCR;
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) A.m[a][b] = cA[b * 4 + a];
+      M3 R;
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) R.m[a][b] = trans.R[a][b];
+      M3 RA = mul(R, A);
+      M3 RART = mul(RA, transpose(R));
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) RCR.m[a][b] = cB[b * 4 + a] + RART.m[a][b];
+      M3 Mi = inverse(RCR);  // 4x4 with (3,3)=1 inverted then (3,3)=0  ==  3x3 block inverse
+      double* M = &mahalanobis[(size_t)i * 16];
+      for (int q2 = 0; q2 < 16; ++q2) M[q2] = 0.0;
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) M[b * 4 + a] = Mi.m[a][b];
+    }
+  }
+
+  // shared tail of linearize (nano_gicp_impl.hpp:292-339) and compute_error (:345-371).
+  // Partial sums are taken over fixed 4096-point blocks and added in block order, so the result
+  // does not depend on the thread count (the reference's own order is schedule dependent).
+  double accumulate(const Iso& trans, double (*H)[6], double* b) {
+    const int n = input->n;
+    const int BLK = 4096;
+    const int nblk = (n + BLK - 1) / BLK;
+    std::vector<double> part((size_t)nblk * 43, 0.0);
+    const bool want = H != nullptr && b != nullptr;
+#pragma omp parallel for num_threads(num_threads) schedule(dynamic, 1)
+    for (int blk = 0; blk < nblk; ++blk) {
+      double* P = &part[(size_t)blk * 43];
+      const int i1 = std::min(n, (blk + 1) * BLK);
+      for (int i = blk * BLK; i < i1; ++i) {
+        const int ti = correspondences[i];
+        if (ti < 0) continue;
+        double pa[3], pb[3], tp[3], e[3];
+        for (int a = 0; a < 3; ++a) {
+          pa[a] = (double)input->xyzw[4 * (size_t)i + a];
+          pb[a] = (double)target->xyzw[4 * (size_t)ti + a];
+        }
+        iso_apply(trans, pa, tp);
+        for (int a = 0; a < 3; ++a) e[a] = pb[a] - tp[a];
+        const double* M = &mahalanobis[(size_t)i * 16];
+        double Me[3];
+        for (int a = 0; a < 3; ++a) Me[a] = M[0 * 4 + a] * e[0] + M[1 * 4 + a] * e[1] + M[2 * 4 + a] * e[2];
+        P[42] += e[0] * Me[0] + e[1] * Me[1] + e[2] * Me[2];
+        if (!want) continue;
+        // J (3x6) = [ skew(T p_A) | -I ]   (so3.hpp:63-74, nano_gicp_impl.hpp:318-320)
+        double J[3][6] = {{0, -tp[2], tp[1], -1, 0, 0}, {tp[2], 0, -tp[0], 0, -1, 0}, {-tp[1], tp[0], 0, 0, 0, -1}};
+        double MJ[3][6];
+        for (int a = 0; a < 3; ++a)
+          for (int c = 0; c < 6; ++c) MJ[a][c] = M[0 * 4 + a] * J[0][c] + M[1 * 4 + a] * J[1][c] + M[2 * 4 + a] * J[2][c];
+        for (int r = 0; r < 6; ++r) {
+          for (int c = 0; c < 6; ++c) P[r * 6 + c] += J[0][r] * MJ[0][c] + J[1][r] * MJ[1][c] + J[2][r] * MJ[2][c];
+          P[36 + r] += J[0][r] * Me[0] + J[1][r] * Me[1] + J[2][r] * Me[2];
+        }
+      }
+    }
+    double sum = 0.0;
+    if (want) {
+      for (int r = 0; r < 6; ++r) {
+        b[r] = 0.0;
+        for (int c = 0; c < 6; ++c) H[r][c] = 0.0;
+      }
+    }
+    for (int blk = 0; blk < nblk; ++blk) {
+      const double* P = &part[(size_t)blk * 43];
+      sum += P[42];
+      if (want)
+        for (int r = 0; r < 6; ++r) {
+          b[r] += P[36 + r];
+          for (int c = 0; c < 6; ++c) H[r][c] += P[r * 6 + c];
+        }
+    }
+    return sum;
+  }
+
+  double linearize(const Iso& trans, double (*H)[6], double* b) {
+    ++n_linearize;
+    update_correspondences(trans);
+    return accumulate(trans, H, b);
+  }
+  double compute_error(const Iso& trans) {
+    ++n_compute_error;
+    return accumulate(trans, nullptr, nullptr);
+  }
+
+  // lsq_registration_impl.hpp:129-139
+  bool is_converged(const Iso& delta) const {
+    double rmax = 0.0, tmax = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) rmax = std::max(rmax, 1.0 / rotation_epsilon * std::fabs(delta.R[i][j] - (i == j ? 1.0 : 0.0)));
+      tmax = std::max(tmax, 1.0 / transformation_epsilon * std::fabs(delta.t[i]));
+    }
+    return std::max(rmax, tmax) < 1;
+  }
+
+  static Iso delta_from(const double d[6]) {
+    Iso delta;
+    so3_exp_matrix(d, delta.R);
+    for (int i = 0; i < 3; ++i) delta.t[i] = d[3 + i];
+    return delta;
+  }
+
+  // lsq_registration_impl.hpp:156-173
+  bool step_gn(Iso& x0, Iso& delta) {
+    double H[6][6], b[6], nb[6], d[6];
+    linearize(x0, H, b);
+    for (int i = 0; i < 6; ++i) nb[i] = -b[i];
+    ldlt6_solve(H, nb, d);
+    delta = delta_from(d);
+    x0 = iso_mul(delta, x0);
+    std::memcpy(final_hessian, H, sizeof(H));
+    return true;
+  }
+
+  // lsq_registration_impl.hpp:176-232
+  bool step_lm(Iso& x0, Iso& delta) {
+    double H[6][6], b[6];
+    const double y0 = linearize(x0, H, b);
+    if (lm_lambda < 0.0) {
+      double mx = 0.0;
+      for (int i = 0; i < 6; ++i) mx = std::max(mx, std::fabs(H[i][i]));
+      lm_lambda = lm_init_lambda_factor * mx;
+    }
+    double nu = 2.0;
+    for (int i = 0; i < lm_max_iterations; ++i) {
+      double A[6][6], nb[6], d[6];
+      for (int r = 0; r < 6; ++r) {
+        nb[r] = -b[r];
+        for (int c = 0; c < 6; ++c) A[r][c] = H[r][c] + (r == c ? lm_lambda : 0.0);
+      }
+      ldlt6_solve(A, nb, d);
+      delta = delta_from(d);
+      const Iso xi = iso_mul(delta, x0);
+      const double yi = compute_error(xi);
+      double den = 0.0;
+      for (int r = 0; r < 6; ++r) den += d[r] * (lm_lambda * d[r] - b[r]);
+      const double rho = (y0 - yi) / den;
+      if (rho < 0) {
+        if (is_converged(delta)) return true;
+        lm_lambda = nu * lm_lambda;
+        nu = 2 * nu;
+        continue;
+      }
+      x0 = xi;
+      lm_lambda = lm_lambda * std::max(1.0 / 3.0, 1 - std::pow(2 * rho - 1, 3));
+      std::memcpy(final_hessian, H, sizeof(H));
+      return true;
+    }
+    return false;
+  }
+
+  // nano_gicp_impl.hpp:184-196 + lsq_registration_impl.hpp:96-126
+  bool align(const float* guess16) {
+    if (!input || !target) return false;
+    if (source_covs.size() != (size_t)input->n * 16)
+      if (!covariances(*input, k_correspondences, reg_method, source_covs, num_threads)) return false;
+    if (target_covs.size() != (size_t)target->n * 16)
+      if (!covariances(*target, k_correspondences, reg_method, target_covs, num_threads)) return false;
+    double g[16];
+    for (int i = 0; i < 16; ++i) g[i] = (double)guess16[i];
+    Iso x0 = iso_from_colmajor16(g);
+    lm_lambda = -1.0;
+    converged = false;
+    lm_failed = false;
+    n_linearize = n_compute_error = 0;
+    nr_iterations = 0;
+    for (int i = 0; i < max_iterations && !converged; ++i) {
+      nr_iterations = i;
+      Iso delta;
+      const bool ok = optimizer == 0 ? step_gn(x0, delta) : step_lm(x0, delta);
+      if (!ok) {
+        lm_failed = true;  // reference prints "lm not converged!!" and leaves the loop
+        break;
+      }
+      converged = is_converged(delta);
+    }
+    for (int i = 0; i < 16; ++i) final_transformation[i] = 0.0f;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) final_transformation[j * 4 + i] = (float)x0.R[i][j];
+      final_transformation[12 + i] = (float)x0.t[i];
+    }
+    final_transformation[15] = 1.0f;
+    return true;
+  }
+};
+
+}  // namespace
+
+// =============================================================================================
+// C interface (ctypes-friendly). 4x4 matrices are column-major, like Eigen.
+// =============================================================================================
+extern "C" {
+
+int oracle_load_reference_nanoflann(const char* so_path) {
+  if (g_ref.lib) return 0;
+  void* lib = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
+  if (!lib) return -1;
+  g_ref.build = (void* (*)(const float*, int, int))dlsym(lib, "ref_kdtree_build");
+  g_ref.free_ = (void (*)(void*))dlsym(lib, "ref_kdtree_free");
+  g_ref.knn = (int (*)(void*, const float*, int, int*, float*))dlsym(lib, "ref_kdtree_knn");
+  if (!g_ref.build || !g_ref.free_ || !g_ref.knn) {
+    dlclose(lib);
+    g_ref = RefApi();
+    return -2;
+  }
+  g_ref.lib = lib;
+  return 0;
+}
+
+int oracle_max_threads() { return omp_get_max_threads(); }
+
+// ---- clouds ---------------------------------------------------------------------------------
+void* oracle_cloud_create(const float* xyz, int n, int stride_floats) {
+  auto* sp = new std::shared_ptr<Cloud>(std::make_shared<Cloud>());
+  Cloud& c = **sp;
+  c.n = n;
+  c.xyzw.resize((size_t)n * 4);
+  for (int i = 0; i < n; ++i) {
+    for (int a = 0; a < 3; ++a) c.xyzw[4 * (size_t)i + a] = xyz[(size_t)i * stride_floats + a];
+    c.xyzw[4 * (size_t)i + 3] = 1.0f;
+  }
+  return sp;
+}
+void oracle_cloud_free(void* h) { delete static_cast<std::shared_ptr<Cloud>*>(h); }
+int oracle_cloud_size(void* h) { return (*static_cast<std::shared_ptr<Cloud>*>(h))->n; }
+int oracle_cloud_build_tree(void* h, int backend) { return (*static_cast<std::shared_ptr<Cloud>*>(h))->build(backend) ? 0 : -1; }
+
+int oracle_cloud_knn(void* h, const float* queries, int nq, int qstride_floats, int k, int* idx_out, float* d2_out, int threads) {
+  const Cloud& c = **static_cast<std::shared_ptr<Cloud>*>(h);
+  if (c.backend < 0) return -1;
+  if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for num_threads(threads) schedule(guided, 8)
+  for (int i = 0; i < nq; ++i) c.knn(queries + (size_t)i * qstride_floats, k, idx_out + (size_t)i * k, d2_out + (size_t)i * k);
+  return 0;
+}
+
+// brute-force canonical kNN (validates the kd-tree on small inputs)
+int oracle_knn_bruteforce(const float* xyz, int n, int stride_floats, const float* queries, int nq, int qstride_floats, int k,
+                          int* idx_out, float* d2_out) {
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int qi = 0; qi < nq; ++qi) {
+    TopK rs(k, idx_out + (size_t)qi * k, d2_out + (size_t)qi * k);
+    const float* q = queries + (size_t)qi * qstride_floats;
+    for (int i = 0; i < n; ++i) {
+      const float d = sqdist3(q, xyz + (size_t)i * stride_floats);
+      if (rs.admits(d, i)) rs.add(d, i);
+    }
+    for (int i = rs.count; i < k; ++i) {
+      rs.idx[i] = -1;
+      rs.d[i] = std::numeric_limits<float>::infinity();
+    }
+  }
+  return 0;
+}
+
+int oracle_cloud_covariances(void* h, int k, int method, double* out16, int threads) {
+  const Cloud& c = **static_cast<std::shared_ptr<Cloud>*>(h);
+  std::vector<double> out;
+  if (threads <= 0) threads = omp_get_max_threads();
+  if (!covariances(c, k, method, out, threads)) return -1;
+  std::memcpy(out16, out.data(), out.size() * sizeof(double));
+  return 0;
+}
+
+// ---- small math hooks so tests can check the restated linear algebra against numpy ------------
+void oracle_math_sym_eig3(const double* a9_rowmajor, double* w3, double* v9_rowmajor) {
+  M3 A, V;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) A.m[i][j] = a9_rowmajor[i * 3 + j];
+  sym_eig3(A, w3, V);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) v9_rowmajor[i * 3 + j] = V.m[i][j];
+}
+void oracle_math_inverse3(const double* a9, double* out9) {
+  M3 A;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) A.m[i][j] = a9[i * 3 + j];
+  M3 R = inverse(A);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) out9[i * 3 + j] = R.m[i][j];
+}
+void oracle_math_ldlt6_solve(const double* a36, const double* rhs6, double* x6) {
+  double A[6][6];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) A[i][j] = a36[i * 6 + j];
+  ldlt6_solve(A, rhs6, x6);
+}
+void oracle_math_so3_exp(const double* omega3, double* r9_rowmajor) {
+  double R[3][3];
+  so3_exp_matrix(omega3, R);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r9_rowmajor[i * 3 + j] = R[i][j];
+}
+
+// ---- engine ---------------------------------------------------------------------------------
+void* oracle_gicp_create() { return new Engine(); }
+void oracle_gicp_free(void* g) { delete static_cast<Engine*>(g); }
+
+void oracle_gicp_set_num_threads(void* g, int n) { static_cast<Engine*>(g)->num_threads = n > 0 ? n : omp_get_max_threads(); }
+void oracle_gicp_set_knn_backend(void* g, int be) { static_cast<Engine*>(g)->knn_backend = be; }
+void oracle_gicp_set_correspondence_randomness(void* g, int k) { static_cast<Engine*>(g)->k_correspondences = k; }
+void oracle_gicp_set_regularization_method(void* g, int m) { static_cast<Engine*>(g)->reg_method = m; }
+void oracle_gicp_set_max_correspondence_distance(void* g, double d) { static_cast<Engine*>(g)->corr_dist_threshold = d; }
+void oracle_gicp_set_maximum_iterations(void* g, int n) { static_cast<Engine*>(g)->max_iterations = n; }
+void oracle_gicp_set_transformation_epsilon(void* g, double e) { static_cast<Engine*>(g)->transformation_epsilon = e; }
+void oracle_gicp_set_rotation_epsilon(void* g, double e) { static_cast<Engine*>(g)->rotation_epsilon = e; }
+void oracle_gicp_set_initial_lambda_factor(void* g, double f) { static_cast<Engine*>(g)->lm_init_lambda_factor = f; }
+void oracle_gicp_set_lm_max_iterations(void* g, int n) { static_cast<Engine*>(g)->lm_max_iterations = n; }
+void oracle_gicp_set_optimizer(void* g, int t) { static_cast<Engine*>(g)->optimizer = t; }
+
+// setInputSource / setInputTarget (nano_gicp_impl.hpp:133-155): same cloud -> no-op; else store,
+// (re)build the kd-tree with the engine's backend if the cloud has none of that kind, clear covs.
+static void ensure_tree(Engine* e, std::shared_ptr<Cloud>& c) {
+  if (c->backend != e->knn_backend) c->build(e->knn_backend);
+}
+void oracle_gicp_set_input_source(void* g, void* cloud) {
+  Engine* e = static_cast<Engine*>(g);
+  auto& c = *static_cast<std::shared_ptr<Cloud>*>(cloud);
+  if (e->input == c) return;
+  e->input = c;
+  ensure_tree(e, c);
+  e->source_covs.clear();
+}
+void oracle_gicp_set_input_target(void* g, void* cloud) {
+  Engine* e = static_cast<Engine*>(g);
+  auto& c = *static_cast<std::shared_ptr<Cloud>*>(cloud);
+  if (e->target == c) return;
+  e->target = c;
+  ensure_tree(e, c);
+  e->target_covs.clear();
+}
+// registerInputSource (:123-130): store only, no tree, covariances untouched
+void oracle_gicp_register_input_source(void* g, void* cloud) {
+  Engine* e = static_cast<Engine*>(g);
+  auto& c = *static_cast<std::shared_ptr<Cloud>*>(cloud);
+  if (e->input == c) return;
+  e->input = c;
+}
+void oracle_gicp_clear_source(void* g) {
+  Engine* e = static_cast<Engine*>(g);
+  e->input.reset();
+  e->source_covs.clear();
+}
+void oracle_gicp_clear_target(void* g) {
+  Engine* e = static_cast<Engine*>(g);
+  e->target.reset();
+  e->target_covs.clear();
+}
+void oracle_gicp_clear_source_covs(void* g) { static_cast<Engine*>(g)->source_covs.clear(); }
+void oracle_gicp_clear_target_covs(void* g) { static_cast<Engine*>(g)->target_covs.clear(); }
+void oracle_gicp_set_source_covariances(void* g, const double* m16, int n) {
+  static_cast<Engine*>(g)->source_covs.assign(m16, m16 + (size_t)n * 16);
+}
+void oracle_gicp_set_target_covariances(void* g, const double* m16, int n) {
+  static_cast<Engine*>(g)->target_covs.assign(m16, m16 + (size_t)n * 16);
+}
+int oracle_gicp_source_covs_size(void* g) { return (int)(static_cast<Engine*>(g)->source_covs.size() / 16); }
+int oracle_gicp_target_covs_size(void* g) { return (int)(static_cast<Engine*>(g)->target_covs.size() / 16); }
+void oracle_gicp_get_source_covariances(void* g, double* out) {
+  Engine* e = static_cast<Engine*>(g);
+  std::memcpy(out, e->source_covs.data(), e->source_covs.size() * sizeof(double));
+}
+void oracle_gicp_get_target_covariances(void* g, double* out) {
+  Engine* e = static_cast<Engine*>(g);
+  std::memcpy(out, e->target_covs.data(), e->target_covs.size() * sizeof(double));
+}
+int oracle_gicp_calculate_source_covariances(void* g) {
+  Engine* e = static_cast<Engine*>(g);
+  if (!e->input) return -1;
+  ensure_tree(e, e->input);
+  return covariances(*e->input, e->k_correspondences, e->reg_method, e->source_covs, e->num_threads) ? 0 : -1;
+}
+int oracle_gicp_calculate_target_covariances(void* g) {
+  Engine* e = static_cast<Engine*>(g);
+  if (!e->target) return -1;
+  ensure_tree(e, e->target);
+  return covariances(*e->target, e->k_correspondences, e->reg_method, e->target_covs, e->num_threads) ? 0 : -1;
+}
+// swapSourceAndTarget (:98-106)
+void oracle_gicp_swap_source_and_target(void* g) {
+  Engine* e = static_cast<Engine*>(g);
+  e->input.swap(e->target);
+  e->source_covs.swap(e->target_covs);
+  e->correspondences.clear();
+  e->sq_distances.clear();
+}
+
+int oracle_gicp_align(void* g, const float* guess16, float* final16, int* converged, int* nr_iterations, double* hessian36,
+                      int* n_linearize, int* n_compute_error, int* lm_failed) {
+  Engine* e = static_cast<Engine*>(g);
+  if (!e->align(guess16)) return -1;
+  std::memcpy(final16, e->final_transformation, sizeof(float) * 16);
+  if (converged) *converged = e->converged ? 1 : 0;
+  if (nr_iterations) *nr_iterations = e->nr_iterations;
+  if (hessian36)
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) hessian36[j * 6 + i] = e->final_hessian[i][j];
+  if (n_linearize) *n_linearize = e->n_linearize;
+  if (n_compute_error) *n_compute_error = e->n_compute_error;
+  if (lm_failed) *lm_failed = e->lm_failed ? 1 : 0;
+  return 0;
+}
+
+// direct access to the cost function at a given transform (column-major 4x4 double)
+int oracle_gicp_linearize(void* g, const double* T16, double* H36, double* b6, double* err) {
+  Engine* e = static_cast<Engine*>(g);
+  if (!e->input || !e->target) return -1;
+  if (e->source_covs.size() != (size_t)e->input->n * 16 || e->target_covs.size() != (size_t)e->target->n * 16) return -2;
+  double H[6][6], b[6];
+  *err = e->linearize(iso_from_colmajor16(T16), H, b);
+  for (int i = 0; i < 6; ++i) {
+    b6[i] = b[i];
+    for (int j = 0; j < 6; ++j) H36[j * 6 + i] = H[i][j];
+  }
+  return 0;
+}
+int oracle_gicp_compute_error(void* g, const double* T16, double* err) {
+  Engine* e = static_cast<Engine*>(g);
+  if (!e->input || e->correspondences.size() != (size_t)e->input->n) return -1;
+  *err = e->compute_error(iso_from_colmajor16(T16));
+  return 0;
+}
+int oracle_gicp_get_correspondences(void* g, int* corr, float* sqd) {
+  Engine* e = static_cast<Engine*>(g);
+  if (corr) std::memcpy(corr, e->correspondences.data(), e->correspondences.size() * sizeof(int));
+  if (sqd) std::memcpy(sqd, e->sq_distances.data(), e->sq_distances.size() * sizeof(float));
+  return (int)e->correspondences.size();
+}
+int oracle_gicp_get_mahalanobis(void* g, double* out16) {
+  Engine* e = static_cast<Engine*>(g);
+  std::memcpy(out16, e->mahalanobis.data(), e->mahalanobis.size() * sizeof(double));
+  return (int)(e->mahalanobis.size() / 16);
+}
+// getResiduals(std::vector<double>&, trans) (:225-232): sqrt of the last linearize's sq_distances_
+int oracle_gicp_get_residuals(void* g, double* out) {
+  Engine* e = static_cast<Engine*>(g);
+  for (size_t i = 0; i < e->sq_distances.size(); ++i) out[i] = std::sqrt((double)e->sq_distances[i]);
+  return (int)e->sq_distances.size();
+}
+// getResiduals(std::vector<Vector3f>&, trans) (:199-222): B - trans*A in float, 0 without a match
+int oracle_gicp_get_residual_vectors(void* g, const float* T16, float* out3) {
+  Engine* e = static_cast<Engine*>(g);
+  if (!e->input || !e->target) return -1;
+  const int n = e->input->n;
+  if (e->correspondences.size() != (size_t)n) return -1;
+  float R[3][3], t[3];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) R[i][j] = T16[j * 4 + i];
+    t[i] = T16[12 + i];
+  }
+  for (int i = 0; i < n; ++i) {
+    const int ti = e->correspondences[i];
+    if (ti < 0) {
+      out3[3 * i] = out3[3 * i + 1] = out3[3 * i + 2] = 0.0f;
+      continue;
+    }
+    float q[3];
+    iso_apply_f(R, t, &e->input->xyzw[4 * (size_t)i], q);
+    for (int a = 0; a < 3; ++a) out3[3 * i + a] = e->target->xyzw[4 * (size_t)ti + a] - q[a];
+  }
+  return n;
+}
+
+}  // extern "C"

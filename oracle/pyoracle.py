@@ -1,0 +1,359 @@
+"""ctypes binding of oracle/_build/liboracle_gicp.so — ORACLE / TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (dynamic_direct_lidar_odometry_b200/) never does.
+
+Matrix convention at this boundary: numpy arrays are ordinary row-major `M[i, j]`; the C side is
+column-major like Eigen, so 4x4 / 6x6 matrices are transposed on the way in and out.  Covariances
+travel as (n, 4, 4) float64 (`Eigen::Matrix4d` per point; symmetric, so no transpose is needed).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "_build" / "liboracle_gicp.so"
+REF_LIB_PATH = HERE / "_ref" / "libnanoflann_ref.so"
+REFERENCE_ROOT = Path("/root/reference")
+
+BACKEND_CANONICAL = 0
+BACKEND_NANOFLANN_REF = 1
+
+REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = range(5)
+OPT_GAUSS_NEWTON, OPT_LEVENBERG_MARQUARDT = 0, 1
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> None:
+    """Compile the restatement, and the reference nanoflann when /root/reference is present."""
+    src = HERE / "oracle_gicp.cpp"
+    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(HERE), "-B", "all"], check=True, capture_output=True)
+    ref_hdr = REFERENCE_ROOT / "dynamic_direct_lidar_odometry/include/nano_gicp/impl/nanoflann_impl.hpp"
+    shim = HERE / "ref_nanoflann_shim.cpp"
+    if ref_hdr.exists() and (force or not REF_LIB_PATH.exists() or REF_LIB_PATH.stat().st_mtime < shim.stat().st_mtime):
+        subprocess.run(["make", "-C", str(HERE), "-B", "ref"], check=True, capture_output=True)
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        build()
+    L = C.CDLL(str(LIB_PATH))
+    vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+    sig = {
+        "oracle_load_reference_nanoflann": (ci, [C.c_char_p]),
+        "oracle_max_threads": (ci, []),
+        "oracle_cloud_create": (vp, [_f32p, ci, ci]),
+        "oracle_cloud_free": (None, [vp]),
+        "oracle_cloud_size": (ci, [vp]),
+        "oracle_cloud_build_tree": (ci, [vp, ci]),
+        "oracle_cloud_knn": (ci, [vp, _f32p, ci, ci, ci, _i32p, _f32p, ci]),
+        "oracle_knn_bruteforce": (ci, [_f32p, ci, ci, _f32p, ci, ci, ci, _i32p, _f32p]),
+        "oracle_cloud_covariances": (ci, [vp, ci, ci, _f64p, ci]),
+        "oracle_math_sym_eig3": (None, [_f64p, _f64p, _f64p]),
+        "oracle_math_inverse3": (None, [_f64p, _f64p]),
+        "oracle_math_ldlt6_solve": (None, [_f64p, _f64p, _f64p]),
+        "oracle_math_so3_exp": (None, [_f64p, _f64p]),
+        "oracle_gicp_create": (vp, []),
+        "oracle_gicp_free": (None, [vp]),
+        "oracle_gicp_set_num_threads": (None, [vp, ci]),
+        "oracle_gicp_set_knn_backend": (None, [vp, ci]),
+        "oracle_gicp_set_correspondence_randomness": (None, [vp, ci]),
+        "oracle_gicp_set_regularization_method": (None, [vp, ci]),
+        "oracle_gicp_set_max_correspondence_distance": (None, [vp, cd]),
+        "oracle_gicp_set_maximum_iterations": (None, [vp, ci]),
+        "oracle_gicp_set_transformation_epsilon": (None, [vp, cd]),
+        "oracle_gicp_set_rotation_epsilon": (None, [vp, cd]),
+        "oracle_gicp_set_initial_lambda_factor": (None, [vp, cd]),
+        "oracle_gicp_set_lm_max_iterations": (None, [vp, ci]),
+        "oracle_gicp_set_optimizer": (None, [vp, ci]),
+        "oracle_gicp_set_input_source": (None, [vp, vp]),
+        "oracle_gicp_set_input_target": (None, [vp, vp]),
+        "oracle_gicp_register_input_source": (None, [vp, vp]),
+        "oracle_gicp_clear_source": (None, [vp]),
+        "oracle_gicp_clear_target": (None, [vp]),
+        "oracle_gicp_clear_source_covs": (None, [vp]),
+        "oracle_gicp_clear_target_covs": (None, [vp]),
+        "oracle_gicp_set_source_covariances": (None, [vp, _f64p, ci]),
+        "oracle_gicp_set_target_covariances": (None, [vp, _f64p, ci]),
+        "oracle_gicp_source_covs_size": (ci, [vp]),
+        "oracle_gicp_target_covs_size": (ci, [vp]),
+        "oracle_gicp_get_source_covariances": (None, [vp, _f64p]),
+        "oracle_gicp_get_target_covariances": (None, [vp, _f64p]),
+        "oracle_gicp_calculate_source_covariances": (ci, [vp]),
+        "oracle_gicp_calculate_target_covariances": (ci, [vp]),
+        "oracle_gicp_swap_source_and_target": (None, [vp]),
+        "oracle_gicp_align": (ci, [vp, _f32p, _f32p, C.POINTER(ci), C.POINTER(ci), _f64p, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
+        "oracle_gicp_linearize": (ci, [vp, _f64p, _f64p, _f64p, C.POINTER(cd)]),
+        "oracle_gicp_compute_error": (ci, [vp, _f64p, C.POINTER(cd)]),
+        "oracle_gicp_get_correspondences": (ci, [vp, _i32p, _f32p]),
+        "oracle_gicp_get_mahalanobis": (ci, [vp, _f64p]),
+        "oracle_gicp_get_residuals": (ci, [vp, _f64p]),
+        "oracle_gicp_get_residual_vectors": (ci, [vp, _f32p, _f32p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def have_reference_nanoflann() -> bool:
+    return REF_LIB_PATH.exists()
+
+
+_ref_loaded = False
+
+
+def load_reference_nanoflann() -> bool:
+    global _ref_loaded
+    if _ref_loaded:
+        return True
+    if not REF_LIB_PATH.exists():
+        return False
+    _ref_loaded = lib().oracle_load_reference_nanoflann(str(REF_LIB_PATH).encode()) == 0
+    return _ref_loaded
+
+
+def max_threads() -> int:
+    return int(lib().oracle_max_threads())
+
+
+def _as_points(points) -> np.ndarray:
+    p = np.ascontiguousarray(points, dtype=np.float32)
+    if p.ndim != 2 or p.shape[1] not in (3, 4):
+        raise ValueError("points must be (n,3) or (n,4) float32")
+    return p
+
+
+class Cloud:
+    """A point cloud plus (optionally) a kd-tree over it — `pcl::PointCloud` + `KdTreeFLANN`."""
+
+    def __init__(self, points):
+        self.points = _as_points(points)
+        self.n = self.points.shape[0]
+        self._h = lib().oracle_cloud_create(self.points, self.n, self.points.shape[1])
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_cloud_free(self._h)
+            self._h = None
+
+    def build_tree(self, backend: int = BACKEND_CANONICAL) -> "Cloud":
+        if backend == BACKEND_NANOFLANN_REF and not load_reference_nanoflann():
+            raise RuntimeError("oracle/_ref/libnanoflann_ref.so is not available")
+        if lib().oracle_cloud_build_tree(self._h, backend) != 0:
+            raise RuntimeError("tree build failed")
+        return self
+
+    def knn(self, queries, k: int, threads: int = 0):
+        q = _as_points(queries)
+        idx = np.empty((q.shape[0], k), dtype=np.int32)
+        d2 = np.empty((q.shape[0], k), dtype=np.float32)
+        if lib().oracle_cloud_knn(self._h, q, q.shape[0], q.shape[1], k, idx, d2, threads) != 0:
+            raise RuntimeError("kNN before build_tree")
+        return idx, d2
+
+    def covariances(self, k: int = 20, method: int = REG_PLANE, threads: int = 0) -> np.ndarray:
+        out = np.empty((self.n, 4, 4), dtype=np.float64)
+        if lib().oracle_cloud_covariances(self._h, k, method, out.reshape(-1), threads) != 0:
+            raise RuntimeError("covariances failed (no tree, or fewer than k points)")
+        return out
+
+
+def knn_bruteforce(points, queries, k: int):
+    p, q = _as_points(points), _as_points(queries)
+    idx = np.empty((q.shape[0], k), dtype=np.int32)
+    d2 = np.empty((q.shape[0], k), dtype=np.float32)
+    lib().oracle_knn_bruteforce(p, p.shape[0], p.shape[1], q, q.shape[0], q.shape[1], k, idx, d2)
+    return idx, d2
+
+
+def _cm(M: np.ndarray, dtype) -> np.ndarray:
+    """row-major numpy matrix -> flat column-major buffer"""
+    return np.ascontiguousarray(np.asarray(M, dtype=dtype).T).reshape(-1)
+
+
+class AlignResult:
+    def __init__(self, T, converged, iterations, hessian, n_linearize, n_compute_error, lm_failed):
+        self.T = T
+        self.converged = converged
+        self.iterations = iterations
+        self.hessian = hessian
+        self.n_linearize = n_linearize
+        self.n_compute_error = n_compute_error
+        self.lm_failed = lm_failed
+
+
+class NanoGICP:
+    """The reference's `nano_gicp::NanoGICP` method surface over the CPU restatement."""
+
+    def __init__(self, backend: int = BACKEND_CANONICAL, threads: int = 0):
+        self._g = lib().oracle_gicp_create()
+        self._clouds = {}
+        if backend == BACKEND_NANOFLANN_REF and not load_reference_nanoflann():
+            raise RuntimeError("oracle/_ref/libnanoflann_ref.so is not available")
+        lib().oracle_gicp_set_knn_backend(self._g, backend)
+        lib().oracle_gicp_set_num_threads(self._g, threads)
+
+    def __del__(self):
+        if getattr(self, "_g", None):
+            lib().oracle_gicp_free(self._g)
+            self._g = None
+
+    # knobs (nano_gicp.hpp:83-85, lsq_registration.hpp:89-93, pcl::Registration setters)
+    def setNumThreads(self, n): lib().oracle_gicp_set_num_threads(self._g, n)
+    def setCorrespondenceRandomness(self, k): lib().oracle_gicp_set_correspondence_randomness(self._g, k)
+    def setRegularizationMethod(self, m): lib().oracle_gicp_set_regularization_method(self._g, m)
+    def setMaxCorrespondenceDistance(self, d): lib().oracle_gicp_set_max_correspondence_distance(self._g, d)
+    def setMaximumIterations(self, n): lib().oracle_gicp_set_maximum_iterations(self._g, n)
+    def setTransformationEpsilon(self, e): lib().oracle_gicp_set_transformation_epsilon(self._g, e)
+    def setRotationEpsilon(self, e): lib().oracle_gicp_set_rotation_epsilon(self._g, e)
+    def setInitialLambdaFactor(self, f): lib().oracle_gicp_set_initial_lambda_factor(self._g, f)
+    def setLMMaxIterations(self, n): lib().oracle_gicp_set_lm_max_iterations(self._g, n)
+    def setOptimizer(self, t): lib().oracle_gicp_set_optimizer(self._g, t)
+
+    # state plumbing (nano_gicp_impl.hpp:98-181)
+    def setInputSource(self, cloud: Cloud):
+        self._src = cloud
+        lib().oracle_gicp_set_input_source(self._g, cloud._h)
+
+    def setInputTarget(self, cloud: Cloud):
+        self._tgt = cloud
+        lib().oracle_gicp_set_input_target(self._g, cloud._h)
+
+    def registerInputSource(self, cloud: Cloud):
+        self._src = cloud
+        lib().oracle_gicp_register_input_source(self._g, cloud._h)
+
+    def clearSource(self): lib().oracle_gicp_clear_source(self._g)
+    def clearTarget(self): lib().oracle_gicp_clear_target(self._g)
+    def clearSourceCovariances(self): lib().oracle_gicp_clear_source_covs(self._g)
+    def clearTargetCovariances(self): lib().oracle_gicp_clear_target_covs(self._g)
+
+    def setSourceCovariances(self, covs):
+        c = np.ascontiguousarray(covs, dtype=np.float64)
+        lib().oracle_gicp_set_source_covariances(self._g, c.reshape(-1), c.shape[0])
+
+    def setTargetCovariances(self, covs):
+        c = np.ascontiguousarray(covs, dtype=np.float64)
+        lib().oracle_gicp_set_target_covariances(self._g, c.reshape(-1), c.shape[0])
+
+    def getSourceCovariances(self) -> np.ndarray:
+        n = lib().oracle_gicp_source_covs_size(self._g)
+        out = np.empty((n, 4, 4), dtype=np.float64)
+        if n:
+            lib().oracle_gicp_get_source_covariances(self._g, out.reshape(-1))
+        return out
+
+    def getTargetCovariances(self) -> np.ndarray:
+        n = lib().oracle_gicp_target_covs_size(self._g)
+        out = np.empty((n, 4, 4), dtype=np.float64)
+        if n:
+            lib().oracle_gicp_get_target_covariances(self._g, out.reshape(-1))
+        return out
+
+    def calculateSourceCovariances(self) -> bool:
+        return lib().oracle_gicp_calculate_source_covariances(self._g) == 0
+
+    def calculateTargetCovariances(self) -> bool:
+        return lib().oracle_gicp_calculate_target_covariances(self._g) == 0
+
+    def swapSourceAndTarget(self):
+        lib().oracle_gicp_swap_source_and_target(self._g)
+
+    # registration (lsq_registration_impl.hpp:96-126)
+    def align(self, guess=None) -> AlignResult:
+        g = np.eye(4, dtype=np.float32) if guess is None else np.asarray(guess, dtype=np.float32)
+        out = np.empty(16, dtype=np.float32)
+        H = np.empty(36, dtype=np.float64)
+        conv, it, nl, ne, fail = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        rc = lib().oracle_gicp_align(self._g, _cm(g, np.float32), out, C.byref(conv), C.byref(it), H, C.byref(nl), C.byref(ne), C.byref(fail))
+        if rc != 0:
+            raise RuntimeError("oracle align failed (missing clouds or too few points)")
+        self._last = AlignResult(out.reshape(4, 4).T.copy(), bool(conv.value), it.value, H.reshape(6, 6).T.copy(), nl.value, ne.value, bool(fail.value))
+        return self._last
+
+    def getFinalTransformation(self): return self._last.T
+    def hasConverged(self): return self._last.converged
+    def getFinalHessian(self): return self._last.hessian
+
+    # cost-function hooks (protected in the reference; exposed for parity checks)
+    def linearize(self, T):
+        H = np.empty(36, dtype=np.float64)
+        b = np.empty(6, dtype=np.float64)
+        err = C.c_double()
+        rc = lib().oracle_gicp_linearize(self._g, _cm(T, np.float64), H, b, C.byref(err))
+        if rc != 0:
+            raise RuntimeError(f"oracle linearize failed ({rc})")
+        return err.value, H.reshape(6, 6).T.copy(), b
+
+    def compute_error(self, T) -> float:
+        err = C.c_double()
+        if lib().oracle_gicp_compute_error(self._g, _cm(T, np.float64), C.byref(err)) != 0:
+            raise RuntimeError("compute_error before linearize")
+        return err.value
+
+    def correspondences(self):
+        n = self._src.n
+        corr = np.empty(n, dtype=np.int32)
+        sqd = np.empty(n, dtype=np.float32)
+        m = lib().oracle_gicp_get_correspondences(self._g, corr, sqd)
+        return corr[:m], sqd[:m]
+
+    def mahalanobis(self) -> np.ndarray:
+        out = np.empty((self._src.n, 4, 4), dtype=np.float64)
+        lib().oracle_gicp_get_mahalanobis(self._g, out.reshape(-1))
+        return out
+
+    def getResiduals(self, T=None) -> np.ndarray:
+        out = np.empty(self._src.n, dtype=np.float64)
+        m = lib().oracle_gicp_get_residuals(self._g, out)
+        return out[:m]
+
+    def getResidualVectors(self, T) -> np.ndarray:
+        out = np.empty((self._src.n, 3), dtype=np.float32)
+        if lib().oracle_gicp_get_residual_vectors(self._g, _cm(T, np.float32), out.reshape(-1)) < 0:
+            raise RuntimeError("getResiduals before align")
+        return out
+
+
+# ---- restated linear algebra, exposed for the numpy cross-checks --------------------------------
+def math_sym_eig3(A):
+    w = np.empty(3)
+    V = np.empty(9)
+    lib().oracle_math_sym_eig3(np.ascontiguousarray(A, dtype=np.float64).reshape(-1), w, V)
+    return w, V.reshape(3, 3)
+
+
+def math_inverse3(A):
+    out = np.empty(9)
+    lib().oracle_math_inverse3(np.ascontiguousarray(A, dtype=np.float64).reshape(-1), out)
+    return out.reshape(3, 3)
+
+
+def math_ldlt6_solve(A, rhs):
+    x = np.empty(6)
+    lib().oracle_math_ldlt6_solve(np.ascontiguousarray(A, dtype=np.float64).reshape(-1), np.ascontiguousarray(rhs, dtype=np.float64), x)
+    return x
+
+
+def math_so3_exp(omega):
+    R = np.empty(9)
+    lib().oracle_math_so3_exp(np.ascontiguousarray(omega, dtype=np.float64), R)
+    return R.reshape(3, 3)
