@@ -68,6 +68,10 @@ SIGNATURES = {
     "ddlo_runtime_timer_end": [_vp, C.POINTER(C.c_float)],
     "ddlo_runtime_launch_count": [_vp, C.POINTER(C.c_longlong)],
     "ddlo_runtime_flush_l2": [_vp, C.c_size_t],
+    "ddlo_runtime_event_record": [_vp, C.c_int],
+    "ddlo_runtime_event_elapsed": [_vp, C.c_int, C.c_int, C.POINTER(C.c_float)],
+    "ddlo_host_alloc": [C.c_size_t, _vpp],
+    "ddlo_host_free": [_vp],
     "ddlo_cloud_create": [_vp, _vp, C.c_int, C.c_int, _vpp],
     "ddlo_cloud_create_from_device": [_vp, _vp, C.c_int, _vpp],
     "ddlo_cloud_retain": [_vp],
@@ -105,6 +109,8 @@ SIGNATURES = {
     "ddlo_gicp_calculate_target_covariances": [_vp],
     "ddlo_gicp_swap_source_and_target": [_vp],
     "ddlo_gicp_align": [_vp, _vp, C.POINTER(AlignResult)],
+    "ddlo_gicp_align_async": [_vp, _vp],
+    "ddlo_gicp_align_finish": [_vp, C.POINTER(AlignResult)],
     "ddlo_gicp_aligned_cloud": [_vp, _vpp],
     "ddlo_gicp_linearize": [_vp, _vp, _vp, _vp, C.POINTER(C.c_double)],
     "ddlo_gicp_compute_error": [_vp, _vp, C.POINTER(C.c_double)],

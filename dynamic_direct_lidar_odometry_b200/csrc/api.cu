@@ -89,7 +89,7 @@ static void cloud_free(ddlo_cloud* c) {
   cudaStream_t st = c->rt->stream;
   if (c->pts) cudaFreeAsync(c->pts, st);
   if (c->spts) cudaFreeAsync(c->spts, st);
-  if (c->boxes) cudaFreeAsync(c->boxes, st);
+  if (c->nodes) cudaFreeAsync(c->nodes, st);
   delete c;
 }
 static void covs_free(ddlo_covs* v) {
@@ -120,6 +120,8 @@ struct ddlo_gicp {
   AlignOut* d_out = nullptr;
   float last_T[16];
   bool has_last_T = false;
+  bool align_pending = false;
+  int pending_covs_computed = 0;
 };
 
 static void set_cloud(ddlo_cloud*& slot, ddlo_cloud* c) {
@@ -158,6 +160,7 @@ int ddlo_runtime_create(int device, ddlo_runtime** out) {
   DDLO_CUDA(cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking));
   DDLO_CUDA(cudaEventCreate(&rt->ev0));
   DDLO_CUDA(cudaEventCreate(&rt->ev1));
+  for (auto& e : rt->slots) DDLO_CUDA(cudaEventCreate(&e));
   DDLO_CUDA(cudaDeviceGetAttribute(&rt->num_sms, cudaDevAttrMultiProcessorCount, device));
   cudaMemPool_t pool;
   DDLO_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -183,6 +186,7 @@ int ddlo_runtime_destroy(ddlo_runtime* rt) {
   if (rt->h_pinned) cudaFreeHost(rt->h_pinned);
   cudaEventDestroy(rt->ev0);
   cudaEventDestroy(rt->ev1);
+  for (auto& e : rt->slots) cudaEventDestroy(e);
   cudaStreamDestroy(rt->stream);
   delete rt;
   return DDLO_OK;
@@ -232,6 +236,31 @@ int ddlo_runtime_flush_l2(ddlo_runtime* rt, size_t bytes) {
   }
   k_fill<<<rt->num_sms * 8, 256, 0, rt->stream>>>(static_cast<float4*>(rt->flush_buf), bytes / 16);
   DDLO_CUDA(cudaGetLastError());
+  return DDLO_OK;
+}
+
+int ddlo_runtime_event_record(ddlo_runtime* rt, int slot) {
+  if (!rt || slot < 0 || slot >= 16) return fail(DDLO_E_INVALID, "bad runtime or event slot");
+  DDLO_TRY(use_device(rt));
+  DDLO_CUDA(cudaEventRecord(rt->slots[slot], rt->stream));
+  return DDLO_OK;
+}
+
+int ddlo_runtime_event_elapsed(ddlo_runtime* rt, int a, int b, float* elapsed_ms) {
+  if (!rt || !elapsed_ms || a < 0 || a >= 16 || b < 0 || b >= 16) return fail(DDLO_E_INVALID, "bad runtime or event slot");
+  DDLO_TRY(use_device(rt));
+  DDLO_CUDA(cudaEventSynchronize(rt->slots[b]));
+  DDLO_CUDA(cudaEventElapsedTime(elapsed_ms, rt->slots[a], rt->slots[b]));
+  return DDLO_OK;
+}
+
+int ddlo_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(DDLO_E_INVALID, "out is null");
+  DDLO_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+  return DDLO_OK;
+}
+int ddlo_host_free(void* p) {
+  if (p) DDLO_CUDA(cudaFreeHost(p));
   return DDLO_OK;
 }
 
@@ -756,18 +785,33 @@ static void fill_result(const AlignOut* o, int covs_computed, ddlo_align_result*
   r->lm_lambda = o->lm_lambda;
 }
 
-int ddlo_gicp_align(ddlo_gicp* g, const float* guess16, ddlo_align_result* result) {
+int ddlo_gicp_align_async(ddlo_gicp* g, const float* guess16) {
+  if (!g) return fail(DDLO_E_INVALID, "engine is null");
+  g->pending_covs_computed = 0;
+  DDLO_TRY(enqueue_align(g, guess16, &g->pending_covs_computed));
+  g->align_pending = true;
+  return DDLO_OK;
+}
+
+int ddlo_gicp_align_finish(ddlo_gicp* g, ddlo_align_result* result) {
   if (!g || !result) return fail(DDLO_E_INVALID, "null argument");
-  int covs_computed = 0;
-  DDLO_TRY(enqueue_align(g, guess16, &covs_computed));
+  if (!g->align_pending) return fail(DDLO_E_NOT_READY, "align_finish without align_async");
+  g->align_pending = false;
   ddlo_runtime* rt = g->rt;
+  DDLO_TRY(use_device(rt));
   DDLO_TRY(ensure_pinned(rt, sizeof(AlignOut)));
   DDLO_CUDA(cudaMemcpyAsync(rt->h_pinned, g->d_out, sizeof(AlignOut), cudaMemcpyDeviceToHost, rt->stream));
   DDLO_CUDA(cudaStreamSynchronize(rt->stream));
-  fill_result(static_cast<const AlignOut*>(rt->h_pinned), covs_computed, result);
+  fill_result(static_cast<const AlignOut*>(rt->h_pinned), g->pending_covs_computed, result);
   std::memcpy(g->last_T, result->final_transformation, sizeof(g->last_T));
   g->has_last_T = true;
   return DDLO_OK;
+}
+
+int ddlo_gicp_align(ddlo_gicp* g, const float* guess16, ddlo_align_result* result) {
+  if (!g || !result) return fail(DDLO_E_INVALID, "null argument");
+  DDLO_TRY(ddlo_gicp_align_async(g, guess16));
+  return ddlo_gicp_align_finish(g, result);
 }
 
 int ddlo_gicp_align_batch(ddlo_gicp* const* engines, int m, const float* guesses16, ddlo_align_result* results) {

@@ -33,28 +33,30 @@ int fail(int code, const std::string& msg);
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// kNN index: Morton-ordered points + an implicit 8-wide tree of axis-aligned boxes.
+// kNN index: Morton-ordered points + an explicit octree over Morton prefixes.
 //
-//   spts[i]           i-th point in Morton order, .w carries the ORIGINAL index (int bits);
-//                     padded with +inf points to a multiple of 64.
-//   level L-1 (leaf)  node j covers spts[8j .. 8j+7]
-//   level l < L-1     node j covers nodes 8j .. 8j+7 of level l+1
-//   level 0           at most 8 nodes (one group)
-// Boxes are stored per GROUP of 8 sibling nodes as 12 float4 (SoA):
-//   [lo.x x8][lo.y x8][lo.z x8][hi.x x8][hi.y x8][hi.z x8]
-// so that one node visit is 12 coalescable 16-byte loads.  Unused slots hold lo=+inf, hi=-inf,
-// whose distance bound is +inf and therefore never qualifies.
+//   spts[i]   i-th point in Morton order (30-bit code, 10 bits per axis on one isotropic lattice over
+//             the cloud's bounding box); .w carries the ORIGINAL index (int bits).
+//   cell      the set of points sharing the first 3t bits of the code (level t, t = 0..10); cells of
+//             one level are disjoint cubes, so the tight boxes of sibling cells are disjoint too.
+//   leaf      the largest cell holding at most kLeafMax points (level-10 cells are leaves whatever
+//             their size); a contiguous run spts[start, start+count).
+//   node      every cell above a leaf; 256 bytes = 16 float4:
+//               [0..11]  boxes of the 8 child cells, SoA: lo.x x8, lo.y x8, lo.z x8, hi.x x8, hi.y x8, hi.z x8
+//               [12..15] 8 child references (int2): {node id, -1} internal, {start, count>0} leaf, {0,0} empty
+//             empty slots keep lo=+inf, hi=-inf, whose distance bound is +inf and never qualifies.
+//   node 0 is the root (level 0, the whole cloud); ids are breadth-first.
 // ---------------------------------------------------------------------------------------------
-constexpr int kMaxLevels = 8;
-constexpr int kBranch = 8;
-constexpr int kLeaf = 8;
+constexpr int kLeafMax = 16;
+constexpr int kMortonLevels = 10;
+constexpr int kNodeF4 = 16;     // float4 per node
+constexpr int kStackDepth = 80; // pending internal children: <= 7 per level, <= 11 levels
 
 struct IndexView {
   const float4* spts;
-  const float4* box[kMaxLevels];
-  int cnt[kMaxLevels];
+  const float4* nodes;
   int n;
-  int nlev;
+  int n_nodes;
 };
 
 // 6 doubles per point: xx, xy, xz, yy, yz, zz (the 3x3 block of the reference's Matrix4d)
@@ -72,6 +74,7 @@ struct ddlo_runtime {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t slots[16] = {};
   int num_sms = 0;
   long long launches = 0;
   void* flush_buf = nullptr;
@@ -92,9 +95,8 @@ struct ddlo_cloud {
   float4* pts = nullptr;  // original order, w = 1
   // index (optional)
   bool has_index = false;
-  int npad = 0;           // padded length of spts (multiple of 64)
-  float4* spts = nullptr;
-  float4* boxes = nullptr;  // all levels, contiguous
+  float4* spts = nullptr;   // Morton order, w = original index
+  float4* nodes = nullptr;  // octree nodes, kNodeF4 float4 each
   ddlo::IndexView view{};
 };
 

@@ -2,12 +2,26 @@
 // KdTreeFLANN::setInputCloud -> KDTreeSingleIndexAdaptor::buildIndex / divideTree
 // (R/nanoflann.hpp:137-143, R/impl/nanoflann_impl.hpp:1335-1347, 987-1143).
 //
-//   1. k_bounds   cloud bounding box (ordered-int atomics) + finite check
-//   2. k_morton   30-bit Morton key of every point on a uniform 1024^3 lattice over the box
-//   3. radix sort (key, original index) pairs                         [cub::DeviceRadixSort]
-//   4. k_leaves   gather points into Morton order (w := original index) and box every 8 of them
-//   5. k_level    box every 8 boxes, once per upper level
+// The structure is an octree over Morton prefixes (see common.cuh).  It is built without any
+// level-by-level dependency, from the sorted codes alone:
+//
+//   1. k_bounds    cloud bounding box (ordered-int atomics) + finite check
+//   2. k_morton    30-bit Morton key of every point
+//   3. radix sort  (key, original index) pairs                         [cub::DeviceRadixSort]
+//   4. k_cells     per point: the level L(i) of its leaf cell = 1 + the longest prefix that any
+//                  window of kLeafMax+1 consecutive sorted points containing i still shares; the
+//                  flag "i is the first point of an internal cell of level t" for t = 0..9; the
+//                  gather of the point into Morton order
+//   5. inclusive scan of the level-major flags                         [cub::DeviceScan]
+//                  -> breadth-first node ids: the level-t node holding point i is S[t][i] - 1
+//   6. k_init_nodes, k_emit: every first point of a cell writes that cell into its parent node
+//                  (leaf: range + box; internal: child id) and every leaf folds its box into the
+//                  slots of all its ancestors with ordered-int atomics
+//   7. k_finalize  ordered ints -> floats
+//
+// One 4-byte read-back (the node count, after step 5) sizes the node array exactly.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
 
@@ -21,6 +35,8 @@ __device__ __forceinline__ float ord2f(unsigned o) {
   const unsigned u = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o;
   return __uint_as_float(u);
 }
+constexpr unsigned kOrdPosInf = 0xff800000u;  // f2ord(+inf)
+constexpr unsigned kOrdNegInf = 0x007fffffu;  // f2ord(-inf)
 
 // bounds: [0..2] ordered min, [3..5] ordered max, [6] non-finite counter
 __global__ void __launch_bounds__(256) k_bounds(const float4* __restrict__ pts, int n, unsigned* __restrict__ bounds) {
@@ -83,65 +99,91 @@ __global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ pts, 
   vals[i] = i;
 }
 
-__device__ __forceinline__ void store_box(float4* __restrict__ level, int node, float lx, float ly, float lz, float hx, float hy,
-                                          float hz) {
-  float* g = reinterpret_cast<float*>(level + (size_t)(node >> 3) * 12) + (node & 7);
-  g[0] = lx;
-  g[8] = ly;
-  g[16] = lz;
-  g[24] = hx;
-  g[32] = hy;
-  g[40] = hz;
+// number of leading 3-bit digits two 30-bit codes share (10 if equal)
+__device__ __forceinline__ int common_digits(unsigned a, unsigned b) {
+  const unsigned x = a ^ b;
+  return x ? (__clz(x) - 2) / 3 : kMortonLevels;
 }
 
-// one thread per padded point slot (npad = groups * 64); 8 consecutive lanes form one leaf
-__global__ void __launch_bounds__(256) k_leaves(const float4* __restrict__ pts, const int* __restrict__ perm, int n, int npad,
-                                                float4* __restrict__ spts, float4* __restrict__ leaf_level) {
+__global__ void __launch_bounds__(256) k_cells(const unsigned* __restrict__ keys, const int* __restrict__ perm,
+                                               const float4* __restrict__ pts, int n, unsigned char* __restrict__ leaf_level,
+                                               int* __restrict__ flags /*[10][n]*/, float4* __restrict__ spts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npad) return;  // npad is a multiple of 64 and blockDim of 32: whole warps leave together
-  const float inf = __int_as_float(0x7f800000);
-  float lx = inf, ly = inf, lz = inf, hx = -inf, hy = -inf, hz = -inf;
-  float4 out = make_float4(inf, inf, inf, __int_as_float(-1));
-  if (i < n) {
-    const int o = perm[i];
-    const float4 p = pts[o];
-    out = make_float4(p.x, p.y, p.z, __int_as_float(o));
-    lx = hx = p.x;
-    ly = hy = p.y;
-    lz = hz = p.z;
-  }
-  spts[i] = out;
+  if (i >= n) return;
+  const unsigned key = keys[i];
+  // longest prefix shared by kLeafMax+1 consecutive points around i: that cell is too big for a leaf
+  int g = -1;
+  const int j0 = max(0, i - kLeafMax), j1 = min(i, n - 1 - kLeafMax);
+  for (int j = j0; j <= j1; ++j) g = max(g, common_digits(__ldg(keys + j), __ldg(keys + j + kLeafMax)));
+  const int L = min(kMortonLevels, max(1, g + 1));
+  leaf_level[i] = (unsigned char)L;
+  const int cd = i == 0 ? -1 : common_digits(key, __ldg(keys + i - 1));
 #pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
-    lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o));
-    ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
-    lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
-    hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
-    hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
-    hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
-  }
-  if ((i & 7) == 0) store_box(leaf_level, i >> 3, lx, ly, lz, hx, hy, hz);
+  for (int t = 0; t < kMortonLevels; ++t) flags[(size_t)t * n + i] = (t < L && cd < t) ? 1 : 0;
+  const int o = perm[i];
+  const float4 p = pts[o];
+  spts[i] = make_float4(p.x, p.y, p.z, __int_as_float(o));
 }
 
-// one thread per node slot of `level` (slots = groups * 8); children are group `node` of `child_level`
-__global__ void __launch_bounds__(256) k_level(const float4* __restrict__ child_level, int child_groups, float4* __restrict__ level,
-                                               int slots) {
-  const int node = blockIdx.x * blockDim.x + threadIdx.x;
-  if (node >= slots) return;
-  const float inf = __int_as_float(0x7f800000);
-  float lx = inf, ly = inf, lz = inf, hx = -inf, hy = -inf, hz = -inf;
-  if (node < child_groups) {
-    const float4* g = child_level + (size_t)node * 12;
-    const float4 a0 = g[0], a1 = g[1], b0 = g[2], b1 = g[3], c0 = g[4], c1 = g[5];
-    const float4 d0 = g[6], d1 = g[7], e0 = g[8], e1 = g[9], f0 = g[10], f1 = g[11];
-    lx = fminf(fminf(fminf(a0.x, a0.y), fminf(a0.z, a0.w)), fminf(fminf(a1.x, a1.y), fminf(a1.z, a1.w)));
-    ly = fminf(fminf(fminf(b0.x, b0.y), fminf(b0.z, b0.w)), fminf(fminf(b1.x, b1.y), fminf(b1.z, b1.w)));
-    lz = fminf(fminf(fminf(c0.x, c0.y), fminf(c0.z, c0.w)), fminf(fminf(c1.x, c1.y), fminf(c1.z, c1.w)));
-    hx = fmaxf(fmaxf(fmaxf(d0.x, d0.y), fmaxf(d0.z, d0.w)), fmaxf(fmaxf(d1.x, d1.y), fmaxf(d1.z, d1.w)));
-    hy = fmaxf(fmaxf(fmaxf(e0.x, e0.y), fmaxf(e0.z, e0.w)), fmaxf(fmaxf(e1.x, e1.y), fmaxf(e1.z, e1.w)));
-    hz = fmaxf(fmaxf(fmaxf(f0.x, f0.y), fmaxf(f0.z, f0.w)), fmaxf(fmaxf(f1.x, f1.y), fmaxf(f1.z, f1.w)));
+// one thread per 32-bit word of the node array
+__global__ void __launch_bounds__(256) k_init_nodes(unsigned* __restrict__ words, size_t n_words) {
+  const size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  const int k = (int)(w & 63);
+  words[w] = k < 24 ? kOrdPosInf : (k < 48 ? kOrdNegInf : 0u);
+}
+
+__device__ __forceinline__ void merge_box(unsigned* node_words, int slot, const unsigned o[6]) {
+  atomicMin(node_words + slot, o[0]);
+  atomicMin(node_words + 8 + slot, o[1]);
+  atomicMin(node_words + 16 + slot, o[2]);
+  atomicMax(node_words + 24 + slot, o[3]);
+  atomicMax(node_words + 32 + slot, o[4]);
+  atomicMax(node_words + 40 + slot, o[5]);
+}
+
+__global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys, const unsigned char* __restrict__ leaf_level,
+                                              const int* __restrict__ S /*[10][n] inclusive scan*/, const float4* __restrict__ spts, int n,
+                                              unsigned* __restrict__ nodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned key = keys[i];
+  const int L = leaf_level[i];
+  const int cd = i == 0 ? -1 : common_digits(key, __ldg(keys + i - 1));
+  // i is the first point of its level-t cell for every t > cd; cells of level t <= L exist in the tree
+  for (int t = max(1, cd + 1); t <= L; ++t) {
+    const int parent = S[(size_t)(t - 1) * n + i] - 1;
+    const int slot = (key >> (3 * (kMortonLevels - t))) & 7;
+    unsigned* pw = nodes + (size_t)parent * 64;
+    if (t < L) {  // internal child: its box is assembled by the leaves below it
+      pw[48 + 2 * slot] = (unsigned)(S[(size_t)t * n + i] - 1);
+      pw[49 + 2 * slot] = 0xffffffffu;
+      continue;
+    }
+    // leaf: the run of points sharing the first t digits
+    int e = i + 1;
+    while (e < n && common_digits(__ldg(keys + e), key) >= t) ++e;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int j = i; j < e; ++j) {
+      const float4 p = spts[j];
+      lo[0] = fminf(lo[0], p.x), lo[1] = fminf(lo[1], p.y), lo[2] = fminf(lo[2], p.z);
+      hi[0] = fmaxf(hi[0], p.x), hi[1] = fmaxf(hi[1], p.y), hi[2] = fmaxf(hi[2], p.z);
+    }
+    const unsigned o[6] = {f2ord(lo[0]), f2ord(lo[1]), f2ord(lo[2]), f2ord(hi[0]), f2ord(hi[1]), f2ord(hi[2])};
+    pw[48 + 2 * slot] = (unsigned)i;
+    pw[49 + 2 * slot] = (unsigned)(e - i);
+    merge_box(pw, slot, o);
+    for (int u = t - 1; u >= 1; --u) {
+      const int anc_parent = S[(size_t)(u - 1) * n + i] - 1;
+      merge_box(nodes + (size_t)anc_parent * 64, (key >> (3 * (kMortonLevels - u))) & 7, o);
+    }
   }
-  store_box(level, node, lx, ly, lz, hx, hy, hz);
+}
+
+__global__ void __launch_bounds__(256) k_finalize(unsigned* __restrict__ words, size_t n_words) {
+  const size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  if ((w & 63) < 48) words[w] = __float_as_uint(ord2f(words[w]));
 }
 
 static int ensure_scratch(ddlo_runtime* rt, size_t bytes) {
@@ -165,83 +207,69 @@ int build_index(ddlo_cloud* c) {
   ddlo_runtime* rt = c->rt;
   const int n = c->n;
   if (n <= 0) return fail(DDLO_E_EMPTY, "build_index: empty cloud");
+  if (n > (1 << 30)) return fail(DDLO_E_UNSUPPORTED, "build_index: cloud too large");
   cudaStream_t st = rt->stream;
 
-  // level sizes: cnt[L-1] = leaves, cnt[l] = ceil(cnt[l+1] / 8), cnt[0] <= 8
-  int cnt_rev[kMaxLevels];
-  int nlev = 0;
-  int m = (n + kLeaf - 1) / kLeaf;
-  for (;;) {
-    if (nlev >= kMaxLevels) return fail(DDLO_E_UNSUPPORTED, "build_index: cloud too large");
-    cnt_rev[nlev++] = m;
-    if (m <= kBranch) break;
-    m = (m + kBranch - 1) / kBranch;
-  }
-  int cnt[kMaxLevels], groups[kMaxLevels];
-  size_t total_groups = 0;
-  for (int l = 0; l < nlev; ++l) {
-    cnt[l] = cnt_rev[nlev - 1 - l];
-    groups[l] = (cnt[l] + kBranch - 1) / kBranch;
-    total_groups += groups[l];
-  }
-  const int npad = groups[nlev - 1] * kBranch * kLeaf;
-
-  // scratch: bounds (8 u32) | keys | keys_alt | vals | vals_alt | cub temp
-  size_t cub_bytes = 0;
+  // scratch: bounds (8 u32) | keys | keys_alt | vals | vals_alt | leaf_level | flags[10][n] | cub temp
+  size_t sort_bytes = 0, scan_bytes = 0;
   cub::DoubleBuffer<unsigned> kb0(nullptr, nullptr);
   cub::DoubleBuffer<int> vb0(nullptr, nullptr);
-  DDLO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, kb0, vb0, n, 0, 30, st));
+  DDLO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, kb0, vb0, n, 0, 30, st));
+  const size_t n_flags = (size_t)kMortonLevels * n;
+  DDLO_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (int*)nullptr, (int*)nullptr, (long long)n_flags, st));
+  const size_t cub_bytes = std::max(sort_bytes, scan_bytes);
   const size_t off_keys = 256, sz = align256((size_t)n * 4);
-  const size_t need = off_keys + 4 * sz + align256(cub_bytes);
-  DDLO_TRY(ensure_scratch(rt, need));
+  const size_t off_lvl = off_keys + 4 * sz, off_flags = off_lvl + align256((size_t)n);
+  const size_t off_cub = off_flags + align256(n_flags * 4);
+  DDLO_TRY(ensure_scratch(rt, off_cub + align256(cub_bytes)));
   char* base = static_cast<char*>(rt->d_scratch);
   unsigned* bounds = reinterpret_cast<unsigned*>(base);
   unsigned* keys = reinterpret_cast<unsigned*>(base + off_keys);
   unsigned* keys_alt = reinterpret_cast<unsigned*>(base + off_keys + sz);
   int* vals = reinterpret_cast<int*>(base + off_keys + 2 * sz);
   int* vals_alt = reinterpret_cast<int*>(base + off_keys + 3 * sz);
-  void* cub_tmp = base + off_keys + 4 * sz;
+  unsigned char* leaf_level = reinterpret_cast<unsigned char*>(base + off_lvl);
+  int* flags = reinterpret_cast<int*>(base + off_flags);
+  void* cub_tmp = base + off_cub;
 
-  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->spts), (size_t)npad * sizeof(float4), st));
-  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->boxes), total_groups * 12 * sizeof(float4), st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->spts), (size_t)n * sizeof(float4), st));
 
   DDLO_CUDA(cudaMemsetAsync(bounds, 0xff, 12, st));
   DDLO_CUDA(cudaMemsetAsync(bounds + 3, 0x00, 16, st));
   const int tb = 256;
-  const int gb = std::min((n + tb - 1) / tb, rt->num_sms * 8);
-  k_bounds<<<gb, tb, 0, st>>>(c->pts, n, bounds);
-  k_morton<<<(n + tb - 1) / tb, tb, 0, st>>>(c->pts, n, bounds, keys, vals);
-  rt->launches += 2;
+  const int nb = (n + tb - 1) / tb;
+  k_bounds<<<std::min(nb, rt->num_sms * 8), tb, 0, st>>>(c->pts, n, bounds);
+  k_morton<<<nb, tb, 0, st>>>(c->pts, n, bounds, keys, vals);
   cub::DoubleBuffer<unsigned> kb(keys, keys_alt);
   cub::DoubleBuffer<int> vb(vals, vals_alt);
-  DDLO_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, kb, vb, n, 0, 30, st));
-  rt->launches += 4;  // onesweep: histogram + 4 digit passes are library kernels; counted loosely
-
-  float4* lvl_ptr[kMaxLevels];
-  {
-    float4* p = c->boxes;
-    for (int l = 0; l < nlev; ++l) {
-      lvl_ptr[l] = p;
-      p += (size_t)groups[l] * 12;
-    }
-  }
-  k_leaves<<<(npad + tb - 1) / tb, tb, 0, st>>>(c->pts, vb.Current(), n, npad, c->spts, lvl_ptr[nlev - 1]);
-  rt->launches += 1;
-  for (int l = nlev - 2; l >= 0; --l) {
-    const int slots = groups[l] * kBranch;
-    k_level<<<(slots + tb - 1) / tb, tb, 0, st>>>(lvl_ptr[l + 1], groups[l + 1], lvl_ptr[l], slots);
-    rt->launches += 1;
-  }
+  DDLO_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, kb, vb, n, 0, 30, st));
+  // (the radix-sort and scan passes are CUB library kernels and are not counted as ours)
+  k_cells<<<nb, tb, 0, st>>>(kb.Current(), vb.Current(), c->pts, n, leaf_level, flags, c->spts);
+  DDLO_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_bytes, flags, flags, (long long)n_flags, st));
+  rt->launches += 3;
   DDLO_CUDA(cudaGetLastError());
 
-  c->npad = npad;
+  // the one read-back of the build: how many nodes the tree has
+  int* h_count = static_cast<int*>(rt->h_pinned);
+  DDLO_CUDA(cudaMemcpyAsync(h_count, flags + (n_flags - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+  DDLO_CUDA(cudaStreamSynchronize(st));
+  const int n_nodes = *h_count;
+  if (n_nodes < 1) return fail(DDLO_E_CUDA, "build_index: node count came back empty");
+
+  const size_t n_words = (size_t)n_nodes * 64;
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->nodes), n_words * 4, st));
+  unsigned* words = reinterpret_cast<unsigned*>(c->nodes);
+  const int wb = (int)((n_words + tb - 1) / tb);
+  k_init_nodes<<<wb, tb, 0, st>>>(words, n_words);
+  k_emit<<<nb, tb, 0, st>>>(kb.Current(), leaf_level, flags, c->spts, n, words);
+  k_finalize<<<wb, tb, 0, st>>>(words, n_words);
+  rt->launches += 3;
+  DDLO_CUDA(cudaGetLastError());
+
   c->view.spts = c->spts;
+  c->view.nodes = c->nodes;
   c->view.n = n;
-  c->view.nlev = nlev;
-  for (int l = 0; l < kMaxLevels; ++l) {
-    c->view.box[l] = l < nlev ? lvl_ptr[l] : nullptr;
-    c->view.cnt[l] = l < nlev ? cnt[l] : 0;
-  }
+  c->view.n_nodes = n_nodes;
   c->has_index = true;
   return DDLO_OK;
 }

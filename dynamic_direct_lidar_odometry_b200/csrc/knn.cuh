@@ -1,4 +1,4 @@
-// Exact k-nearest-neighbour traversal of the 8-wide box tree (device code).
+// Exact k-nearest-neighbour traversal of the Morton-prefix octree (device code).
 //
 // Replaces nanoflann's KDTreeSingleIndexAdaptor::findNeighbors / searchLevel + KNNResultSet
 // (R/impl/nanoflann_impl.hpp:1365-1384, 1495-1566, 161-243) for the two searches the engine does:
@@ -111,84 +111,79 @@ __device__ __forceinline__ float pick8(const float b[8], int c) {
 }
 
 template <class RS>
-__device__ __forceinline__ void scan_leaf(const float4* __restrict__ spts, int leaf, float qx, float qy, float qz, RS& rs) {
-  const float4* p = spts + (size_t)leaf * kLeaf;
-#pragma unroll
-  for (int j = 0; j < kLeaf; ++j) {
+__device__ __forceinline__ void scan_leaf(const float4* __restrict__ spts, int start, int count, float qx, float qy, float qz, RS& rs) {
+  const float4* p = spts + start;
+#pragma unroll 4
+  for (int j = 0; j < count; ++j) {
     const float4 v = __ldg(p + j);
-    const float dist = sqdist3_rn(qx, qy, qz, v.x, v.y, v.z);  // padding points are +inf -> dist = +inf
-    rs.offer(dist, __float_as_int(v.w), leaf * kLeaf + j);
+    rs.offer(sqdist3_rn(qx, qy, qz, v.x, v.y, v.z), __float_as_int(v.w), start + j);
   }
 }
 
-// Depth-first traversal, nearest child first, without a stack in memory: the pending children of
-// the node being expanded on each level are one byte of `pend` (8 levels x 8 children).
+// Depth-first traversal.  At a node: the child boxes that can still hold a better candidate are
+// found (bound <= current k-th distance; "<=" so that an equal-distance point with a smaller index
+// is not missed); leaf children are scanned on the spot, which tightens the k-th distance before
+// the internal children are looked at; of those the nearest is entered directly and the others go
+// on a small per-thread stack together with their bound, so that a stale entry is discarded on
+// pop without touching memory.
 template <class RS>
 __device__ __forceinline__ void knn_traverse(const IndexView& ix, float qx, float qy, float qz, RS& rs) {
   if (ix.n <= 0) return;
-  const int leaf_lvl = ix.nlev - 1;
-  unsigned long long pend = 0ull;
-  int lvl = 0;
-  unsigned group = 0;  // index of the group being expanded on level `lvl` (= its parent's node id)
+  unsigned long long stack[kStackDepth];  // (bound bits << 32) | node id; bounds are >= 0 so the bits order like floats
+  int sp = 0;
+  unsigned node = 0;
   for (;;) {
+    const float4* g = ix.nodes + (size_t)node * kNodeF4;
     float b[8];
-    group_bounds(ix.box[lvl] + (size_t)group * 12, qx, qy, qz, b);
-    bool descended = false;
-    if (lvl == leaf_lvl) {
-      // children are leaves: visit the nearest first, then every other one that still qualifies
-      // (the bound is re-tested against the shrinking k-th distance right before each visit)
-      const float w = rs.worst();
-      unsigned m = 0;
-      int c = 0;
-      float bmin = FLT_MAX;
+    group_bounds(g, qx, qy, qz, b);
+    const int2* refs = reinterpret_cast<const int2*>(g + 12);
+    const float w = rs.worst();
+    unsigned m = 0;
 #pragma unroll
-      for (int s = 0; s < 8; ++s)
-        if (b[s] <= w) {
-          m |= 1u << s;
-          if (b[s] < bmin) {
-            bmin = b[s];
-            c = s;
-          }
-        }
-      while (m) {
-        m &= ~(1u << c);
-        if (pick8(b, c) <= rs.worst()) scan_leaf(ix.spts, (int)(group * 8 + c), qx, qy, qz, rs);
-        c = __ffs(m) - 1;
-      }
-    } else {
-      const float w = rs.worst();
-      unsigned m = 0;
-      int cmin = -1;
-      float bmin = 0.0f;
-#pragma unroll
-      for (int s = 0; s < 8; ++s)
-        if (b[s] <= w) {
-          m |= 1u << s;
-          if (cmin < 0 || b[s] < bmin) {
-            bmin = b[s];
-            cmin = s;
-          }
-        }
-      if (m) {
-        m &= ~(1u << cmin);
-        pend = (pend & ~(0xffull << (8 * lvl))) | ((unsigned long long)m << (8 * lvl));
-        group = group * 8 + cmin;
-        ++lvl;
-        descended = true;
+    for (int s = 0; s < 8; ++s)
+      if (b[s] <= w) m |= 1u << s;
+    // leaves first
+    unsigned inner = 0;
+    for (unsigned mm = m; mm;) {
+      const int s = __ffs(mm) - 1;
+      mm &= mm - 1;
+      const int2 r = __ldg(refs + s);
+      if (r.y > 0) {
+        if (pick8(b, s) <= rs.worst()) scan_leaf(ix.spts, r.x, r.y, qx, qy, qz, rs);
+      } else {
+        inner |= 1u << s;
       }
     }
-    if (descended) continue;
-    // pop: climb until some level has a pending child, then descend into it
+    // internal children: nearest is entered now, the rest are stacked
+    float best_b = 0.0f;
+    int best_n = -1;
+    const float w2 = rs.worst();
+    for (; inner;) {
+      const int s = __ffs(inner) - 1;
+      inner &= inner - 1;
+      const float bs = pick8(b, s);
+      if (!(bs <= w2)) continue;
+      const int child = __ldg(refs + s).x;
+      float push_b;
+      int push_n;
+      if (best_n < 0 || bs < best_b) {
+        push_b = best_b, push_n = best_n;
+        best_b = bs, best_n = child;
+      } else {
+        push_b = bs, push_n = child;
+      }
+      if (push_n >= 0 && sp < kStackDepth) stack[sp++] = ((unsigned long long)__float_as_uint(push_b) << 32) | (unsigned)push_n;
+    }
+    if (best_n >= 0) {
+      node = (unsigned)best_n;
+      continue;
+    }
+    // pop the next entry that can still matter
     for (;;) {
-      if (lvl == 0) return;
-      --lvl;
-      group >>= 3;
-      const unsigned m = (unsigned)((pend >> (8 * lvl)) & 0xffull);
-      if (m) {
-        const int c = __ffs(m) - 1;
-        pend &= ~(1ull << (8 * lvl + c));
-        group = group * 8 + c;
-        ++lvl;
+      if (sp == 0) return;
+      const unsigned long long e = stack[--sp];
+      if (__uint_as_float((unsigned)(e >> 32)) <= rs.worst()) {
+        node = (unsigned)(e & 0xffffffffull);
         break;
       }
     }

@@ -63,6 +63,29 @@ class Runtime:
     def flush_l2(self, nbytes: int = 256 << 20):
         B.check(B.load().ddlo_runtime_flush_l2(self._h, nbytes))
 
+    def event_record(self, slot: int):
+        B.check(B.load().ddlo_runtime_event_record(self._h, slot))
+
+    def event_elapsed(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        B.check(B.load().ddlo_runtime_event_elapsed(self._h, a, b, C.byref(ms)))
+        return ms.value
+
+
+def pinned_array(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array in page-locked host memory (cudaMallocHost through the ABI); freed with the array."""
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dt.itemsize
+    p = C.c_void_p()
+    B.check(B.load().ddlo_host_alloc(nbytes, C.byref(p)))
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[id(buf)] = (buf, p)
+    return arr
+
+
+_PINNED = {}
+
 
 class PointCloud:
     """`pcl::PointCloud<PointXYZI>::Ptr` living on the device, plus its kNN index once built
@@ -346,6 +369,17 @@ class NanoGICP:
         r = B.AlignResult()
         g = None if guess is None else np.ascontiguousarray(np.asarray(guess, dtype=np.float32).T)
         B.check(B.load().ddlo_gicp_align(self._g, None if g is None else B.ptr(g), C.byref(r)))
+        self._last = AlignInfo(r)
+        return self._last
+
+    def align_async(self, guess=None) -> None:
+        """enqueue align() on the runtime's stream without waiting (see ddlo_gicp_align_async)"""
+        g = None if guess is None else np.ascontiguousarray(np.asarray(guess, dtype=np.float32).T)
+        B.check(B.load().ddlo_gicp_align_async(self._g, None if g is None else B.ptr(g)))
+
+    def align_finish(self) -> AlignInfo:
+        r = B.AlignResult()
+        B.check(B.load().ddlo_gicp_align_finish(self._g, C.byref(r)))
         self._last = AlignInfo(r)
         return self._last
 

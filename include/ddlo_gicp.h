@@ -106,6 +106,12 @@ int ddlo_runtime_timer_end(ddlo_runtime* rt, float* elapsed_ms); /* synchronises
 int ddlo_runtime_launch_count(ddlo_runtime* rt, long long* count);
 /* write `bytes` of device scratch (L2 flush between timed iterations) */
 int ddlo_runtime_flush_l2(ddlo_runtime* rt, size_t bytes);
+/* 16 CUDA-event slots on the runtime's stream, for per-stage timing inside one step */
+int ddlo_runtime_event_record(ddlo_runtime* rt, int slot);
+int ddlo_runtime_event_elapsed(ddlo_runtime* rt, int slot_begin, int slot_end, float* elapsed_ms); /* synchronises on slot_end */
+/* page-locked host memory for callers that want true asynchronous uploads */
+int ddlo_host_alloc(size_t bytes, void** out);
+int ddlo_host_free(void* p);
 
 /* ---- clouds: pcl::PointCloud + nanoflann::KdTreeFLANN ------------------------------------------ */
 /* Upload n points from HOST memory; point i starts at (const char*)xyz + i*stride_bytes and holds
@@ -174,6 +180,11 @@ int ddlo_gicp_swap_source_and_target(ddlo_gicp* g);
  * LM / GN loop runs on the device; the host sees one launch and one small read-back.
  * guess16 == NULL means identity. */
 int ddlo_gicp_align(ddlo_gicp* g, const float* guess16, ddlo_align_result* result);
+/* The same in two halves: _async only enqueues the work on the runtime's stream (missing covariances,
+ * then the single align kernel); _finish copies the result back and synchronises.  Between the two
+ * the host is free, and CUDA events recorded around _async time the device work alone. */
+int ddlo_gicp_align_async(ddlo_gicp* g, const float* guess16);
+int ddlo_gicp_align_finish(ddlo_gicp* g, ddlo_align_result* result);
 /* the `output` cloud of align(): the source moved by the final transformation (:125) */
 int ddlo_gicp_aligned_cloud(ddlo_gicp* g, ddlo_cloud** out);
 

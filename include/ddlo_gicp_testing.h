@@ -1,0 +1,20 @@
+/*
+ * ddlo_gicp_testing.h — host-callable copies of the device arithmetic, exported by
+ * libddlo_gicp_b200.so for CPU-side unit tests (they compile the very same __host__ __device__
+ * functions the kernels run, csrc/math.cuh).  Not part of the drop-in boundary.
+ */
+#ifndef DDLO_GICP_TESTING_H
+#define DDLO_GICP_TESTING_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* symmetric 3x3 as 6 doubles xx,xy,xz,yy,yz,zz; V row-major, eigenvalues descending */
+void ddlo_math_sym3_eig(const double* sym6, double* w3, double* V9);
+void ddlo_math_regularize(const double* sym6, int method, double* out6); /* nano_gicp_impl.hpp:401-437 */
+void ddlo_math_ldlt6_solve(const double* A36, const double* rhs6, double* x6); /* Eigen::LDLT, lsq_registration_impl.hpp:190 */
+void ddlo_math_so3_exp(const double* omega3, double* R9);                       /* gicp/so3.hpp:101-124 */
+void ddlo_math_sym3_inverse(const double* sym6, double* out6);
+#ifdef __cplusplus
+}
+#endif
+#endif

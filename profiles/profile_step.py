@@ -1,0 +1,25 @@
+"""One C2 step (index + covariances + align) for ncu captures:  python profiles/profile_step.py [reps]"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from dynamic_direct_lidar_odometry_b200 import nano_gicp as ng  # noqa: E402
+from dynamic_direct_lidar_odometry_b200 import synth  # noqa: E402
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+src, tgt, guess = synth.workload_c2()
+rt = ng.Runtime(0)
+eng = ng.NanoGICP(rt)
+target = ng.PointCloud(rt, tgt)
+eng.setInputTarget(target)
+eng.calculateTargetCovariances()
+for _ in range(reps):
+    eng.setInputSource(ng.PointCloud(rt, src))
+    eng.calculateSourceCovariances()
+    r = eng.align(guess)
+    eng.clearSource()
+print("iterations", r.iterations, "converged", r.converged, "lin", r.n_linearize, "err", r.n_compute_error)
+del eng, target
+rt.close()
