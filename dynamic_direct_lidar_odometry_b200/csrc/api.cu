@@ -560,7 +560,7 @@ int ddlo_gicp_create(ddlo_runtime* rt, ddlo_gicp** out) {
   if (!g) return fail(DDLO_E_INVALID, "out of host memory");
   g->rt = rt;
   ddlo_params_default(&g->p);
-  g->partial_stride = std::max(rt->max_coop_blocks_align, 1024);
+  g->partial_stride = std::max(rt->max_coop_blocks_align, 64);
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&g->partials), (size_t)2 * kNumSums * g->partial_stride * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->d_out), sizeof(AlignOut));
   if (e != cudaSuccess) {
@@ -758,10 +758,7 @@ static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, 
   return DDLO_OK;
 }
 
-static int align_blocks(const ddlo_gicp* g) {
-  const int want = (g->src->n + kAlignThreads - 1) / kAlignThreads;
-  return std::max(1, std::min(want, g->rt->max_coop_blocks_align));
-}
+static int align_blocks(const ddlo_gicp* g) { return gicp_blocks_for(g->src->n, g->rt->max_coop_blocks_align); }
 
 static int enqueue_align(ddlo_gicp* g, const float* guess16, int* covs_computed) {
   GicpArgs a;
@@ -858,8 +855,7 @@ int ddlo_gicp_linearize(ddlo_gicp* g, const double* T16, double* H36, double* b6
   DDLO_TRY(prepare(g, false, nullptr, &a));
   std::memset(a.guess, 0, sizeof(a.guess));
   std::memcpy(a.T_step, T16, sizeof(a.T_step));
-  const int blocks = std::min(std::max(1, (a.ns + kAlignThreads - 1) / kAlignThreads), g->partial_stride);
-  DDLO_TRY(launch_linearize_step(g->rt, a, blocks));
+  DDLO_TRY(launch_linearize_step(g->rt, a, align_blocks(g)));
   g->corr_n = a.ns;
   AlignOut o;
   DDLO_TRY(read_out(g, &o));
@@ -891,8 +887,7 @@ int ddlo_gicp_compute_error(ddlo_gicp* g, const double* T16, double* error) {
   DDLO_TRY(prepare(g, false, nullptr, &a));
   std::memset(a.guess, 0, sizeof(a.guess));
   std::memcpy(a.T_step, T16, sizeof(a.T_step));
-  const int blocks = std::min(std::max(1, (a.ns + kAlignThreads - 1) / kAlignThreads), g->partial_stride);
-  DDLO_TRY(launch_error_step(g->rt, a, blocks));
+  DDLO_TRY(launch_error_step(g->rt, a, align_blocks(g)));
   AlignOut o;
   DDLO_TRY(read_out(g, &o));
   *error = o.sums[0];

@@ -1,18 +1,22 @@
 // The GICP cost function and the Levenberg-Marquardt / Gauss-Newton driver, on the device.
 //
-//   lin_point          NanoGICP::update_correspondences + the body of linearize
+//   nn_phase + lin_point   NanoGICP::update_correspondences + the body of linearize
 //                                                    (nano_gicp_impl.hpp:235-275, 292-328)
-//   err_point          the body of compute_error     (nano_gicp_impl.hpp:349-368)
-//   k_align            LsqRegistration::computeTransformation, step_lm, step_gn, is_converged
+//   err_point              the body of compute_error (nano_gicp_impl.hpp:349-368)
+//   k_align                LsqRegistration::computeTransformation, step_lm, step_gn, is_converged
 //                                                    (lsq_registration_impl.hpp:96-232)
 //
-// k_align is ONE cooperative launch per align(): every outer iteration does the fused
-// 1-NN + Mahalanobis + H/b pass over the source points, a grid-wide fp64 reduction
-// (warp shuffle -> block -> per-block partials in L2 -> fixed-order sum), then the 6x6 LM solve
-// and the trial-error passes, with grid.sync() between phases and no host involvement.  Every
-// block evaluates the (tiny) LM controller redundantly from the same reduced sums, which keeps the
-// control flow uniform across the grid without a broadcast step.  Reductions have a fixed order,
-// so results are bit-reproducible run to run.
+// k_align is ONE cooperative launch per align(), one 1024-thread block per SM.  A block owns a
+// contiguous slice of the source points.  Every outer iteration it runs
+//   phase A  1-NN of the moved source points in the target octree, one query per 8-lane sub-warp
+//            (knn.cuh), results parked in shared memory;
+//   phase B  one thread per point: Mahalanobis matrix, residual, the 28 sums of J^T M J / J^T M e /
+//            e^T M e, reduced warp -> block in fp64;
+// then a grid-wide reduction (per-block partials in L2, grid.sync, every block adds them in the
+// same fixed order), the 6x6 LM solve, and the trial-error passes, all without the host.  Every
+// block evaluates the (tiny) LM controller redundantly from identical sums, which keeps the
+// control flow uniform across the grid without a broadcast.  Reductions have a fixed order, so
+// results are bit-reproducible run to run.
 #include <cooperative_groups.h>
 
 #include "gicp.cuh"
@@ -22,7 +26,10 @@ namespace cg = cooperative_groups;
 
 namespace ddlo {
 
-// accumulator layout: [0..5] H_rr upper, [6..14] H_rt row-major, [15..20] H_tt upper, [21..23] b_r,
+constexpr int kAlignWarps = kAlignThreads / 32;
+constexpr int kAlignSubs = kAlignThreads / kSubLanes;
+
+// sum layout: [0..5] H_rr upper, [6..14] H_rt row-major, [15..20] H_tt upper, [21..23] b_r,
 // [24..26] b_t, [27] sum of e^T M e
 struct LmShared {
   Iso3 x0, xi, delta;
@@ -31,6 +38,17 @@ struct LmShared {
   double y0, yi, lambda, nu, final_error;
   double final_H[36];
   int action, converged, step_ok, lm_failed, n_lin, n_err, nr_iter;
+};
+
+// dynamic shared memory of the align / step kernels
+struct AlignSmem {
+  unsigned long long stacks[kAlignSubs * kStackDepth];
+  double red[kAlignWarps * kNumSums];
+  double tot[kNumSums];
+  float nn_d[kAlignThreads];
+  int nn_idx[kAlignThreads];
+  int nn_pos[kAlignThreads];
+  LmShared lm;
 };
 
 __device__ __forceinline__ void iso_to_float(const Iso3& T, float* Rf, float* tf) {
@@ -72,56 +90,64 @@ __device__ __forceinline__ double quad_form(const Sym3& M, double ex, double ey,
   return ex * mx + ey * my + ez * mz;
 }
 
-// one source point of update_correspondences + linearize
-__device__ __forceinline__ void lin_point(const GicpArgs& a, const LmShared& s, int i, double* acc) {
-  const float4 pa = __ldg(a.src_pts + i);
-  const float qx = xform_f(s.Rf + 0, s.tf[0], pa.x, pa.y, pa.z);
-  const float qy = xform_f(s.Rf + 3, s.tf[1], pa.x, pa.y, pa.z);
-  const float qz = xform_f(s.Rf + 6, s.tf[2], pa.x, pa.y, pa.z);
-  Best1 best;
-  knn_traverse(a.tgt, qx, qy, qz, best);
-  a.sqd[i] = best.d;
-  const int j = (best.idx >= 0 && (double)best.d < a.thr2) ? best.idx : -1;
-  a.corr[i] = j;
-  if (j < 0) return;
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
 
-  const float4 pb = __ldg(a.tgt.spts + best.pos);
-  const Sym3 CA = load_sym3(a.src_cov + (size_t)i * kCovStride);
-  const Sym3 CB = load_sym3(a.tgt_cov + (size_t)j * kCovStride);
-  Sym3 RCR = sym3_rotate(s.x0.r, CA);
-  RCR.xx += CB.xx, RCR.xy += CB.xy, RCR.xz += CB.xz, RCR.yy += CB.yy, RCR.yz += CB.yz, RCR.zz += CB.zz;
-  const Sym3 M = sym3_inverse(RCR);
-  store_sym3(a.mahal + (size_t)i * kCovStride, M);
+// Phase B for one point (called by all 32 lanes of a warp; `valid` lanes own a point): the
+// Mahalanobis matrix and the point's 28 contributions, summed over the warp into red_w[0..27].
+// Kept out of line so that its fp64 register appetite does not leak into the search loop.
+__device__ __noinline__ void lin_point(const GicpArgs& a, const LmShared& s, bool valid, int i, float nn_d, int nn_idx, int nn_pos,
+                                       double* __restrict__ red_w) {
+  double c[kNumSums];
+#pragma unroll
+  for (int k = 0; k < kNumSums; ++k) c[k] = 0.0;
+  if (valid) {
+    a.sqd[i] = nn_d;
+    const int j = (nn_pos >= 0 && (double)nn_d < a.thr2) ? nn_idx : -1;
+    a.corr[i] = j;
+    if (j >= 0) {
+      const float4 pa = __ldg(a.src_pts + i);
+      const float4 pb = __ldg(a.tgt.spts + nn_pos);
+      const Sym3 CA = load_sym3(a.src_cov + (size_t)i * kCovStride);
+      const Sym3 CB = load_sym3(a.tgt_cov + (size_t)j * kCovStride);
+      Sym3 RCR = sym3_rotate(s.x0.r, CA);
+      RCR.xx += CB.xx, RCR.xy += CB.xy, RCR.xz += CB.xz, RCR.yy += CB.yy, RCR.yz += CB.yz, RCR.zz += CB.zz;
+      const Sym3 M = sym3_inverse(RCR);
+      store_sym3(a.mahal + (size_t)i * kCovStride, M);
 
-  const double x = xform_d(s.x0.r + 0, s.x0.t[0], (double)pa.x, (double)pa.y, (double)pa.z);
-  const double y = xform_d(s.x0.r + 3, s.x0.t[1], (double)pa.x, (double)pa.y, (double)pa.z);
-  const double z = xform_d(s.x0.r + 6, s.x0.t[2], (double)pa.x, (double)pa.y, (double)pa.z);
-  const double ex = (double)pb.x - x, ey = (double)pb.y - y, ez = (double)pb.z - z;
-  double mex, mey, mez;
-  acc[27] += quad_form(M, ex, ey, ez, mex, mey, mez);
-
-  // G = S^T M with S = skew(T p_A);  J = [S | -I]
-  const double g00 = z * M.xy - y * M.xz, g01 = z * M.yy - y * M.yz, g02 = z * M.yz - y * M.zz;
-  const double g10 = x * M.xz - z * M.xx, g11 = x * M.yz - z * M.xy, g12 = x * M.zz - z * M.xz;
-  const double g20 = y * M.xx - x * M.xy, g21 = y * M.xy - x * M.yy, g22 = y * M.xz - x * M.yz;
-  // H_rr = G S (symmetric)
-  acc[0] += z * g01 - y * g02;
-  acc[1] += x * g02 - z * g00;
-  acc[2] += y * g00 - x * g01;
-  acc[3] += x * g12 - z * g10;
-  acc[4] += y * g10 - x * g11;
-  acc[5] += y * g20 - x * g21;
-  // H_rt = -G
-  acc[6] -= g00, acc[7] -= g01, acc[8] -= g02;
-  acc[9] -= g10, acc[10] -= g11, acc[11] -= g12;
-  acc[12] -= g20, acc[13] -= g21, acc[14] -= g22;
-  // H_tt = M
-  acc[15] += M.xx, acc[16] += M.xy, acc[17] += M.xz, acc[18] += M.yy, acc[19] += M.yz, acc[20] += M.zz;
-  // b_r = G e, b_t = -M e
-  acc[21] += g00 * ex + g01 * ey + g02 * ez;
-  acc[22] += g10 * ex + g11 * ey + g12 * ez;
-  acc[23] += g20 * ex + g21 * ey + g22 * ez;
-  acc[24] -= mex, acc[25] -= mey, acc[26] -= mez;
+      const double x = xform_d(s.x0.r + 0, s.x0.t[0], (double)pa.x, (double)pa.y, (double)pa.z);
+      const double y = xform_d(s.x0.r + 3, s.x0.t[1], (double)pa.x, (double)pa.y, (double)pa.z);
+      const double z = xform_d(s.x0.r + 6, s.x0.t[2], (double)pa.x, (double)pa.y, (double)pa.z);
+      const double ex = (double)pb.x - x, ey = (double)pb.y - y, ez = (double)pb.z - z;
+      double mex, mey, mez;
+      c[27] = quad_form(M, ex, ey, ez, mex, mey, mez);
+      // G = S^T M with S = skew(T p_A);  J = [S | -I]
+      const double g00 = z * M.xy - y * M.xz, g01 = z * M.yy - y * M.yz, g02 = z * M.yz - y * M.zz;
+      const double g10 = x * M.xz - z * M.xx, g11 = x * M.yz - z * M.xy, g12 = x * M.zz - z * M.xz;
+      const double g20 = y * M.xx - x * M.xy, g21 = y * M.xy - x * M.yy, g22 = y * M.xz - x * M.yz;
+      // H_rr = G S (symmetric)
+      c[0] = z * g01 - y * g02, c[1] = x * g02 - z * g00, c[2] = y * g00 - x * g01;
+      c[3] = x * g12 - z * g10, c[4] = y * g10 - x * g11, c[5] = y * g20 - x * g21;
+      // H_rt = -G
+      c[6] = -g00, c[7] = -g01, c[8] = -g02, c[9] = -g10, c[10] = -g11, c[11] = -g12, c[12] = -g20, c[13] = -g21, c[14] = -g22;
+      // H_tt = M
+      c[15] = M.xx, c[16] = M.xy, c[17] = M.xz, c[18] = M.yy, c[19] = M.yz, c[20] = M.zz;
+      // b_r = G e, b_t = -M e
+      c[21] = g00 * ex + g01 * ey + g02 * ez;
+      c[22] = g10 * ex + g11 * ey + g12 * ez;
+      c[23] = g20 * ex + g21 * ey + g22 * ez;
+      c[24] = -mex, c[25] = -mey, c[26] = -mez;
+    }
+  }
+  const bool lane0 = (threadIdx.x & 31) == 0;
+#pragma unroll
+  for (int k = 0; k < kNumSums; ++k) {
+    const double v = warp_sum(c[k]);
+    if (lane0) red_w[k] += v;
+  }
 }
 
 // one source point of compute_error: stored correspondence and Mahalanobis matrix, new transform
@@ -139,23 +165,76 @@ __device__ __forceinline__ double err_point(const GicpArgs& a, const Iso3& T, in
   return quad_form(M, ex, ey, ez, mx, my, mz);
 }
 
-// ---- reductions -------------------------------------------------------------------------------
-// block: warp shuffle tree, then a fixed-order sum over the warps; result -> dst[c * stride + block]
-template <int NCOMP>
-__device__ __forceinline__ void block_reduce_store(const double* acc, double* s_red /*[warps][NCOMP]*/, double* dst, int stride) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-#pragma unroll
-  for (int c = 0; c < NCOMP; ++c) {
-    double v = acc[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) s_red[warp * NCOMP + c] = v;
+// the slice of source points block `b` of `nb` owns
+__device__ __forceinline__ void block_slice(int ns, int b, int nb, int& p0, int& p1) {
+  const int per = (ns + nb - 1) / nb;
+  p0 = min(ns, b * per);
+  p1 = min(ns, p0 + per);
+}
+
+// linearize over the block's slice; leaves the block's 28 sums in dst[c * stride + blockIdx.x]
+__device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm, double* dst, int stride) {
+  const Sub sb = make_sub();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sw = threadIdx.x / kSubLanes;
+  for (int k = lane; k < kNumSums; k += 32) sm.red[warp * kNumSums + k] = 0.0;
+  int p0, p1;
+  block_slice(a.ns, blockIdx.x, gridDim.x, p0, p1);
+  for (int base = p0; base < p1; base += kAlignThreads) {
+    const int lim = min(p1, base + kAlignThreads);
+    __syncthreads();  // nn_* of the previous sub-slice fully consumed
+    // ---- phase A: update_correspondences' search, one query per sub-warp
+    for (int r = 0; base + r * kAlignSubs < lim; ++r) {
+      const int slot = r * kAlignSubs + sw;
+      const int i = base + slot;
+      const bool active = i < lim;
+      float qx = 0.f, qy = 0.f, qz = 0.f;
+      if (active) {
+        const float4 pa = __ldg(a.src_pts + i);
+        qx = xform_f(sm.lm.Rf + 0, sm.lm.tf[0], pa.x, pa.y, pa.z);
+        qy = xform_f(sm.lm.Rf + 3, sm.lm.tf[1], pa.x, pa.y, pa.z);
+        qz = xform_f(sm.lm.Rf + 6, sm.lm.tf[2], pa.x, pa.y, pa.z);
+      }
+      Best1Sub best;
+      knn_traverse_sub(a.tgt, active, qx, qy, qz, best, sm.stacks + (size_t)sw * kStackDepth, sb);
+      if (active && sb.sl == 0) {
+        sm.nn_d[slot] = best.d;
+        sm.nn_idx[slot] = best.idx;
+        sm.nn_pos[slot] = best.pos;
+      }
+    }
+    __syncthreads();
+    // ---- phase B: one thread per point
+    if (base + warp * 32 < lim) {
+      const int i = base + threadIdx.x;
+      const bool valid = i < lim;
+      lin_point(a, sm.lm, valid, i, valid ? sm.nn_d[threadIdx.x] : 0.f, valid ? sm.nn_idx[threadIdx.x] : -1,
+                valid ? sm.nn_pos[threadIdx.x] : -1, sm.red + warp * kNumSums);
+    }
   }
   __syncthreads();
-  if (threadIdx.x < NCOMP) {
+  if (threadIdx.x < kNumSums) {
     double v = 0.0;
-    for (int w = 0; w < nwarp; ++w) v += s_red[w * NCOMP + threadIdx.x];
+    for (int w = 0; w < kAlignWarps; ++w) v += sm.red[w * kNumSums + threadIdx.x];
     __stcg(dst + (size_t)threadIdx.x * stride + blockIdx.x, v);
+  }
+  __syncthreads();
+}
+
+// compute_error over the block's slice; the block's sum goes to dst[blockIdx.x]
+__device__ __forceinline__ void error_block(const GicpArgs& a, const Iso3& T, AlignSmem& sm, double* dst) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int p0, p1;
+  block_slice(a.ns, blockIdx.x, gridDim.x, p0, p1);
+  double e = 0.0;
+  for (int i = p0 + threadIdx.x; i < p1; i += kAlignThreads) e += err_point(a, T, i);
+  e = warp_sum(e);
+  if (lane == 0) sm.red[warp] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < kAlignWarps; ++w) v += sm.red[w];
+    __stcg(dst + blockIdx.x, v);
   }
   __syncthreads();
 }
@@ -167,24 +246,20 @@ __device__ __forceinline__ void grid_sum(const double* src, int stride, int nblk
   for (int c = warp; c < NCOMP; c += nwarp) {
     double v = 0.0;
     for (int b = lane; b < nblk; b += 32) v += __ldcg(src + (size_t)c * stride + b);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    v = warp_sum(v);
     if (lane == 0) s_tot[c] = v;
   }
   __syncthreads();
 }
 
 __device__ __forceinline__ void unpack_sums(const double* t, double* H /*row-major 6x6*/, double* b, double& err) {
-  // H_rr
   H[0] = t[0], H[1] = t[1], H[2] = t[2], H[7] = t[3], H[8] = t[4], H[14] = t[5];
   H[6] = t[1], H[12] = t[2], H[13] = t[4];
-  // H_rt and its transpose
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) {
       H[6 * r + 3 + c] = t[6 + 3 * r + c];
       H[6 * (3 + c) + r] = t[6 + 3 * r + c];
     }
-  // H_tt
   H[21] = t[15], H[22] = t[16], H[23] = t[17], H[28] = t[18], H[29] = t[19], H[35] = t[20];
   H[27] = t[16], H[33] = t[17], H[34] = t[19];
   for (int r = 0; r < 6; ++r) b[r] = t[21 + r];
@@ -215,7 +290,7 @@ __device__ __forceinline__ void iso_from_colmajor(const double* m, Iso3& T) {
 }
 
 // solve (H + lambda I) d = -b, delta = [exp(d_0..2) | d_3..5]
-__device__ __forceinline__ void lm_solve(LmShared& s, double lambda) {
+__device__ __noinline__ void lm_solve(LmShared& s, double lambda) {
   double A[36], nb[6];
   for (int i = 0; i < 36; ++i) A[i] = s.H[i];
   for (int i = 0; i < 6; ++i) {
@@ -227,12 +302,11 @@ __device__ __forceinline__ void lm_solve(LmShared& s, double lambda) {
   for (int i = 0; i < 3; ++i) s.delta.t[i] = s.d[3 + i];
 }
 
-__global__ void __launch_bounds__(kAlignThreads, 2) k_align(const GicpArgs a) {
+__global__ void __launch_bounds__(kAlignThreads, 1) k_align(const GicpArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ LmShared s;
-  __shared__ double s_red[(kAlignThreads / 32) * kNumSums];
-  __shared__ double s_tot[kNumSums];
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AlignSmem& sm = *reinterpret_cast<AlignSmem*>(smem_raw);
+  LmShared& s = sm.lm;
   const int nblk = gridDim.x;
   int seq = 0;  // reduction counter: partial buffers alternate so a fast block can not overwrite
                 // sums a slow block is still reading
@@ -258,20 +332,15 @@ __global__ void __launch_bounds__(kAlignThreads, 2) k_align(const GicpArgs a) {
     }
     __syncthreads();
 
-    // ---- linearize(x0): correspondences, Mahalanobis, H, b, error ---------------------------
-    {
-      double acc[kNumSums];
-#pragma unroll
-      for (int c = 0; c < kNumSums; ++c) acc[c] = 0.0;
-      for (int i = gtid; i < a.ns; i += gsize) lin_point(a, s, i, acc);
-      block_reduce_store<kNumSums>(acc, s_red, a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride, a.partial_stride);
-    }
+    // ---- linearize(x0) -----------------------------------------------------------------------
+    double* part = a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride;
+    linearize_block(a, sm, part, a.partial_stride);
     grid.sync();
-    grid_sum<kNumSums>(a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride, a.partial_stride, nblk, s_tot);
+    grid_sum<kNumSums>(part, a.partial_stride, nblk, sm.tot);
     ++seq;
 
     if (threadIdx.x == 0) {
-      unpack_sums(s_tot, s.H, s.b, s.y0);
+      unpack_sums(sm.tot, s.H, s.b, s.y0);
       s.n_lin += 1;
       s.step_ok = 0;
       if (a.optimizer == DDLO_OPT_GAUSS_NEWTON) {
@@ -300,17 +369,14 @@ __global__ void __launch_bounds__(kAlignThreads, 2) k_align(const GicpArgs a) {
           s.xi = iso_mul(s.delta, s.x0);
         }
         __syncthreads();
-        {
-          double e = 0.0;
-          for (int i = gtid; i < a.ns; i += gsize) e += err_point(a, s.xi, i);
-          block_reduce_store<1>(&e, s_red, a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride, a.partial_stride);
-        }
+        double* epart = a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride;
+        error_block(a, s.xi, sm, epart);
         grid.sync();
-        grid_sum<1>(a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride, a.partial_stride, nblk, s_tot);
+        grid_sum<1>(epart, a.partial_stride, nblk, sm.tot);
         ++seq;
         if (threadIdx.x == 0) {
           s.n_err += 1;
-          s.yi = s_tot[0];
+          s.yi = sm.tot[0];
           double den = 0.0;
           for (int r = 0; r < 6; ++r) den += s.d[r] * (s.lambda * s.d[r] - s.b[r]);
           const double rho = (s.y0 - s.yi) / den;
@@ -368,32 +434,26 @@ __global__ void __launch_bounds__(kAlignThreads, 2) k_align(const GicpArgs a) {
 }
 
 // ---- stepwise hooks (parity tests compare H, b, error, correspondences with the oracle) ---------
-__global__ void __launch_bounds__(kAlignThreads, 2) k_linearize_step(const GicpArgs a) {
-  __shared__ LmShared s;
-  __shared__ double s_red[(kAlignThreads / 32) * kNumSums];
+__global__ void __launch_bounds__(kAlignThreads, 1) k_linearize_step(const GicpArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AlignSmem& sm = *reinterpret_cast<AlignSmem*>(smem_raw);
   if (threadIdx.x == 0) {
-    iso_from_colmajor(a.T_step, s.x0);
-    iso_to_float(s.x0, s.Rf, s.tf);
+    iso_from_colmajor(a.T_step, sm.lm.x0);
+    iso_to_float(sm.lm.x0, sm.lm.Rf, sm.lm.tf);
   }
   __syncthreads();
-  double acc[kNumSums];
-#pragma unroll
-  for (int c = 0; c < kNumSums; ++c) acc[c] = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x) lin_point(a, s, i, acc);
-  block_reduce_store<kNumSums>(acc, s_red, a.partials, a.partial_stride);
+  linearize_block(a, sm, a.partials, a.partial_stride);
 }
 
-__global__ void __launch_bounds__(kAlignThreads, 2) k_error_step(const GicpArgs a) {
-  __shared__ Iso3 T;
-  __shared__ double s_red[(kAlignThreads / 32)];
-  if (threadIdx.x == 0) iso_from_colmajor(a.T_step, T);
+__global__ void __launch_bounds__(kAlignThreads, 1) k_error_step(const GicpArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AlignSmem& sm = *reinterpret_cast<AlignSmem*>(smem_raw);
+  if (threadIdx.x == 0) iso_from_colmajor(a.T_step, sm.lm.xi);
   __syncthreads();
-  double e = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x) e += err_point(a, T, i);
-  block_reduce_store<1>(&e, s_red, a.partials, a.partial_stride);
+  error_block(a, sm.lm.xi, sm, a.partials);
 }
 
-__global__ void __launch_bounds__(kAlignThreads) k_sum_partials(const double* partials, int stride, int nblk, int ncomp, AlignOut* out) {
+__global__ void __launch_bounds__(256) k_sum_partials(const double* partials, int stride, int nblk, int ncomp, AlignOut* out) {
   __shared__ double s_tot[kNumSums];
   if (ncomp == 1)
     grid_sum<1>(partials, stride, nblk, s_tot);
@@ -431,9 +491,21 @@ __global__ void __launch_bounds__(256) k_transform_cloud(const float4* __restric
 }
 
 // ---- launchers ----------------------------------------------------------------------------------
+static int set_smem_attrs() {
+  static bool done = false;
+  if (done) return DDLO_OK;
+  const int bytes = (int)sizeof(AlignSmem);
+  DDLO_CUDA(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  DDLO_CUDA(cudaFuncSetAttribute(k_linearize_step, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  DDLO_CUDA(cudaFuncSetAttribute(k_error_step, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done = true;
+  return DDLO_OK;
+}
+
 int gicp_max_coop_blocks(int device, int* blocks_per_sm) {
+  DDLO_TRY(set_smem_attrs());
   int per_sm = 0;
-  DDLO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align, kAlignThreads, 0));
+  DDLO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align, kAlignThreads, sizeof(AlignSmem)));
   int coop = 0;
   DDLO_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
   if (!coop) return fail(DDLO_E_UNSUPPORTED, "device lacks cooperative launch");
@@ -441,24 +513,32 @@ int gicp_max_coop_blocks(int device, int* blocks_per_sm) {
   return DDLO_OK;
 }
 
+int gicp_blocks_for(int ns, int max_blocks) {
+  const int want = (ns + kAlignSubs - 1) / kAlignSubs;  // at least one search round of work per block
+  return std::max(1, std::min(want, max_blocks));
+}
+
 int launch_align(ddlo_runtime* rt, const GicpArgs& args, int blocks) {
+  DDLO_TRY(set_smem_attrs());
   void* kargs[] = {const_cast<GicpArgs*>(&args)};
-  DDLO_CUDA(cudaLaunchCooperativeKernel((const void*)k_align, dim3(blocks), dim3(kAlignThreads), kargs, 0, rt->stream));
+  DDLO_CUDA(cudaLaunchCooperativeKernel((const void*)k_align, dim3(blocks), dim3(kAlignThreads), kargs, sizeof(AlignSmem), rt->stream));
   rt->launches += 1;
   return DDLO_OK;
 }
 
 int launch_linearize_step(ddlo_runtime* rt, const GicpArgs& args, int blocks) {
-  k_linearize_step<<<blocks, kAlignThreads, 0, rt->stream>>>(args);
-  k_sum_partials<<<1, kAlignThreads, 0, rt->stream>>>(args.partials, args.partial_stride, blocks, kNumSums, args.out);
+  DDLO_TRY(set_smem_attrs());
+  k_linearize_step<<<blocks, kAlignThreads, sizeof(AlignSmem), rt->stream>>>(args);
+  k_sum_partials<<<1, 256, 0, rt->stream>>>(args.partials, args.partial_stride, blocks, kNumSums, args.out);
   rt->launches += 2;
   DDLO_CUDA(cudaGetLastError());
   return DDLO_OK;
 }
 
 int launch_error_step(ddlo_runtime* rt, const GicpArgs& args, int blocks) {
-  k_error_step<<<blocks, kAlignThreads, 0, rt->stream>>>(args);
-  k_sum_partials<<<1, kAlignThreads, 0, rt->stream>>>(args.partials, args.partial_stride, blocks, 1, args.out);
+  DDLO_TRY(set_smem_attrs());
+  k_error_step<<<blocks, kAlignThreads, sizeof(AlignSmem), rt->stream>>>(args);
+  k_sum_partials<<<1, 256, 0, rt->stream>>>(args.partials, args.partial_stride, blocks, 1, args.out);
   rt->launches += 2;
   DDLO_CUDA(cudaGetLastError());
   return DDLO_OK;

@@ -49,6 +49,7 @@ int launch_residual_vectors(ddlo_runtime* rt, const float4* src, const float4* t
                             float* d_out3);
 int launch_transform_cloud(ddlo_runtime* rt, const float4* src, int n, const float* T16_host, float4* dst);
 
-constexpr int kAlignThreads = 256;
+constexpr int kAlignThreads = 1024;  // one block per SM: 128 search sub-warps
+int gicp_blocks_for(int ns, int max_blocks);
 
 }  // namespace ddlo

@@ -1,9 +1,16 @@
-// Exact k-nearest-neighbour traversal of the Morton-prefix octree (device code).
+// Exact k-nearest-neighbour search in the Morton-prefix octree (device code).
 //
 // Replaces nanoflann's KDTreeSingleIndexAdaptor::findNeighbors / searchLevel + KNNResultSet
 // (R/impl/nanoflann_impl.hpp:1365-1384, 1495-1566, 161-243) for the two searches the engine does:
 // k-NN of every point of a cloud in itself (covariances) and 1-NN of a moved source point in the
 // target (correspondences).
+//
+// Mapping.  One query is served by a SUB-WARP of 8 lanes (4 queries per warp): a node has 8 child
+// boxes, so lane s tests child s with one coalesced 32-byte load per box component, and a leaf's
+// points are scanned 8 at a time.  All lanes of a sub-warp hold the same traversal state; the four
+// sub-warps of a warp run in lock step and idle when their query is finished.  Compared with one
+// thread per query this removes the divergence between neighbouring queries and multiplies the
+// number of resident warps by eight, which is what hides the L2 latency of the pointer chase.
 //
 // Exactness.  The squared distance is evaluated exactly as nanoflann's L2_Simple_Adaptor does
 // (nanoflann_impl.hpp:508-517): d2 = fl(fl(fl(dx*dx) + fl(dy*dy)) + fl(dz*dz)) in float, with
@@ -17,6 +24,10 @@
 #include "common.cuh"
 
 namespace ddlo {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kSubLanes = 8;
+constexpr int kIdxSentinel = 0x7fffffff;
 
 __device__ __forceinline__ float sqdist3_rn(float qx, float qy, float qz, float px, float py, float pz) {
   const float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
@@ -34,157 +45,247 @@ __device__ __forceinline__ float box_bound_rn(float qx, float qy, float qz, floa
   return __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
 }
 
-// bounds of the 8 sibling boxes of one group
-__device__ __forceinline__ void group_bounds(const float4* __restrict__ g, float qx, float qy, float qz, float b[8]) {
-  const float4 lx0 = __ldg(g + 0), lx1 = __ldg(g + 1), ly0 = __ldg(g + 2), ly1 = __ldg(g + 3), lz0 = __ldg(g + 4), lz1 = __ldg(g + 5);
-  const float4 hx0 = __ldg(g + 6), hx1 = __ldg(g + 7), hy0 = __ldg(g + 8), hy1 = __ldg(g + 9), hz0 = __ldg(g + 10), hz1 = __ldg(g + 11);
-  b[0] = box_bound_rn(qx, qy, qz, lx0.x, ly0.x, lz0.x, hx0.x, hy0.x, hz0.x);
-  b[1] = box_bound_rn(qx, qy, qz, lx0.y, ly0.y, lz0.y, hx0.y, hy0.y, hz0.y);
-  b[2] = box_bound_rn(qx, qy, qz, lx0.z, ly0.z, lz0.z, hx0.z, hy0.z, hz0.z);
-  b[3] = box_bound_rn(qx, qy, qz, lx0.w, ly0.w, lz0.w, hx0.w, hy0.w, hz0.w);
-  b[4] = box_bound_rn(qx, qy, qz, lx1.x, ly1.x, lz1.x, hx1.x, hy1.x, hz1.x);
-  b[5] = box_bound_rn(qx, qy, qz, lx1.y, ly1.y, lz1.y, hx1.y, hy1.y, hz1.y);
-  b[6] = box_bound_rn(qx, qy, qz, lx1.z, ly1.z, lz1.z, hx1.z, hy1.z, hz1.z);
-  b[7] = box_bound_rn(qx, qy, qz, lx1.w, ly1.w, lz1.w, hx1.w, hy1.w, hz1.w);
+// (d, i) lexicographic order
+__device__ __forceinline__ bool lex_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+
+struct Sub {
+  int sl;          // lane inside the sub-warp, 0..7
+  int base;        // first lane of the sub-warp inside the warp
+  unsigned shift;  // bit offset of the sub-warp's byte in a warp ballot
+};
+__device__ __forceinline__ Sub make_sub() {
+  const int lane = threadIdx.x & 31;
+  Sub s;
+  s.sl = lane & 7;
+  s.base = lane & ~7;
+  s.shift = (unsigned)(lane & ~7);
+  return s;
 }
+__device__ __forceinline__ unsigned sub_ballot(bool p, const Sub& sb) { return (__ballot_sync(kFull, p) >> sb.shift) & 0xffu; }
 
 // ---- result sets ------------------------------------------------------------------------------
 // Both rank candidates by (d2, original index).  `worst()` is the current k-th distance, FLT_MAX
-// until k candidates are known; like nanoflann (KNNResultSet::init, :181-187) a candidate whose
-// distance is not below FLT_MAX is never admitted.
+// until k candidates are known; like nanoflann (KNNResultSet::init, nanoflann_impl.hpp:181-187) a
+// candidate whose distance is not below FLT_MAX is never admitted.  All members are uniform across
+// the 8 lanes of a sub-warp.  Empty = (FLT_MAX, kIdxSentinel), the largest possible pair.
 
-struct Best1 {
+// k = 1: best candidate in registers
+struct Best1Sub {
   float d = FLT_MAX;
-  int idx = -1;   // original index
-  int pos = -1;   // position in spts
+  int idx = kIdxSentinel;  // original index
+  int pos = -1;            // position in spts
   __device__ __forceinline__ float worst() const { return d; }
-  __device__ __forceinline__ void offer(float dist, int oidx, int p) {
-    if (dist < d || (dist == d && oidx < idx)) {
-      d = dist;
-      idx = oidx;
-      pos = p;
-    }
-  }
-};
-
-// k entries per thread in shared memory, entry j of thread t at [j * stride + t] (conflict free)
-struct TopKShared {
-  float* d;
-  int* idx;
-  int k;
-  int stride;
-  __device__ __forceinline__ void init(float* d_, int* idx_, int k_, int stride_, int t) {
-    d = d_ + t;
-    idx = idx_ + t;
-    k = k_;
-    stride = stride_;
-    for (int j = 0; j < k; ++j) {
-      d[j * stride] = FLT_MAX;
-      idx[j * stride] = -1;
-    }
-  }
-  __device__ __forceinline__ float worst() const { return d[(k - 1) * stride]; }
-  __device__ __forceinline__ void offer(float dist, int oidx, int /*pos*/) {
-    const float wd = d[(k - 1) * stride];
-    if (!(dist < wd || (dist == wd && oidx < idx[(k - 1) * stride]))) return;
-    int j = k - 1;
-    while (j > 0) {
-      const float pd = d[(j - 1) * stride];
-      if (pd > dist || (pd == dist && idx[(j - 1) * stride] > oidx)) {
-        d[j * stride] = pd;
-        idx[j * stride] = idx[(j - 1) * stride];
-        --j;
-      } else {
-        break;
+  __device__ __forceinline__ void scan(bool doit, const float4* __restrict__ spts, int start, int count, float qx, float qy, float qz,
+                                       const Sub& sb) {
+    float ld = d;
+    int li = idx, lp = pos;
+    if (doit) {
+      for (int j = sb.sl; j < count; j += kSubLanes) {
+        const float4 v = __ldg(spts + start + j);
+        const float dist = sqdist3_rn(qx, qy, qz, v.x, v.y, v.z);
+        const int oi = __float_as_int(v.w);
+        if (dist < FLT_MAX && lex_less(dist, oi, ld, li)) {
+          ld = dist;
+          li = oi;
+          lp = start + j;
+        }
       }
     }
-    d[j * stride] = dist;
-    idx[j * stride] = oidx;
+#pragma unroll
+    for (int o = 1; o < kSubLanes; o <<= 1) {
+      const float od = __shfl_xor_sync(kFull, ld, o);
+      const int oi = __shfl_xor_sync(kFull, li, o);
+      const int op = __shfl_xor_sync(kFull, lp, o);
+      if (lex_less(od, oi, ld, li)) {
+        ld = od;
+        li = oi;
+        lp = op;
+      }
+    }
+    d = ld;
+    idx = li;
+    pos = lp;
   }
 };
 
-__device__ __forceinline__ float pick8(const float b[8], int c) {
-  float r = b[0];
-#pragma unroll
-  for (int s = 1; s < 8; ++s) r = (c == s) ? b[s] : r;
-  return r;
-}
-
-template <class RS>
-__device__ __forceinline__ void scan_leaf(const float4* __restrict__ spts, int start, int count, float qx, float qy, float qz, RS& rs) {
-  const float4* p = spts + start;
-#pragma unroll 4
-  for (int j = 0; j < count; ++j) {
-    const float4 v = __ldg(p + j);
-    rs.offer(sqdist3_rn(qx, qy, qz, v.x, v.y, v.z), __float_as_int(v.w), start + j);
+// general k: k unsorted (d, i) pairs in shared memory plus the tracked maximum.  Empty slots hold
+// the sentinel, so "replace the maximum" also fills the set.
+struct TopKSub {
+  float* sd;
+  int* si;
+  int k;
+  float wd;
+  int wi;
+  int wslot;
+  __device__ __forceinline__ void init(float* sd_, int* si_, int k_, const Sub& sb) {
+    sd = sd_;
+    si = si_;
+    k = k_;
+    for (int e = sb.sl; e < k; e += kSubLanes) {
+      sd[e] = FLT_MAX;
+      si[e] = kIdxSentinel;
+    }
+    wd = FLT_MAX;
+    wi = kIdxSentinel;
+    wslot = k - 1;
+    __syncwarp();
   }
-}
+  __device__ __forceinline__ float worst() const { return wd; }
+  // maximum over the k slots; equal pairs (only sentinels can be equal) resolved by slot so that
+  // every lane agrees.  Contains warp-wide shuffles: must be executed by all 32 lanes.
+  __device__ __forceinline__ void find_max(const Sub& sb) {
+    float md = -1.0f;
+    int mi = -1, ms = -1;
+    for (int e = sb.sl; e < k; e += kSubLanes) {
+      const float ed = sd[e];
+      const int ei = si[e];
+      if (ms < 0 || lex_less(md, mi, ed, ei) || (ed == md && ei == mi && e > ms)) {
+        md = ed;
+        mi = ei;
+        ms = e;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < kSubLanes; o <<= 1) {
+      const float od = __shfl_xor_sync(kFull, md, o);
+      const int oi = __shfl_xor_sync(kFull, mi, o);
+      const int os = __shfl_xor_sync(kFull, ms, o);
+      if (os >= 0 && (ms < 0 || lex_less(md, mi, od, oi) || (od == md && oi == mi && os > ms))) {
+        md = od;
+        mi = oi;
+        ms = os;
+      }
+    }
+    wd = md;
+    wi = mi;
+    wslot = ms;
+  }
+  __device__ __forceinline__ void scan(bool doit, const float4* __restrict__ spts, int start, int count, float qx, float qy, float qz,
+                                       const Sub& sb) {
+    for (int r = 0; __any_sync(kFull, doit && r < count); r += kSubLanes) {
+      const int j = r + sb.sl;
+      const bool have = doit && j < count;
+      float dist = FLT_MAX;
+      int oi = kIdxSentinel;
+      if (have) {
+        const float4 v = __ldg(spts + start + j);
+        dist = sqdist3_rn(qx, qy, qz, v.x, v.y, v.z);
+        oi = __float_as_int(v.w);
+      }
+      unsigned cb = sub_ballot(have && dist < FLT_MAX && lex_less(dist, oi, wd, wi), sb);
+      while (__any_sync(kFull, cb != 0u)) {
+        const bool act = cb != 0u;
+        const int c = act ? __ffs(cb) - 1 : 0;
+        cb &= cb - 1u;
+        const float dc = __shfl_sync(kFull, dist, sb.base + c);
+        const int ic = __shfl_sync(kFull, oi, sb.base + c);
+        const bool upd = act && lex_less(dc, ic, wd, wi);  // the bar may have dropped since the ballot
+        if (upd && sb.sl == 0) {
+          sd[wslot] = dc;
+          si[wslot] = ic;
+        }
+        __syncwarp();
+        find_max(sb);
+      }
+    }
+  }
+  // ascending (d, i) order into one output row; sentinels become (-1, +inf)
+  __device__ __forceinline__ void write_sorted(int* __restrict__ idx_out, float* __restrict__ d_out, const Sub& sb) const {
+    for (int e = sb.sl; e < k; e += kSubLanes) {
+      const float ed = sd[e];
+      const int ei = si[e];
+      int rank = 0;
+      for (int f = 0; f < k; ++f) rank += (lex_less(sd[f], si[f], ed, ei) || (sd[f] == ed && si[f] == ei && f < e)) ? 1 : 0;
+      const bool empty = ei == kIdxSentinel;
+      idx_out[rank] = empty ? -1 : ei;
+      if (d_out) d_out[rank] = empty ? __int_as_float(0x7f800000) : ed;
+    }
+  }
+};
 
-// Depth-first traversal.  At a node: the child boxes that can still hold a better candidate are
-// found (bound <= current k-th distance; "<=" so that an equal-distance point with a smaller index
-// is not missed); leaf children are scanned on the spot, which tightens the k-th distance before
-// the internal children are looked at; of those the nearest is entered directly and the others go
-// on a small per-thread stack together with their bound, so that a stale entry is discarded on
-// pop without touching memory.
+// Depth-first traversal by one sub-warp.  At a node: lane s bounds child s; children whose bound
+// can still beat the k-th distance ("<=", so that an equal-distance point with a smaller index is
+// not missed) are handled leaves first, nearest first, each re-tested against the shrinking bar
+// right before its scan; of the internal ones the nearest is entered directly and the others are
+// pushed, with their bound, on the sub-warp's stack in shared memory, so that a stale entry is
+// dropped on pop without touching global memory.
+// MUST be called by all 32 lanes of a warp; `active` is uniform per sub-warp; `stack` has
+// kStackDepth entries per sub-warp.
 template <class RS>
-__device__ __forceinline__ void knn_traverse(const IndexView& ix, float qx, float qy, float qz, RS& rs) {
-  if (ix.n <= 0) return;
-  unsigned long long stack[kStackDepth];  // (bound bits << 32) | node id; bounds are >= 0 so the bits order like floats
+__device__ __forceinline__ void knn_traverse_sub(const IndexView& ix, bool active, float qx, float qy, float qz, RS& rs,
+                                                 unsigned long long* __restrict__ stack, const Sub& sb) {
+  bool run = active && ix.n > 0;
   int sp = 0;
   unsigned node = 0;
-  for (;;) {
-    const float4* g = ix.nodes + (size_t)node * kNodeF4;
-    float b[8];
-    group_bounds(g, qx, qy, qz, b);
-    const int2* refs = reinterpret_cast<const int2*>(g + 12);
-    const float w = rs.worst();
-    unsigned m = 0;
+  const float inf = __int_as_float(0x7f800000);
+  while (__any_sync(kFull, run)) {
+    __syncwarp();
+    float b = inf;
+    int2 ref = make_int2(0, 0);
+    if (run) {
+      const float* g = reinterpret_cast<const float*>(ix.nodes + (size_t)node * kNodeF4);
+      const float lx = __ldg(g + sb.sl), ly = __ldg(g + 8 + sb.sl), lz = __ldg(g + 16 + sb.sl);
+      const float hx = __ldg(g + 24 + sb.sl), hy = __ldg(g + 32 + sb.sl), hz = __ldg(g + 40 + sb.sl);
+      ref = __ldg(reinterpret_cast<const int2*>(g + 48) + sb.sl);
+      b = box_bound_rn(qx, qy, qz, lx, ly, lz, hx, hy, hz);
+    }
+    const bool qual = run && b <= rs.worst();
+    // ---- leaf children, nearest first
+    unsigned ml = sub_ballot(qual && ref.y > 0, sb);
+    while (__any_sync(kFull, ml != 0u)) {
+      float mb = ((ml >> sb.sl) & 1u) ? b : inf;
+      int mc = sb.sl;
 #pragma unroll
-    for (int s = 0; s < 8; ++s)
-      if (b[s] <= w) m |= 1u << s;
-    // leaves first
-    unsigned inner = 0;
-    for (unsigned mm = m; mm;) {
-      const int s = __ffs(mm) - 1;
-      mm &= mm - 1;
-      const int2 r = __ldg(refs + s);
-      if (r.y > 0) {
-        if (pick8(b, s) <= rs.worst()) scan_leaf(ix.spts, r.x, r.y, qx, qy, qz, rs);
-      } else {
-        inner |= 1u << s;
+      for (int o = 1; o < kSubLanes; o <<= 1) {
+        const float ob = __shfl_xor_sync(kFull, mb, o);
+        const int oc = __shfl_xor_sync(kFull, mc, o);
+        if (ob < mb || (ob == mb && oc < mc)) {
+          mb = ob;
+          mc = oc;
+        }
+      }
+      const bool had = ml != 0u;
+      ml &= ~(1u << mc);
+      const int st = __shfl_sync(kFull, ref.x, sb.base + mc);
+      const int cnt = __shfl_sync(kFull, ref.y, sb.base + mc);
+      rs.scan(had && mb <= rs.worst(), ix.spts, st, cnt, qx, qy, qz, sb);
+    }
+    // ---- internal children
+    const bool qi = qual && ref.y < 0 && b <= rs.worst();
+    const unsigned mi = sub_ballot(qi, sb);
+    float nb = qi ? b : inf;
+    int nc = sb.sl;
+#pragma unroll
+    for (int o = 1; o < kSubLanes; o <<= 1) {
+      const float ob = __shfl_xor_sync(kFull, nb, o);
+      const int oc = __shfl_xor_sync(kFull, nc, o);
+      if (ob < nb || (ob == nb && oc < nc)) {
+        nb = ob;
+        nc = oc;
       }
     }
-    // internal children: nearest is entered now, the rest are stacked
-    float best_b = 0.0f;
-    int best_n = -1;
-    const float w2 = rs.worst();
-    for (; inner;) {
-      const int s = __ffs(inner) - 1;
-      inner &= inner - 1;
-      const float bs = pick8(b, s);
-      if (!(bs <= w2)) continue;
-      const int child = __ldg(refs + s).x;
-      float push_b;
-      int push_n;
-      if (best_n < 0 || bs < best_b) {
-        push_b = best_b, push_n = best_n;
-        best_b = bs, best_n = child;
+    const unsigned rest = mi & ~(1u << nc);
+    if (qi && sb.sl != nc) {
+      const int at = sp + __popc(rest & ((1u << sb.sl) - 1u));
+      stack[at] = ((unsigned long long)__float_as_uint(b) << 32) | (unsigned)ref.x;
+    }
+    const int next = __shfl_sync(kFull, ref.x, sb.base + nc);
+    __syncwarp();
+    if (run) {
+      if (mi) {
+        sp += __popc(rest);
+        node = (unsigned)next;
       } else {
-        push_b = bs, push_n = child;
-      }
-      if (push_n >= 0 && sp < kStackDepth) stack[sp++] = ((unsigned long long)__float_as_uint(push_b) << 32) | (unsigned)push_n;
-    }
-    if (best_n >= 0) {
-      node = (unsigned)best_n;
-      continue;
-    }
-    // pop the next entry that can still matter
-    for (;;) {
-      if (sp == 0) return;
-      const unsigned long long e = stack[--sp];
-      if (__uint_as_float((unsigned)(e >> 32)) <= rs.worst()) {
-        node = (unsigned)(e & 0xffffffffull);
-        break;
+        // pop the next entry that can still matter (bounds are >= 0, so their bits order like floats)
+        run = false;
+        while (sp > 0) {
+          const unsigned long long e = stack[--sp];
+          if (__uint_as_float((unsigned)(e >> 32)) <= rs.worst()) {
+            node = (unsigned)(e & 0xffffffffull);
+            run = true;
+            break;
+          }
+        }
       }
     }
   }

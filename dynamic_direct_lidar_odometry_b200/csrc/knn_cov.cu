@@ -1,53 +1,50 @@
 // k-NN queries and per-point covariances.
-//   k_knn_queries   KdTreeFLANN::nearestKSearch for a batch of external queries  (nanoflann.hpp:146-156)
-//   k_covariances   NanoGICP::calculate_covariances                              (nano_gicp_impl.hpp:374-441)
-// One thread per query; the k-entry result set of each thread lives in shared memory (entry-major,
-// bank-conflict free); the fp64 covariance and its regularisation are fused behind the search so
-// neighbour indices never travel through HBM.
+//   k_knn             KdTreeFLANN::nearestKSearch for a batch of queries        (nanoflann.hpp:146-156)
+//   k_cov_from_knn    the arithmetic of NanoGICP::calculate_covariances         (nano_gicp_impl.hpp:392-437)
+// The search runs one query per 8-lane sub-warp (knn.cuh) with the k-entry result set and the
+// traversal stack in shared memory; the fp64 covariance + regularisation then runs one thread per
+// point on the neighbour rows the search left in L2.
 #include "common.cuh"
 #include "knn.cuh"
 #include "math.cuh"
 
 namespace ddlo {
 
-constexpr int kKnnThreads = 128;
+constexpr int kKnnThreads = 256;
+constexpr int kKnnSubs = kKnnThreads / kSubLanes;  // queries per block
 
-__global__ void __launch_bounds__(kKnnThreads) k_knn_queries(IndexView ix, const float4* __restrict__ queries, int nq, int k,
-                                                              int* __restrict__ idx_out, float* __restrict__ d_out) {
-  extern __shared__ unsigned char smem[];
-  float* sd = reinterpret_cast<float*>(smem);
-  int* si = reinterpret_cast<int*>(smem + sizeof(float) * k * kKnnThreads);
-  const int q = blockIdx.x * kKnnThreads + threadIdx.x;
-  TopKShared rs;
-  rs.init(sd, si, k, kKnnThreads, threadIdx.x);
-  if (q >= nq) return;
-  const float4 v = queries[q];
-  knn_traverse(ix, v.x, v.y, v.z, rs);
-  for (int j = 0; j < k; ++j) {
-    const int id = rs.idx[j * rs.stride];
-    idx_out[(size_t)q * k + j] = id;
-    d_out[(size_t)q * k + j] = id < 0 ? __int_as_float(0x7f800000) : rs.d[j * rs.stride];
+// self_mode = 0: query q is queries[q], output row q
+// self_mode = 1: query q is the q-th point of the index in Morton order, output row = its original index
+__global__ void __launch_bounds__(kKnnThreads) k_knn(IndexView ix, const float4* __restrict__ queries, int nq, int k, int self_mode,
+                                                      int* __restrict__ idx_out, float* __restrict__ d_out) {
+  extern __shared__ unsigned long long smem_knn[];
+  unsigned long long* stacks = smem_knn;                                             // [kKnnSubs][kStackDepth]
+  float* sd = reinterpret_cast<float*>(smem_knn + (size_t)kKnnSubs * kStackDepth);  // [kKnnSubs][k]
+  int* si = reinterpret_cast<int*>(sd + (size_t)kKnnSubs * k);                      // [kKnnSubs][k]
+  const Sub sb = make_sub();
+  const int sw = threadIdx.x / kSubLanes;
+  const int q = blockIdx.x * kKnnSubs + sw;
+  const bool active = q < nq;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) v = self_mode ? __ldg(ix.spts + q) : __ldg(queries + q);
+  TopKSub rs;
+  rs.init(sd + (size_t)sw * k, si + (size_t)sw * k, k, sb);
+  knn_traverse_sub(ix, active, v.x, v.y, v.z, rs, stacks + (size_t)sw * kStackDepth, sb);
+  if (active) {
+    const size_t row = self_mode ? (size_t)__float_as_int(v.w) : (size_t)q;
+    rs.write_sorted(idx_out + row * k, d_out ? d_out + row * k : nullptr, sb);
   }
 }
 
-// thread t handles the t-th point in MORTON order (neighbouring threads walk neighbouring paths)
-__global__ void __launch_bounds__(kKnnThreads) k_covariances(IndexView ix, const float4* __restrict__ pts, int k, int method,
-                                                              double* __restrict__ covs) {
-  extern __shared__ unsigned char smem[];
-  float* sd = reinterpret_cast<float*>(smem);
-  int* si = reinterpret_cast<int*>(smem + sizeof(float) * k * kKnnThreads);
-  const int s = blockIdx.x * kKnnThreads + threadIdx.x;
-  TopKShared rs;
-  rs.init(sd, si, k, kKnnThreads, threadIdx.x);
-  if (s >= ix.n) return;
-  const float4 v = __ldg(ix.spts + s);
-  const int self = __float_as_int(v.w);
-  knn_traverse(ix, v.x, v.y, v.z, rs);
-
-  // neighbors.colwise() -= neighbors.rowwise().mean(); cov = N N^T / k   (:392-399), all fp64
+// neighbors.colwise() -= neighbors.rowwise().mean(); cov = N N^T / k; regularise   (:392-437), all fp64
+__global__ void __launch_bounds__(256) k_cov_from_knn(const float4* __restrict__ pts, int n, const int* __restrict__ knn_idx, int k,
+                                                      int method, double* __restrict__ covs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int* row = knn_idx + (size_t)i * k;
   double mx = 0.0, my = 0.0, mz = 0.0;
   for (int j = 0; j < k; ++j) {
-    const float4 p = __ldg(pts + rs.idx[j * rs.stride]);
+    const float4 p = __ldg(pts + __ldg(row + j));
     mx += (double)p.x;
     my += (double)p.y;
     mz += (double)p.z;
@@ -58,7 +55,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_covariances(IndexView ix, const
   mz /= kd;
   Sym3 c = {0, 0, 0, 0, 0, 0};
   for (int j = 0; j < k; ++j) {
-    const float4 p = __ldg(pts + rs.idx[j * rs.stride]);
+    const float4 p = __ldg(pts + __ldg(row + j));
     const double dx = (double)p.x - mx, dy = (double)p.y - my, dz = (double)p.z - mz;
     c.xx += dx * dx;
     c.xy += dx * dy;
@@ -69,29 +66,39 @@ __global__ void __launch_bounds__(kKnnThreads) k_covariances(IndexView ix, const
   }
   c.xx /= kd, c.xy /= kd, c.xz /= kd, c.yy /= kd, c.yz /= kd, c.zz /= kd;
   const Sym3 r = regularize_cov(c, method);
-  double2* out = reinterpret_cast<double2*>(covs + (size_t)self * kCovStride);
+  double2* out = reinterpret_cast<double2*>(covs + (size_t)i * kCovStride);
   out[0] = make_double2(r.xx, r.xy);
   out[1] = make_double2(r.xz, r.yy);
   out[2] = make_double2(r.yz, r.zz);
 }
 
+static int knn_smem(int k, size_t* bytes) {
+  *bytes = (size_t)kKnnSubs * kStackDepth * 8 + (size_t)kKnnSubs * k * 8;
+  if (*bytes > 200 * 1024) return fail(DDLO_E_UNSUPPORTED, "k too large for the shared-memory result set");
+  if (*bytes > 48 * 1024) DDLO_CUDA(cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*bytes));
+  return DDLO_OK;
+}
+
 int launch_knn_queries(ddlo_cloud* c, const float4* d_queries, int nq, int k, int* d_idx, float* d_d2) {
-  const size_t smem = (size_t)k * kKnnThreads * 8;
-  if (smem > 200 * 1024) return fail(DDLO_E_UNSUPPORTED, "k too large for the shared-memory result set");
-  if (smem > 48 * 1024) DDLO_CUDA(cudaFuncSetAttribute(k_knn_queries, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_knn_queries<<<(nq + kKnnThreads - 1) / kKnnThreads, kKnnThreads, smem, c->rt->stream>>>(c->view, d_queries, nq, k, d_idx, d_d2);
+  size_t smem = 0;
+  DDLO_TRY(knn_smem(k, &smem));
+  k_knn<<<(nq + kKnnSubs - 1) / kKnnSubs, kKnnThreads, smem, c->rt->stream>>>(c->view, d_queries, nq, k, 0, d_idx, d_d2);
   c->rt->launches += 1;
   DDLO_CUDA(cudaGetLastError());
   return DDLO_OK;
 }
 
 int launch_covariances(ddlo_cloud* c, int k, int method, double* d_covs) {
-  const size_t smem = (size_t)k * kKnnThreads * 8;
-  if (smem > 200 * 1024) return fail(DDLO_E_UNSUPPORTED, "k too large for the shared-memory result set");
-  if (smem > 48 * 1024) DDLO_CUDA(cudaFuncSetAttribute(k_covariances, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_covariances<<<(c->n + kKnnThreads - 1) / kKnnThreads, kKnnThreads, smem, c->rt->stream>>>(c->view, c->pts, k, method, d_covs);
-  c->rt->launches += 1;
+  size_t smem = 0;
+  DDLO_TRY(knn_smem(k, &smem));
+  ddlo_runtime* rt = c->rt;
+  int* d_idx = nullptr;
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_idx), (size_t)c->n * k * sizeof(int), rt->stream));
+  k_knn<<<(c->n + kKnnSubs - 1) / kKnnSubs, kKnnThreads, smem, rt->stream>>>(c->view, nullptr, c->n, k, 1, d_idx, nullptr);
+  k_cov_from_knn<<<(c->n + 255) / 256, 256, 0, rt->stream>>>(c->pts, c->n, d_idx, k, method, d_covs);
+  rt->launches += 2;
   DDLO_CUDA(cudaGetLastError());
+  DDLO_CUDA(cudaFreeAsync(d_idx, rt->stream));
   return DDLO_OK;
 }
 
