@@ -165,29 +165,29 @@ __device__ __forceinline__ double err_point(const GicpArgs& a, const Iso3& T, in
   return quad_form(M, ex, ey, ez, mx, my, mz);
 }
 
-// the slice of source points block `b` of `nb` owns
-__device__ __forceinline__ void block_slice(int ns, int b, int nb, int& p0, int& p1) {
-  const int per = (ns + nb - 1) / nb;
-  p0 = min(ns, b * per);
-  p1 = min(ns, p0 + per);
-}
+// Static work distribution: the source points are dealt to the blocks in chunks of 4 consecutive
+// points (one warp's worth of sub-warp queries), round-robin, so that every block sees the same
+// mix of cheap and expensive queries and the blocks reach the grid barrier together.  Block b's
+// local slot s is point ((s / 4) * nb + b) * 4 + s % 4; the mapping is fixed, so the summation
+// order (and with it every bit of H, b and the error) is reproducible.
+__device__ __forceinline__ int slots_per_block(int ns, int nb) { return 4 * (((ns + 3) / 4 + nb - 1) / nb); }
+__device__ __forceinline__ int slot_point(int slot, int b, int nb) { return ((slot >> 2) * nb + b) * 4 + (slot & 3); }
 
-// linearize over the block's slice; leaves the block's 28 sums in dst[c * stride + blockIdx.x]
+// linearize over the block's points; leaves the block's 28 sums in dst[c * stride + blockIdx.x]
 __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm, double* dst, int stride) {
   const Sub sb = make_sub();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sw = threadIdx.x / kSubLanes;
   for (int k = lane; k < kNumSums; k += 32) sm.red[warp * kNumSums + k] = 0.0;
-  int p0, p1;
-  block_slice(a.ns, blockIdx.x, gridDim.x, p0, p1);
-  for (int base = p0; base < p1; base += kAlignThreads) {
-    const int lim = min(p1, base + kAlignThreads);
-    __syncthreads();  // nn_* of the previous sub-slice fully consumed
+  const int nslots = slots_per_block(a.ns, gridDim.x);
+  for (int base = 0; base < nslots; base += kAlignThreads) {
+    const int lim = min(nslots, base + kAlignThreads);
+    __syncthreads();  // nn_* of the previous pass fully consumed
     // ---- phase A: update_correspondences' search, one query per sub-warp
     for (int r = 0; base + r * kAlignSubs < lim; ++r) {
-      const int slot = r * kAlignSubs + sw;
-      const int i = base + slot;
-      const bool active = i < lim;
+      const int slot = base + r * kAlignSubs + sw;
+      const int i = slot_point(slot, blockIdx.x, gridDim.x);
+      const bool active = slot < lim && i < a.ns;
       float qx = 0.f, qy = 0.f, qz = 0.f;
       if (active) {
         const float4 pa = __ldg(a.src_pts + i);
@@ -198,16 +198,17 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
       Best1Sub best;
       knn_traverse_sub(a.tgt, active, qx, qy, qz, best, sm.stacks + (size_t)sw * kStackDepth, sb);
       if (active && sb.sl == 0) {
-        sm.nn_d[slot] = best.d;
-        sm.nn_idx[slot] = best.idx;
-        sm.nn_pos[slot] = best.pos;
+        sm.nn_d[slot - base] = best.d;
+        sm.nn_idx[slot - base] = best.idx;
+        sm.nn_pos[slot - base] = best.pos;
       }
     }
     __syncthreads();
     // ---- phase B: one thread per point
     if (base + warp * 32 < lim) {
-      const int i = base + threadIdx.x;
-      const bool valid = i < lim;
+      const int slot = base + threadIdx.x;
+      const int i = slot_point(slot, blockIdx.x, gridDim.x);
+      const bool valid = slot < lim && i < a.ns;
       lin_point(a, sm.lm, valid, i, valid ? sm.nn_d[threadIdx.x] : 0.f, valid ? sm.nn_idx[threadIdx.x] : -1,
                 valid ? sm.nn_pos[threadIdx.x] : -1, sm.red + warp * kNumSums);
     }
@@ -221,13 +222,15 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
   __syncthreads();
 }
 
-// compute_error over the block's slice; the block's sum goes to dst[blockIdx.x]
+// compute_error over the block's points; the block's sum goes to dst[blockIdx.x]
 __device__ __forceinline__ void error_block(const GicpArgs& a, const Iso3& T, AlignSmem& sm, double* dst) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int p0, p1;
-  block_slice(a.ns, blockIdx.x, gridDim.x, p0, p1);
+  const int nslots = slots_per_block(a.ns, gridDim.x);
   double e = 0.0;
-  for (int i = p0 + threadIdx.x; i < p1; i += kAlignThreads) e += err_point(a, T, i);
+  for (int slot = threadIdx.x; slot < nslots; slot += kAlignThreads) {
+    const int i = slot_point(slot, blockIdx.x, gridDim.x);
+    if (i < a.ns) e += err_point(a, T, i);
+  }
   e = warp_sum(e);
   if (lane == 0) sm.red[warp] = e;
   __syncthreads();

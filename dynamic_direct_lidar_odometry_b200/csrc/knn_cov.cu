@@ -15,24 +15,31 @@ constexpr int kKnnSubs = kKnnThreads / kSubLanes;  // queries per block
 
 // self_mode = 0: query q is queries[q], output row q
 // self_mode = 1: query q is the q-th point of the index in Morton order, output row = its original index
+// R > 0: k <= 8R, result set in registers (TopKRegSub<R>); R == 0: any k, result set in shared memory
+template <int R>
 __global__ void __launch_bounds__(kKnnThreads) k_knn(IndexView ix, const float4* __restrict__ queries, int nq, int k, int self_mode,
                                                       int* __restrict__ idx_out, float* __restrict__ d_out) {
   extern __shared__ unsigned long long smem_knn[];
-  unsigned long long* stacks = smem_knn;                                             // [kKnnSubs][kStackDepth]
-  float* sd = reinterpret_cast<float*>(smem_knn + (size_t)kKnnSubs * kStackDepth);  // [kKnnSubs][k]
-  int* si = reinterpret_cast<int*>(sd + (size_t)kKnnSubs * k);                      // [kKnnSubs][k]
+  unsigned long long* stacks = smem_knn;  // [kKnnSubs][kStackDepth]
   const Sub sb = make_sub();
   const int sw = threadIdx.x / kSubLanes;
   const int q = blockIdx.x * kKnnSubs + sw;
   const bool active = q < nq;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) v = self_mode ? __ldg(ix.spts + q) : __ldg(queries + q);
-  TopKSub rs;
-  rs.init(sd + (size_t)sw * k, si + (size_t)sw * k, k, sb);
-  knn_traverse_sub(ix, active, v.x, v.y, v.z, rs, stacks + (size_t)sw * kStackDepth, sb);
-  if (active) {
-    const size_t row = self_mode ? (size_t)__float_as_int(v.w) : (size_t)q;
-    rs.write_sorted(idx_out + row * k, d_out ? d_out + row * k : nullptr, sb);
+  const size_t row = !active ? 0 : (self_mode ? (size_t)__float_as_int(v.w) : (size_t)q);
+  if constexpr (R > 0) {
+    TopKRegSub<R> rs;
+    rs.init(k);
+    knn_traverse_sub(ix, active, v.x, v.y, v.z, rs, stacks + (size_t)sw * kStackDepth, sb);
+    if (active) rs.write_sorted(idx_out + row * k, d_out ? d_out + row * k : nullptr, sb);
+  } else {
+    float* sd = reinterpret_cast<float*>(smem_knn + (size_t)kKnnSubs * kStackDepth);  // [kKnnSubs][k]
+    int* si = reinterpret_cast<int*>(sd + (size_t)kKnnSubs * k);                      // [kKnnSubs][k]
+    TopKSub rs;
+    rs.init(sd + (size_t)sw * k, si + (size_t)sw * k, k, sb);
+    knn_traverse_sub(ix, active, v.x, v.y, v.z, rs, stacks + (size_t)sw * kStackDepth, sb);
+    if (active) rs.write_sorted(idx_out + row * k, d_out ? d_out + row * k : nullptr, sb);
   }
 }
 
@@ -72,33 +79,45 @@ __global__ void __launch_bounds__(256) k_cov_from_knn(const float4* __restrict__
   out[2] = make_double2(r.yz, r.zz);
 }
 
-static int knn_smem(int k, size_t* bytes) {
-  *bytes = (size_t)kKnnSubs * kStackDepth * 8 + (size_t)kKnnSubs * k * 8;
-  if (*bytes > 200 * 1024) return fail(DDLO_E_UNSUPPORTED, "k too large for the shared-memory result set");
-  if (*bytes > 48 * 1024) DDLO_CUDA(cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*bytes));
+static int launch_knn(ddlo_runtime* rt, const IndexView& view, const float4* d_queries, int nq, int k, int self_mode, int* d_idx,
+                      float* d_d2) {
+  const int blocks = (nq + kKnnSubs - 1) / kKnnSubs;
+  const size_t stack_bytes = (size_t)kKnnSubs * kStackDepth * 8;
+  if (k <= 8) {
+    k_knn<1><<<blocks, kKnnThreads, stack_bytes, rt->stream>>>(view, d_queries, nq, k, self_mode, d_idx, d_d2);
+  } else if (k <= 16) {
+    k_knn<2><<<blocks, kKnnThreads, stack_bytes, rt->stream>>>(view, d_queries, nq, k, self_mode, d_idx, d_d2);
+  } else if (k <= 24) {
+    k_knn<3><<<blocks, kKnnThreads, stack_bytes, rt->stream>>>(view, d_queries, nq, k, self_mode, d_idx, d_d2);
+  } else if (k <= 32) {
+    k_knn<4><<<blocks, kKnnThreads, stack_bytes, rt->stream>>>(view, d_queries, nq, k, self_mode, d_idx, d_d2);
+  } else {
+    const size_t bytes = stack_bytes + (size_t)kKnnSubs * k * 8;
+    if (bytes > 200 * 1024) return fail(DDLO_E_UNSUPPORTED, "k too large for the shared-memory result set");
+    if (bytes > 48 * 1024) DDLO_CUDA(cudaFuncSetAttribute(k_knn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    k_knn<0><<<blocks, kKnnThreads, bytes, rt->stream>>>(view, d_queries, nq, k, self_mode, d_idx, d_d2);
+  }
+  rt->launches += 1;
+  DDLO_CUDA(cudaGetLastError());
   return DDLO_OK;
 }
 
 int launch_knn_queries(ddlo_cloud* c, const float4* d_queries, int nq, int k, int* d_idx, float* d_d2) {
-  size_t smem = 0;
-  DDLO_TRY(knn_smem(k, &smem));
-  k_knn<<<(nq + kKnnSubs - 1) / kKnnSubs, kKnnThreads, smem, c->rt->stream>>>(c->view, d_queries, nq, k, 0, d_idx, d_d2);
-  c->rt->launches += 1;
-  DDLO_CUDA(cudaGetLastError());
-  return DDLO_OK;
+  return launch_knn(c->rt, c->view, d_queries, nq, k, 0, d_idx, d_d2);
 }
 
 int launch_covariances(ddlo_cloud* c, int k, int method, double* d_covs) {
-  size_t smem = 0;
-  DDLO_TRY(knn_smem(k, &smem));
   ddlo_runtime* rt = c->rt;
   int* d_idx = nullptr;
   DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_idx), (size_t)c->n * k * sizeof(int), rt->stream));
-  k_knn<<<(c->n + kKnnSubs - 1) / kKnnSubs, kKnnThreads, smem, rt->stream>>>(c->view, nullptr, c->n, k, 1, d_idx, nullptr);
-  k_cov_from_knn<<<(c->n + 255) / 256, 256, 0, rt->stream>>>(c->pts, c->n, d_idx, k, method, d_covs);
-  rt->launches += 2;
+  int rc = launch_knn(rt, c->view, nullptr, c->n, k, 1, d_idx, nullptr);
+  if (rc == DDLO_OK) {
+    k_cov_from_knn<<<(c->n + 255) / 256, 256, 0, rt->stream>>>(c->pts, c->n, d_idx, k, method, d_covs);
+    rt->launches += 1;
+  }
+  cudaFreeAsync(d_idx, rt->stream);
+  if (rc != DDLO_OK) return rc;
   DDLO_CUDA(cudaGetLastError());
-  DDLO_CUDA(cudaFreeAsync(d_idx, rt->stream));
   return DDLO_OK;
 }
 
