@@ -90,6 +90,8 @@ static void cloud_free(ddlo_cloud* c) {
   if (c->pts) cudaFreeAsync(c->pts, st);
   if (c->spts) cudaFreeAsync(c->spts, st);
   if (c->nodes) cudaFreeAsync(c->nodes, st);
+  if (c->meta) cudaFreeAsync(c->meta, st);
+  if (c->node_of_point) cudaFreeAsync(c->node_of_point, st);
   delete c;
 }
 static void covs_free(ddlo_covs* v) {
@@ -112,6 +114,7 @@ struct ddlo_gicp {
   // per-source-point workspace (correspondences_, sq_distances_, mahalanobis_)
   int ws_n = 0;
   int* corr = nullptr;
+  int* nn_raw = nullptr;
   float* sqd = nullptr;
   double* mahal = nullptr;
   int corr_n = 0;  // number of valid entries (0 after swap/clear: correspondences_.clear())
@@ -580,6 +583,7 @@ int ddlo_gicp_destroy(ddlo_gicp* g) {
   set_covs(g->src_cov, nullptr);
   set_covs(g->tgt_cov, nullptr);
   if (g->corr) cudaFree(g->corr);
+  if (g->nn_raw) cudaFree(g->nn_raw);
   if (g->sqd) cudaFree(g->sqd);
   if (g->mahal) cudaFree(g->mahal);
   if (g->partials) cudaFree(g->partials);
@@ -708,11 +712,13 @@ static int ensure_workspace(ddlo_gicp* g, int ns) {
   if (g->ws_n >= ns) return DDLO_OK;
   DDLO_CUDA(cudaStreamSynchronize(g->rt->stream));
   if (g->corr) cudaFree(g->corr);
+  if (g->nn_raw) cudaFree(g->nn_raw);
   if (g->sqd) cudaFree(g->sqd);
   if (g->mahal) cudaFree(g->mahal);
-  g->corr = nullptr, g->sqd = nullptr, g->mahal = nullptr, g->ws_n = 0;
+  g->corr = nullptr, g->nn_raw = nullptr, g->sqd = nullptr, g->mahal = nullptr, g->ws_n = 0;
   const size_t cap = (size_t)ns + ns / 4 + 256;
   DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->corr), cap * sizeof(int)));
+  DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->nn_raw), cap * sizeof(int)));
   DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->sqd), cap * sizeof(float)));
   DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->mahal), cap * kCovStride * sizeof(double)));
   g->ws_n = (int)cap;
@@ -743,6 +749,7 @@ static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, 
   a->tgt_cov = g->tgt_cov->c;
   a->ns = g->src->n;
   a->corr = g->corr;
+  a->nn_raw = g->nn_raw;
   a->sqd = g->sqd;
   a->mahal = g->mahal;
   a->partials = g->partials;

@@ -46,6 +46,8 @@ int fail(int code, const std::string& msg);
 //               [12..15] 8 child references (int2): {node id, -1} internal, {start, count>0} leaf, {0,0} empty
 //             empty slots keep lo=+inf, hi=-inf, whose distance bound is +inf and never qualifies.
 //   node 0 is the root (level 0, the whole cloud); ids are breadth-first.
+//   meta / node_of_point let a search that already knows a nearby point of the cloud start deep in
+//   the tree instead of at the root (knn.cuh, ball_in_cell).
 // ---------------------------------------------------------------------------------------------
 constexpr int kLeafMax = 16;
 constexpr int kMortonLevels = 10;
@@ -55,6 +57,10 @@ constexpr int kStackDepth = 80; // pending internal children: <= 7 per level, <=
 struct IndexView {
   const float4* spts;
   const float4* nodes;
+  const int4* meta;          // per node: {parent id (-1 root), level, cell origin on the 10-bit lattice (x | y<<10 | z<<20), 0}
+  const int* node_of_point;  // per ORIGINAL point index: the node whose leaf child holds the point
+  float lo[3];               // lattice origin and scale used for the Morton codes: u = (p - lo) * scale
+  float scale;
   int n;
   int n_nodes;
 };
@@ -97,6 +103,8 @@ struct ddlo_cloud {
   bool has_index = false;
   float4* spts = nullptr;   // Morton order, w = original index
   float4* nodes = nullptr;  // octree nodes, kNodeF4 float4 each
+  int4* meta = nullptr;
+  int* node_of_point = nullptr;
   ddlo::IndexView view{};
 };
 

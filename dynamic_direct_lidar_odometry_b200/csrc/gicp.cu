@@ -47,7 +47,6 @@ struct AlignSmem {
   double tot[kNumSums];
   float nn_d[kAlignThreads];
   int nn_idx[kAlignThreads];
-  int nn_pos[kAlignThreads];
   LmShared lm;
 };
 
@@ -99,18 +98,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Phase B for one point (called by all 32 lanes of a warp; `valid` lanes own a point): the
 // Mahalanobis matrix and the point's 28 contributions, summed over the warp into red_w[0..27].
 // Kept out of line so that its fp64 register appetite does not leak into the search loop.
-__device__ __noinline__ void lin_point(const GicpArgs& a, const LmShared& s, bool valid, int i, float nn_d, int nn_idx, int nn_pos,
+__device__ __noinline__ void lin_point(const GicpArgs& a, const LmShared& s, bool valid, int i, float nn_d, int nn_idx,
                                        double* __restrict__ red_w) {
   double c[kNumSums];
 #pragma unroll
   for (int k = 0; k < kNumSums; ++k) c[k] = 0.0;
   if (valid) {
     a.sqd[i] = nn_d;
-    const int j = (nn_pos >= 0 && (double)nn_d < a.thr2) ? nn_idx : -1;
+    const bool found = nn_idx != kIdxSentinel;
+    const int j = (found && (double)nn_d < a.thr2) ? nn_idx : -1;
     a.corr[i] = j;
+    a.nn_raw[i] = found ? nn_idx : -1;  // seed of the next search, kept even beyond the distance threshold
     if (j >= 0) {
       const float4 pa = __ldg(a.src_pts + i);
-      const float4 pb = __ldg(a.tgt.spts + nn_pos);
+      const float4 pb = __ldg(a.tgt_pts + j);
       const Sym3 CA = load_sym3(a.src_cov + (size_t)i * kCovStride);
       const Sym3 CB = load_sym3(a.tgt_cov + (size_t)j * kCovStride);
       Sym3 RCR = sym3_rotate(s.x0.r, CA);
@@ -165,52 +166,81 @@ __device__ __forceinline__ double err_point(const GicpArgs& a, const Iso3& T, in
   return quad_form(M, ex, ey, ez, mx, my, mz);
 }
 
-// Static work distribution: the source points are dealt to the blocks in chunks of 4 consecutive
-// points (one warp's worth of sub-warp queries), round-robin, so that every block sees the same
-// mix of cheap and expensive queries and the blocks reach the grid barrier together.  Block b's
-// local slot s is point ((s / 4) * nb + b) * 4 + s % 4; the mapping is fixed, so the summation
-// order (and with it every bit of H, b and the error) is reproducible.
-__device__ __forceinline__ int slots_per_block(int ns, int nb) { return 4 * (((ns + 3) / 4 + nb - 1) / nb); }
-__device__ __forceinline__ int slot_point(int slot, int b, int nb) { return ((slot >> 2) * nb + b) * 4 + (slot & 3); }
+// Static work distribution.  The source points are dealt to the blocks `deal` consecutive points
+// at a time (one warp's worth: 4 sub-warps x R rounds), round-robin, so that every block sees the
+// same mix of cheap and expensive queries and the blocks reach the grid barrier together, while the
+// four queries a warp works on and the successive queries of one sub-warp stay neighbours in the
+// scan.  The mapping is fixed, so the summation order (and with it every bit of H, b and the error)
+// is reproducible.
+struct Deal {
+  int deal;    // points handed to a warp at once
+  int nslots;  // slots of one block (multiple of deal)
+  int nb, b;
+  __device__ __forceinline__ int point(int slot) const { return ((slot / deal) * nb + b) * deal + slot % deal; }
+};
+__device__ __forceinline__ Deal make_deal(int ns) {
+  Deal d;
+  d.nb = gridDim.x;
+  d.b = blockIdx.x;
+  const int per = (ns + d.nb - 1) / d.nb;
+  const int r0 = max(1, min(kAlignThreads / kAlignSubs, (per + kAlignSubs - 1) / kAlignSubs));
+  d.deal = 4 * r0;
+  d.nslots = d.deal * (((ns + d.deal - 1) / d.deal + d.nb - 1) / d.nb);
+  return d;
+}
 
-// linearize over the block's points; leaves the block's 28 sums in dst[c * stride + blockIdx.x]
-__device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm, double* dst, int stride) {
+// linearize over the block's points; leaves the block's 28 sums in dst[c * stride + blockIdx.x].
+// have_prev: corr/nn_raw hold the matches of the previous linearize of the same source cloud.
+__device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm, bool have_prev, double* dst, int stride) {
   const Sub sb = make_sub();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int sw = threadIdx.x / kSubLanes;
+  const int g = lane >> 3;
   for (int k = lane; k < kNumSums; k += 32) sm.red[warp * kNumSums + k] = 0.0;
-  const int nslots = slots_per_block(a.ns, gridDim.x);
-  for (int base = 0; base < nslots; base += kAlignThreads) {
-    const int lim = min(nslots, base + kAlignThreads);
+  const Deal dl = make_deal(a.ns);
+  unsigned long long* stack = sm.stacks + (size_t)(threadIdx.x / kSubLanes) * kStackDepth;
+  for (int base = 0; base < dl.nslots; base += kAlignThreads) {
+    const int lim = min(dl.nslots, base + kAlignThreads);
+    const int R = (lim - base + kAlignSubs - 1) / kAlignSubs;
     __syncthreads();  // nn_* of the previous pass fully consumed
-    // ---- phase A: update_correspondences' search, one query per sub-warp
-    for (int r = 0; base + r * kAlignSubs < lim; ++r) {
-      const int slot = base + r * kAlignSubs + sw;
-      const int i = slot_point(slot, blockIdx.x, gridDim.x);
+    // ---- phase A: update_correspondences' search, one query per sub-warp, R rounds
+    int last = -1;  // match of this sub-warp's previous query (a neighbour in the scan)
+    for (int r = 0; r < R; ++r) {
+      const int slot = base + warp * (4 * R) + g * R + r;
+      const int i = dl.point(slot);
       const bool active = slot < lim && i < a.ns;
       float qx = 0.f, qy = 0.f, qz = 0.f;
+      int start = 0;
+      Best1Sub best;
       if (active) {
         const float4 pa = __ldg(a.src_pts + i);
         qx = xform_f(sm.lm.Rf + 0, sm.lm.tf[0], pa.x, pa.y, pa.z);
         qy = xform_f(sm.lm.Rf + 3, sm.lm.tf[1], pa.x, pa.y, pa.z);
         qz = xform_f(sm.lm.Rf + 6, sm.lm.tf[2], pa.x, pa.y, pa.z);
+        int j0 = have_prev ? __ldcg(a.nn_raw + i) : -1;
+        if (j0 < 0) j0 = last;
+        if (j0 >= 0) {
+          const float4 t = __ldg(a.tgt_pts + j0);
+          best.seed(sqdist3_rn(qx, qy, qz, t.x, t.y, t.z), j0);
+          // everything that can beat the seed lies in the smallest lattice cube around the seed's
+          // leaf that holds the ball |x - q|^2 <= d_seed: search below that node, not from the root
+          if (best.idx == j0) start = start_node_for(a.tgt, j0, qx, qy, qz, best.d);
+        }
       }
-      Best1Sub best;
-      knn_traverse_sub(a.tgt, active, qx, qy, qz, best, sm.stacks + (size_t)sw * kStackDepth, sb);
+      knn_traverse_sub(a.tgt, active, qx, qy, qz, best, stack, sb, start);
+      last = (active && best.idx != kIdxSentinel) ? best.idx : -1;
       if (active && sb.sl == 0) {
         sm.nn_d[slot - base] = best.d;
         sm.nn_idx[slot - base] = best.idx;
-        sm.nn_pos[slot - base] = best.pos;
       }
     }
     __syncthreads();
     // ---- phase B: one thread per point
     if (base + warp * 32 < lim) {
       const int slot = base + threadIdx.x;
-      const int i = slot_point(slot, blockIdx.x, gridDim.x);
+      const int i = dl.point(slot);
       const bool valid = slot < lim && i < a.ns;
-      lin_point(a, sm.lm, valid, i, valid ? sm.nn_d[threadIdx.x] : 0.f, valid ? sm.nn_idx[threadIdx.x] : -1,
-                valid ? sm.nn_pos[threadIdx.x] : -1, sm.red + warp * kNumSums);
+      lin_point(a, sm.lm, valid, i, valid ? sm.nn_d[threadIdx.x] : 0.f, valid ? sm.nn_idx[threadIdx.x] : kIdxSentinel,
+                sm.red + warp * kNumSums);
     }
   }
   __syncthreads();
@@ -225,10 +255,10 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
 // compute_error over the block's points; the block's sum goes to dst[blockIdx.x]
 __device__ __forceinline__ void error_block(const GicpArgs& a, const Iso3& T, AlignSmem& sm, double* dst) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nslots = slots_per_block(a.ns, gridDim.x);
+  const Deal dl = make_deal(a.ns);
   double e = 0.0;
-  for (int slot = threadIdx.x; slot < nslots; slot += kAlignThreads) {
-    const int i = slot_point(slot, blockIdx.x, gridDim.x);
+  for (int slot = threadIdx.x; slot < dl.nslots; slot += kAlignThreads) {
+    const int i = dl.point(slot);
     if (i < a.ns) e += err_point(a, T, i);
   }
   e = warp_sum(e);
@@ -337,7 +367,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_align(const GicpArgs a) {
 
     // ---- linearize(x0) -----------------------------------------------------------------------
     double* part = a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride;
-    linearize_block(a, sm, part, a.partial_stride);
+    linearize_block(a, sm, it > 0, part, a.partial_stride);
     grid.sync();
     grid_sum<kNumSums>(part, a.partial_stride, nblk, sm.tot);
     ++seq;
@@ -445,7 +475,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_linearize_step(const GicpA
     iso_to_float(sm.lm.x0, sm.lm.Rf, sm.lm.tf);
   }
   __syncthreads();
-  linearize_block(a, sm, a.partials, a.partial_stride);
+  linearize_block(a, sm, false, a.partials, a.partial_stride);
 }
 
 __global__ void __launch_bounds__(kAlignThreads, 1) k_error_step(const GicpArgs a) {

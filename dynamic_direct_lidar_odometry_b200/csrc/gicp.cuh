@@ -27,6 +27,7 @@ struct GicpArgs {
   const double* tgt_cov;    // nt * 6, original order
   int ns;
   int* corr;                // correspondences_   (ns)
+  int* nn_raw;              // nearest target index before thresholding (ns): seeds the next search
   float* sqd;               // sq_distances_      (ns)
   double* mahal;            // mahalanobis_       (ns * 6)
   double* partials;         // [2][kNumSums][partial_stride]

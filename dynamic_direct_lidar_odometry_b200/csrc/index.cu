@@ -23,6 +23,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <cmath>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace ddlo {
@@ -142,11 +145,21 @@ __device__ __forceinline__ void merge_box(unsigned* node_words, int slot, const 
   atomicMax(node_words + 40 + slot, o[5]);
 }
 
+__device__ __forceinline__ unsigned compact10(unsigned v) {  // inverse of spread10
+  v &= 0x09249249u;
+  v = (v | (v >> 2)) & 0x030c30c3u;
+  v = (v | (v >> 4)) & 0x0300f00fu;
+  v = (v | (v >> 8)) & 0x030000ffu;
+  v = (v | (v >> 16)) & 0x3ffu;
+  return v;
+}
+
 __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys, const unsigned char* __restrict__ leaf_level,
                                               const int* __restrict__ S /*[10][n] inclusive scan*/, const float4* __restrict__ spts, int n,
-                                              unsigned* __restrict__ nodes) {
+                                              unsigned* __restrict__ nodes, int4* __restrict__ meta, int* __restrict__ node_of_point) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (i == 0) meta[0] = make_int4(-1, 0, 0, 0);  // root
   const unsigned key = keys[i];
   const int L = leaf_level[i];
   const int cd = i == 0 ? -1 : common_digits(key, __ldg(keys + i - 1));
@@ -156,8 +169,12 @@ __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys,
     const int slot = (key >> (3 * (kMortonLevels - t))) & 7;
     unsigned* pw = nodes + (size_t)parent * 64;
     if (t < L) {  // internal child: its box is assembled by the leaves below it
-      pw[48 + 2 * slot] = (unsigned)(S[(size_t)t * n + i] - 1);
+      const int child = S[(size_t)t * n + i] - 1;
+      pw[48 + 2 * slot] = (unsigned)child;
       pw[49 + 2 * slot] = 0xffffffffu;
+      const unsigned keep = ~((1u << (kMortonLevels - t)) - 1u) & 0x3ffu;  // the t leading bits of each axis
+      const unsigned origin = (compact10(key) & keep) | ((compact10(key >> 1) & keep) << 10) | ((compact10(key >> 2) & keep) << 20);
+      meta[child] = make_int4(parent, t, (int)origin, 0);
       continue;
     }
     // leaf: the run of points sharing the first t digits
@@ -166,6 +183,7 @@ __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys,
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int j = i; j < e; ++j) {
       const float4 p = spts[j];
+      node_of_point[__float_as_int(p.w)] = parent;
       lo[0] = fminf(lo[0], p.x), lo[1] = fminf(lo[1], p.y), lo[2] = fminf(lo[2], p.z);
       hi[0] = fmaxf(hi[0], p.x), hi[1] = fmaxf(hi[1], p.y), hi[2] = fmaxf(hi[2], p.z);
     }
@@ -184,6 +202,13 @@ __global__ void __launch_bounds__(256) k_finalize(unsigned* __restrict__ words, 
   const size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (w >= n_words) return;
   if ((w & 63) < 48) words[w] = __float_as_uint(ord2f(words[w]));
+}
+
+static float host_ord2f(unsigned o) {
+  const unsigned u = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o;
+  float f;
+  std::memcpy(&f, &u, sizeof(f));
+  return f;
 }
 
 static int ensure_scratch(ddlo_runtime* rt, size_t bytes) {
@@ -249,25 +274,42 @@ int build_index(ddlo_cloud* c) {
   rt->launches += 3;
   DDLO_CUDA(cudaGetLastError());
 
-  // the one read-back of the build: how many nodes the tree has
+  // the one read-back of the build: how many nodes the tree has, and the lattice of the codes
   int* h_count = static_cast<int*>(rt->h_pinned);
+  unsigned* h_bounds = reinterpret_cast<unsigned*>(h_count + 4);
   DDLO_CUDA(cudaMemcpyAsync(h_count, flags + (n_flags - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+  DDLO_CUDA(cudaMemcpyAsync(h_bounds, bounds, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   DDLO_CUDA(cudaStreamSynchronize(st));
   const int n_nodes = *h_count;
   if (n_nodes < 1) return fail(DDLO_E_CUDA, "build_index: node count came back empty");
+  if (h_bounds[6] != 0u) return fail(DDLO_E_NONFINITE, "build_index: the cloud holds NaN or Inf coordinates");
+  float blo[3], bhi[3];
+  for (int a = 0; a < 3; ++a) {
+    blo[a] = host_ord2f(h_bounds[a]);
+    bhi[a] = host_ord2f(h_bounds[3 + a]);
+  }
+  // same float expressions as k_morton
+  const float ext = std::fmax(std::fmax(bhi[0] - blo[0], bhi[1] - blo[1]), std::fmax(bhi[2] - blo[2], 1e-30f));
+  const float scale = 1023.0f / ext;
 
   const size_t n_words = (size_t)n_nodes * 64;
   DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->nodes), n_words * 4, st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->meta), (size_t)n_nodes * sizeof(int4), st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->node_of_point), (size_t)n * sizeof(int), st));
   unsigned* words = reinterpret_cast<unsigned*>(c->nodes);
   const int wb = (int)((n_words + tb - 1) / tb);
   k_init_nodes<<<wb, tb, 0, st>>>(words, n_words);
-  k_emit<<<nb, tb, 0, st>>>(kb.Current(), leaf_level, flags, c->spts, n, words);
+  k_emit<<<nb, tb, 0, st>>>(kb.Current(), leaf_level, flags, c->spts, n, words, c->meta, c->node_of_point);
   k_finalize<<<wb, tb, 0, st>>>(words, n_words);
   rt->launches += 3;
   DDLO_CUDA(cudaGetLastError());
 
   c->view.spts = c->spts;
   c->view.nodes = c->nodes;
+  c->view.meta = c->meta;
+  c->view.node_of_point = c->node_of_point;
+  for (int a = 0; a < 3; ++a) c->view.lo[a] = blo[a];
+  c->view.scale = scale;
   c->view.n = n;
   c->view.n_nodes = n_nodes;
   c->has_index = true;

@@ -62,23 +62,39 @@ __device__ __forceinline__ Sub make_sub() {
   return s;
 }
 __device__ __forceinline__ unsigned sub_ballot(bool p, const Sub& sb) { return (__ballot_sync(kFull, p) >> sb.shift) & 0xffu; }
-
+// Slot (0..7) of the lane holding the smallest non-negative float among the lanes with `cand`, -1 if
+// none.  Three butterfly steps on one packed key: the float's bits (which order like unsigned ints
+// for v >= 0) with the 3 low mantissa bits replaced by the slot.  The choice only steers the order
+// in which children are visited, so losing 3 mantissa bits of the bound is harmless; pruning always
+// uses the exact bound.  (redux.sync with a sub-warp mask would serialise the four sub-warps.)
+__device__ __forceinline__ int sub_argmin(bool cand, float v, const Sub& sb) {
+  unsigned key = cand ? ((__float_as_uint(v) & 0xfffffff8u) | (unsigned)sb.sl) : 0xffffffffu;
+#pragma unroll
+  for (int o = 1; o < kSubLanes; o <<= 1) key = min(key, __shfl_xor_sync(kFull, key, o));
+  return key == 0xffffffffu ? -1 : (int)(key & 7u);
+}
 // ---- result sets ------------------------------------------------------------------------------
 // Both rank candidates by (d2, original index).  `worst()` is the current k-th distance, FLT_MAX
 // until k candidates are known; like nanoflann (KNNResultSet::init, nanoflann_impl.hpp:181-187) a
 // candidate whose distance is not below FLT_MAX is never admitted.  All members are uniform across
 // the 8 lanes of a sub-warp.  Empty = (FLT_MAX, kIdxSentinel), the largest possible pair.
 
-// k = 1: best candidate in registers
+// k = 1: best candidate in registers.  It may be seeded with any real point of the cloud (its exact
+// distance and index): a seed only shrinks the search, the result stays the exact (d, i) minimum.
 struct Best1Sub {
   float d = FLT_MAX;
   int idx = kIdxSentinel;  // original index
-  int pos = -1;            // position in spts
   __device__ __forceinline__ float worst() const { return d; }
+  __device__ __forceinline__ void seed(float dist, int oi) {
+    if (dist < FLT_MAX && lex_less(dist, oi, d, idx)) {
+      d = dist;
+      idx = oi;
+    }
+  }
   __device__ __forceinline__ void scan(bool doit, const float4* __restrict__ spts, int start, int count, float qx, float qy, float qz,
                                        const Sub& sb) {
     float ld = d;
-    int li = idx, lp = pos;
+    int li = idx;
     if (doit) {
       for (int j = sb.sl; j < count; j += kSubLanes) {
         const float4 v = __ldg(spts + start + j);
@@ -87,24 +103,23 @@ struct Best1Sub {
         if (dist < FLT_MAX && lex_less(dist, oi, ld, li)) {
           ld = dist;
           li = oi;
-          lp = start + j;
         }
       }
     }
+    // (d, idx) minimum over the sub-warp: first the distance alone (bits of d >= 0 order like
+    // unsigned ints), then the index among the lanes that hold it - one lane, except on exact ties
+    unsigned md = __float_as_uint(ld);
 #pragma unroll
-    for (int o = 1; o < kSubLanes; o <<= 1) {
-      const float od = __shfl_xor_sync(kFull, ld, o);
-      const int oi = __shfl_xor_sync(kFull, li, o);
-      const int op = __shfl_xor_sync(kFull, lp, o);
-      if (lex_less(od, oi, ld, li)) {
-        ld = od;
-        li = oi;
-        lp = op;
-      }
+    for (int o = 1; o < kSubLanes; o <<= 1) md = min(md, __shfl_xor_sync(kFull, md, o));
+    const unsigned who = sub_ballot(__float_as_uint(ld) == md, sb);
+    unsigned mi = (unsigned)__shfl_sync(kFull, li, sb.base + __ffs(who) - 1);
+    if (__any_sync(kFull, (who & (who - 1u)) != 0u)) {
+      mi = __float_as_uint(ld) == md ? (unsigned)li : 0xffffffffu;
+#pragma unroll
+      for (int o = 1; o < kSubLanes; o <<= 1) mi = min(mi, __shfl_xor_sync(kFull, mi, o));
     }
-    d = ld;
-    idx = li;
-    pos = lp;
+    d = __uint_as_float(md);
+    idx = (int)mi;
   }
 };
 
@@ -295,6 +310,40 @@ struct TopKRegSub {
   }
 };
 
+// ---- starting deep in the tree ------------------------------------------------------------------
+// A node is a cube of the Morton lattice.  If the ball around the query with the current k-th
+// distance as squared radius lies inside that cube, no point outside the node's subtree can enter
+// the result, so the search may start (or stop climbing) there.  The test is made on the lattice in
+// float, with the radius inflated by 1e-5 relative and 1e-3 lattice units absolute: far more than
+// the rounding of u = (p - lo) * scale (a few 1e-4 lattice units at u <= 1023) and of the float
+// distances, so every point within the ball provably got a code inside the cube.  Cubes on the
+// lattice border are open-ended because out-of-range coordinates were clamped into them.
+__device__ __forceinline__ bool ball_in_cell(const IndexView& ix, const int4 m, float qx, float qy, float qz, float worst) {
+  if (m.y == 0) return true;  // the root holds everything
+  if (!(worst < FLT_MAX)) return false;
+  const float ur = sqrtf(worst) * 1.00001f * ix.scale + 1e-3f;
+  const float w = (float)(1 << (kMortonLevels - m.y));
+  const float q[3] = {qx, qy, qz};
+  bool ok = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float u = (q[a] - ix.lo[a]) * ix.scale;
+    const float c0 = (float)((m.z >> (10 * a)) & 1023);
+    ok = ok && (c0 == 0.0f || u - ur >= c0) && (c0 + w >= 1024.0f || u + ur < c0 + w);
+  }
+  return ok;
+}
+
+// the deepest node around a known point of the cloud (original index j) whose cube holds the ball
+__device__ __forceinline__ int start_node_for(const IndexView& ix, int j, float qx, float qy, float qz, float worst) {
+  int node = __ldg(ix.node_of_point + j);
+  for (;;) {
+    const int4 m = __ldg(ix.meta + node);
+    if (ball_in_cell(ix, m, qx, qy, qz, worst)) return node;
+    node = m.x;
+  }
+}
+
 // Depth-first traversal by one sub-warp.  At a node: lane s bounds child s; children whose bound
 // can still beat the k-th distance ("<=", so that an equal-distance point with a smaller index is
 // not missed) are handled leaves first, nearest first, each re-tested against the shrinking bar
@@ -303,12 +352,14 @@ struct TopKRegSub {
 // dropped on pop without touching global memory.
 // MUST be called by all 32 lanes of a warp; `active` is uniform per sub-warp; `stack` has
 // kStackDepth entries per sub-warp.
+// `start` is the node to search below (0 = the whole cloud); `skip` (or -1) is a child NODE of
+// `start` that has been searched already and is left out.
 template <class RS>
 __device__ __forceinline__ void knn_traverse_sub(const IndexView& ix, bool active, float qx, float qy, float qz, RS& rs,
-                                                 unsigned long long* __restrict__ stack, const Sub& sb) {
+                                                 unsigned long long* __restrict__ stack, const Sub& sb, int start = 0, int skip = -1) {
   bool run = active && ix.n > 0;
   int sp = 0;
-  unsigned node = 0;
+  unsigned node = (unsigned)start;
   const float inf = __int_as_float(0x7f800000);
   while (__any_sync(kFull, run)) {
     __syncwarp();
@@ -320,22 +371,15 @@ __device__ __forceinline__ void knn_traverse_sub(const IndexView& ix, bool activ
       const float hx = __ldg(g + 24 + sb.sl), hy = __ldg(g + 32 + sb.sl), hz = __ldg(g + 40 + sb.sl);
       ref = __ldg(reinterpret_cast<const int2*>(g + 48) + sb.sl);
       b = box_bound_rn(qx, qy, qz, lx, ly, lz, hx, hy, hz);
+      if (ref.y < 0 && ref.x == skip) b = inf;  // only `start` can have this child; ids are unique
     }
     const bool qual = run && b <= rs.worst();
     // ---- leaf children, nearest first
     unsigned ml = sub_ballot(qual && ref.y > 0, sb);
     while (__any_sync(kFull, ml != 0u)) {
-      float mb = ((ml >> sb.sl) & 1u) ? b : inf;
-      int mc = sb.sl;
-#pragma unroll
-      for (int o = 1; o < kSubLanes; o <<= 1) {
-        const float ob = __shfl_xor_sync(kFull, mb, o);
-        const int oc = __shfl_xor_sync(kFull, mc, o);
-        if (ob < mb || (ob == mb && oc < mc)) {
-          mb = ob;
-          mc = oc;
-        }
-      }
+      const int am = sub_argmin(((ml >> sb.sl) & 1u) != 0u, b, sb);
+      const int mc = am < 0 ? 0 : am;
+      const float mb = __shfl_sync(kFull, b, sb.base + mc);
       const bool had = ml != 0u;
       ml &= ~(1u << mc);
       const int st = __shfl_sync(kFull, ref.x, sb.base + mc);
@@ -345,17 +389,8 @@ __device__ __forceinline__ void knn_traverse_sub(const IndexView& ix, bool activ
     // ---- internal children
     const bool qi = qual && ref.y < 0 && b <= rs.worst();
     const unsigned mi = sub_ballot(qi, sb);
-    float nb = qi ? b : inf;
-    int nc = sb.sl;
-#pragma unroll
-    for (int o = 1; o < kSubLanes; o <<= 1) {
-      const float ob = __shfl_xor_sync(kFull, nb, o);
-      const int oc = __shfl_xor_sync(kFull, nc, o);
-      if (ob < nb || (ob == nb && oc < nc)) {
-        nb = ob;
-        nc = oc;
-      }
-    }
+    const int an = sub_argmin(qi, b, sb);
+    const int nc = an < 0 ? 0 : an;
     const unsigned rest = mi & ~(1u << nc);
     if (qi && sb.sl != nc) {
       const int at = sp + __popc(rest & ((1u << sb.sl) - 1u));

@@ -28,17 +28,42 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(IndexView ix, const float4*
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) v = self_mode ? __ldg(ix.spts + q) : __ldg(queries + q);
   const size_t row = !active ? 0 : (self_mode ? (size_t)__float_as_int(v.w) : (size_t)q);
+  unsigned long long* stack = stacks + (size_t)sw * kStackDepth;
+  auto search = [&](auto& rs) {
+    if (!self_mode) {
+      knn_traverse_sub(ix, active, v.x, v.y, v.z, rs, stack, sb);
+      return;
+    }
+    // The query is a point of the cloud: search the node that holds its leaf, then climb.  At each
+    // ancestor only the part not searched yet is visited, and the climb stops as soon as the ball
+    // of the current k-th distance fits into the ancestor's cube (at the latest at the root).
+    int node = active ? __ldg(ix.node_of_point + __float_as_int(v.w)) : 0;
+    int skip = -1;
+    bool going = active;
+    while (__any_sync(kFull, going)) {
+      knn_traverse_sub(ix, going, v.x, v.y, v.z, rs, stack, sb, node, skip);
+      if (going) {
+        const int4 m = __ldg(ix.meta + node);
+        if (ball_in_cell(ix, m, v.x, v.y, v.z, rs.worst())) {
+          going = false;
+        } else {
+          skip = node;
+          node = m.x;
+        }
+      }
+    }
+  };
   if constexpr (R > 0) {
     TopKRegSub<R> rs;
     rs.init(k);
-    knn_traverse_sub(ix, active, v.x, v.y, v.z, rs, stacks + (size_t)sw * kStackDepth, sb);
+    search(rs);
     if (active) rs.write_sorted(idx_out + row * k, d_out ? d_out + row * k : nullptr, sb);
   } else {
     float* sd = reinterpret_cast<float*>(smem_knn + (size_t)kKnnSubs * kStackDepth);  // [kKnnSubs][k]
     int* si = reinterpret_cast<int*>(sd + (size_t)kKnnSubs * k);                      // [kKnnSubs][k]
     TopKSub rs;
     rs.init(sd + (size_t)sw * k, si + (size_t)sw * k, k, sb);
-    knn_traverse_sub(ix, active, v.x, v.y, v.z, rs, stacks + (size_t)sw * kStackDepth, sb);
+    search(rs);
     if (active) rs.write_sorted(idx_out + row * k, d_out ? d_out + row * k : nullptr, sb);
   }
 }
