@@ -129,6 +129,7 @@ TESTING_SIGNATURES = {
     "ddlo_math_sym3_eig": [_vp, _vp, _vp],
     "ddlo_math_regularize": [_vp, C.c_int, _vp],
     "ddlo_math_ldlt6_solve": [_vp, _vp, _vp],
+    "ddlo_math_ldlt6_solve_fast": [_vp, _vp, _vp],
     "ddlo_math_so3_exp": [_vp, _vp],
     "ddlo_math_sym3_inverse": [_vp, _vp],
 }
@@ -161,6 +162,8 @@ def load() -> C.CDLL:
         fn = getattr(L, name)
         fn.restype = None
         fn.argtypes = args
+    L.ddlo_gicp_debug_timeline.restype = C.c_int
+    L.ddlo_gicp_debug_timeline.argtypes = [_vp, _vp, C.c_int]
     _lib = L
     return L
 

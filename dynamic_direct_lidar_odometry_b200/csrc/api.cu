@@ -965,6 +965,17 @@ int ddlo_gicp_get_residual_vectors(ddlo_gicp* g, const float* T16, float* out_xy
   return DDLO_OK;
 }
 
+// debugging aid (declared in ddlo_gicp_testing.h): the phase timeline block 0 recorded during the last
+// align; entries are tag << 56 | globaltimer ns.  Returns the number of entries written.
+int ddlo_gicp_debug_timeline(ddlo_gicp* g, unsigned long long* out, int capacity) {
+  if (!g || !out) return fail(DDLO_E_INVALID, "null argument");
+  AlignOut o;
+  if (read_out(g, &o) != DDLO_OK) return DDLO_E_CUDA;
+  const int n = std::min(std::min(o.n_stamps, 128), capacity);
+  for (int i = 0; i < n; ++i) out[i] = o.stamps[i];
+  return n;
+}
+
 // ---- host-callable copies of the device math (CPU tests of the exact code the kernels run) --------------
 void ddlo_math_sym3_eig(const double* sym6, double* w3, double* V9) {
   Sym3 s{sym6[0], sym6[1], sym6[2], sym6[3], sym6[4], sym6[5]};
@@ -976,6 +987,7 @@ void ddlo_math_regularize(const double* sym6, int method, double* out6) {
   out6[0] = r.xx, out6[1] = r.xy, out6[2] = r.xz, out6[3] = r.yy, out6[4] = r.yz, out6[5] = r.zz;
 }
 void ddlo_math_ldlt6_solve(const double* A36, const double* rhs6, double* x6) { ldlt6_solve(A36, rhs6, x6); }
+void ddlo_math_ldlt6_solve_fast(const double* A36, const double* rhs6, double* x6) { ldlt6_solve_fast(A36, rhs6, x6); }
 void ddlo_math_so3_exp(const double* omega3, double* R9) { so3_exp_matrix(omega3, R9); }
 void ddlo_math_sym3_inverse(const double* sym6, double* out6) {
   Sym3 s{sym6[0], sym6[1], sym6[2], sym6[3], sym6[4], sym6[5]};

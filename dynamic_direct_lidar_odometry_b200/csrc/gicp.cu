@@ -47,6 +47,7 @@ struct AlignSmem {
   double tot[kNumSums];
   float nn_d[kAlignThreads];
   int nn_idx[kAlignThreads];
+  int next;  // phase A work counter
   LmShared lm;
 };
 
@@ -166,31 +167,28 @@ __device__ __forceinline__ double err_point(const GicpArgs& a, const Iso3& T, in
   return quad_form(M, ex, ey, ez, mx, my, mz);
 }
 
-// Static work distribution.  The source points are dealt to the blocks `deal` consecutive points
-// at a time (one warp's worth: 4 sub-warps x R rounds), round-robin, so that every block sees the
-// same mix of cheap and expensive queries and the blocks reach the grid barrier together, while the
-// four queries a warp works on and the successive queries of one sub-warp stay neighbours in the
-// scan.  The mapping is fixed, so the summation order (and with it every bit of H, b and the error)
-// is reproducible.
+// Work distribution.  The source points are dealt to the blocks four consecutive points at a time
+// (one query per sub-warp of a warp), round-robin, so that every block holds the same mix of cheap
+// and expensive queries and the blocks reach the grid barrier together.  Inside a block the warps
+// pull these groups of four from a shared counter, so a warp stuck on a long search does not hold
+// the others back.  Which warp serves a group never shows in the result: matches are parked per
+// slot and all sums are taken per slot in phase B, in a fixed order, so every bit of H, b and the
+// error is reproducible.
 struct Deal {
-  int deal;    // points handed to a warp at once
-  int nslots;  // slots of one block (multiple of deal)
+  int nslots;  // slots of one block (multiple of 4)
   int nb, b;
-  __device__ __forceinline__ int point(int slot) const { return ((slot / deal) * nb + b) * deal + slot % deal; }
+  __device__ __forceinline__ int point(int slot) const { return (((slot >> 2) * nb + b) << 2) + (slot & 3); }
 };
 __device__ __forceinline__ Deal make_deal(int ns) {
   Deal d;
   d.nb = gridDim.x;
   d.b = blockIdx.x;
-  const int per = (ns + d.nb - 1) / d.nb;
-  const int r0 = max(1, min(kAlignThreads / kAlignSubs, (per + kAlignSubs - 1) / kAlignSubs));
-  d.deal = 4 * r0;
-  d.nslots = d.deal * (((ns + d.deal - 1) / d.deal + d.nb - 1) / d.nb);
+  d.nslots = 4 * (((ns + 3) / 4 + d.nb - 1) / d.nb);
   return d;
 }
 
 // linearize over the block's points; leaves the block's 28 sums in dst[c * stride + blockIdx.x].
-// have_prev: corr/nn_raw hold the matches of the previous linearize of the same source cloud.
+// have_prev: nn_raw holds the matches of the previous linearize of the same source cloud.
 __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm, bool have_prev, double* dst, int stride) {
   const Sub sb = make_sub();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -200,14 +198,18 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
   unsigned long long* stack = sm.stacks + (size_t)(threadIdx.x / kSubLanes) * kStackDepth;
   for (int base = 0; base < dl.nslots; base += kAlignThreads) {
     const int lim = min(dl.nslots, base + kAlignThreads);
-    const int R = (lim - base + kAlignSubs - 1) / kAlignSubs;
-    __syncthreads();  // nn_* of the previous pass fully consumed
-    // ---- phase A: update_correspondences' search, one query per sub-warp, R rounds
-    int last = -1;  // match of this sub-warp's previous query (a neighbour in the scan)
-    for (int r = 0; r < R; ++r) {
-      const int slot = base + warp * (4 * R) + g * R + r;
+    const int n_items = (lim - base) >> 2;
+    if (threadIdx.x == 0) sm.next = 0;
+    __syncthreads();  // counter reset; nn_* of the previous pass fully consumed
+    // ---- phase A: update_correspondences' search, one query per sub-warp
+    for (;;) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(&sm.next, 1);
+      item = __shfl_sync(kFull, item, 0);
+      if (item >= n_items) break;
+      const int slot = base + (item << 2) + g;
       const int i = dl.point(slot);
-      const bool active = slot < lim && i < a.ns;
+      const bool active = i < a.ns;
       float qx = 0.f, qy = 0.f, qz = 0.f;
       int start = 0;
       Best1Sub best;
@@ -216,8 +218,7 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
         qx = xform_f(sm.lm.Rf + 0, sm.lm.tf[0], pa.x, pa.y, pa.z);
         qy = xform_f(sm.lm.Rf + 3, sm.lm.tf[1], pa.x, pa.y, pa.z);
         qz = xform_f(sm.lm.Rf + 6, sm.lm.tf[2], pa.x, pa.y, pa.z);
-        int j0 = have_prev ? __ldcg(a.nn_raw + i) : -1;
-        if (j0 < 0) j0 = last;
+        const int j0 = have_prev ? __ldcg(a.nn_raw + i) : -1;
         if (j0 >= 0) {
           const float4 t = __ldg(a.tgt_pts + j0);
           best.seed(sqdist3_rn(qx, qy, qz, t.x, t.y, t.z), j0);
@@ -227,7 +228,6 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
         }
       }
       knn_traverse_sub(a.tgt, active, qx, qy, qz, best, stack, sb, start);
-      last = (active && best.idx != kIdxSentinel) ? best.idx : -1;
       if (active && sb.sl == 0) {
         sm.nn_d[slot - base] = best.d;
         sm.nn_idx[slot - base] = best.idx;
@@ -330,10 +330,23 @@ __device__ __noinline__ void lm_solve(LmShared& s, double lambda) {
     A[7 * i] += lambda;
     nb[i] = -s.b[i];
   }
-  ldlt6_solve(A, nb, s.d);
+  ldlt6_solve_fast(A, nb, s.d);
   so3_exp_matrix(s.d, s.delta.r);
   for (int i = 0; i < 3; ++i) s.delta.t[i] = s.d[3 + i];
 }
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// phase tags of the timeline block 0 leaves in AlignOut::stamps
+enum { kTagStart = 1, kTagLinDone = 2, kTagLinSynced = 3, kTagLinSummed = 4, kTagSolved = 5, kTagErrDone = 6, kTagErrSynced = 7, kTagDecided = 8, kTagEnd = 9 };
+#define DDLO_STAMP(tag)                                                                                         \
+  do {                                                                                                          \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_stamps < 128)                                                  \
+      a.out->stamps[n_stamps++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00ffffffffffffffull); \
+  } while (0)
 
 __global__ void __launch_bounds__(kAlignThreads, 1) k_align(const GicpArgs a) {
   cg::grid_group grid = cg::this_grid();
@@ -343,6 +356,8 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_align(const GicpArgs a) {
   const int nblk = gridDim.x;
   int seq = 0;  // reduction counter: partial buffers alternate so a fast block can not overwrite
                 // sums a slow block is still reading
+  int n_stamps = 0;
+  DDLO_STAMP(kTagStart);
 
   if (threadIdx.x == 0) {
     iso_from_colmajor(a.guess, s.x0);
@@ -368,9 +383,12 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_align(const GicpArgs a) {
     // ---- linearize(x0) -----------------------------------------------------------------------
     double* part = a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride;
     linearize_block(a, sm, it > 0, part, a.partial_stride);
+    DDLO_STAMP(kTagLinDone);
     grid.sync();
+    DDLO_STAMP(kTagLinSynced);
     grid_sum<kNumSums>(part, a.partial_stride, nblk, sm.tot);
     ++seq;
+    DDLO_STAMP(kTagLinSummed);
 
     if (threadIdx.x == 0) {
       unpack_sums(sm.tot, s.H, s.b, s.y0);
@@ -402,9 +420,12 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_align(const GicpArgs a) {
           s.xi = iso_mul(s.delta, s.x0);
         }
         __syncthreads();
+        DDLO_STAMP(kTagSolved);
         double* epart = a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride;
         error_block(a, s.xi, sm, epart);
+        DDLO_STAMP(kTagErrDone);
         grid.sync();
+        DDLO_STAMP(kTagErrSynced);
         grid_sum<1>(epart, a.partial_stride, nblk, sm.tot);
         ++seq;
         if (threadIdx.x == 0) {
@@ -433,6 +454,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_align(const GicpArgs a) {
           }
         }
         __syncthreads();
+        DDLO_STAMP(kTagDecided);
         if (s.action) break;
       }
     }
@@ -463,6 +485,8 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_align(const GicpArgs a) {
     o->n_compute_error = s.n_err;
     o->final_error = s.final_error;
     o->lm_lambda = s.lambda;
+    DDLO_STAMP(kTagEnd);
+    o->n_stamps = n_stamps;
   }
 }
 

@@ -17,6 +17,9 @@ struct AlignOut {
   double final_error;
   double lm_lambda;
   double sums[kNumSums];  // stepwise hooks: H upper / b / error of the last reduction
+  // phase timeline of the last align (block 0, %globaltimer ns): tag << 56 | time
+  unsigned long long stamps[128];
+  int n_stamps;
 };
 
 struct GicpArgs {

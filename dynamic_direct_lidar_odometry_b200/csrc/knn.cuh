@@ -85,6 +85,11 @@ struct Best1Sub {
   float d = FLT_MAX;
   int idx = kIdxSentinel;  // original index
   __device__ __forceinline__ float worst() const { return d; }
+  // (d, idx) as one 64-bit key: for d >= 0 the float's bits order like an unsigned int, so the
+  // lexicographic minimum is the plain unsigned minimum of (bits(d) << 32 | idx)
+  static __device__ __forceinline__ unsigned long long pack(float dist, int oi) {
+    return ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)oi;
+  }
   __device__ __forceinline__ void seed(float dist, int oi) {
     if (dist < FLT_MAX && lex_less(dist, oi, d, idx)) {
       d = dist;
@@ -93,33 +98,18 @@ struct Best1Sub {
   }
   __device__ __forceinline__ void scan(bool doit, const float4* __restrict__ spts, int start, int count, float qx, float qy, float qz,
                                        const Sub& sb) {
-    float ld = d;
-    int li = idx;
+    unsigned long long key = pack(d, idx);
     if (doit) {
       for (int j = sb.sl; j < count; j += kSubLanes) {
         const float4 v = __ldg(spts + start + j);
         const float dist = sqdist3_rn(qx, qy, qz, v.x, v.y, v.z);
-        const int oi = __float_as_int(v.w);
-        if (dist < FLT_MAX && lex_less(dist, oi, ld, li)) {
-          ld = dist;
-          li = oi;
-        }
+        if (dist < FLT_MAX) key = min(key, pack(dist, __float_as_int(v.w)));
       }
     }
-    // (d, idx) minimum over the sub-warp: first the distance alone (bits of d >= 0 order like
-    // unsigned ints), then the index among the lanes that hold it - one lane, except on exact ties
-    unsigned md = __float_as_uint(ld);
 #pragma unroll
-    for (int o = 1; o < kSubLanes; o <<= 1) md = min(md, __shfl_xor_sync(kFull, md, o));
-    const unsigned who = sub_ballot(__float_as_uint(ld) == md, sb);
-    unsigned mi = (unsigned)__shfl_sync(kFull, li, sb.base + __ffs(who) - 1);
-    if (__any_sync(kFull, (who & (who - 1u)) != 0u)) {
-      mi = __float_as_uint(ld) == md ? (unsigned)li : 0xffffffffu;
-#pragma unroll
-      for (int o = 1; o < kSubLanes; o <<= 1) mi = min(mi, __shfl_xor_sync(kFull, mi, o));
-    }
-    d = __uint_as_float(md);
-    idx = (int)mi;
+    for (int o = 1; o < kSubLanes; o <<= 1) key = min(key, __shfl_xor_sync(kFull, key, o));
+    d = __uint_as_float((unsigned)(key >> 32));
+    idx = (int)(unsigned)(key & 0xffffffffull);
   }
 };
 
@@ -318,28 +308,40 @@ struct TopKRegSub {
 // the rounding of u = (p - lo) * scale (a few 1e-4 lattice units at u <= 1023) and of the float
 // distances, so every point within the ball provably got a code inside the cube.  Cubes on the
 // lattice border are open-ended because out-of-range coordinates were clamped into them.
-__device__ __forceinline__ bool ball_in_cell(const IndexView& ix, const int4 m, float qx, float qy, float qz, float worst) {
+struct Ball {  // the query and its radius on the lattice
+  float u[3];
+  float ur;
+  bool finite;
+};
+__device__ __forceinline__ Ball make_ball(const IndexView& ix, float qx, float qy, float qz, float worst) {
+  Ball b;
+  b.finite = worst < FLT_MAX;
+  b.ur = sqrtf(worst) * 1.00001f * ix.scale + 1e-3f;
+  b.u[0] = (qx - ix.lo[0]) * ix.scale;
+  b.u[1] = (qy - ix.lo[1]) * ix.scale;
+  b.u[2] = (qz - ix.lo[2]) * ix.scale;
+  return b;
+}
+__device__ __forceinline__ bool ball_in_cell(const Ball& b, const int4 m) {
   if (m.y == 0) return true;  // the root holds everything
-  if (!(worst < FLT_MAX)) return false;
-  const float ur = sqrtf(worst) * 1.00001f * ix.scale + 1e-3f;
+  if (!b.finite) return false;
   const float w = (float)(1 << (kMortonLevels - m.y));
-  const float q[3] = {qx, qy, qz};
   bool ok = true;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const float u = (q[a] - ix.lo[a]) * ix.scale;
     const float c0 = (float)((m.z >> (10 * a)) & 1023);
-    ok = ok && (c0 == 0.0f || u - ur >= c0) && (c0 + w >= 1024.0f || u + ur < c0 + w);
+    ok = ok && (c0 == 0.0f || b.u[a] - b.ur >= c0) && (c0 + w >= 1024.0f || b.u[a] + b.ur < c0 + w);
   }
   return ok;
 }
 
 // the deepest node around a known point of the cloud (original index j) whose cube holds the ball
 __device__ __forceinline__ int start_node_for(const IndexView& ix, int j, float qx, float qy, float qz, float worst) {
+  const Ball b = make_ball(ix, qx, qy, qz, worst);
   int node = __ldg(ix.node_of_point + j);
   for (;;) {
     const int4 m = __ldg(ix.meta + node);
-    if (ball_in_cell(ix, m, qx, qy, qz, worst)) return node;
+    if (ball_in_cell(b, m)) return node;
     node = m.x;
   }
 }

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(IndexView ix, const float4*
       knn_traverse_sub(ix, going, v.x, v.y, v.z, rs, stack, sb, node, skip);
       if (going) {
         const int4 m = __ldg(ix.meta + node);
-        if (ball_in_cell(ix, m, v.x, v.y, v.z, rs.worst())) {
+        if (ball_in_cell(make_ball(ix, v.x, v.y, v.z, rs.worst()), m)) {
           going = false;
         } else {
           skip = node;

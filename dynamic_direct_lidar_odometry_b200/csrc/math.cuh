@@ -255,4 +255,57 @@ DDLO_HD void ldlt6_solve(const double* A_in, const double* rhs, double* x) {
   for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
 }
 
+// The same solve for a symmetric POSITIVE DEFINITE matrix (what H + lambda I is in practice), with
+// every index known at compile time so that the whole factorisation lives in registers: LDL^T in
+// natural order, which is backward stable for SPD input.  Any non-positive pivot hands over to
+// the pivoting routine above.
+DDLO_HD void ldlt6_solve_fast(const double* A_in, const double* rhs, double* x) {
+  double L[6][6], D[6];
+  bool spd = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double d = A_in[7 * j];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k < j) d -= L[j][k] * L[j][k] * D[k];
+    D[j] = d;
+    spd = spd && (d > 0.0);
+    const double inv = 1.0 / d;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (i > j) {
+        double v = A_in[6 * i + j];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          if (k < j) v -= L[i][k] * L[j][k] * D[k];
+        L[i][j] = v * inv;
+      }
+  }
+  if (!spd) {
+    ldlt6_solve(A_in, rhs, x);
+    return;
+  }
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double v = rhs[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k < i) v -= L[i][k] * y[k];
+    y[i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) y[i] /= D[i];
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double v = y[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k > i) v -= L[k][i] * y[k];
+    y[i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = y[i];
+}
+
 }  // namespace ddlo

@@ -383,6 +383,18 @@ class NanoGICP:
         self._last = AlignInfo(r)
         return self._last
 
+    TIMELINE_TAGS = {1: "start", 2: "lin_done", 3: "lin_synced", 4: "lin_summed", 5: "solved", 6: "err_done", 7: "err_synced", 8: "decided", 9: "end"}
+
+    def debug_timeline(self):
+        """[(tag, microseconds since kernel start)] recorded by block 0 during the last align (profiling aid)."""
+        buf = np.zeros(128, dtype=np.uint64)
+        n = B.load().ddlo_gicp_debug_timeline(self._g, B.ptr(buf), 128)
+        if n < 0:
+            B.check(n)
+        t = [(int(v >> np.uint64(56)), int(v & np.uint64(0x00FFFFFFFFFFFFFF))) for v in buf[:n]]
+        t0 = t[0][1] if t else 0
+        return [(self.TIMELINE_TAGS.get(tag, str(tag)), (ns - t0) / 1e3) for tag, ns in t]
+
     def getFinalTransformation(self) -> np.ndarray: return self._last.T
     def hasConverged(self) -> bool: return self._last.converged
     def getFinalHessian(self) -> np.ndarray: return self._last.hessian

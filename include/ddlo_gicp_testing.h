@@ -12,8 +12,12 @@ extern "C" {
 void ddlo_math_sym3_eig(const double* sym6, double* w3, double* V9);
 void ddlo_math_regularize(const double* sym6, int method, double* out6); /* nano_gicp_impl.hpp:401-437 */
 void ddlo_math_ldlt6_solve(const double* A36, const double* rhs6, double* x6); /* Eigen::LDLT, lsq_registration_impl.hpp:190 */
+void ddlo_math_ldlt6_solve_fast(const double* A36, const double* rhs6, double* x6); /* register-resident SPD path of the kernel */
 void ddlo_math_so3_exp(const double* omega3, double* R9);                       /* gicp/so3.hpp:101-124 */
 void ddlo_math_sym3_inverse(const double* sym6, double* out6);
+/* phase timeline of the last align (block 0): entries are tag << 56 | %globaltimer ns; returns the count */
+struct ddlo_gicp;
+int ddlo_gicp_debug_timeline(struct ddlo_gicp* g, unsigned long long* out, int capacity);
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,10 @@ for _ in range(reps):
     eng.calculateSourceCovariances()
     r = eng.align(guess)
     eng.clearSource()
+prev = 0.0
+for tag, us in eng.debug_timeline():
+    print(f"  {tag:12s} {us:9.1f} us  (+{us - prev:7.1f})")
+    prev = us
 print("iterations", r.iterations, "converged", r.converged, "lin", r.n_linearize, "err", r.n_compute_error)
 del eng, target
 rt.close()
