@@ -337,3 +337,69 @@ def test_c2_properties(rt, oracle):
     # (3) oracle agreement on a sample of moved source points
     oidx, od2 = oracle.Cloud(tgt).build_tree().knn(src[:4096], 20)
     assert np.array_equal(idx, oidx) and np.array_equal(d2.view(np.uint32), od2.view(np.uint32))
+
+
+# ------------------------------------------------------------------------- committed golden fixtures
+def test_against_golden_fixtures(rt):
+    """tests/golden/*.npz (made by tests/golden/make_golden.py from the oracle and, for kNN, from the
+    reference's own nanoflann): the CUDA path must reproduce them without any oracle in the loop."""
+    from pathlib import Path
+
+    G = Path(__file__).resolve().parent / "golden"
+    g = np.load(G / "knn_small.npz")
+    cloud = ng.PointCloud(rt, g["tgt"])
+    idx, d2 = cloud.nearestKSearch(g["src"][:, :3], 20)
+    assert np.array_equal(idx, g["idx20"]) and np.array_equal(d2.view(np.uint32), g["d20"].view(np.uint32))
+    if "ref_idx20" in g:  # the reference's nanoflann itself, away from exact ties
+        distinct = (np.diff(g["d20"], axis=1) > 0).all(axis=1)
+        assert np.array_equal(idx[distinct], g["ref_idx20"][distinct]) and np.array_equal(d2, g["ref_d20"])
+    idx1, d1 = cloud.nearestKSearch(g["src"][:, :3], 1)
+    assert np.array_equal(idx1, g["idx1"]) and np.array_equal(d1, g["d1"])
+
+    c = np.load(G / "cov_small.npz")
+    raw = c["method0"][:, :3, :3]
+    w = np.linalg.eigvalsh(raw)
+    ok = (w[:, 1] - w[:, 0]) > 1e-6 * w[:, 2]
+    for m in range(5):
+        covs = ng.Covariances.compute(ng.PointCloud(rt, c["tgt"]), 20, m).to_host()
+        ref = c[f"method{m}"]
+        per_point = np.linalg.norm((covs - ref).reshape(len(ref), -1), axis=1) / np.linalg.norm(ref.reshape(len(ref), -1), axis=1)
+        assert per_point[ok if m in (1, 2, 3) else slice(None)].max() < REL, m
+
+    s = np.load(G / "gicp_small.npz")
+    eng = ng.NanoGICP(rt)
+    eng.setInputSource(ng.PointCloud(rt, s["src"]))
+    eng.setInputTarget(ng.PointCloud(rt, s["tgt"]))
+    eng.setSourceCovariances(s["src_covs"])
+    eng.setTargetCovariances(s["tgt_covs"])
+    e, H, b = eng.linearize(s["T"])
+    corr, sqd = eng.correspondences()
+    assert np.array_equal(corr, s["corr"]) and np.array_equal(sqd, s["sqd"])
+    assert rel_err(H, s["H"]) < REL and rel_err(b, s["b"]) < REL and abs(e - float(s["err"])) < REL * abs(e)
+    assert abs(eng.compute_error(s["T2"]) - float(s["err2"])) < REL * float(s["err2"])
+    for name, opt in (("lm", ng.OPT_LEVENBERG_MARQUARDT), ("gn", ng.OPT_GAUSS_NEWTON)):
+        eng.setOptimizer(opt)
+        r = eng.align()
+        assert (r.converged, r.iterations, r.n_linearize, r.n_compute_error) == tuple(s[f"{name}_meta"])
+        assert np.abs(r.T[:3, 3] - s[f"{name}_T"][:3, 3]).max() < POSE_T and rot_angle(r.T[:3, :3], s[f"{name}_T"][:3, :3]) < POSE_R
+        assert rel_err(r.hessian, s[f"{name}_H"]) < 1e-5
+
+
+def test_c2_align_matches_oracle(rt, oracle):
+    """BASELINE config C2 end to end: the headline registration agrees with the oracle in iteration
+    counts and pose (the oracle needs ~1 s for it)."""
+    src, tgt, guess = synth.workload_c2()
+    g = ng.NanoGICP(rt)
+    g.setInputSource(ng.PointCloud(rt, src))
+    g.setInputTarget(ng.PointCloud(rt, tgt))
+    o = oracle.NanoGICP()
+    o.setInputSource(oracle.Cloud(src))
+    o.setInputTarget(oracle.Cloud(tgt))
+    r, ro = g.align(guess), o.align(guess)
+    assert (r.converged, r.iterations, r.n_linearize, r.n_compute_error) == (ro.converged, ro.iterations, ro.n_linearize, ro.n_compute_error)
+    _check_pose(r, ro)
+    gc, gd = g.correspondences()
+    oc, od = o.correspondences()
+    assert np.array_equal(gc, oc) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    gt = synth.pose(50)
+    assert np.abs(r.T[:3, 3] - gt[:3, 3]).max() < 0.02  # and it is the right answer: within 2 cm of ground truth
