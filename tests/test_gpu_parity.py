@@ -403,3 +403,76 @@ def test_c2_align_matches_oracle(rt, oracle):
     assert np.array_equal(gc, oc) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
     gt = synth.pose(50)
     assert np.abs(r.T[:3, 3] - gt[:3, 3]).max() < 0.02  # and it is the right answer: within 2 cm of ground truth
+
+
+# ----------------------------------------------------------------------------- the C++ shim (host side)
+def test_cpp_shim_replays_odomnode_protocol(rt, tmp_path):
+    """tests/cpp/shim_protocol.cpp drives nano_gicp::NanoGICP (the C++ header that keeps the reference's
+    class interface) through OdomNode's call sequence; the same sequence through the Python mirror of
+    the C ABI must give the same transforms bit for bit (same library, same kernels)."""
+    import subprocess
+    from pathlib import Path
+
+    exe = Path(__file__).resolve().parent / "cpp" / "_build" / "shim_protocol"
+    if not exe.exists():
+        import __graft_entry__ as ge
+
+        ge.build_cpp_tests()
+    w = synth.make_world()
+    scans = [synth.scan(f, 16, 256, w) for f in range(4)]
+    path = tmp_path / "scans.bin"
+    with open(path, "wb") as fh:
+        fh.write(np.int32(len(scans)).tobytes())
+        for s in scans:
+            fh.write(np.int32(len(s)).tobytes())
+            fh.write(np.ascontiguousarray(s, dtype=np.float32).tobytes())
+    out = subprocess.run([str(exe), str(path)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    got = {}
+    for line in out.stdout.splitlines():
+        f = line.split()
+        if f[0] in ("s2s", "s2m"):
+            got[(f[0], int(f[1]))] = (int(f[2]), int(f[3]), np.array(f[4:], dtype=np.float32).reshape(4, 4))
+        elif f[0] == "res":
+            got[("res", int(f[1]))] = (int(f[2]), float(f[3]), int(f[4]))
+        elif f[0] == "covs":
+            assert int(f[1]) == int(f[2]) == len(scans[0]) and float(f[3]) > 0
+
+    s2s, s2m = ng.NanoGICP(rt), ng.NanoGICP(rt)
+    for e in (s2s, s2m):
+        e.setCorrespondenceRandomness(10)
+        e.setMaxCorrespondenceDistance(1.0)
+        e.setMaximumIterations(32)
+        e.setTransformationEpsilon(0.01)
+    first = ng.PointCloud(rt, scans[0])
+    s2s.setInputTarget(first)
+    s2s.calculateTargetCovariances()
+    s2s.setInputSource(first)
+    s2s.calculateSourceCovariances()
+    s2m.setInputTarget(first)
+    s2m.setTargetCovariances(s2s.getSourceCovariances())
+    T = np.eye(4, dtype=np.float32)
+    for f in range(1, 4):
+        cur = ng.PointCloud(rt, scans[f])
+        s2s.setInputSource(cur)
+        s2m.registerInputSource(cur)
+        s2m.source_kdtree_ = s2s.source_kdtree_
+        s2m.source_covs_ = None
+        r1 = s2s.align()
+        Tg = np.zeros((4, 4), dtype=np.float32)  # float32 product with the same summation order as the C++ test
+        for i in range(4):
+            for j in range(4):
+                acc = np.float32(0)
+                for k in range(4):
+                    acc = np.float32(acc + np.float32(T[i, k] * r1.T[k, j]))
+                Tg[i, j] = acc
+        s2m.source_covs_ = s2s.source_covs_
+        s2s.swapSourceAndTarget()
+        r2 = s2m.align(Tg)
+        T = r2.T
+        c1, c2 = got[("s2s", f)], got[("s2m", f)]
+        assert (c1[0], c1[1]) == (int(r1.converged), r1.iterations) and np.array_equal(c1[2], r1.T)
+        assert (c2[0], c2[1]) == (int(r2.converged), r2.iterations) and np.array_equal(c2[2], r2.T)
+        res = s2m.getResiduals()
+        n, total, n_out = got[("res", f)]
+        assert n == len(res) == n_out and abs(total - res.sum()) <= 1e-9 * res.sum()
