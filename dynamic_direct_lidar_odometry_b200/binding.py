@@ -162,6 +162,8 @@ def load() -> C.CDLL:
         fn = getattr(L, name)
         fn.restype = None
         fn.argtypes = args
+    L.ddlo_gicp_debug_block_times.restype = C.c_int
+    L.ddlo_gicp_debug_block_times.argtypes = [_vp, _vp, C.c_int]
     L.ddlo_gicp_debug_timeline.restype = C.c_int
     L.ddlo_gicp_debug_timeline.argtypes = [_vp, _vp, C.c_int]
     _lib = L

@@ -121,6 +121,7 @@ struct ddlo_gicp {
   double* partials = nullptr;
   int partial_stride = 0;
   AlignOut* d_out = nullptr;
+  unsigned long long* d_blk_times = nullptr;  // [8][partial_stride][4]
   float last_T[16];
   bool has_last_T = false;
   bool align_pending = false;
@@ -566,6 +567,7 @@ int ddlo_gicp_create(ddlo_runtime* rt, ddlo_gicp** out) {
   g->partial_stride = std::max(rt->max_coop_blocks_align, 64);
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&g->partials), (size_t)2 * kNumSums * g->partial_stride * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->d_out), sizeof(AlignOut));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->d_blk_times), (size_t)8 * g->partial_stride * 4 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     delete g;
     return fail(DDLO_E_CUDA, std::string("cudaMalloc(engine): ") + cudaGetErrorString(e));
@@ -588,6 +590,7 @@ int ddlo_gicp_destroy(ddlo_gicp* g) {
   if (g->mahal) cudaFree(g->mahal);
   if (g->partials) cudaFree(g->partials);
   if (g->d_out) cudaFree(g->d_out);
+  if (g->d_blk_times) cudaFree(g->d_blk_times);
   delete g;
   return DDLO_OK;
 }
@@ -762,6 +765,7 @@ static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, 
   a->rot_eps = g->p.rotation_epsilon;
   a->lm_init_lambda_factor = g->p.lm_init_lambda_factor;
   a->out = g->d_out;
+  a->blk_times = g->d_blk_times;
   return DDLO_OK;
 }
 
@@ -974,6 +978,19 @@ int ddlo_gicp_debug_timeline(ddlo_gicp* g, unsigned long long* out, int capacity
   const int n = std::min(std::min(o.n_stamps, 128), capacity);
   for (int i = 0; i < n; ++i) out[i] = o.stamps[i];
   return n;
+}
+
+// debugging aid: per-block phase times of the first 8 linearize passes of the last align,
+// out[pass][block][4] in ns; returns the number of blocks the kernel ran with.
+int ddlo_gicp_debug_block_times(ddlo_gicp* g, unsigned long long* out, int capacity_blocks) {
+  if (!g || !out || !g->src) return fail(DDLO_E_INVALID, "null argument");
+  const int nb = align_blocks(g);
+  if (capacity_blocks < nb) return fail(DDLO_E_SIZE, "capacity too small");
+  DDLO_CUDA(cudaStreamSynchronize(g->rt->stream));
+  for (int p = 0; p < 8; ++p)
+    DDLO_CUDA(cudaMemcpy(out + (size_t)p * capacity_blocks * 4, g->d_blk_times + (size_t)p * nb * 4, (size_t)nb * 4 * sizeof(unsigned long long),
+                         cudaMemcpyDeviceToHost));
+  return nb;
 }
 
 // ---- host-callable copies of the device math (CPU tests of the exact code the kernels run) --------------

@@ -48,6 +48,7 @@ struct AlignSmem {
   float nn_d[kAlignThreads];
   int nn_idx[kAlignThreads];
   int next;  // phase A work counter
+  unsigned long long t_search;  // %globaltimer when this block finished its last search phase (profiling)
   LmShared lm;
 };
 
@@ -88,6 +89,12 @@ __device__ __forceinline__ double quad_form(const Sym3& M, double ex, double ey,
   my = M.xy * ex + M.yy * ey + M.yz * ez;
   mz = M.xz * ex + M.yz * ey + M.zz * ez;
   return ex * mx + ey * my + ez * mz;
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -234,6 +241,7 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
       }
     }
     __syncthreads();
+    if (threadIdx.x == 0) sm.t_search = globaltimer_ns();
     // ---- phase B: one thread per point
     if (base + warp * 32 < lim) {
       const int slot = base + threadIdx.x;
@@ -335,20 +343,15 @@ __device__ __noinline__ void lm_solve(LmShared& s, double lambda) {
   for (int i = 0; i < 3; ++i) s.delta.t[i] = s.d[3 + i];
 }
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
 // phase tags of the timeline block 0 leaves in AlignOut::stamps
-enum { kTagStart = 1, kTagLinDone = 2, kTagLinSynced = 3, kTagLinSummed = 4, kTagSolved = 5, kTagErrDone = 6, kTagErrSynced = 7, kTagDecided = 8, kTagEnd = 9 };
+enum { kTagSearchDone = 10, kTagStart = 1, kTagLinDone = 2, kTagLinSynced = 3, kTagLinSummed = 4, kTagSolved = 5, kTagErrDone = 6, kTagErrSynced = 7, kTagDecided = 8, kTagEnd = 9 };
 #define DDLO_STAMP(tag)                                                                                         \
   do {                                                                                                          \
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_stamps < 128)                                                  \
       a.out->stamps[n_stamps++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00ffffffffffffffull); \
   } while (0)
 
-__global__ void __launch_bounds__(kAlignThreads, 1) k_align(const GicpArgs a) {
+__global__ void __launch_bounds__(kAlignThreads, kAlignBlocksPerSM) k_align(const GicpArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AlignSmem& sm = *reinterpret_cast<AlignSmem*>(smem_raw);
@@ -382,9 +385,18 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_align(const GicpArgs a) {
 
     // ---- linearize(x0) -----------------------------------------------------------------------
     double* part = a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride;
+    unsigned long long* bt = (a.blk_times && it < 8) ? a.blk_times + ((size_t)it * nblk + blockIdx.x) * 4 : nullptr;
+    if (bt && threadIdx.x == 0) bt[0] = globaltimer_ns();
     linearize_block(a, sm, it > 0, part, a.partial_stride);
+    if (bt && threadIdx.x == 0) {
+      bt[1] = sm.t_search;
+      bt[2] = globaltimer_ns();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_stamps < 128)
+      a.out->stamps[n_stamps++] = ((unsigned long long)kTagSearchDone << 56) | (sm.t_search & 0x00ffffffffffffffull);
     DDLO_STAMP(kTagLinDone);
     grid.sync();
+    if (bt && threadIdx.x == 0) bt[3] = globaltimer_ns();
     DDLO_STAMP(kTagLinSynced);
     grid_sum<kNumSums>(part, a.partial_stride, nblk, sm.tot);
     ++seq;
@@ -491,7 +503,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_align(const GicpArgs a) {
 }
 
 // ---- stepwise hooks (parity tests compare H, b, error, correspondences with the oracle) ---------
-__global__ void __launch_bounds__(kAlignThreads, 1) k_linearize_step(const GicpArgs a) {
+__global__ void __launch_bounds__(kAlignThreads, kAlignBlocksPerSM) k_linearize_step(const GicpArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AlignSmem& sm = *reinterpret_cast<AlignSmem*>(smem_raw);
   if (threadIdx.x == 0) {
@@ -502,7 +514,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) k_linearize_step(const GicpA
   linearize_block(a, sm, false, a.partials, a.partial_stride);
 }
 
-__global__ void __launch_bounds__(kAlignThreads, 1) k_error_step(const GicpArgs a) {
+__global__ void __launch_bounds__(kAlignThreads, kAlignBlocksPerSM) k_error_step(const GicpArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AlignSmem& sm = *reinterpret_cast<AlignSmem*>(smem_raw);
   if (threadIdx.x == 0) iso_from_colmajor(a.T_step, sm.lm.xi);

@@ -43,6 +43,7 @@ struct GicpArgs {
   float guess[16];          // column-major Eigen::Matrix4f
   double T_step[16];        // stepwise hooks: transform to evaluate at (column-major)
   AlignOut* out;
+  unsigned long long* blk_times;  // profiling: [pass < 8][block][4] %globaltimer at pass start / search done / phase B done / after grid sync
 };
 
 int gicp_max_coop_blocks(int device, int* blocks_per_sm);
@@ -53,7 +54,8 @@ int launch_residual_vectors(ddlo_runtime* rt, const float4* src, const float4* t
                             float* d_out3);
 int launch_transform_cloud(ddlo_runtime* rt, const float4* src, int n, const float* T16_host, float4* dst);
 
-constexpr int kAlignThreads = 1024;  // one block per SM: 128 search sub-warps
+constexpr int kAlignThreads = 1024;  // one block per SM: 128 search sub-warps (512 threads with 128 registers was tried: slower search)
+constexpr int kAlignBlocksPerSM = 1;  // (768 x 2 was tried: more warps, but the fp64 phase spills and the pass gets slower)
 int gicp_blocks_for(int ns, int max_blocks);
 
 }  // namespace ddlo

@@ -208,82 +208,70 @@ struct TopKSub {
   }
 };
 
-// k <= 8*R: the candidates sorted by (d, i) in registers, R per lane, position = lane * R + r, so
-// lane 0 holds the R smallest.  Inserting one candidate is a shift of the tail by one position:
-// every slot takes its left neighbour if that neighbour is greater than the candidate, the
-// candidate itself if only the slot's own content is greater, else keeps its content.  The bar is
-// the entry at position k-1, re-broadcast after every insertion.
+// k <= 8*R: the candidates sorted in registers, R per lane, position = lane * R + r, so lane 0 holds
+// the R smallest.  A candidate is one 64-bit key, bits(d) << 32 | index: for d >= 0 the unsigned
+// order of the keys is the lexicographic (d, i) order.  Inserting one candidate is a shift of the
+// tail by one position: every slot takes its left neighbour if that neighbour is greater than the
+// candidate, the candidate itself if only the slot's own content is greater, else keeps its
+// content.  The bar is the entry at position k-1, re-broadcast after every insertion, optionally
+// capped from outside by any proven upper bound of the k-th distance (`cap`: e.g. the largest
+// distance to k arbitrary points of the cloud), which keeps far candidates out while the list fills.
 template <int R>
 struct TopKRegSub {
-  float ed[R];
-  int ei[R];
+  unsigned long long e[R];
+  unsigned long long bar;  // candidates must be < bar
+  unsigned long long capk; // (cap, sentinel index): admits every index at distance == cap
   int k;
-  float wd;
-  int wi;
-  __device__ __forceinline__ void init(int k_) {
+  static __device__ __forceinline__ unsigned long long pack(float dist, int oi) {
+    return ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)oi;
+  }
+  __device__ __forceinline__ void init(int k_, float cap = FLT_MAX) {
     k = k_;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      ed[r] = FLT_MAX;
-      ei[r] = kIdxSentinel;
-    }
-    wd = FLT_MAX;
-    wi = kIdxSentinel;
+    for (int r = 0; r < R; ++r) e[r] = pack(FLT_MAX, kIdxSentinel);
+    capk = pack(cap, kIdxSentinel);
+    bar = capk;
   }
-  __device__ __forceinline__ float worst() const { return wd; }
-  // all 32 lanes; (dc, ic) uniform per sub-warp; `upd` uniform per sub-warp
-  __device__ __forceinline__ void insert(bool upd, float dc, int ic, const Sub& sb) {
-    float pd = __shfl_up_sync(kFull, ed[R - 1], 1);
-    int pi = __shfl_up_sync(kFull, ei[R - 1], 1);
-    if (sb.sl == 0) {  // nothing to the left of position 0
-      pd = -1.0f;
-      pi = -1;
-    }
+  __device__ __forceinline__ float worst() const { return __uint_as_float((unsigned)(bar >> 32)); }
+  // all 32 lanes; `c` and `upd` uniform per sub-warp
+  __device__ __forceinline__ void insert(bool upd, unsigned long long c, const Sub& sb) {
+    unsigned long long left = __shfl_up_sync(kFull, e[R - 1], 1);
+    if (sb.sl == 0) left = 0ull;  // nothing to the left of position 0
     if (upd) {
-      bool gl = lex_less(dc, ic, pd, pi);  // left neighbour greater than the candidate
+      bool gl = c < left;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const bool gr = lex_less(dc, ic, ed[r], ei[r]);
-        const float nd = gl ? pd : (gr ? dc : ed[r]);
-        const int ni = gl ? pi : (gr ? ic : ei[r]);
-        pd = ed[r];
-        pi = ei[r];
-        ed[r] = nd;
-        ei[r] = ni;
+        const bool gr = c < e[r];
+        const unsigned long long nv = gl ? left : (gr ? c : e[r]);
+        left = e[r];
+        e[r] = nv;
         gl = gr;
       }
     }
     const int kr = (k - 1) % R, kl = sb.base + (k - 1) / R;
-    float sd = ed[0];
-    int si = ei[0];
+    unsigned long long kth = e[0];
 #pragma unroll
-    for (int r = 1; r < R; ++r) {
-      sd = kr == r ? ed[r] : sd;
-      si = kr == r ? ei[r] : si;
-    }
-    wd = __shfl_sync(kFull, sd, kl);
-    wi = __shfl_sync(kFull, si, kl);
+    for (int r = 1; r < R; ++r) kth = kr == r ? e[r] : kth;
+    kth = __shfl_sync(kFull, kth, kl);
+    bar = min(kth, capk);
   }
   __device__ __forceinline__ void scan(bool doit, const float4* __restrict__ spts, int start, int count, float qx, float qy, float qz,
                                        const Sub& sb) {
     for (int r = 0; __any_sync(kFull, doit && r < count); r += kSubLanes) {
       const int j = r + sb.sl;
-      const bool have = doit && j < count;
-      float dist = FLT_MAX;
-      int oi = kIdxSentinel;
-      if (have) {
+      unsigned long long key = ~0ull;
+      if (doit && j < count) {
         const float4 v = __ldg(spts + start + j);
-        dist = sqdist3_rn(qx, qy, qz, v.x, v.y, v.z);
-        oi = __float_as_int(v.w);
+        const float dist = sqdist3_rn(qx, qy, qz, v.x, v.y, v.z);
+        if (dist < FLT_MAX) key = pack(dist, __float_as_int(v.w));
       }
-      unsigned cb = sub_ballot(have && dist < FLT_MAX && lex_less(dist, oi, wd, wi), sb);
+      unsigned cb = sub_ballot(key < bar, sb);
       while (__any_sync(kFull, cb != 0u)) {
         const bool act = cb != 0u;
         const int c = act ? __ffs(cb) - 1 : 0;
         cb &= cb - 1u;
-        const float dc = __shfl_sync(kFull, dist, sb.base + c);
-        const int ic = __shfl_sync(kFull, oi, sb.base + c);
-        insert(act && lex_less(dc, ic, wd, wi), dc, ic, sb);  // the bar may have dropped since the ballot
+        const unsigned long long ck = __shfl_sync(kFull, key, sb.base + c);
+        insert(act && ck < bar, ck, sb);  // the bar may have dropped since the ballot
       }
     }
   }
@@ -292,9 +280,10 @@ struct TopKRegSub {
     for (int r = 0; r < R; ++r) {
       const int p = sb.sl * R + r;
       if (p < k) {
-        const bool empty = ei[r] == kIdxSentinel;
-        idx_out[p] = empty ? -1 : ei[r];
-        if (d_out) d_out[p] = empty ? __int_as_float(0x7f800000) : ed[r];
+        const int oi = (int)(unsigned)(e[r] & 0xffffffffull);
+        const bool empty = oi == kIdxSentinel;
+        idx_out[p] = empty ? -1 : oi;
+        if (d_out) d_out[p] = empty ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(e[r] >> 32));
       }
     }
   }

@@ -54,8 +54,24 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(IndexView ix, const float4*
     }
   };
   if constexpr (R > 0) {
+    // Self queries know k points of the cloud for free: the k consecutive Morton positions around
+    // the query.  The largest distance among them bounds the k-th neighbour distance from above.
+    float cap = FLT_MAX;
+    if (self_mode && ix.n >= k) {
+      float far = 0.0f;
+      if (active) {
+        const int w0 = min(max(q - k / 2, 0), ix.n - k);
+        for (int j = sb.sl; j < k; j += kSubLanes) {
+          const float4 p = __ldg(ix.spts + w0 + j);
+          far = fmaxf(far, sqdist3_rn(v.x, v.y, v.z, p.x, p.y, p.z));
+        }
+      }
+#pragma unroll
+      for (int o = 1; o < kSubLanes; o <<= 1) far = fmaxf(far, __shfl_xor_sync(kFull, far, o));
+      if (active && far < FLT_MAX) cap = far;
+    }
     TopKRegSub<R> rs;
-    rs.init(k);
+    rs.init(k, cap);
     search(rs);
     if (active) rs.write_sorted(idx_out + row * k, d_out ? d_out + row * k : nullptr, sb);
   } else {

@@ -383,7 +383,7 @@ class NanoGICP:
         self._last = AlignInfo(r)
         return self._last
 
-    TIMELINE_TAGS = {1: "start", 2: "lin_done", 3: "lin_synced", 4: "lin_summed", 5: "solved", 6: "err_done", 7: "err_synced", 8: "decided", 9: "end"}
+    TIMELINE_TAGS = {1: "start", 2: "lin_done", 3: "lin_synced", 4: "lin_summed", 5: "solved", 6: "err_done", 7: "err_synced", 8: "decided", 9: "end", 10: "search_done"}
 
     def debug_timeline(self):
         """[(tag, microseconds since kernel start)] recorded by block 0 during the last align (profiling aid)."""
@@ -394,6 +394,16 @@ class NanoGICP:
         t = [(int(v >> np.uint64(56)), int(v & np.uint64(0x00FFFFFFFFFFFFFF))) for v in buf[:n]]
         t0 = t[0][1] if t else 0
         return [(self.TIMELINE_TAGS.get(tag, str(tag)), (ns - t0) / 1e3) for tag, ns in t]
+
+    def debug_block_times(self):
+        """(passes<=8, blocks, 4) float64 microseconds: pass start / search done / phase B done / after the grid sync."""
+        cap = 1024
+        buf = np.zeros((8, cap, 4), dtype=np.uint64)
+        nb = B.load().ddlo_gicp_debug_block_times(self._g, B.ptr(buf), cap)
+        if nb < 0:
+            B.check(nb)
+        t = buf[:, :nb, :].astype(np.float64)
+        return (t - t[0, :, 0].min()) / 1e3
 
     def getFinalTransformation(self) -> np.ndarray: return self._last.T
     def hasConverged(self) -> bool: return self._last.converged

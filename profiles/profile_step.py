@@ -16,14 +16,19 @@ target = ng.PointCloud(rt, tgt)
 eng.setInputTarget(target)
 eng.calculateTargetCovariances()
 for _ in range(reps):
+    eng.clearSource()
     eng.setInputSource(ng.PointCloud(rt, src))
     eng.calculateSourceCovariances()
     r = eng.align(guess)
-    eng.clearSource()
 prev = 0.0
 for tag, us in eng.debug_timeline():
     print(f"  {tag:12s} {us:9.1f} us  (+{us - prev:7.1f})")
     prev = us
+bt = eng.debug_block_times()
+for p in range(min(r.n_linearize, 8)):
+    st, sd, bd, sy = bt[p, :, 0], bt[p, :, 1], bt[p, :, 2], bt[p, :, 3]
+    print(f"  pass {p}: start {st.min():7.1f}..{st.max():7.1f}  search {np.percentile(sd - st, [0, 50, 100]).round(1)}  "
+          f"phaseB {np.percentile(bd - sd, [0, 50, 100]).round(1)}  wait {np.percentile(sy - bd, [0, 50, 100]).round(1)}")
 print("iterations", r.iterations, "converged", r.converged, "lin", r.n_linearize, "err", r.n_compute_error)
 del eng, target
 rt.close()
