@@ -114,7 +114,12 @@ struct ddlo_gicp {
   // per-source-point workspace (correspondences_, sq_distances_, mahalanobis_)
   int ws_n = 0;
   int* corr = nullptr;
-  int* nn_raw = nullptr;
+  int2* nn_seed = nullptr;
+  // target covariances permuted into the Morton order of the target index (cache keyed by the two handles)
+  double* tcov_sorted = nullptr;
+  size_t tcov_sorted_cap = 0;
+  ddlo_cloud* tcov_for_cloud = nullptr;
+  ddlo_covs* tcov_for_covs = nullptr;
   float* sqd = nullptr;
   double* mahal = nullptr;
   int corr_n = 0;  // number of valid entries (0 after swap/clear: correspondences_.clear())
@@ -567,7 +572,7 @@ int ddlo_gicp_create(ddlo_runtime* rt, ddlo_gicp** out) {
   g->partial_stride = std::max(rt->max_coop_blocks_align, 64);
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&g->partials), (size_t)2 * kNumSums * g->partial_stride * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->d_out), sizeof(AlignOut));
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->d_blk_times), (size_t)8 * g->partial_stride * 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->d_blk_times), (size_t)8 * g->partial_stride * 8 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     delete g;
     return fail(DDLO_E_CUDA, std::string("cudaMalloc(engine): ") + cudaGetErrorString(e));
@@ -585,7 +590,10 @@ int ddlo_gicp_destroy(ddlo_gicp* g) {
   set_covs(g->src_cov, nullptr);
   set_covs(g->tgt_cov, nullptr);
   if (g->corr) cudaFree(g->corr);
-  if (g->nn_raw) cudaFree(g->nn_raw);
+  if (g->nn_seed) cudaFree(g->nn_seed);
+  if (g->tcov_sorted) cudaFree(g->tcov_sorted);
+  set_cloud(g->tcov_for_cloud, nullptr);
+  set_covs(g->tcov_for_covs, nullptr);
   if (g->sqd) cudaFree(g->sqd);
   if (g->mahal) cudaFree(g->mahal);
   if (g->partials) cudaFree(g->partials);
@@ -711,17 +719,54 @@ int ddlo_gicp_swap_source_and_target(ddlo_gicp* g) {
   return DDLO_OK;
 }
 
+// covs_sorted[p] = covs[original index of the p-th point in Morton order]
+__global__ void __launch_bounds__(256) k_permute_covs(const float4* __restrict__ spts, int n, const double* __restrict__ covs,
+                                                      double* __restrict__ covs_sorted) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int o = __float_as_int(spts[p].w);
+  const double2* in = reinterpret_cast<const double2*>(covs + (size_t)o * kCovStride);
+  double2* out = reinterpret_cast<double2*>(covs_sorted + (size_t)p * kCovStride);
+  out[0] = in[0];
+  out[1] = in[1];
+  out[2] = in[2];
+}
+
+// The kernels gather the matched target covariance by the match's position in the Morton order, so
+// that neighbouring source points (whose matches are neighbours too) touch the same DRAM pages.
+// The permuted copy is rebuilt only when the target cloud or its covariance vector changes.
+static int ensure_sorted_target_covs(ddlo_gicp* g) {
+  if (g->tcov_for_cloud == g->tgt && g->tcov_for_covs == g->tgt_cov && g->tcov_sorted) return DDLO_OK;
+  const size_t n = (size_t)g->tgt->n;
+  if (g->tcov_sorted_cap < n) {
+    if (g->tcov_sorted) {
+      DDLO_CUDA(cudaStreamSynchronize(g->rt->stream));
+      DDLO_CUDA(cudaFree(g->tcov_sorted));
+      g->tcov_sorted = nullptr;
+      g->tcov_sorted_cap = 0;
+    }
+    DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->tcov_sorted), n * kCovStride * sizeof(double)));
+    g->tcov_sorted_cap = n;
+  }
+  k_permute_covs<<<(int)((n + 255) / 256), 256, 0, g->rt->stream>>>(g->tgt->spts, (int)n, g->tgt_cov->c, g->tcov_sorted);
+  g->rt->launches += 1;
+  DDLO_CUDA(cudaGetLastError());
+  set_cloud(g->tcov_for_cloud, g->tgt);  // retained: the key can not be recycled while cached
+  set_covs(g->tcov_for_covs, g->tgt_cov);
+  return DDLO_OK;
+}
+
 static int ensure_workspace(ddlo_gicp* g, int ns) {
   if (g->ws_n >= ns) return DDLO_OK;
   DDLO_CUDA(cudaStreamSynchronize(g->rt->stream));
   if (g->corr) cudaFree(g->corr);
-  if (g->nn_raw) cudaFree(g->nn_raw);
+  if (g->nn_seed) cudaFree(g->nn_seed);
   if (g->sqd) cudaFree(g->sqd);
   if (g->mahal) cudaFree(g->mahal);
-  g->corr = nullptr, g->nn_raw = nullptr, g->sqd = nullptr, g->mahal = nullptr, g->ws_n = 0;
+  g->corr = nullptr, g->nn_seed = nullptr, g->sqd = nullptr, g->mahal = nullptr, g->ws_n = 0;
   const size_t cap = (size_t)ns + ns / 4 + 256;
   DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->corr), cap * sizeof(int)));
-  DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->nn_raw), cap * sizeof(int)));
+  DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->nn_seed), cap * sizeof(int2)));
   DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->sqd), cap * sizeof(float)));
   DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->mahal), cap * kCovStride * sizeof(double)));
   g->ws_n = (int)cap;
@@ -745,14 +790,15 @@ static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, 
     if (covs_computed) *covs_computed = 1;
   }
   DDLO_TRY(ensure_workspace(g, g->src->n));
+  DDLO_TRY(ensure_sorted_target_covs(g));
   a->tgt = g->tgt->view;
   a->src_pts = g->src->pts;
   a->src_cov = g->src_cov->c;
   a->tgt_pts = g->tgt->pts;
-  a->tgt_cov = g->tgt_cov->c;
+  a->tgt_cov = g->tcov_sorted;
   a->ns = g->src->n;
   a->corr = g->corr;
-  a->nn_raw = g->nn_raw;
+  a->nn_seed = g->nn_seed;
   a->sqd = g->sqd;
   a->mahal = g->mahal;
   a->partials = g->partials;
@@ -777,6 +823,7 @@ static int enqueue_align(ddlo_gicp* g, const float* guess16, int* covs_computed)
   static const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   std::memcpy(a.guess, guess16 ? guess16 : I16, sizeof(a.guess));
   std::memset(a.T_step, 0, sizeof(a.T_step));
+  DDLO_CUDA(cudaMemsetAsync(g->d_blk_times, 0, (size_t)8 * g->partial_stride * 8 * sizeof(unsigned long long), g->rt->stream));
   DDLO_TRY(launch_align(g->rt, a, align_blocks(g)));
   g->corr_n = g->p.max_iterations > 0 ? g->src->n : g->corr_n;
   return DDLO_OK;
@@ -988,7 +1035,7 @@ int ddlo_gicp_debug_block_times(ddlo_gicp* g, unsigned long long* out, int capac
   if (capacity_blocks < nb) return fail(DDLO_E_SIZE, "capacity too small");
   DDLO_CUDA(cudaStreamSynchronize(g->rt->stream));
   for (int p = 0; p < 8; ++p)
-    DDLO_CUDA(cudaMemcpy(out + (size_t)p * capacity_blocks * 4, g->d_blk_times + (size_t)p * nb * 4, (size_t)nb * 4 * sizeof(unsigned long long),
+    DDLO_CUDA(cudaMemcpy(out + (size_t)p * capacity_blocks * 8, g->d_blk_times + (size_t)p * nb * 8, (size_t)nb * 8 * sizeof(unsigned long long),
                          cudaMemcpyDeviceToHost));
   return nb;
 }

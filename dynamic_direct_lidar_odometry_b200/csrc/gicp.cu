@@ -47,6 +47,7 @@ struct AlignSmem {
   double tot[kNumSums];
   float nn_d[kAlignThreads];
   int nn_idx[kAlignThreads];
+  int nn_pos[kAlignThreads];
   int next;  // phase A work counter
   unsigned long long t_search;  // %globaltimer when this block finished its last search phase (profiling)
   LmShared lm;
@@ -106,7 +107,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Phase B for one point (called by all 32 lanes of a warp; `valid` lanes own a point): the
 // Mahalanobis matrix and the point's 28 contributions, summed over the warp into red_w[0..27].
 // Kept out of line so that its fp64 register appetite does not leak into the search loop.
-__device__ __noinline__ void lin_point(const GicpArgs& a, const LmShared& s, bool valid, int i, float nn_d, int nn_idx,
+__device__ __noinline__ void lin_point(const GicpArgs& a, const LmShared& s, bool valid, int i, float nn_d, int nn_idx, int nn_pos,
                                        double* __restrict__ red_w) {
   double c[kNumSums];
 #pragma unroll
@@ -116,12 +117,14 @@ __device__ __noinline__ void lin_point(const GicpArgs& a, const LmShared& s, boo
     const bool found = nn_idx != kIdxSentinel;
     const int j = (found && (double)nn_d < a.thr2) ? nn_idx : -1;
     a.corr[i] = j;
-    a.nn_raw[i] = found ? nn_idx : -1;  // seed of the next search, kept even beyond the distance threshold
+    // seed of the next search (kept even beyond the distance threshold): where the match sits in the
+    // Morton order and the node above its leaf
+    a.nn_seed[i] = found ? make_int2(nn_pos, __ldg(a.tgt.node_of_point + nn_idx)) : make_int2(-1, -1);
     if (j >= 0) {
       const float4 pa = __ldg(a.src_pts + i);
-      const float4 pb = __ldg(a.tgt_pts + j);
+      const float4 pb = __ldg(a.tgt.spts + nn_pos);
       const Sym3 CA = load_sym3(a.src_cov + (size_t)i * kCovStride);
-      const Sym3 CB = load_sym3(a.tgt_cov + (size_t)j * kCovStride);
+      const Sym3 CB = load_sym3(a.tgt_cov + (size_t)nn_pos * kCovStride);
       Sym3 RCR = sym3_rotate(s.x0.r, CA);
       RCR.xx += CB.xx, RCR.xy += CB.xy, RCR.xz += CB.xz, RCR.yy += CB.yy, RCR.yz += CB.yz, RCR.zz += CB.zz;
       const Sym3 M = sym3_inverse(RCR);
@@ -164,7 +167,7 @@ __device__ __forceinline__ double err_point(const GicpArgs& a, const Iso3& T, in
   const int j = __ldcg(a.corr + i);
   if (j < 0) return 0.0;
   const float4 pa = __ldg(a.src_pts + i);
-  const float4 pb = __ldg(a.tgt_pts + j);
+  const float4 pb = __ldg(a.tgt.spts + __ldcg(a.nn_seed + i).x);
   const Sym3 M = load_sym3_cg(a.mahal + (size_t)i * kCovStride);
   const double x = xform_d(T.r + 0, T.t[0], (double)pa.x, (double)pa.y, (double)pa.z);
   const double y = xform_d(T.r + 3, T.t[1], (double)pa.x, (double)pa.y, (double)pa.z);
@@ -196,7 +199,8 @@ __device__ __forceinline__ Deal make_deal(int ns) {
 
 // linearize over the block's points; leaves the block's 28 sums in dst[c * stride + blockIdx.x].
 // have_prev: nn_raw holds the matches of the previous linearize of the same source cloud.
-__device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm, bool have_prev, double* dst, int stride) {
+__device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm, bool have_prev, double* dst, int stride,
+                                                unsigned long long* bt = nullptr) {
   const Sub sb = make_sub();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 3;
@@ -218,26 +222,40 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
       const int i = dl.point(slot);
       const bool active = i < a.ns;
       float qx = 0.f, qy = 0.f, qz = 0.f;
-      int start = 0;
+      int node = 0, skip = -1;
       Best1Sub best;
       if (active) {
         const float4 pa = __ldg(a.src_pts + i);
         qx = xform_f(sm.lm.Rf + 0, sm.lm.tf[0], pa.x, pa.y, pa.z);
         qy = xform_f(sm.lm.Rf + 3, sm.lm.tf[1], pa.x, pa.y, pa.z);
         qz = xform_f(sm.lm.Rf + 6, sm.lm.tf[2], pa.x, pa.y, pa.z);
-        const int j0 = have_prev ? __ldcg(a.nn_raw + i) : -1;
-        if (j0 >= 0) {
-          const float4 t = __ldg(a.tgt_pts + j0);
-          best.seed(sqdist3_rn(qx, qy, qz, t.x, t.y, t.z), j0);
-          // everything that can beat the seed lies in the smallest lattice cube around the seed's
-          // leaf that holds the ball |x - q|^2 <= d_seed: search below that node, not from the root
-          if (best.idx == j0) start = start_node_for(a.tgt, j0, qx, qy, qz, best.d);
+        const int2 sd = have_prev ? __ldcg(a.nn_seed + i) : make_int2(-1, -1);
+        if (sd.x >= 0) {
+          // The previous iteration's match is a real point of the target: its distance bounds the
+          // answer, and the search starts at the node above its leaf and climbs only while the
+          // ball of the best distance found so far sticks out of the node's cube.
+          const float4 t = __ldg(a.tgt.spts + sd.x);
+          best.seed(sqdist3_rn(qx, qy, qz, t.x, t.y, t.z), __float_as_int(t.w), sd.x);
+          node = sd.y;
         }
       }
-      knn_traverse_sub(a.tgt, active, qx, qy, qz, best, stack, sb, start);
+      bool going = active;
+      while (__any_sync(kFull, going)) {
+        knn_traverse_sub(a.tgt, going, qx, qy, qz, best, stack, sb, node, skip);
+        if (going) {
+          const int4 m = __ldg(a.tgt.meta + node);
+          if (ball_in_cell(make_ball(a.tgt, qx, qy, qz, best.d), m)) {
+            going = false;
+          } else {
+            skip = node;
+            node = m.x;
+          }
+        }
+      }
       if (active && sb.sl == 0) {
         sm.nn_d[slot - base] = best.d;
         sm.nn_idx[slot - base] = best.idx;
+        sm.nn_pos[slot - base] = best.pos;
       }
     }
     __syncthreads();
@@ -247,17 +265,25 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
       const int slot = base + threadIdx.x;
       const int i = dl.point(slot);
       const bool valid = slot < lim && i < a.ns;
+      const unsigned long long t0 = globaltimer_ns();
       lin_point(a, sm.lm, valid, i, valid ? sm.nn_d[threadIdx.x] : 0.f, valid ? sm.nn_idx[threadIdx.x] : kIdxSentinel,
-                sm.red + warp * kNumSums);
+                valid ? sm.nn_pos[threadIdx.x] : -1, sm.red + warp * kNumSums);
+      if (bt && lane == 0) {
+        const unsigned long long dt = globaltimer_ns() - t0;
+        atomicMax(bt + 4, dt);
+        atomicMax(bt + 5, 0xffffffffull - dt);
+      }
     }
   }
   __syncthreads();
+  if (bt && threadIdx.x == 0) bt[6] = globaltimer_ns();
   if (threadIdx.x < kNumSums) {
     double v = 0.0;
     for (int w = 0; w < kAlignWarps; ++w) v += sm.red[w * kNumSums + threadIdx.x];
     __stcg(dst + (size_t)threadIdx.x * stride + blockIdx.x, v);
   }
   __syncthreads();
+  if (bt && threadIdx.x == 0) bt[7] = globaltimer_ns();
 }
 
 // compute_error over the block's points; the block's sum goes to dst[blockIdx.x]
@@ -385,9 +411,9 @@ __global__ void __launch_bounds__(kAlignThreads, kAlignBlocksPerSM) k_align(cons
 
     // ---- linearize(x0) -----------------------------------------------------------------------
     double* part = a.partials + (size_t)(seq & 1) * kNumSums * a.partial_stride;
-    unsigned long long* bt = (a.blk_times && it < 8) ? a.blk_times + ((size_t)it * nblk + blockIdx.x) * 4 : nullptr;
+    unsigned long long* bt = (a.blk_times && it < 8) ? a.blk_times + ((size_t)it * nblk + blockIdx.x) * 8 : nullptr;
     if (bt && threadIdx.x == 0) bt[0] = globaltimer_ns();
-    linearize_block(a, sm, it > 0, part, a.partial_stride);
+    linearize_block(a, sm, it > 0, part, a.partial_stride, bt);
     if (bt && threadIdx.x == 0) {
       bt[1] = sm.t_search;
       bt[2] = globaltimer_ns();

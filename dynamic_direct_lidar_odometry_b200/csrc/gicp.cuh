@@ -27,10 +27,10 @@ struct GicpArgs {
   const float4* src_pts;    // ns, original order
   const double* src_cov;    // ns * 6
   const float4* tgt_pts;    // nt, original order (compute_error gathers matched points here)
-  const double* tgt_cov;    // nt * 6, original order
+  const double* tgt_cov;    // nt * 6, MORTON order of the target index (gathers of neighbouring matches share DRAM pages)
   int ns;
   int* corr;                // correspondences_   (ns)
-  int* nn_raw;              // nearest target index before thresholding (ns): seeds the next search
+  int2* nn_seed;            // per source point {match position in spts, node above its leaf} or {-1,-1}: seeds the next search
   float* sqd;               // sq_distances_      (ns)
   double* mahal;            // mahalanobis_       (ns * 6)
   double* partials;         // [2][kNumSums][partial_stride]
@@ -43,7 +43,7 @@ struct GicpArgs {
   float guess[16];          // column-major Eigen::Matrix4f
   double T_step[16];        // stepwise hooks: transform to evaluate at (column-major)
   AlignOut* out;
-  unsigned long long* blk_times;  // profiling: [pass < 8][block][4] %globaltimer at pass start / search done / phase B done / after grid sync
+  unsigned long long* blk_times;  // profiling: [pass < 8][block][8] %globaltimer at pass start / search done / phase B done / after grid sync, then max and (2^32-1 - min) lin_point duration
 };
 
 int gicp_max_coop_blocks(int device, int* blocks_per_sm);

@@ -84,32 +84,42 @@ __device__ __forceinline__ int sub_argmin(bool cand, float v, const Sub& sb) {
 struct Best1Sub {
   float d = FLT_MAX;
   int idx = kIdxSentinel;  // original index
+  int pos = -1;            // position in spts (Morton order)
   __device__ __forceinline__ float worst() const { return d; }
   // (d, idx) as one 64-bit key: for d >= 0 the float's bits order like an unsigned int, so the
   // lexicographic minimum is the plain unsigned minimum of (bits(d) << 32 | idx)
   static __device__ __forceinline__ unsigned long long pack(float dist, int oi) {
     return ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)oi;
   }
-  __device__ __forceinline__ void seed(float dist, int oi) {
+  __device__ __forceinline__ void seed(float dist, int oi, int p) {
     if (dist < FLT_MAX && lex_less(dist, oi, d, idx)) {
       d = dist;
       idx = oi;
+      pos = p;
     }
   }
   __device__ __forceinline__ void scan(bool doit, const float4* __restrict__ spts, int start, int count, float qx, float qy, float qz,
                                        const Sub& sb) {
     unsigned long long key = pack(d, idx);
+    int lp = pos;
     if (doit) {
       for (int j = sb.sl; j < count; j += kSubLanes) {
         const float4 v = __ldg(spts + start + j);
         const float dist = sqdist3_rn(qx, qy, qz, v.x, v.y, v.z);
-        if (dist < FLT_MAX) key = min(key, pack(dist, __float_as_int(v.w)));
+        const unsigned long long k2 = pack(dist, __float_as_int(v.w));
+        if (dist < FLT_MAX && k2 < key) {
+          key = k2;
+          lp = start + j;
+        }
       }
     }
+    unsigned long long m = key;
 #pragma unroll
-    for (int o = 1; o < kSubLanes; o <<= 1) key = min(key, __shfl_xor_sync(kFull, key, o));
-    d = __uint_as_float((unsigned)(key >> 32));
-    idx = (int)(unsigned)(key & 0xffffffffull);
+    for (int o = 1; o < kSubLanes; o <<= 1) m = min(m, __shfl_xor_sync(kFull, m, o));
+    const unsigned who = sub_ballot(key == m, sb);  // never empty; all eight when nothing improved
+    pos = __shfl_sync(kFull, lp, sb.base + __ffs(who) - 1);
+    d = __uint_as_float((unsigned)(m >> 32));
+    idx = (int)(unsigned)(m & 0xffffffffull);
   }
 };
 

@@ -396,14 +396,19 @@ class NanoGICP:
         return [(self.TIMELINE_TAGS.get(tag, str(tag)), (ns - t0) / 1e3) for tag, ns in t]
 
     def debug_block_times(self):
-        """(passes<=8, blocks, 4) float64 microseconds: pass start / search done / phase B done / after the grid sync."""
+        """(passes<=8, blocks, 6) microseconds: pass start / search done / phase B done / after the grid sync / slowest and fastest lin_point call."""
         cap = 1024
-        buf = np.zeros((8, cap, 4), dtype=np.uint64)
+        buf = np.zeros((8, cap, 8), dtype=np.uint64)
         nb = B.load().ddlo_gicp_debug_block_times(self._g, B.ptr(buf), cap)
         if nb < 0:
             B.check(nb)
         t = buf[:, :nb, :].astype(np.float64)
-        return (t - t[0, :, 0].min()) / 1e3
+        out = np.zeros((8, nb, 8))
+        out[:, :, :4] = (t[:, :, :4] - t[0, :, 0].min()) / 1e3
+        out[:, :, 6:8] = (t[:, :, 6:8] - t[0, :, 0].min()) / 1e3
+        out[:, :, 4] = t[:, :, 4] / 1e3                      # slowest lin_point call of the block
+        out[:, :, 5] = (4294967295.0 - t[:, :, 5]) / 1e3     # fastest
+        return out
 
     def getFinalTransformation(self) -> np.ndarray: return self._last.T
     def hasConverged(self) -> bool: return self._last.converged

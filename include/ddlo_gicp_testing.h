@@ -17,7 +17,7 @@ void ddlo_math_so3_exp(const double* omega3, double* R9);                       
 void ddlo_math_sym3_inverse(const double* sym6, double* out6);
 /* phase timeline of the last align (block 0): entries are tag << 56 | %globaltimer ns; returns the count */
 struct ddlo_gicp;
-/* per-block phase times (ns) of the first 8 linearize passes: out[pass][capacity_blocks][4]; returns block count */
+/* per-block phase times (ns) of the first 8 linearize passes: out[pass][capacity_blocks][8]; returns block count */
 int ddlo_gicp_debug_block_times(struct ddlo_gicp* g, unsigned long long* out, int capacity_blocks);
 int ddlo_gicp_debug_timeline(struct ddlo_gicp* g, unsigned long long* out, int capacity);
 #ifdef __cplusplus

@@ -28,7 +28,9 @@ bt = eng.debug_block_times()
 for p in range(min(r.n_linearize, 8)):
     st, sd, bd, sy = bt[p, :, 0], bt[p, :, 1], bt[p, :, 2], bt[p, :, 3]
     print(f"  pass {p}: start {st.min():7.1f}..{st.max():7.1f}  search {np.percentile(sd - st, [0, 50, 100]).round(1)}  "
-          f"phaseB {np.percentile(bd - sd, [0, 50, 100]).round(1)}  wait {np.percentile(sy - bd, [0, 50, 100]).round(1)}")
+          f"phaseB {np.percentile(bd - sd, [0, 50, 100]).round(1)}  wait {np.percentile(sy - bd, [0, 50, 100]).round(1)}  "
+          f"sync2-search {np.percentile(bt[p, :, 6] - sd, [0, 50, 100]).round(1)} final {np.percentile(bt[p, :, 7] - bt[p, :, 6], [0, 50, 100]).round(1)} "
+          f"lin_point max/warp {np.percentile(bt[p, :, 4], [0, 50, 100]).round(1)} min/warp {np.percentile(bt[p, :, 5], [0, 50, 100]).round(1)}")
 print("iterations", r.iterations, "converged", r.converged, "lin", r.n_linearize, "err", r.n_compute_error)
 del eng, target
 rt.close()
