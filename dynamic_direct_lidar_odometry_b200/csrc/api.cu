@@ -24,6 +24,7 @@ int fail(int code, const std::string& msg) {
 int build_index(ddlo_cloud* c);
 int launch_knn_queries(ddlo_cloud* c, const float4* d_queries, int nq, int k, int* d_idx, float* d_d2);
 int launch_covariances(ddlo_cloud* c, int k, int method, double* d_covs);
+int index_nonfinite_count(ddlo_cloud* c, int* count);
 
 // raw strided host points -> float4 (x, y, z, 1)
 __global__ void __launch_bounds__(256) k_repack(const unsigned char* __restrict__ raw, int n, int stride, float4* __restrict__ out) {
@@ -92,6 +93,7 @@ static void cloud_free(ddlo_cloud* c) {
   if (c->nodes) cudaFreeAsync(c->nodes, st);
   if (c->meta) cudaFreeAsync(c->meta, st);
   if (c->node_of_point) cudaFreeAsync(c->node_of_point, st);
+  if (c->lattice) cudaFreeAsync(c->lattice, st);
   delete c;
 }
 static void covs_free(ddlo_covs* v) {
@@ -390,6 +392,9 @@ int ddlo_cloud_knn(ddlo_cloud* c, const float* queries, int nq, int qstride_byte
   cudaFreeAsync(d_d2, st);
   DDLO_CUDA(cudaStreamSynchronize(st));
   if (rc != DDLO_OK) return rc;
+  int bad = 0;
+  DDLO_TRY(index_nonfinite_count(c, &bad));
+  if (bad) return fail(DDLO_E_NONFINITE, "kNN: the cloud holds NaN or Inf coordinates");
   if (counts)
     for (int i = 0; i < nq; ++i) counts[i] = std::min(k, c->n);
   return DDLO_OK;
@@ -793,6 +798,7 @@ static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, 
   DDLO_TRY(ensure_sorted_target_covs(g));
   a->tgt = g->tgt->view;
   a->src_pts = g->src->pts;
+  a->src_lattice = g->src->has_index ? g->src->lattice : nullptr;
   a->src_cov = g->src_cov->c;
   a->tgt_pts = g->tgt->pts;
   a->tgt_cov = g->tcov_sorted;
@@ -860,6 +866,7 @@ int ddlo_gicp_align_finish(ddlo_gicp* g, ddlo_align_result* result) {
   fill_result(static_cast<const AlignOut*>(rt->h_pinned), g->pending_covs_computed, result);
   std::memcpy(g->last_T, result->final_transformation, sizeof(g->last_T));
   g->has_last_T = true;
+  if (result->flags & DDLO_FLAG_NONFINITE) return fail(DDLO_E_NONFINITE, "align: an input cloud holds NaN or Inf coordinates");
   return DDLO_OK;
 }
 

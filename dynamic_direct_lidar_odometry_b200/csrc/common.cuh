@@ -59,10 +59,8 @@ struct IndexView {
   const float4* nodes;
   const int4* meta;          // per node: {parent id (-1 root), level, cell origin on the 10-bit lattice (x | y<<10 | z<<20), 0}
   const int* node_of_point;  // per ORIGINAL point index: the node whose leaf child holds the point
-  float lo[3];               // lattice origin and scale used for the Morton codes: u = (p - lo) * scale
-  float scale;
+  const float* lattice;      // device: {lo.x, lo.y, lo.z, scale} of the Morton lattice, u = (p - lo) * scale
   int n;
-  int n_nodes;
 };
 
 // 6 doubles per point: xx, xy, xz, yy, yz, zz (the 3x3 block of the reference's Matrix4d)
@@ -105,6 +103,7 @@ struct ddlo_cloud {
   float4* nodes = nullptr;  // octree nodes, kNodeF4 float4 each
   int4* meta = nullptr;
   int* node_of_point = nullptr;
+  float* lattice = nullptr;  // 4 floats + the node count (int) behind them
   ddlo::IndexView view{};
 };
 

@@ -517,7 +517,8 @@ __global__ void __launch_bounds__(kAlignThreads, kAlignBlocksPerSM) k_align(cons
     o->final_transformation[15] = 1.0f;
     for (int i = 0; i < 6; ++i)
       for (int j = 0; j < 6; ++j) o->final_hessian[6 * j + i] = s.final_H[6 * i + j];
-    o->flags = (s.converged ? DDLO_FLAG_CONVERGED : 0) | (s.lm_failed ? DDLO_FLAG_LM_FAILED : 0);
+    const bool bad = reinterpret_cast<const int*>(a.tgt.lattice)[4] != 0 || (a.src_lattice && reinterpret_cast<const int*>(a.src_lattice)[4] != 0);
+    o->flags = (s.converged ? DDLO_FLAG_CONVERGED : 0) | (s.lm_failed ? DDLO_FLAG_LM_FAILED : 0) | (bad ? DDLO_FLAG_NONFINITE : 0);
     o->nr_iterations = s.nr_iter;
     o->n_linearize = s.n_lin;
     o->n_compute_error = s.n_err;

@@ -25,6 +25,7 @@ struct AlignOut {
 struct GicpArgs {
   IndexView tgt;            // target kNN index (Morton-ordered points + box tree)
   const float4* src_pts;    // ns, original order
+  const float* src_lattice; // lattice record of the source index (non-finite counter at [4]) or nullptr
   const double* src_cov;    // ns * 6
   const float4* tgt_pts;    // nt, original order (compute_error gathers matched points here)
   const double* tgt_cov;    // nt * 6, MORTON order of the target index (gathers of neighbouring matches share DRAM pages)

@@ -315,10 +315,11 @@ struct Ball {  // the query and its radius on the lattice
 __device__ __forceinline__ Ball make_ball(const IndexView& ix, float qx, float qy, float qz, float worst) {
   Ball b;
   b.finite = worst < FLT_MAX;
-  b.ur = sqrtf(worst) * 1.00001f * ix.scale + 1e-3f;
-  b.u[0] = (qx - ix.lo[0]) * ix.scale;
-  b.u[1] = (qy - ix.lo[1]) * ix.scale;
-  b.u[2] = (qz - ix.lo[2]) * ix.scale;
+  const float4 lat = __ldg(reinterpret_cast<const float4*>(ix.lattice));
+  b.ur = sqrtf(worst) * 1.00001f * lat.w + 1e-3f;
+  b.u[0] = (qx - lat.x) * lat.w;
+  b.u[1] = (qy - lat.y) * lat.w;
+  b.u[2] = (qz - lat.z) * lat.w;
   return b;
 }
 __device__ __forceinline__ bool ball_in_cell(const Ball& b, const int4 m) {

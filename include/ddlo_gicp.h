@@ -56,7 +56,8 @@ enum { DDLO_OPT_GAUSS_NEWTON = 0, DDLO_OPT_LEVENBERG_MARQUARDT = 1 };
 enum {
   DDLO_FLAG_CONVERGED = 1,      /* converged_ (lsq_registration_impl.hpp:121) */
   DDLO_FLAG_LM_FAILED = 2,      /* step_lm ran out of trials: the reference prints "lm not converged!!" (:117) */
-  DDLO_FLAG_COVS_COMPUTED = 4   /* align had to compute missing covariances (nano_gicp_impl.hpp:186-193) */
+  DDLO_FLAG_COVS_COMPUTED = 4,  /* align had to compute missing covariances (nano_gicp_impl.hpp:186-193) */
+  DDLO_FLAG_NONFINITE = 8       /* an input cloud holds NaN/Inf coordinates: align returns DDLO_E_NONFINITE */
 };
 
 typedef struct ddlo_runtime ddlo_runtime; /* device + stream + scratch */
