@@ -84,12 +84,22 @@ class ClockSampler:
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            t0 = time.time()  # nvidia-smi needs a moment to attach: wait for its first line (bounded)
+            while time.time() - t0 < 3.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def mark(self):
+        """number of samples so far (to select the ones taken during the timed region)"""
+        try:
+            return sum(1 for _ in open(self.path))
+        except Exception:
+            return 0
+
+    def stop(self, first: int = 0):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if not self.proc:
             return out
@@ -100,7 +110,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         try:
-            for line in open(self.path):
+            for line in list(open(self.path))[first:]:
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
@@ -242,8 +252,12 @@ def run_ours(args):
         rt.synchronize()
 
     sampler = ClockSampler(local_rank)
+    first_sample = 0
     if rank == 0:
         sampler.start()
+        for _ in range(50):  # keep the GPU under load while the sampler spins up, so that its first samples are loaded ones
+            device_step(False)
+        first_sample = sampler.mark()
     launches0 = rt.launch_count()
     barrier()
     stage = []
@@ -261,7 +275,7 @@ def run_ours(args):
         dt, info_e, res = e2e_step()
         e2e_times.append(dt)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(first_sample) if rank == 0 else None
     e2e_total = sum(e2e_times)
 
     if dist is not None:
@@ -309,7 +323,7 @@ def run_ours(args):
             cpu_step(po, ceng, src, guess)
             ceng.clearSource()
             ct, n = 0.0, 0
-            while ct < 10.0 and n < 12:
+            while ct < 12.0 and n < 400:
                 dt, r = cpu_step(po, ceng, src, guess)
                 ceng.clearSource()
                 ct += dt
@@ -328,7 +342,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
