@@ -138,7 +138,11 @@ _lib = None
 
 
 def library_path() -> Path:
-    return _build.LIB_PATH
+    """The in-tree library; DDLO_GICP_LIB selects another build of the same sources (kernel tuning experiments)."""
+    import os
+
+    override = os.environ.get("DDLO_GICP_LIB")
+    return Path(override) if override else _build.LIB_PATH
 
 
 def load() -> C.CDLL:
@@ -164,6 +168,8 @@ def load() -> C.CDLL:
         fn.argtypes = args
     L.ddlo_gicp_debug_block_times.restype = C.c_int
     L.ddlo_gicp_debug_block_times.argtypes = [_vp, _vp, C.c_int]
+    L.ddlo_gicp_debug_visits.restype = C.c_int
+    L.ddlo_gicp_debug_visits.argtypes = [_vp, _vp, C.c_int]
     L.ddlo_gicp_debug_timeline.restype = C.c_int
     L.ddlo_gicp_debug_timeline.argtypes = [_vp, _vp, C.c_int]
     _lib = L

@@ -37,7 +37,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB_PATH
     LIB_DIR.mkdir(exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB_PATH), *[str(CSRC / s) for s in SOURCES]]
+    extra = os.environ.get("DDLO_NVCC_EXTRA", "").split()  # e.g. -DDDLO_VISIT_STATS for profiles/visit_stats.py
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", str(LIB_PATH), *[str(CSRC / s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

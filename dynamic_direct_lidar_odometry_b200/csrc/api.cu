@@ -128,6 +128,8 @@ struct ddlo_gicp {
   double* partials = nullptr;
   int partial_stride = 0;
   AlignOut* d_out = nullptr;
+  int4* d_dbg = nullptr;  // DDLO_VISIT_STATS builds only
+  int d_dbg_n = 0;
   unsigned long long* d_blk_times = nullptr;  // [8][partial_stride][4]
   float last_T[16];
   bool has_last_T = false;
@@ -818,6 +820,15 @@ static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, 
   a->lm_init_lambda_factor = g->p.lm_init_lambda_factor;
   a->out = g->d_out;
   a->blk_times = g->d_blk_times;
+  a->dbg_visits = nullptr;
+#ifdef DDLO_VISIT_STATS
+  if (g->d_dbg_n < g->src->n) {
+    if (g->d_dbg) cudaFree(g->d_dbg);
+    DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->d_dbg), (size_t)4 * g->src->n * sizeof(int4)));
+    g->d_dbg_n = g->src->n;
+  }
+  a->dbg_visits = g->d_dbg;
+#endif
   return DDLO_OK;
 }
 
@@ -1045,6 +1056,20 @@ int ddlo_gicp_debug_block_times(ddlo_gicp* g, unsigned long long* out, int capac
     DDLO_CUDA(cudaMemcpy(out + (size_t)p * capacity_blocks * 8, g->d_blk_times + (size_t)p * nb * 8, (size_t)nb * 8 * sizeof(unsigned long long),
                          cudaMemcpyDeviceToHost));
   return nb;
+}
+
+// DDLO_VISIT_STATS builds only: per source point {node visits, leaf scans, warp steps, 0} of the first 4
+// linearize passes of the last align, out[4][ns][4]; returns ns (0 in regular builds)
+int ddlo_gicp_debug_visits(ddlo_gicp* g, int* out, int capacity_points) {
+  if (!g || !out || !g->src) return fail(DDLO_E_INVALID, "null argument");
+#ifdef DDLO_VISIT_STATS
+  if (!g->d_dbg || capacity_points < g->src->n) return fail(DDLO_E_SIZE, "no statistics / capacity too small");
+  DDLO_CUDA(cudaStreamSynchronize(g->rt->stream));
+  DDLO_CUDA(cudaMemcpy(out, g->d_dbg, (size_t)4 * g->src->n * sizeof(int4), cudaMemcpyDeviceToHost));
+  return g->src->n;
+#else
+  return 0;
+#endif
 }
 
 // ---- host-callable copies of the device math (CPU tests of the exact code the kernels run) --------------

@@ -49,7 +49,10 @@ int fail(int code, const std::string& msg);
 //   meta / node_of_point let a search that already knows a nearby point of the cloud start deep in
 //   the tree instead of at the root (knn.cuh, ball_in_cell).
 // ---------------------------------------------------------------------------------------------
-constexpr int kLeafMax = 16;
+#ifndef DDLO_LEAF_MAX
+#define DDLO_LEAF_MAX 16
+#endif
+constexpr int kLeafMax = DDLO_LEAF_MAX;
 constexpr int kMortonLevels = 10;
 constexpr int kNodeF4 = 16;     // float4 per node
 constexpr int kStackDepth = 80; // pending internal children: <= 7 per level, <= 11 levels

@@ -6,13 +6,14 @@
 //   k_align                LsqRegistration::computeTransformation, step_lm, step_gn, is_converged
 //                                                    (lsq_registration_impl.hpp:96-232)
 //
-// k_align is ONE cooperative launch per align(), one 1024-thread block per SM.  A block owns a
-// contiguous slice of the source points.  Every outer iteration it runs
-//   phase A  1-NN of the moved source points in the target octree, one query per 8-lane sub-warp
-//            (knn.cuh), results parked in shared memory;
-//   phase B  one thread per point: Mahalanobis matrix, residual, the 28 sums of J^T M J / J^T M e /
-//            e^T M e, reduced warp -> block in fp64;
-// then a grid-wide reduction (per-block partials in L2, grid.sync, every block adds them in the
+// k_align is ONE cooperative launch per align(), one 1024-thread block per SM.  The source points
+// are dealt to the blocks 16 at a time.  Every outer iteration a block runs
+//   phase A  1-NN of the moved source points in the target octree, one query per PAIR of lanes
+//            (knn_pair.cuh), seeded with the previous iteration's match; pairs pull queries from a
+//            queue in shared memory and park the matches per slot;
+//   phase B  one thread per point: Mahalanobis matrix, residual, the 28 contributions to
+//            J^T M J / J^T M e / e^T M e in fp64, parked per slot in shared memory;
+// then adds the parked contributions in a fixed order, followed by a grid-wide reduction (per-block partials in L2, grid.sync, every block adds them in the
 // same fixed order), the 6x6 LM solve, and the trial-error passes, all without the host.  Every
 // block evaluates the (tiny) LM controller redundantly from identical sums, which keeps the
 // control flow uniform across the grid without a broadcast.  Reductions have a fixed order, so
@@ -21,13 +22,18 @@
 
 #include "gicp.cuh"
 #include "knn.cuh"
+#include "knn_pair.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace ddlo {
 
 constexpr int kAlignWarps = kAlignThreads / 32;
-constexpr int kAlignSubs = kAlignThreads / kSubLanes;
+constexpr int kAlignPairs = kAlignThreads / 2;  // source points (slots) of one round of a block
+#ifndef DDLO_SEARCH_WARPS
+#define DDLO_SEARCH_WARPS 32
+#endif
+constexpr int kSearchWarps = DDLO_SEARCH_WARPS;  // warps that search (16 queries in flight each, refilled from the round's queue)
 
 // sum layout: [0..5] H_rr upper, [6..14] H_rt row-major, [15..20] H_tt upper, [21..23] b_r,
 // [24..26] b_t, [27] sum of e^T M e
@@ -42,14 +48,15 @@ struct LmShared {
 
 // dynamic shared memory of the align / step kernels
 struct AlignSmem {
-  unsigned long long stacks[kAlignSubs * kStackDepth];
-  double red[kAlignWarps * kNumSums];
+  double contrib[kNumSums * kAlignPairs];  // [component][slot]: per-point contributions of the current round
+  float nn_d[kAlignPairs];                 // matches of the current round, parked per slot
+  int nn_idx[kAlignPairs];
+  int nn_pos[kAlignPairs];
+  int next;                                // phase A queue head
+  double red[kAlignWarps];
+  double acc[kNumSums];  // the block's sums over the rounds done so far
   double tot[kNumSums];
-  float nn_d[kAlignThreads];
-  int nn_idx[kAlignThreads];
-  int nn_pos[kAlignThreads];
-  int next;  // phase A work counter
-  unsigned long long t_search;  // %globaltimer when this block finished its last search phase (profiling)
+  unsigned long long t_search;  // %globaltimer when the last warp of this block finished its search (profiling)
   LmShared lm;
 };
 
@@ -104,62 +111,61 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Phase B for one point (called by all 32 lanes of a warp; `valid` lanes own a point): the
-// Mahalanobis matrix and the point's 28 contributions, summed over the warp into red_w[0..27].
+// Phase B for one point (one thread): the Mahalanobis matrix and the point's 28 contributions,
+// written to contrib[component * kAlignPairs].  Every slot of the round gets its column written
+// (zeros without a correspondence), so the block sum needs no mask.
 // Kept out of line so that its fp64 register appetite does not leak into the search loop.
 __device__ __noinline__ void lin_point(const GicpArgs& a, const LmShared& s, bool valid, int i, float nn_d, int nn_idx, int nn_pos,
-                                       double* __restrict__ red_w) {
-  double c[kNumSums];
-#pragma unroll
-  for (int k = 0; k < kNumSums; ++k) c[k] = 0.0;
+                                       double* __restrict__ contrib) {
+  int j = -1;
   if (valid) {
     a.sqd[i] = nn_d;
     const bool found = nn_idx != kIdxSentinel;
-    const int j = (found && (double)nn_d < a.thr2) ? nn_idx : -1;
+    j = (found && (double)nn_d < a.thr2) ? nn_idx : -1;
     a.corr[i] = j;
     // seed of the next search (kept even beyond the distance threshold): where the match sits in the
     // Morton order and the node above its leaf
     a.nn_seed[i] = found ? make_int2(nn_pos, __ldg(a.tgt.node_of_point + nn_idx)) : make_int2(-1, -1);
-    if (j >= 0) {
-      const float4 pa = __ldg(a.src_pts + i);
-      const float4 pb = __ldg(a.tgt.spts + nn_pos);
-      const Sym3 CA = load_sym3(a.src_cov + (size_t)i * kCovStride);
-      const Sym3 CB = load_sym3(a.tgt_cov + (size_t)nn_pos * kCovStride);
-      Sym3 RCR = sym3_rotate(s.x0.r, CA);
-      RCR.xx += CB.xx, RCR.xy += CB.xy, RCR.xz += CB.xz, RCR.yy += CB.yy, RCR.yz += CB.yz, RCR.zz += CB.zz;
-      const Sym3 M = sym3_inverse(RCR);
-      store_sym3(a.mahal + (size_t)i * kCovStride, M);
-
-      const double x = xform_d(s.x0.r + 0, s.x0.t[0], (double)pa.x, (double)pa.y, (double)pa.z);
-      const double y = xform_d(s.x0.r + 3, s.x0.t[1], (double)pa.x, (double)pa.y, (double)pa.z);
-      const double z = xform_d(s.x0.r + 6, s.x0.t[2], (double)pa.x, (double)pa.y, (double)pa.z);
-      const double ex = (double)pb.x - x, ey = (double)pb.y - y, ez = (double)pb.z - z;
-      double mex, mey, mez;
-      c[27] = quad_form(M, ex, ey, ez, mex, mey, mez);
-      // G = S^T M with S = skew(T p_A);  J = [S | -I]
-      const double g00 = z * M.xy - y * M.xz, g01 = z * M.yy - y * M.yz, g02 = z * M.yz - y * M.zz;
-      const double g10 = x * M.xz - z * M.xx, g11 = x * M.yz - z * M.xy, g12 = x * M.zz - z * M.xz;
-      const double g20 = y * M.xx - x * M.xy, g21 = y * M.xy - x * M.yy, g22 = y * M.xz - x * M.yz;
-      // H_rr = G S (symmetric)
-      c[0] = z * g01 - y * g02, c[1] = x * g02 - z * g00, c[2] = y * g00 - x * g01;
-      c[3] = x * g12 - z * g10, c[4] = y * g10 - x * g11, c[5] = y * g20 - x * g21;
-      // H_rt = -G
-      c[6] = -g00, c[7] = -g01, c[8] = -g02, c[9] = -g10, c[10] = -g11, c[11] = -g12, c[12] = -g20, c[13] = -g21, c[14] = -g22;
-      // H_tt = M
-      c[15] = M.xx, c[16] = M.xy, c[17] = M.xz, c[18] = M.yy, c[19] = M.yz, c[20] = M.zz;
-      // b_r = G e, b_t = -M e
-      c[21] = g00 * ex + g01 * ey + g02 * ez;
-      c[22] = g10 * ex + g11 * ey + g12 * ez;
-      c[23] = g20 * ex + g21 * ey + g22 * ez;
-      c[24] = -mex, c[25] = -mey, c[26] = -mez;
-    }
   }
-  const bool lane0 = (threadIdx.x & 31) == 0;
+  if (j < 0) {
 #pragma unroll
-  for (int k = 0; k < kNumSums; ++k) {
-    const double v = warp_sum(c[k]);
-    if (lane0) red_w[k] += v;
+    for (int k = 0; k < kNumSums; ++k) contrib[k * kAlignPairs] = 0.0;
+    return;
   }
+  const float4 pa = __ldg(a.src_pts + i);
+  const float4 pb = __ldg(a.tgt.spts + nn_pos);
+  const Sym3 CA = load_sym3(a.src_cov + (size_t)i * kCovStride);
+  const Sym3 CB = load_sym3(a.tgt_cov + (size_t)nn_pos * kCovStride);
+  Sym3 RCR = sym3_rotate(s.x0.r, CA);
+  RCR.xx += CB.xx, RCR.xy += CB.xy, RCR.xz += CB.xz, RCR.yy += CB.yy, RCR.yz += CB.yz, RCR.zz += CB.zz;
+  const Sym3 M = sym3_inverse(RCR);
+  store_sym3(a.mahal + (size_t)i * kCovStride, M);
+
+  const double x = xform_d(s.x0.r + 0, s.x0.t[0], (double)pa.x, (double)pa.y, (double)pa.z);
+  const double y = xform_d(s.x0.r + 3, s.x0.t[1], (double)pa.x, (double)pa.y, (double)pa.z);
+  const double z = xform_d(s.x0.r + 6, s.x0.t[2], (double)pa.x, (double)pa.y, (double)pa.z);
+  const double ex = (double)pb.x - x, ey = (double)pb.y - y, ez = (double)pb.z - z;
+  double mex, mey, mez;
+#define DDLO_C(k) contrib[(k) * kAlignPairs]
+  DDLO_C(27) = quad_form(M, ex, ey, ez, mex, mey, mez);
+  // G = S^T M with S = skew(T p_A);  J = [S | -I]
+  const double g00 = z * M.xy - y * M.xz, g01 = z * M.yy - y * M.yz, g02 = z * M.yz - y * M.zz;
+  const double g10 = x * M.xz - z * M.xx, g11 = x * M.yz - z * M.xy, g12 = x * M.zz - z * M.xz;
+  const double g20 = y * M.xx - x * M.xy, g21 = y * M.xy - x * M.yy, g22 = y * M.xz - x * M.yz;
+  // H_rr = G S (symmetric)
+  DDLO_C(0) = z * g01 - y * g02, DDLO_C(1) = x * g02 - z * g00, DDLO_C(2) = y * g00 - x * g01;
+  DDLO_C(3) = x * g12 - z * g10, DDLO_C(4) = y * g10 - x * g11, DDLO_C(5) = y * g20 - x * g21;
+  // H_rt = -G
+  DDLO_C(6) = -g00, DDLO_C(7) = -g01, DDLO_C(8) = -g02, DDLO_C(9) = -g10, DDLO_C(10) = -g11, DDLO_C(11) = -g12;
+  DDLO_C(12) = -g20, DDLO_C(13) = -g21, DDLO_C(14) = -g22;
+  // H_tt = M
+  DDLO_C(15) = M.xx, DDLO_C(16) = M.xy, DDLO_C(17) = M.xz, DDLO_C(18) = M.yy, DDLO_C(19) = M.yz, DDLO_C(20) = M.zz;
+  // b_r = G e, b_t = -M e
+  DDLO_C(21) = g00 * ex + g01 * ey + g02 * ez;
+  DDLO_C(22) = g10 * ex + g11 * ey + g12 * ez;
+  DDLO_C(23) = g20 * ex + g21 * ey + g22 * ez;
+  DDLO_C(24) = -mex, DDLO_C(25) = -mey, DDLO_C(26) = -mez;
+#undef DDLO_C
 }
 
 // one source point of compute_error: stored correspondence and Mahalanobis matrix, new transform
@@ -177,111 +183,162 @@ __device__ __forceinline__ double err_point(const GicpArgs& a, const Iso3& T, in
   return quad_form(M, ex, ey, ez, mx, my, mz);
 }
 
-// Work distribution.  The source points are dealt to the blocks four consecutive points at a time
-// (one query per sub-warp of a warp), round-robin, so that every block holds the same mix of cheap
-// and expensive queries and the blocks reach the grid barrier together.  Inside a block the warps
-// pull these groups of four from a shared counter, so a warp stuck on a long search does not hold
-// the others back.  Which warp serves a group never shows in the result: matches are parked per
-// slot and all sums are taken per slot in phase B, in a fixed order, so every bit of H, b and the
-// error is reproducible.
+// Work distribution.  The source points are dealt to the blocks sixteen consecutive points at a
+// time (the queries of one warp: neighbours in the scan, so their searches walk the same nodes),
+// round-robin, so that every block holds the same mix of cheap and expensive queries and the blocks
+// reach the grid barrier together.  The assignment is static and all sums are taken per slot in a
+// fixed order, so every bit of H, b and the error is reproducible run to run.
 struct Deal {
-  int nslots;  // slots of one block (multiple of 4)
+  int nslots;  // slots of one block (multiple of 16)
   int nb, b;
-  __device__ __forceinline__ int point(int slot) const { return (((slot >> 2) * nb + b) << 2) + (slot & 3); }
+  __device__ __forceinline__ int point(int slot) const { return (((slot >> 4) * nb + b) << 4) + (slot & 15); }
 };
 __device__ __forceinline__ Deal make_deal(int ns) {
   Deal d;
   d.nb = gridDim.x;
   d.b = blockIdx.x;
-  d.nslots = 4 * (((ns + 3) / 4 + d.nb - 1) / d.nb);
+  d.nslots = 16 * (((ns + 15) / 16 + d.nb - 1) / d.nb);
   return d;
 }
 
-// linearize over the block's points; leaves the block's 28 sums in dst[c * stride + blockIdx.x].
-// have_prev: nn_raw holds the matches of the previous linearize of the same source cloud.
-__device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm, bool have_prev, double* dst, int stride,
-                                                unsigned long long* bt = nullptr) {
-  const Sub sb = make_sub();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 3;
-  for (int k = lane; k < kNumSums; k += 32) sm.red[warp * kNumSums + k] = 0.0;
-  const Deal dl = make_deal(a.ns);
-  unsigned long long* stack = sm.stacks + (size_t)(threadIdx.x / kSubLanes) * kStackDepth;
-  for (int base = 0; base < dl.nslots; base += kAlignThreads) {
-    const int lim = min(dl.nslots, base + kAlignThreads);
-    const int n_items = (lim - base) >> 2;
-    if (threadIdx.x == 0) sm.next = 0;
-    __syncthreads();  // counter reset; nn_* of the previous pass fully consumed
-    // ---- phase A: update_correspondences' search, one query per sub-warp
-    for (;;) {
-      int item = 0;
-      if (lane == 0) item = atomicAdd(&sm.next, 1);
-      item = __shfl_sync(kFull, item, 0);
-      if (item >= n_items) break;
-      const int slot = base + (item << 2) + g;
-      const int i = dl.point(slot);
-      const bool active = i < a.ns;
-      float qx = 0.f, qy = 0.f, qz = 0.f;
-      int node = 0, skip = -1;
-      Best1Sub best;
-      if (active) {
-        const float4 pa = __ldg(a.src_pts + i);
-        qx = xform_f(sm.lm.Rf + 0, sm.lm.tf[0], pa.x, pa.y, pa.z);
-        qy = xform_f(sm.lm.Rf + 3, sm.lm.tf[1], pa.x, pa.y, pa.z);
-        qz = xform_f(sm.lm.Rf + 6, sm.lm.tf[2], pa.x, pa.y, pa.z);
-        const int2 sd = have_prev ? __ldcg(a.nn_seed + i) : make_int2(-1, -1);
-        if (sd.x >= 0) {
-          // The previous iteration's match is a real point of the target: its distance bounds the
-          // answer, and the search starts at the node above its leaf and climbs only while the
-          // ball of the best distance found so far sticks out of the node's cube.
-          const float4 t = __ldg(a.tgt.spts + sd.x);
-          best.seed(sqdist3_rn(qx, qy, qz, t.x, t.y, t.z), __float_as_int(t.w), sd.x);
-          node = sd.y;
+// Phase A of one round: update_correspondences' 1-NN search for the slots [base, base + nround) of
+// this block.  Executed by the first kSearchWarps warps.  A pair of lanes serves one query at a
+// time and fetches the next one from the round's queue (sm.next) as soon as it is done, so that a
+// long search holds back neither the other pairs of its warp nor the block.  Which pair serves a
+// slot never shows in the result: matches are parked per slot.
+__device__ __forceinline__ void search_round(const GicpArgs& a, AlignSmem& sm, const Deal& dl, int base, int nround, bool have_prev) {
+  const int lane = threadIdx.x & 31, h = lane & 1;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  Best1Pair best;
+  unsigned node = 0;   // node to visit next
+  unsigned start = 0;  // root of the subtree being searched
+  int skip = -1, t = -1, sp = 0;
+  bool run = false, sub_done = false, exhausted = false;
+  unsigned long long stk[kPairStack];
+#ifdef DDLO_VISIT_STATS
+  int n_vis = 0, n_steps = 0;
+#endif
+  for (;;) {
+    if (__any_sync(kFull, !run)) {
+      if (sub_done) {
+        // The subtree below `node` is searched.  Done if the ball of the best distance lies inside
+        // the node's cube (always true at the root); else continue with the rest of the parent.
+        sub_done = false;
+        const int4 m = __ldg(a.tgt.meta + start);
+        if (ball_in_cell(make_ball(a.tgt, qx, qy, qz, best.d), m)) {
+          if (h == 0) {
+            sm.nn_d[t] = best.d;
+            sm.nn_idx[t] = best.idx;
+            sm.nn_pos[t] = best.pos;
+#ifdef DDLO_VISIT_STATS
+            if (a.dbg_visits && sm.lm.n_lin < 4) a.dbg_visits[(size_t)sm.lm.n_lin * a.ns + dl.point(base + t)] = make_int4(n_vis, 0, n_steps, 0);
+#endif
+          }
+        } else {
+          skip = (int)start;
+          start = node = (unsigned)m.x;
+          sp = 0;
+          run = true;
         }
       }
-      bool going = active;
-      while (__any_sync(kFull, going)) {
-        knn_traverse_sub(a.tgt, going, qx, qy, qz, best, stack, sb, node, skip);
-        if (going) {
-          const int4 m = __ldg(a.tgt.meta + node);
-          if (ball_in_cell(make_ball(a.tgt, qx, qy, qz, best.d), m)) {
-            going = false;
+      const bool need = !run && !exhausted;
+      const unsigned nm = __ballot_sync(kFull, need && h == 0);
+      if (nm) {
+        const int leader = __ffs(nm) - 1;
+        int first = 0;
+        if (lane == leader) first = atomicAdd(&sm.next, __popc(nm));
+        first = __shfl_sync(kFull, first, leader);
+        if (need) {
+          t = first + __popc(nm & ((1u << (lane & ~1)) - 1u));
+          if (t >= nround) {
+            exhausted = true;
           } else {
-            skip = node;
-            node = m.x;
+            const int i = dl.point(base + t);
+            best = Best1Pair();
+            if (i < a.ns && a.tgt.n > 0) {
+              const float4 pa = __ldg(a.src_pts + i);
+              qx = xform_f(sm.lm.Rf + 0, sm.lm.tf[0], pa.x, pa.y, pa.z);
+              qy = xform_f(sm.lm.Rf + 3, sm.lm.tf[1], pa.x, pa.y, pa.z);
+              qz = xform_f(sm.lm.Rf + 6, sm.lm.tf[2], pa.x, pa.y, pa.z);
+              start = 0;
+              skip = -1;
+              sp = 0;
+              const int2 sd = have_prev ? __ldcg(a.nn_seed + i) : make_int2(-1, -1);
+              if (sd.x >= 0) {
+                // The previous iteration's match is a real point of the target: its distance bounds the
+                // answer, and the search starts at the node above its leaf and climbs only while the
+                // ball of the best distance found so far sticks out of the node's cube.
+                const float4 tp = __ldg(a.tgt.spts + sd.x);
+                best.seed(sqdist3_rn(qx, qy, qz, tp.x, tp.y, tp.z), __float_as_int(tp.w), sd.x);
+                start = (unsigned)sd.y;
+              }
+              node = start;
+              run = true;
+#ifdef DDLO_VISIT_STATS
+              n_vis = 0;
+              n_steps = 0;
+#endif
+            } else if (h == 0) {  // padding slot of the last group, or an empty target: no match
+              sm.nn_d[t] = FLT_MAX;
+              sm.nn_idx[t] = kIdxSentinel;
+              sm.nn_pos[t] = -1;
+            }
           }
         }
       }
-      if (active && sb.sl == 0) {
-        sm.nn_d[slot - base] = best.d;
-        sm.nn_idx[slot - base] = best.idx;
-        sm.nn_pos[slot - base] = best.pos;
-      }
     }
+    if (!__any_sync(kFull, run)) {
+      if (__all_sync(kFull, exhausted)) break;
+      continue;  // padding slots only: fetch again
+    }
+#ifdef DDLO_VISIT_STATS
+    n_vis += run ? 1 : 0;
+    n_steps += 1;
+#endif
+    const bool was = run;
+    nn1_visit_pair(a.tgt, run, qx, qy, qz, best, node, skip, stk, sp, h);
+    sub_done = was && !run;
+  }
+}
+
+// linearize over the block's points; leaves the block's 28 sums in dst[c * stride + blockIdx.x].
+// have_prev: nn_seed holds the matches of the previous linearize of the same source cloud.
+__device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm, bool have_prev, double* dst, int stride,
+                                                unsigned long long* bt = nullptr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < kNumSums) sm.acc[threadIdx.x] = 0.0;
+  const Deal dl = make_deal(a.ns);
+  for (int base = 0; base < dl.nslots; base += kAlignPairs) {
+    const int nround = min(kAlignPairs, dl.nslots - base);  // multiple of 16
+    if (threadIdx.x == 0) sm.next = 0;
+    __syncthreads();  // queue reset; parked matches and contrib of the previous round consumed; acc initialised
+    // ---- phase A
+    if (warp < kSearchWarps) search_round(a, sm, dl, base, nround, have_prev);
     __syncthreads();
     if (threadIdx.x == 0) sm.t_search = globaltimer_ns();
-    // ---- phase B: one thread per point
-    if (base + warp * 32 < lim) {
-      const int slot = base + threadIdx.x;
-      const int i = dl.point(slot);
-      const bool valid = slot < lim && i < a.ns;
+    // ---- phase B: one thread per point of the round
+    if (threadIdx.x < nround) {
+      const int i = dl.point(base + threadIdx.x);
       const unsigned long long t0 = globaltimer_ns();
-      lin_point(a, sm.lm, valid, i, valid ? sm.nn_d[threadIdx.x] : 0.f, valid ? sm.nn_idx[threadIdx.x] : kIdxSentinel,
-                valid ? sm.nn_pos[threadIdx.x] : -1, sm.red + warp * kNumSums);
+      lin_point(a, sm.lm, i < a.ns, i, sm.nn_d[threadIdx.x], sm.nn_idx[threadIdx.x], sm.nn_pos[threadIdx.x], sm.contrib + threadIdx.x);
       if (bt && lane == 0) {
         const unsigned long long dt = globaltimer_ns() - t0;
         atomicMax(bt + 4, dt);
         atomicMax(bt + 5, 0xffffffffull - dt);
       }
     }
+    __syncthreads();
+    // ---- block sum of this round, fixed order: warp c adds component c over the round's slots
+    if (warp < kNumSums) {
+      double v = 0.0;
+      for (int p = lane; p < nround; p += 32) v += sm.contrib[warp * kAlignPairs + p];
+      v = warp_sum(v);
+      if (lane == 0) sm.acc[warp] += v;
+    }
   }
   __syncthreads();
   if (bt && threadIdx.x == 0) bt[6] = globaltimer_ns();
-  if (threadIdx.x < kNumSums) {
-    double v = 0.0;
-    for (int w = 0; w < kAlignWarps; ++w) v += sm.red[w * kNumSums + threadIdx.x];
-    __stcg(dst + (size_t)threadIdx.x * stride + blockIdx.x, v);
-  }
+  if (threadIdx.x < kNumSums) __stcg(dst + (size_t)threadIdx.x * stride + blockIdx.x, sm.acc[threadIdx.x]);
   __syncthreads();
   if (bt && threadIdx.x == 0) bt[7] = globaltimer_ns();
 }
@@ -536,6 +593,7 @@ __global__ void __launch_bounds__(kAlignThreads, kAlignBlocksPerSM) k_linearize_
   if (threadIdx.x == 0) {
     iso_from_colmajor(a.T_step, sm.lm.x0);
     iso_to_float(sm.lm.x0, sm.lm.Rf, sm.lm.tf);
+    sm.lm.n_lin = 0;
   }
   __syncthreads();
   linearize_block(a, sm, false, a.partials, a.partial_stride);
@@ -610,7 +668,7 @@ int gicp_max_coop_blocks(int device, int* blocks_per_sm) {
 }
 
 int gicp_blocks_for(int ns, int max_blocks) {
-  const int want = (ns + kAlignSubs - 1) / kAlignSubs;  // at least one search round of work per block
+  const int want = (ns + 15) / 16;  // at least one group of 16 points per block
   return std::max(1, std::min(want, max_blocks));
 }
 

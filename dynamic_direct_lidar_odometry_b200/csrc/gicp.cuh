@@ -44,6 +44,7 @@ struct GicpArgs {
   float guess[16];          // column-major Eigen::Matrix4f
   double T_step[16];        // stepwise hooks: transform to evaluate at (column-major)
   AlignOut* out;
+  int4* dbg_visits;         // DDLO_VISIT_STATS builds only: [pass < 4][ns] {node visits, leaf scans, warp steps, 0}
   unsigned long long* blk_times;  // profiling: [pass < 8][block][8] %globaltimer at pass start / search done / phase B done / after grid sync, then max and (2^32-1 - min) lin_point duration
 };
 

@@ -35,8 +35,10 @@ __device__ __forceinline__ float sqdist3_rn(float qx, float qy, float qz, float 
 }
 
 __device__ __forceinline__ float axis_gap(float q, float lo, float hi) {
-  // q - lo (negative) below the box, q - hi (positive) above it, 0 inside; only the square is used
-  return q < lo ? __fsub_rn(q, lo) : (q > hi ? __fsub_rn(q, hi) : 0.0f);
+  // |q - lo| below the box, |q - hi| above it, 0 inside (only the square is used).  Branch-free:
+  // fl(lo - q) == -fl(q - lo) exactly, at most one of the two differences is positive, and an empty
+  // slot (lo = +inf, hi = -inf) gives +inf.
+  return fmaxf(fmaxf(__fsub_rn(lo, q), __fsub_rn(q, hi)), 0.0f);
 }
 
 __device__ __forceinline__ float box_bound_rn(float qx, float qy, float qz, float lx, float ly, float lz, float hx, float hy,

@@ -395,6 +395,16 @@ class NanoGICP:
         t0 = t[0][1] if t else 0
         return [(self.TIMELINE_TAGS.get(tag, str(tag)), (ns - t0) / 1e3) for tag, ns in t]
 
+    def debug_visits(self):
+        """(4, ns, 4) ints {node visits, leaf scans, warp steps, 0} per source point for the first 4 linearize passes;
+        None unless the library was built with -DDDLO_VISIT_STATS."""
+        n = self._src.size() if self._src is not None else 0
+        buf = np.zeros((4, max(n, 1), 4), dtype=np.int32)
+        got = B.load().ddlo_gicp_debug_visits(self._g, B.ptr(buf), n)
+        if got < 0:
+            B.check(got)
+        return buf if got > 0 else None
+
     def debug_block_times(self):
         """(passes<=8, blocks, 6) microseconds: pass start / search done / phase B done / after the grid sync / slowest and fastest lin_point call."""
         cap = 1024

@@ -20,6 +20,9 @@ struct ddlo_gicp;
 /* per-block phase times (ns) of the first 8 linearize passes: out[pass][capacity_blocks][8]; returns block count */
 int ddlo_gicp_debug_block_times(struct ddlo_gicp* g, unsigned long long* out, int capacity_blocks);
 int ddlo_gicp_debug_timeline(struct ddlo_gicp* g, unsigned long long* out, int capacity);
+/* builds with -DDDLO_VISIT_STATS only: search statistics of the first 4 linearize passes, out[4][ns][4] ints
+ * {node visits, leaf scans, lock-step warp steps, 0}; returns ns, or 0 in a regular build */
+int ddlo_gicp_debug_visits(struct ddlo_gicp* g, int* out, int capacity_points);
 #ifdef __cplusplus
 }
 #endif
