@@ -101,7 +101,7 @@ __device__ __forceinline__ double quad_form(const Sym3& M, double ex, double ey,
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");
   return t;
 }
 
@@ -307,15 +307,18 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
                                                 unsigned long long* bt = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < kNumSums) sm.acc[threadIdx.x] = 0.0;
+  if (threadIdx.x == 0) sm.t_search = 0ull;
   const Deal dl = make_deal(a.ns);
   for (int base = 0; base < dl.nslots; base += kAlignPairs) {
     const int nround = min(kAlignPairs, dl.nslots - base);  // multiple of 16
     if (threadIdx.x == 0) sm.next = 0;
     __syncthreads();  // queue reset; parked matches and contrib of the previous round consumed; acc initialised
     // ---- phase A
-    if (warp < kSearchWarps) search_round(a, sm, dl, base, nround, have_prev);
+    if (warp < kSearchWarps) {
+      search_round(a, sm, dl, base, nround, have_prev);
+      if (bt && lane == 0) atomicMax(&sm.t_search, globaltimer_ns());  // when the block's last warp left the search
+    }
     __syncthreads();
-    if (threadIdx.x == 0) sm.t_search = globaltimer_ns();
     // ---- phase B: one thread per point of the round
     if (threadIdx.x < nround) {
       const int i = dl.point(base + threadIdx.x);
