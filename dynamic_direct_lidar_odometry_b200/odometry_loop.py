@@ -1,0 +1,203 @@
+"""The caller side of the registration path, as OdomNode drives it (harness for config C3).
+
+This replays, around two NanoGICP engines, exactly the calls of
+    OdomNode::initializeInputTarget   odom.cc:480-516
+    OdomNode::setInputSources         odom.cc:518-532
+    OdomNode::scanMatching            odom.cc:745-793
+    OdomNode::propagateS2S / S2M      odom.cc:921-955
+    OdomNode::updateKeyframes         odom.cc:1067-1150
+    OdomNode::getSubmapKeyframes      odom.cc:1215-1315 (nearest-keyframe selection + concatenation)
+so that the sequence benchmark (benchmarks/c3_sequence.py) and the sequence parity test exercise the
+engine with the reference's own protocol: S2S align, covariance hand-over to S2M, swapSourceAndTarget,
+shared source index, keyframe covariances computed through the S2S source slot, submap clouds and
+covariances concatenated per selected keyframe and injected with setInputTarget/setTargetCovariances
+only when the selection changed.
+
+It is written against a tiny backend interface (`GpuBackend`: every cloud, covariance vector and submap
+stays on the device) so that the tests can replay the very same loop on their CPU checker with a
+backend of their own (tests/oracle_backend.py); this package has no CPU path.  Out of scope here, as in SURVEY.md §8: IMU prior, voxel filters,
+convex/concave-hull keyframe selection (only the k nearest keyframes are used), ROS I/O.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------- backends
+class GpuBackend:
+    """Clouds / covariances are device handles of the C ABI; nothing crosses PCIe except scans in and poses out."""
+
+    name = "gpu"
+
+    def __init__(self, rt):
+        from . import nano_gicp as ng
+
+        self.ng, self.rt = ng, rt
+
+    def cloud(self, points):
+        return self.ng.PointCloud(self.rt, points)
+
+    def transform(self, cloud, T):  # pcl::transformPointCloud
+        return cloud.transformed(np.asarray(T, dtype=np.float32))
+
+    def concat_clouds(self, parts):  # *submap_cloud += *keyframe
+        return self.ng.PointCloud.concat(self.rt, parts)
+
+    def concat_covs(self, parts):  # submap_normals_.insert(...)
+        return self.ng.Covariances.concat(self.rt, parts)
+
+    def engine(self):
+        return self.ng.NanoGICP(self.rt)
+
+    def share_source(self, s2m, s2s):  # odom.cc:527-531
+        s2m.source_kdtree_ = s2s.source_kdtree_
+        s2m.source_covs_ = None
+
+    def hand_over_source_covs(self, s2m, s2s):  # odom.cc:765
+        s2m.source_covs_ = s2s.source_covs_
+
+    def sync(self):
+        self.rt.synchronize()
+
+
+# ------------------------------------------------------------------------------------------- the loop
+@dataclass
+class LoopConfig:
+    k_correspondences_s2s: int = 20   # gicp_s2s kCorrespondences (engine default; the DLO yaml uses 10)
+    k_correspondences_s2m: int = 20
+    max_correspondence_distance: Optional[float] = None  # None = engine default (FLT_MAX)
+    max_iterations: int = 64
+    keyframe_thresh_dist: float = 1.0   # metres (odom.cc:1169, "rebuilt every 1 m" in SURVEY.md §8d C3)
+    keyframe_thresh_rot: float = 15.0   # degrees
+    submap_knn: int = 10                # odomNode/submap/keyframe/knn
+
+
+@dataclass
+class FrameRecord:
+    T_s2s: np.ndarray
+    T: np.ndarray
+    s2s_iterations: int
+    s2m_iterations: int
+    s2s_converged: bool
+    s2m_converged: bool
+    new_keyframe: bool
+    submap_changed: bool
+    submap_points: int
+    seconds: float
+    residual_mean: float
+
+
+@dataclass
+class Keyframe:
+    position: np.ndarray  # float32 xyz
+    rotation: np.ndarray  # 3x3 float32
+    cloud: object         # world-frame cloud (backend handle)
+    covs: object          # its covariances (backend handle)
+    n: int
+
+
+def _rot_angle_deg(Ra: np.ndarray, Rb: np.ndarray) -> float:
+    """angle of Ra * Rb^-1 in degrees (the quaternion formula of odom.cc:1105-1108, via the trace)"""
+    c = (np.trace(Ra.astype(np.float64) @ Rb.astype(np.float64).T) - 1.0) / 2.0
+    return math.degrees(math.acos(min(1.0, max(-1.0, c))))
+
+
+class OdometryLoop:
+    def __init__(self, backend, cfg: LoopConfig = LoopConfig()):
+        self.b, self.cfg = backend, cfg
+        self.s2s, self.s2m = backend.engine(), backend.engine()
+        for e, k in ((self.s2s, cfg.k_correspondences_s2s), (self.s2m, cfg.k_correspondences_s2m)):
+            e.setCorrespondenceRandomness(k)
+            e.setMaximumIterations(cfg.max_iterations)
+            if cfg.max_correspondence_distance is not None:
+                e.setMaxCorrespondenceDistance(cfg.max_correspondence_distance)
+        self.T = np.eye(4, dtype=np.float32)
+        self.T_s2s_prev = np.eye(4, dtype=np.float32)
+        self.keyframes: List[Keyframe] = []
+        self.submap_idx_prev: List[int] = []
+        self.records: List[FrameRecord] = []
+        self._initialised = False
+
+    # odom.cc:480-516
+    def _initialize_input_target(self, scan_cloud, n):
+        self.s2s.setInputTarget(scan_cloud)
+        self.s2s.calculateTargetCovariances()
+        first = self.b.transform(scan_cloud, self.T)
+        self.s2s.setInputSource(first)  # temporary storage, overwritten by the next setInputSources()
+        self.s2s.calculateSourceCovariances()
+        self.keyframes.append(Keyframe(self.T[:3, 3].copy(), self.T[:3, :3].copy(), first, self.s2s.getSourceCovariances(), n))
+        self._initialised = True
+
+    # odom.cc:1215-1315, nearest keyframes only
+    def _submap_selection(self, position) -> List[int]:
+        d = [float(np.sqrt(np.sum((position.astype(np.float32) - k.position) ** 2, dtype=np.float32))) for k in self.keyframes]
+        order = np.argsort(np.asarray(d), kind="stable")[: self.cfg.submap_knn]
+        kth = d[order[-1]]
+        return sorted(i for i, v in enumerate(d) if v <= kth)  # "all elements smaller or equal to the kth smallest"
+
+    # odom.cc:1067-1150
+    def _update_keyframes(self, scan_cloud, n) -> bool:
+        pos, rot = self.T[:3, 3], self.T[:3, :3]
+        d = [float(np.sqrt(np.sum((pos - k.position) ** 2, dtype=np.float32))) for k in self.keyframes]
+        closest = int(np.argmin(d))
+        num_nearby = sum(1 for v in d if v <= self.cfg.keyframe_thresh_dist * 1.5)
+        dd, theta = d[closest], _rot_angle_deg(rot, self.keyframes[closest].rotation)
+        new = dd > self.cfg.keyframe_thresh_dist or theta > self.cfg.keyframe_thresh_rot
+        if dd <= self.cfg.keyframe_thresh_dist:
+            new = False
+        if dd <= self.cfg.keyframe_thresh_dist and theta > self.cfg.keyframe_thresh_rot and num_nearby <= 1:
+            new = True
+        if new:
+            kf = self.b.transform(scan_cloud, self.T)
+            self.s2s.setInputSource(kf)
+            self.s2s.calculateSourceCovariances()
+            self.keyframes.append(Keyframe(pos.copy(), rot.copy(), kf, self.s2s.getSourceCovariances(), n))
+        return new
+
+    def step(self, scan_points: np.ndarray) -> Optional[FrameRecord]:
+        """One LiDAR frame (registration scan in the sensor frame, Nx4 float32)."""
+        t0 = time.perf_counter()
+        cur = self.b.cloud(scan_points)
+        n = len(scan_points)
+        if not self._initialised:
+            self._initialize_input_target(cur, n)
+            return None
+        # setInputSources (odom.cc:518-532)
+        self.s2s.setInputSource(cur)
+        self.s2m.registerInputSource(cur)
+        self.b.share_source(self.s2m, self.s2s)
+        # scanMatching (odom.cc:745-793)
+        r1 = self.s2s.align()
+        T_s2s = (self.T_s2s_prev @ r1.T.astype(np.float32)).astype(np.float32)  # propagateS2S
+        self.b.hand_over_source_covs(self.s2m, self.s2s)
+        self.s2s.swapSourceAndTarget()
+        sel = self._submap_selection(T_s2s[:3, 3])
+        changed = sel != self.submap_idx_prev
+        if changed:
+            submap = self.b.concat_clouds([self.keyframes[i].cloud for i in sel])
+            covs = self.b.concat_covs([self.keyframes[i].covs for i in sel])
+            self.s2m.setInputTarget(submap)
+            self.s2m.setTargetCovariances(covs)
+            self.submap_idx_prev = sel
+        r2 = self.s2m.align(T_s2s)
+        self.T = r2.T.astype(np.float32)
+        res = self.s2m.getResiduals()
+        self.T_s2s_prev = self.T.copy()  # odom.cc: T_s2s_prev_ = T_ after S2M
+        new_kf = self._update_keyframes(cur, n)
+        self.b.sync()
+        rec = FrameRecord(T_s2s, self.T.copy(), r1.iterations, r2.iterations, r1.converged, r2.converged, new_kf, changed,
+                          sum(self.keyframes[i].n for i in self.submap_idx_prev), time.perf_counter() - t0, float(np.mean(res)))
+        self.records.append(rec)
+        return rec
+
+
+def run_sequence(backend, scans: Sequence[np.ndarray], cfg: LoopConfig = LoopConfig()) -> OdometryLoop:
+    loop = OdometryLoop(backend, cfg)
+    for s in scans:
+        loop.step(s)
+    return loop

@@ -177,3 +177,8 @@ def workload_c2(n_target: int = 500_000, beams: int = 64, cols: int = 1024, src_
     tgt = submap(n_target, frames, beams, cols, w)
     src = scan(src_frame, beams, cols, w)
     return src, tgt, perturbed_guess(pose(src_frame))
+
+
+def workload_c4(n_target: int = 2_000_000, beams: int = 128, cols: int = 2048, src_frame: int = 50):
+    """C4: as C2 with an OS1-128-shaped 128x2048 scan (~262k points) against a 2M-point submap."""
+    return workload_c2(n_target, beams, cols, src_frame)

@@ -476,3 +476,81 @@ def test_cpp_shim_replays_odomnode_protocol(rt, tmp_path):
         res = s2m.getResiduals()
         n, total, n_out = got[("res", f)]
         assert n == len(res) == n_out and abs(total - res.sum()) <= 1e-9 * res.sum()
+
+
+def test_sequence_loop_matches_oracle(rt, oracle):
+    """Config C3 in small: the S2S -> S2M odometry loop with device-resident keyframes and submaps
+    (odometry_loop.py, the protocol of odom.cc:480-532, 745-793, 1067-1150, 1215-1315) against the same loop
+    on the oracle: same iteration counts, same keyframe decisions, poses within the north-star bar per frame."""
+    from dynamic_direct_lidar_odometry_b200 import odometry_loop as ol
+    from oracle_backend import OracleBackend
+
+    w = synth.make_world()
+    scans = [synth.scan(f, 16, 256, w) for f in range(12)]
+    cfg = ol.LoopConfig(k_correspondences_s2s=10, k_correspondences_s2m=10, keyframe_thresh_dist=0.5, submap_knn=3)
+    got = ol.run_sequence(ol.GpuBackend(rt), scans, cfg)
+    want = ol.run_sequence(OracleBackend(oracle), scans, cfg)
+    assert len(got.keyframes) == len(want.keyframes)
+    for g, o in zip(got.records, want.records):
+        assert (g.s2s_iterations, g.s2m_iterations) == (o.s2s_iterations, o.s2m_iterations)
+        assert (g.s2s_converged, g.s2m_converged, g.new_keyframe, g.submap_changed) == (o.s2s_converged, o.s2m_converged, o.new_keyframe, o.submap_changed)
+        assert g.submap_points == o.submap_points
+        assert np.abs(g.T[:3, 3].astype(np.float64) - o.T[:3, 3]).max() < POSE_T
+        assert rot_angle(g.T[:3, :3], o.T[:3, :3]) < POSE_R
+        assert abs(g.residual_mean - o.residual_mean) <= 1e-6 * max(1.0, abs(o.residual_mean))
+
+
+def test_c4_properties(rt):
+    """BASELINE config C4 (128x2048 scan vs 2M-point submap) at full size, through size-independent
+    properties: brute-force agreement on a sample of queries, self-match, sortedness, reproducibility of
+    the registration bit for bit, the right answer against ground truth, and a fixed point: restarting
+    from the converged pose converges immediately to the same pose."""
+    src, tgt, guess = synth.workload_c4()
+    assert len(src) > 250_000 and len(tgt) == 2_000_000
+    T = ng.PointCloud(rt, tgt).build_index()
+    # (1) exact kNN against a float32 brute force restated with the reference's expression tree
+    q = src[:: len(src) // 256][:256, :3]
+    idx, d2 = T.nearestKSearch(q, 5)
+    d = q[:, None, :] - tgt[None, :, :3]
+    bf = ((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]).astype(np.float32)
+    order = np.lexsort((np.broadcast_to(np.arange(len(tgt)), bf.shape), bf), axis=1)[:, :5]
+    assert np.array_equal(idx, order.astype(np.int32))
+    assert np.array_equal(d2.view(np.uint32), np.take_along_axis(bf, order, axis=1).view(np.uint32))
+    # (2) every point finds itself (or a duplicate with a smaller index) at distance 0
+    sample = np.random.default_rng(2).choice(len(tgt), 50000, replace=False)
+    sidx, sd2 = T.nearestKSearch(tgt[sample, :3], 1)
+    assert (sd2 == 0).all() and (sidx[:, 0] <= sample).all()
+    # (3) the registration: right answer, reproducible, fixed point
+    g = ng.NanoGICP(rt)
+    g.setInputSource(ng.PointCloud(rt, src))
+    g.setInputTarget(T)
+    r1 = g.align(guess)
+    r2 = g.align(guess)
+    assert r1.converged and np.array_equal(r1.T, r2.T) and np.array_equal(r1.hessian, r2.hessian)
+    gt = synth.pose(50)
+    assert np.abs(r1.T[:3, 3] - gt[:3, 3]).max() < 0.02
+    r3 = g.align(r1.T)
+    assert r3.converged and r3.iterations == 0
+    assert np.abs(r3.T[:3, 3] - r1.T[:3, 3]).max() < 5e-4  # inside the translation epsilon of the convergence test
+    # (4) residuals are the square roots of the stored squared distances, one per source point
+    res = g.getResiduals()
+    corr, sq = g.correspondences()
+    assert len(res) == len(src) and np.allclose(res, np.sqrt(sq.astype(np.float64)), rtol=0, atol=0)
+
+
+def test_c4_align_matches_oracle(rt, oracle):
+    """BASELINE config C4 end to end against the oracle (the CPU side needs ~10-20 s for the 2M-point submap):
+    same iteration counts, pose within the north-star bar, identical correspondences."""
+    src, tgt, guess = synth.workload_c4()
+    g = ng.NanoGICP(rt)
+    g.setInputSource(ng.PointCloud(rt, src))
+    g.setInputTarget(ng.PointCloud(rt, tgt))
+    o = oracle.NanoGICP()
+    o.setInputSource(oracle.Cloud(src))
+    o.setInputTarget(oracle.Cloud(tgt))
+    r, ro = g.align(guess), o.align(guess)
+    assert (r.converged, r.iterations, r.n_linearize, r.n_compute_error) == (ro.converged, ro.iterations, ro.n_linearize, ro.n_compute_error)
+    _check_pose(r, ro)
+    gc, gd = g.correspondences()
+    oc, od = o.correspondences()
+    assert np.array_equal(gc, oc) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
