@@ -83,6 +83,8 @@ SIGNATURES = {
     "ddlo_cloud_knn": [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp],
     "ddlo_cloud_transform": [_vp, _vp, _vpp],
     "ddlo_cloud_concat": [_vp, _vpp, C.c_int, _vpp],
+    "ddlo_cloud_voxel_filter": [_vp, C.c_float, C.c_float, C.c_float, _vpp],
+    "ddlo_cloud_crop_box": [_vp, _vp, _vp, C.c_int, C.c_int, _vpp],
     "ddlo_covs_compute": [_vp, C.c_int, C.c_int, _vpp],
     "ddlo_covs_from_host": [_vp, _vp, C.c_int, _vpp],
     "ddlo_covs_to_host": [_vp, _vp],

@@ -25,6 +25,9 @@ int build_index(ddlo_cloud* c);
 int launch_knn_queries(ddlo_cloud* c, const float4* d_queries, int nq, int k, int* d_idx, float* d_d2);
 int launch_covariances(ddlo_cloud* c, int k, int method, double* d_covs);
 int index_nonfinite_count(ddlo_cloud* c, int* count);
+int voxel_filter_device(ddlo_runtime* rt, const float4* pts, int n, const float leaf[3], float4** d_out, int* n_out);
+int crop_box_device(ddlo_runtime* rt, const float4* pts, int n, const float lo[3], const float hi[3], int negative, int keep_organized,
+                    float4** d_out, int* n_out);
 
 // raw strided host points -> float4 (x, y, z, 1)
 __global__ void __launch_bounds__(256) k_repack(const unsigned char* __restrict__ raw, int n, int stride, float4* __restrict__ out) {
@@ -417,6 +420,41 @@ int ddlo_cloud_transform(ddlo_cloud* c, const float* T16, ddlo_cloud** out) {
   }
   *out = r;
   return DDLO_OK;
+}
+
+// a cloud handle around a device buffer that is already filled (takes ownership)
+static int cloud_adopt(ddlo_runtime* rt, float4* pts, int n, ddlo_cloud** out) {
+  ddlo_cloud* c = new (std::nothrow) ddlo_cloud();
+  if (!c) {
+    cudaFreeAsync(pts, rt->stream);
+    return fail(DDLO_E_INVALID, "out of host memory");
+  }
+  c->rt = rt;
+  c->n = n;
+  c->pts = pts;
+  *out = c;
+  return DDLO_OK;
+}
+
+int ddlo_cloud_voxel_filter(ddlo_cloud* c, float leaf_x, float leaf_y, float leaf_z, ddlo_cloud** out) {
+  if (!c || !out) return fail(DDLO_E_INVALID, "null argument");
+  *out = nullptr;
+  DDLO_TRY(use_device(c->rt));
+  const float leaf[3] = {leaf_x, leaf_y, leaf_z};
+  float4* d = nullptr;
+  int n = 0;
+  DDLO_TRY(voxel_filter_device(c->rt, c->pts, c->n, leaf, &d, &n));
+  return cloud_adopt(c->rt, d, n, out);
+}
+
+int ddlo_cloud_crop_box(ddlo_cloud* c, const float* min_xyz, const float* max_xyz, int negative, int keep_organized, ddlo_cloud** out) {
+  if (!c || !min_xyz || !max_xyz || !out) return fail(DDLO_E_INVALID, "null argument");
+  *out = nullptr;
+  DDLO_TRY(use_device(c->rt));
+  float4* d = nullptr;
+  int n = 0;
+  DDLO_TRY(crop_box_device(c->rt, c->pts, c->n, min_xyz, max_xyz, negative, keep_organized, &d, &n));
+  return cloud_adopt(c->rt, d, n, out);
 }
 
 int ddlo_cloud_concat(ddlo_runtime* rt, ddlo_cloud* const* parts, int m, ddlo_cloud** out) {

@@ -1,7 +1,10 @@
-// Exact 1-nearest-neighbour search in the Morton-prefix octree, one query per PAIR of lanes.
+// Exact nearest-neighbour search in the Morton-prefix octree, one query per PAIR of lanes.
 //
 // Used by update_correspondences (nano_gicp_impl.hpp:235-275 -> nanoflann_impl.hpp:1365-1384,
-// 1495-1566 with k = 1).  knn.cuh serves a query with 8 lanes, one child box per lane; here a query
+// 1495-1566 with k = 1, result set Best1Pair).  (A k = 20 result set over two lanes was tried for
+// the covariances' self k-NN and lost to the 8-lane one of knn.cuh: with 16 queries behind a warp
+// instruction some query accepts a candidate at nearly every step, so the insertion network runs all
+// the time at low utilisation.)  knn.cuh serves a query with 8 lanes, one child box per lane; here a query
 // owns 2 lanes and every lane bounds 4 children with 128-bit loads.  A warp therefore carries 16
 // queries instead of 4, so that all the source points of one SM (about 443 on the 64x1024 scan) are
 // in flight at once, and the bookkeeping instructions (votes, shuffles, stack handling), which cost
@@ -73,7 +76,8 @@ __device__ __forceinline__ int sel4(const int (&a)[4], int c) { return c == 0 ? 
 // `run`, the query, rs, node and skip are uniform per pair; stk/sp are the lane's own pending
 // children.  `skip` (or -1) is a child NODE of the subtree's start node that has been searched
 // already.  On return `node` is the next node to visit, or run == false when the subtree is done.
-__device__ __forceinline__ void nn1_visit_pair(const IndexView& ix, bool& run, float qx, float qy, float qz, Best1Pair& rs, unsigned& node,
+template <class RS>
+__device__ __forceinline__ void nn1_visit_pair(const IndexView& ix, bool& run, float qx, float qy, float qz, RS& rs, unsigned& node,
                                                int skip, unsigned long long* __restrict__ stk, int& sp, int h) {
   const float inf = __int_as_float(0x7f800000);
   float b[4] = {inf, inf, inf, inf};
@@ -160,7 +164,8 @@ __device__ __forceinline__ void nn1_visit_pair(const IndexView& ix, bool& run, f
 
 // Depth-first search below node `start` by a pair of lanes.  MUST be called by all 32 lanes;
 // `active`, the query and rs are uniform per pair.
-__device__ __forceinline__ void nn1_traverse_pair(const IndexView& ix, bool active, float qx, float qy, float qz, Best1Pair& rs,
+template <class RS>
+__device__ __forceinline__ void nn1_traverse_pair(const IndexView& ix, bool active, float qx, float qy, float qz, RS& rs,
                                                   int start = 0, int skip = -1) {
   const int h = threadIdx.x & 1;
   unsigned long long stk[kPairStack];

@@ -144,6 +144,21 @@ class PointCloud:
         B.check(B.load().ddlo_cloud_transform(self._h, B.ptr(t), C.byref(h)))
         return PointCloud(self.rt, _handle=h)
 
+    def voxel_filtered(self, leaf) -> "PointCloud":
+        """pcl::VoxelGrid with setLeafSize(leaf, leaf, leaf) (or a 3-tuple), on the device (odom.cc:469-474)."""
+        lx, ly, lz = (leaf, leaf, leaf) if np.isscalar(leaf) else leaf
+        h = C.c_void_p()
+        B.check(B.load().ddlo_cloud_voxel_filter(self._h, float(lx), float(ly), float(lz), C.byref(h)))
+        return PointCloud(self.rt, _handle=h)
+
+    def cropped(self, box_min, box_max, negative: bool = False, keep_organized: bool = False) -> "PointCloud":
+        """pcl::CropBox with setMin/setMax (and setNegative / setKeepOrganized), on the device (odom.cc:459-465)."""
+        lo = np.ascontiguousarray(box_min, dtype=np.float32)
+        hi = np.ascontiguousarray(box_max, dtype=np.float32)
+        h = C.c_void_p()
+        B.check(B.load().ddlo_cloud_crop_box(self._h, B.ptr(lo), B.ptr(hi), int(negative), int(keep_organized), C.byref(h)))
+        return PointCloud(self.rt, _handle=h)
+
     @staticmethod
     def concat(rt: Runtime, parts: Sequence["PointCloud"]) -> "PointCloud":
         arr = (C.c_void_p * len(parts))(*[p._h for p in parts])

@@ -136,6 +136,17 @@ int ddlo_cloud_transform(ddlo_cloud* c, const float* T16, ddlo_cloud** out);
 /* concatenation of m clouds (device-side `*submap_cloud_ += *keyframe`, odom.cc:1298-1313) */
 int ddlo_cloud_concat(ddlo_runtime* rt, ddlo_cloud* const* parts, int m, ddlo_cloud** out);
 
+/* Scan preprocessing on the device (the filters OdomNode::preprocessPoints runs right
+ * before this path, odom.cc:442-478, and on every new keyframe, odom.cc:494-499, 1133-1137).
+ * pcl::VoxelGrid<PointXYZI>::filter with setLeafSize(lx, ly, lz): one centroid per occupied voxel, voxels in
+ * ascending index order, non-finite points dropped.  DDLO_E_UNSUPPORTED when the voxel index space does not fit
+ * an int (PCL prints "Leaf size is too small for the input dataset" and passes the cloud through). */
+int ddlo_cloud_voxel_filter(ddlo_cloud* c, float leaf_x, float leaf_y, float leaf_z, ddlo_cloud** out);
+/* pcl::CropBox<PointXYZI>::filter with setMin/setMax (identity box pose): keeps the points inside the box, or
+ * outside with negative != 0 (setNegative); keep_organized != 0 (setKeepOrganized) keeps the size and order and
+ * overwrites removed points with NaN. */
+int ddlo_cloud_crop_box(ddlo_cloud* c, const float* min_xyz, const float* max_xyz, int negative, int keep_organized, ddlo_cloud** out);
+
 /* ---- covariances: std::vector<Eigen::Matrix4d> ---------------------------------------------------- */
 /* NanoGICP::calculate_covariances (nano_gicp_impl.hpp:374-441); builds the index if missing. */
 int ddlo_covs_compute(ddlo_cloud* c, int k, int regularization_method, ddlo_covs** out);

@@ -41,6 +41,7 @@
 #include <limits>
 #include <memory>
 #include <numeric>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -1021,6 +1022,88 @@ int oracle_gicp_get_residual_vectors(void* g, const float* T16, float* out3) {
     for (int a = 0; a < 3; ++a) out3[3 * i + a] = e->target->xyzw[4 * (size_t)ti + a] - q[a];
   }
   return n;
+}
+
+// ---- preprocessing filters ------------------------------------------------------
+// pcl::VoxelGrid<PointXYZI>::applyFilter, PCL 1.10 filters/impl/voxel_grid.hpp (PCL is a system dependency
+// of the reference, R/CMakeLists.txt:8, not vendored: its published algorithm is restated).  Used by
+// OdomNode at odom.cc:469-474, 494-499, 1133-1137.  std::sort's order inside a voxel is unspecified in
+// PCL; this restatement uses a stable sort (original order), one of its valid outcomes.
+// Returns the number of output points, -1 if the index space would overflow an int (PCL warns and
+// passes the input through), -2 on bad arguments.  out_xyzw needs room for n points.
+int oracle_voxel_filter(const float* xyz, int n, int stride_floats, float lx, float ly, float lz, float* out_xyzw) {
+  if (!(lx > 0 && ly > 0 && lz > 0) || n < 0) return -2;
+  const float inv[3] = {1.0f / lx, 1.0f / ly, 1.0f / lz};
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int finite = 0;
+  for (int i = 0; i < n; ++i) {
+    const float* p = xyz + (size_t)i * stride_floats;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = std::min(lo[a], p[a]);
+      hi[a] = std::max(hi[a], p[a]);
+    }
+    ++finite;
+  }
+  if (!finite) return 0;
+  int min_b[3];
+  long long div[3];
+  for (int a = 0; a < 3; ++a) {
+    min_b[a] = static_cast<int>(std::floor(lo[a] * inv[a]));
+    const int max_b = static_cast<int>(std::floor(hi[a] * inv[a]));
+    div[a] = (long long)max_b - min_b[a] + 1;
+  }
+  if (div[0] * div[1] * div[2] > (long long)std::numeric_limits<int>::max()) return -1;
+  const int mul[3] = {1, (int)div[0], (int)(div[0] * div[1])};
+  std::vector<std::pair<unsigned, int>> order;
+  order.reserve(finite);
+  for (int i = 0; i < n; ++i) {
+    const float* p = xyz + (size_t)i * stride_floats;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    const int i0 = static_cast<int>(std::floor(p[0] * inv[0]) - static_cast<float>(min_b[0]));
+    const int i1 = static_cast<int>(std::floor(p[1] * inv[1]) - static_cast<float>(min_b[1]));
+    const int i2 = static_cast<int>(std::floor(p[2] * inv[2]) - static_cast<float>(min_b[2]));
+    order.emplace_back((unsigned)(i0 * mul[0] + i1 * mul[1] + i2 * mul[2]), i);
+  }
+  std::stable_sort(order.begin(), order.end(), [](const std::pair<unsigned, int>& a, const std::pair<unsigned, int>& b) { return a.first < b.first; });
+  int n_out = 0;
+  for (size_t s = 0; s < order.size();) {
+    size_t e = s;
+    float sum[3] = {0.0f, 0.0f, 0.0f};
+    while (e < order.size() && order[e].first == order[s].first) {
+      const float* p = xyz + (size_t)order[e].second * stride_floats;
+      for (int a = 0; a < 3; ++a) sum[a] += p[a];
+      ++e;
+    }
+    const float cnt = static_cast<float>(e - s);
+    for (int a = 0; a < 3; ++a) out_xyzw[4 * n_out + a] = sum[a] / cnt;
+    out_xyzw[4 * n_out + 3] = 1.0f;
+    ++n_out;
+    s = e;
+  }
+  return n_out;
+}
+
+// pcl::CropBox<PointXYZI>::applyFilter (filters/impl/crop_box.hpp) with an identity box pose; used at
+// odom.cc:459-465.  keep_organized: same size, removed points become NaN.  Returns the output size.
+int oracle_crop_box(const float* xyz, int n, int stride_floats, const float* lo, const float* hi, int negative, int keep_organized,
+                    float* out_xyzw) {
+  int n_out = 0;
+  const float nan = std::numeric_limits<float>::quiet_NaN();
+  for (int i = 0; i < n; ++i) {
+    const float* p = xyz + (size_t)i * stride_floats;
+    bool keep = false;
+    if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) {
+      const bool outside = (p[0] < lo[0] || p[1] < lo[1] || p[2] < lo[2]) || (p[0] > hi[0] || p[1] > hi[1] || p[2] > hi[2]);
+      keep = negative ? outside : !outside;
+    }
+    if (keep || keep_organized) {
+      for (int a = 0; a < 3; ++a) out_xyzw[4 * n_out + a] = keep ? p[a] : nan;
+      out_xyzw[4 * n_out + 3] = 1.0f;
+      ++n_out;
+    }
+  }
+  return n_out;
 }
 
 }  // extern "C"

@@ -104,6 +104,8 @@ def lib() -> C.CDLL:
         "oracle_gicp_get_mahalanobis": (ci, [vp, _f64p]),
         "oracle_gicp_get_residuals": (ci, [vp, _f64p]),
         "oracle_gicp_get_residual_vectors": (ci, [vp, _f32p, _f32p]),
+        "oracle_voxel_filter": (ci, [_f32p, ci, ci, C.c_float, C.c_float, C.c_float, _f32p]),
+        "oracle_crop_box": (ci, [_f32p, ci, ci, _f32p, _f32p, ci, ci, _f32p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -174,6 +176,27 @@ class Cloud:
         if lib().oracle_cloud_covariances(self._h, k, method, out.reshape(-1), threads) != 0:
             raise RuntimeError("covariances failed (no tree, or fewer than k points)")
         return out
+
+
+def voxel_filter(points, leaf) -> np.ndarray:
+    """pcl::VoxelGrid restated (oracle_gicp.cpp oracle_voxel_filter): (m, 4) float32 centroids, ascending voxel index."""
+    p = _as_points(points)
+    lx, ly, lz = (leaf, leaf, leaf) if np.isscalar(leaf) else leaf
+    out = np.empty((max(p.shape[0], 1), 4), dtype=np.float32)
+    m = lib().oracle_voxel_filter(p, p.shape[0], p.shape[1], float(lx), float(ly), float(lz), out)
+    if m < 0:
+        raise OverflowError("leaf size too small for the input dataset" if m == -1 else "bad arguments")
+    return out[:m].copy()
+
+
+def crop_box(points, box_min, box_max, negative: bool = False, keep_organized: bool = False) -> np.ndarray:
+    """pcl::CropBox restated (oracle_gicp.cpp oracle_crop_box)."""
+    p = _as_points(points)
+    lo = np.ascontiguousarray(box_min, dtype=np.float32)
+    hi = np.ascontiguousarray(box_max, dtype=np.float32)
+    out = np.empty((max(p.shape[0], 1), 4), dtype=np.float32)
+    m = lib().oracle_crop_box(p, p.shape[0], p.shape[1], lo, hi, int(negative), int(keep_organized), out)
+    return out[:m].copy()
 
 
 def knn_bruteforce(points, queries, k: int):

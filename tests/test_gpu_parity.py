@@ -6,6 +6,7 @@ covariances, H and b within 1e-6 relative; converged poses within 1e-5 m and 1e-
 import numpy as np
 import pytest
 
+from dynamic_direct_lidar_odometry_b200 import binding as B
 from dynamic_direct_lidar_odometry_b200 import nano_gicp as ng
 from dynamic_direct_lidar_odometry_b200 import synth
 
@@ -554,3 +555,51 @@ def test_c4_align_matches_oracle(rt, oracle):
     gc, gd = g.correspondences()
     oc, od = o.correspondences()
     assert np.array_equal(gc, oc) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+
+
+# --------------------------------------------------------------- preprocessing filters
+@pytest.mark.parametrize("leaf", [0.25, 0.5])
+def test_voxel_filter_bit_exact(rt, oracle, leaf):
+    """pcl::VoxelGrid on the device against the oracle's restatement: same voxels, same order, same float
+    centroids bit for bit (both add the points of a voxel in their original order), NaN points dropped."""
+    scan = synth.scan(3, 64, 1024).copy()
+    scan[::97, 0] = np.nan  # what CropBox::setKeepOrganized leaves behind (odom.cc:461-464)
+    got = ng.PointCloud(rt, scan).voxel_filtered(leaf).download()
+    want = oracle.voxel_filter(scan, leaf)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # registering the filtered clouds still works and agrees with the oracle (config C1, "0.25 m voxel" variant)
+    if leaf == 0.25:
+        tgt = synth.scan(2, 64, 1024)
+        tf = ng.PointCloud(rt, tgt).voxel_filtered(leaf)
+        sf = ng.PointCloud(rt, scan).voxel_filtered(leaf)
+        g = ng.NanoGICP(rt)
+        g.setInputSource(sf)
+        g.setInputTarget(tf)
+        o = oracle.NanoGICP()
+        o.setInputSource(oracle.Cloud(want))
+        o.setInputTarget(oracle.Cloud(oracle.voxel_filter(tgt, leaf)))
+        r, ro = g.align(), o.align()
+        assert (r.converged, r.iterations) == (ro.converged, ro.iterations)
+        _check_pose(r, ro)
+
+
+def test_voxel_filter_edges_and_crop_box(rt, oracle):
+    empty = ng.PointCloud(rt, np.zeros((0, 4), np.float32)).voxel_filtered(0.5)
+    assert empty.size() == 0
+    with pytest.raises(B.DdloError) as e:
+        ng.PointCloud(rt, np.array([[0, 0, 0, 1], [1e4, 1e4, 1e4, 1]], np.float32)).voxel_filtered(1e-3)
+    assert e.value.code == -8
+    scan = synth.scan(1, 64, 1024)
+    lo, hi = np.array([-3.0, -3.0, -3.0], np.float32), np.array([3.0, 3.0, 3.0], np.float32)
+    c = ng.PointCloud(rt, scan)
+    for neg in (False, True):
+        got = c.cropped(lo, hi, negative=neg).download()
+        assert np.array_equal(got.view(np.uint32), oracle.crop_box(scan, lo, hi, negative=neg).view(np.uint32))
+    org = c.cropped(lo, hi, negative=True, keep_organized=True).download()
+    want = oracle.crop_box(scan, lo, hi, negative=True, keep_organized=True)
+    assert org.shape == want.shape and np.array_equal(np.isnan(org), np.isnan(want))
+    assert np.array_equal(org[~np.isnan(org)], want[~np.isnan(want)])
+    # the reference's order of filters: crop (organised, NaN) then voxel grid
+    both = c.cropped(lo, hi, negative=True, keep_organized=True).voxel_filtered(0.5).download()
+    assert np.array_equal(both.view(np.uint32), oracle.voxel_filter(want, 0.5).view(np.uint32))
