@@ -119,6 +119,7 @@ SIGNATURES = {
     "ddlo_gicp_get_correspondences": [_vp, _vp, _vp, C.c_int],
     "ddlo_gicp_get_mahalanobis": [_vp, _vp, C.c_int],
     "ddlo_gicp_get_residuals": [_vp, _vp, C.c_int],
+    "ddlo_gicp_get_residuals_async": [_vp, _vp, C.c_int],
     "ddlo_gicp_get_residual_vectors": [_vp, _vp, _vp, C.c_int],
     "ddlo_gicp_align_batch": [_vpp, C.c_int, _vp, C.POINTER(AlignResult)],
 }

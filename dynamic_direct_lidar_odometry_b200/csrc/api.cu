@@ -1038,7 +1038,7 @@ int ddlo_gicp_get_mahalanobis(ddlo_gicp* g, double* mat4x4_out, int capacity) {
   return DDLO_OK;
 }
 
-int ddlo_gicp_get_residuals(ddlo_gicp* g, double* out, int capacity) {
+int ddlo_gicp_get_residuals_async(ddlo_gicp* g, double* out, int capacity) {
   if (!g || !out) return fail(DDLO_E_INVALID, "null argument");
   if (!g->src || g->corr_n != g->src->n) return fail(DDLO_E_NOT_READY, "no residuals: run align first");
   if (capacity < g->corr_n) return fail(DDLO_E_SIZE, "output capacity is smaller than the source cloud");
@@ -1052,7 +1052,12 @@ int ddlo_gicp_get_residuals(ddlo_gicp* g, double* out, int capacity) {
   DDLO_CUDA(cudaGetLastError());
   DDLO_CUDA(cudaMemcpyAsync(out, d_r, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, rt->stream));
   DDLO_CUDA(cudaFreeAsync(d_r, rt->stream));
-  DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+  return DDLO_OK;
+}
+
+int ddlo_gicp_get_residuals(ddlo_gicp* g, double* out, int capacity) {
+  DDLO_TRY(ddlo_gicp_get_residuals_async(g, out, capacity));
+  DDLO_CUDA(cudaStreamSynchronize(g->rt->stream));
   return DDLO_OK;
 }
 

@@ -479,6 +479,13 @@ class NanoGICP:
         B.check(B.load().ddlo_gicp_get_residuals(self._g, B.ptr(out), n))
         return out
 
+    def getResidualsAsync(self, out: np.ndarray) -> None:
+        """Enqueue getResiduals into `out` (float64, ideally from pinned_array); complete after the next
+        align_finish() / Runtime.synchronize().  Lets pose and residuals share one host round trip."""
+        if out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 array")
+        B.check(B.load().ddlo_gicp_get_residuals_async(self._g, B.ptr(out), out.size))
+
     def getResidualVectors(self, T) -> np.ndarray:
         """getResiduals(std::vector<Eigen::Vector3f>&, trans)."""
         n = self._src.size()

@@ -208,6 +208,11 @@ int ddlo_gicp_get_correspondences(ddlo_gicp* g, int* correspondences, float* sq_
 int ddlo_gicp_get_mahalanobis(ddlo_gicp* g, double* mat4x4_out, int capacity);
 /* getResiduals(std::vector<double>&, trans) (:225-232): sqrt(sq_distances_) of the last linearize */
 int ddlo_gicp_get_residuals(ddlo_gicp* g, double* out, int capacity);
+/* The same without a synchronisation of its own: the conversion and the copy are only enqueued on the runtime's
+ * stream, and `out` is complete after the next synchronising call (ddlo_gicp_align_finish, ddlo_runtime_synchronize).
+ * Between ddlo_gicp_align_async and ddlo_gicp_align_finish this makes pose and residuals cost one host round trip.
+ * Meant for page-locked `out` (ddlo_host_alloc); with pageable memory the copy itself blocks. */
+int ddlo_gicp_get_residuals_async(ddlo_gicp* g, double* out, int capacity);
 /* getResiduals(std::vector<Eigen::Vector3f>&, trans) (:199-222) */
 int ddlo_gicp_get_residual_vectors(ddlo_gicp* g, const float* T16, float* out_xyz, int capacity);
 

@@ -603,3 +603,18 @@ def test_voxel_filter_edges_and_crop_box(rt, oracle):
     # the reference's order of filters: crop (organised, NaN) then voxel grid
     both = c.cropped(lo, hi, negative=True, keep_organized=True).voxel_filtered(0.5).download()
     assert np.array_equal(both.view(np.uint32), oracle.voxel_filter(want, 0.5).view(np.uint32))
+
+
+def test_residuals_async_equals_sync(rt, small_pair):
+    """ddlo_gicp_get_residuals_async between align_async and align_finish: one host round trip, same numbers."""
+    src, tgt = small_pair
+    g = ng.NanoGICP(rt)
+    g.setInputSource(ng.PointCloud(rt, src))
+    g.setInputTarget(ng.PointCloud(rt, tgt))
+    out = ng.pinned_array((len(src),), np.float64)
+    out[:] = -1.0
+    g.align_async()
+    g.getResidualsAsync(out)
+    info = g.align_finish()
+    assert info.converged
+    assert np.array_equal(out, g.getResiduals())
