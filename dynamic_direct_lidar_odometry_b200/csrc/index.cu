@@ -201,9 +201,16 @@ __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys,
     o[2] = o[5] = f2ord(p.z);
   }
   const int Lmax = __reduce_max_sync(0xffffffffu, L);
-  for (int t = 1; t <= Lmax; ++t) {
+  // the node ids of the point's cells on all its levels, fetched up front (independent loads: one memory
+  // latency instead of one per level)
+  int nid[kMortonLevels];
+#pragma unroll
+  for (int t = 0; t < kMortonLevels; ++t) nid[t] = (live && t < L) ? __ldg(S + (size_t)t * n + i) - 1 : -1;
+#pragma unroll
+  for (int t = 1; t <= kMortonLevels; ++t) {
+    if (t > Lmax) break;
     const bool in = live && t <= L;
-    const int parent = in ? S[(size_t)(t - 1) * n + i] - 1 : -1;
+    const int parent = in ? nid[t - 1] : -1;
     const int slot = (key >> (3 * (kMortonLevels - t))) & 7;
     const int cell = in ? parent * 8 + slot : -1 - lane;  // run id; dead lanes never join a run
     if (in && t == L) node_of_point[orig] = parent;
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys,
     if (in && cd < t) {
       unsigned* pw = nodes + (size_t)parent * 64;
       if (t < L) {
-        const int child = S[(size_t)t * n + i] - 1;
+        const int child = nid[t < kMortonLevels ? t : 0];  // t < L <= 10 here
         pw[48 + 2 * slot] = (unsigned)child;
         pw[49 + 2 * slot] = 0xffffffffu;
         const unsigned keep = ~((1u << (kMortonLevels - t)) - 1u) & 0x3ffu;  // the t leading bits of each axis
