@@ -618,3 +618,30 @@ def test_residuals_async_equals_sync(rt, small_pair):
     info = g.align_finish()
     assert info.converged
     assert np.array_equal(out, g.getResiduals())
+
+
+@pytest.mark.parametrize("ns", [1, 5, 16, 17, 100, 513, 4095])
+def test_linearize_ragged_source_sizes(rt, oracle, small_pair, ns):
+    """Source sizes around the work-distribution boundaries of the align kernel (groups of 16 points, rounds
+    of 512 slots per block, padding slots): correspondences bit-exact, H / b / error within the bar."""
+    src, tgt = small_pair
+    sub = np.ascontiguousarray(src[:: max(1, len(src) // ns)][:ns])
+    assert len(sub) == ns
+    # covariances come from the full source cloud's oracle values (a 1-point cloud has none of its own)
+    full = oracle.Cloud(src).build_tree().covariances(10)
+    covs = np.ascontiguousarray(full[:: max(1, len(src) // ns)][:ns])
+    g, o = ng.NanoGICP(rt), oracle.NanoGICP()
+    g.setInputSource(ng.PointCloud(rt, sub)); g.setInputTarget(ng.PointCloud(rt, tgt))
+    o.setInputSource(oracle.Cloud(sub)); o.setInputTarget(oracle.Cloud(tgt))
+    o.calculateTargetCovariances()
+    o.setSourceCovariances(covs); g.setSourceCovariances(covs)
+    g.setTargetCovariances(o.getTargetCovariances())
+    T = np.linalg.inv(synth.pose(0)) @ synth.pose(1)
+    for step in range(2):  # the second call starts from the first call's matches (seeded search)
+        T[:3, 3] += [0.02, -0.01, 0.005]
+        e, H, b = g.linearize(T)
+        oe, oH, ob = o.linearize(T)
+        gc, gd = g.correspondences()
+        oc, od = o.correspondences()
+        assert np.array_equal(gc, oc) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+        assert rel_err(H, oH) < REL and rel_err(b, ob) < REL and abs(e - oe) <= REL * abs(oe)
