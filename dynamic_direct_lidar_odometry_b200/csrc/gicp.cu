@@ -213,6 +213,7 @@ __device__ __forceinline__ void search_round(const GicpArgs& a, AlignSmem& sm, c
   unsigned node = 0;   // node to visit next
   unsigned start = 0;  // root of the subtree being searched
   int skip = -1, t = -1, sp = 0;
+  int seed_start = 0, seed_count = 0;  // leaf to seed a fresh query from (pair-uniform), consumed right after the fetch
   bool run = false, sub_done = false, exhausted = false;
   unsigned long long stk[kPairStack];
 #ifdef DDLO_VISIT_STATS
@@ -271,6 +272,30 @@ __device__ __forceinline__ void search_round(const GicpArgs& a, AlignSmem& sm, c
                 const float4 tp = __ldg(a.tgt.spts + sd.x);
                 best.seed(sqdist3_rn(qx, qy, qz, tp.x, tp.y, tp.z), __float_as_int(tp.w), sd.x);
                 start = (unsigned)sd.y;
+              } else {
+                // No previous match: walk down the cells that contain the query itself, one child
+                // reference per level (no boxes), to the leaf it falls into.  That leaf's points seed the
+                // search, which then starts at the node above it exactly like a seeded one.  An empty
+                // slot on the way just means: start at that node without a seed.
+                const float4 lat = __ldg(reinterpret_cast<const float4*>(a.tgt.lattice));
+                const unsigned cx = (unsigned)fminf(fmaxf((qx - lat.x) * lat.w, 0.0f), 1023.0f);
+                const unsigned cy = (unsigned)fminf(fmaxf((qy - lat.y) * lat.w, 0.0f), 1023.0f);
+                const unsigned cz = (unsigned)fminf(fmaxf((qz - lat.z) * lat.w, 0.0f), 1023.0f);
+                unsigned nd = 0;
+                for (int sh = kMortonLevels - 1; sh >= 0; --sh) {
+                  const int slot = (int)(((cx >> sh) & 1u) | (((cy >> sh) & 1u) << 1) | (((cz >> sh) & 1u) << 2));
+                  const int2 ref = __ldg(reinterpret_cast<const int2*>(a.tgt.nodes + (size_t)nd * kNodeF4 + 12) + slot);
+                  if (ref.y < 0) {
+                    nd = (unsigned)ref.x;
+                    continue;
+                  }
+                  if (ref.y > 0) {
+                    seed_start = ref.x;
+                    seed_count = ref.y;
+                  }
+                  break;
+                }
+                start = nd;
               }
               node = start;
               run = true;
@@ -286,6 +311,10 @@ __device__ __forceinline__ void search_round(const GicpArgs& a, AlignSmem& sm, c
           }
         }
       }
+    }
+    if (__any_sync(kFull, seed_count > 0)) {  // new queries without a previous match: seed from their own leaf
+      best.scan(seed_count > 0, a.tgt.spts, seed_start, seed_count, qx, qy, qz, h);
+      seed_count = 0;
     }
     if (!__any_sync(kFull, run)) {
       if (__all_sync(kFull, exhausted)) break;
