@@ -121,6 +121,7 @@ SIGNATURES = {
     "ddlo_gicp_get_residuals": [_vp, _vp, C.c_int],
     "ddlo_gicp_get_residuals_async": [_vp, _vp, C.c_int],
     "ddlo_gicp_get_residual_vectors": [_vp, _vp, _vp, C.c_int],
+    "ddlo_gicp_residual_image": [_vp, C.c_int, C.c_int, C.c_double, C.c_double, _vp],
     "ddlo_gicp_align_batch": [_vpp, C.c_int, _vp, C.POINTER(AlignResult)],
 }
 _SPECIAL = {

@@ -28,6 +28,7 @@ int index_nonfinite_count(ddlo_cloud* c, int* count);
 int voxel_filter_device(ddlo_runtime* rt, const float4* pts, int n, const float leaf[3], float4** d_out, int* n_out);
 int crop_box_device(ddlo_runtime* rt, const float4* pts, int n, const float lo[3], const float hi[3], int negative, int keep_organized,
                     float4** d_out, int* n_out);
+int residual_image_device(ddlo_runtime* rt, const float4* pts, const float* sqd, int n, int w, int h, double a_min, double a_max, float4* d_out);
 
 // raw strided host points -> float4 (x, y, z, 1)
 __global__ void __launch_bounds__(256) k_repack(const unsigned char* __restrict__ raw, int n, int stride, float4* __restrict__ out) {
@@ -1058,6 +1059,26 @@ int ddlo_gicp_get_residuals_async(ddlo_gicp* g, double* out, int capacity) {
 int ddlo_gicp_get_residuals(ddlo_gicp* g, double* out, int capacity) {
   DDLO_TRY(ddlo_gicp_get_residuals_async(g, out, capacity));
   DDLO_CUDA(cudaStreamSynchronize(g->rt->stream));
+  return DDLO_OK;
+}
+
+int ddlo_gicp_residual_image(ddlo_gicp* g, int width, int height, double angle_min, double angle_max, float* out_xyzi) {
+  if (!g || !out_xyzi) return fail(DDLO_E_INVALID, "null argument");
+  if (width <= 0 || height <= 0 || (long long)width * height > (1 << 26) || !(angle_max > angle_min)) return fail(DDLO_E_INVALID, "bad image geometry");
+  if (!g->src || g->corr_n != g->src->n) return fail(DDLO_E_NOT_READY, "no residuals: run align first");
+  ddlo_runtime* rt = g->rt;
+  DDLO_TRY(use_device(rt));
+  const size_t cells = (size_t)width * height;
+  float4* d_img = nullptr;
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_img), cells * sizeof(float4), rt->stream));
+  int rc = residual_image_device(rt, g->src->pts, g->sqd, g->corr_n, width, height, angle_min, angle_max, d_img);
+  if (rc == DDLO_OK) {
+    cudaError_t e = cudaMemcpyAsync(out_xyzi, d_img, cells * sizeof(float4), cudaMemcpyDeviceToHost, rt->stream);
+    if (e != cudaSuccess) rc = fail(DDLO_E_CUDA, cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d_img, rt->stream);
+  if (rc != DDLO_OK) return rc;
+  DDLO_CUDA(cudaStreamSynchronize(rt->stream));
   return DDLO_OK;
 }
 

@@ -1,6 +1,7 @@
 // Scan preprocessing on the device: the two PCL filters OdomNode::preprocessPoints applies right
 // before the registration path (odom.cc:442-478, configured at odom.cc:115-130), and that it applies
-// to every new keyframe (odom.cc:494-499, 1133-1137).  SURVEY.md §8f row 2.
+// to every new keyframe (odom.cc:494-499, 1133-1137).  SURVEY.md §8f row 2.  At the end of the file: the
+// residual image OdomNode builds right after the registration (odom.cc:804-827, §8f row 3).
 //
 //   voxel_filter   pcl::VoxelGrid<PointXYZI>::applyFilter (PCL 1.10, filters/impl/voxel_grid.hpp; PCL is
 //                  not vendored by the reference, its published algorithm is restated): bounding box of
@@ -284,6 +285,64 @@ int crop_box_device(ddlo_runtime* rt, const float4* pts, int n, const float lo[3
   cudaFreeAsync(base, st);
   DDLO_CUDA(cudaGetLastError());
   *n_out = kept;
+  return DDLO_OK;
+}
+
+// ---- residual image ------------------------------------------------------------
+// OdomNode::scanMatching, odom.cc:804-827: the registration scan is projected into a W x H angular image,
+// theta = atan2(x, z), phi = atan2(y, sqrt(x^2 + z^2)), u = int((theta - a_min) / (a_max - a_min) * W), v alike
+// with H (C++ int conversion: truncation toward zero), and cell (v, u) keeps x, y, z and the GICP residual
+// (as intensity) of the LAST scan point that falls into it; the other cells stay zero.  The reference's
+// sequential loop makes "last" the largest point index; here an atomicMax per cell elects it.  Angles are
+// evaluated in double (the reference's float arguments make its overload depend on its include set; the two
+// differ only for points within ~1e-7 rad of a cell border).
+struct ResidualImageSpec {
+  int w, h;
+  double a_min, a_span;
+};
+__device__ __forceinline__ int residual_cell(const float4 p, const ResidualImageSpec& g) {
+  const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
+  const double theta = atan2(x, z);
+  const double phi = atan2(y, sqrt(x * x + z * z));
+  const int u = (int)((theta - g.a_min) / g.a_span * (double)g.w);
+  const int v = (int)((phi - g.a_min) / g.a_span * (double)g.h);
+  if (u < 0 || u >= g.w || v < 0 || v >= g.h) return -1;
+  return v * g.w + u;
+}
+__global__ void __launch_bounds__(256) k_residual_owner(const float4* __restrict__ pts, int n, ResidualImageSpec g, int* __restrict__ owner) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) return;  // atan2 of NaN gives NaN, whose int conversion is undefined: skipped
+  const int c = residual_cell(p, g);
+  if (c >= 0) atomicMax(owner + c, i);
+}
+__global__ void __launch_bounds__(256) k_residual_fill(const float4* __restrict__ pts, const float* __restrict__ sqd, int cells,
+                                                        const int* __restrict__ owner, float4* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cells) return;
+  const int i = owner[c];
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i >= 0) {
+    const float4 p = pts[i];
+    o = make_float4(p.x, p.y, p.z, (float)sqrt((double)sqd[i]));  // residuals[i] = sqrt(sq_distances_[i]) (double), stored as float intensity
+  }
+  out[c] = o;
+}
+
+// d_out: w*h float4 (x, y, z, residual) on the device
+int residual_image_device(ddlo_runtime* rt, const float4* pts, const float* sqd, int n, int w, int h, double a_min, double a_max, float4* d_out) {
+  cudaStream_t st = rt->stream;
+  const int cells = w * h;
+  int* owner = nullptr;
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&owner), (size_t)cells * sizeof(int), st));
+  DDLO_CUDA(cudaMemsetAsync(owner, 0xff, (size_t)cells * sizeof(int), st));  // -1
+  ResidualImageSpec g{w, h, a_min, a_max - a_min};
+  if (n > 0) k_residual_owner<<<(n + 255) / 256, 256, 0, st>>>(pts, n, g, owner);
+  k_residual_fill<<<(cells + 255) / 256, 256, 0, st>>>(pts, sqd, cells, owner, d_out);
+  rt->launches += 2;
+  cudaFreeAsync(owner, st);
+  DDLO_CUDA(cudaGetLastError());
   return DDLO_OK;
 }
 

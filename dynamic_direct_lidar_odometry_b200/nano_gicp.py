@@ -486,6 +486,12 @@ class NanoGICP:
             raise ValueError("out must be a contiguous float64 array")
         B.check(B.load().ddlo_gicp_get_residuals_async(self._g, B.ptr(out), out.size))
 
+    def residualImage(self, width: int = 512, height: int = 512, angle_min: float = -np.pi / 3, angle_max: float = np.pi / 3) -> np.ndarray:
+        """The residual cloud of odom.cc:804-827 as an (height, width, 4) float32 array (x, y, z, residual)."""
+        out = np.empty((height, width, 4), dtype=np.float32)
+        B.check(B.load().ddlo_gicp_residual_image(self._g, width, height, float(angle_min), float(angle_max), B.ptr(out)))
+        return out
+
     def getResidualVectors(self, T) -> np.ndarray:
         """getResiduals(std::vector<Eigen::Vector3f>&, trans)."""
         n = self._src.size()

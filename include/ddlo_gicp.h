@@ -213,6 +213,12 @@ int ddlo_gicp_get_residuals(ddlo_gicp* g, double* out, int capacity);
  * Between ddlo_gicp_align_async and ddlo_gicp_align_finish this makes pose and residuals cost one host round trip.
  * Meant for page-locked `out` (ddlo_host_alloc); with pageable memory the copy itself blocks. */
 int ddlo_gicp_get_residuals_async(ddlo_gicp* g, double* out, int capacity);
+/* The residual cloud OdomNode builds from getResiduals right after the S2M align (odom.cc:804-827; SURVEY.md §8f
+ * row 3): the source scan projected into a width x height angular image, theta = atan2(x, z) and
+ * phi = atan2(y, sqrt(x^2 + z^2)) both mapped from [angle_min, angle_max) (the fork uses 512 x 512, -60..+60 deg);
+ * cell (v, u) holds x, y, z and the residual of the last scan point that falls into it, other cells are zero.
+ * out_xyzi: HOST, height * width * 4 floats, row-major. */
+int ddlo_gicp_residual_image(ddlo_gicp* g, int width, int height, double angle_min, double angle_max, float* out_xyzi);
 /* getResiduals(std::vector<Eigen::Vector3f>&, trans) (:199-222) */
 int ddlo_gicp_get_residual_vectors(ddlo_gicp* g, const float* T16, float* out_xyz, int capacity);
 

@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
         "oracle_gicp_get_residual_vectors": (ci, [vp, _f32p, _f32p]),
         "oracle_voxel_filter": (ci, [_f32p, ci, ci, C.c_float, C.c_float, C.c_float, _f32p]),
         "oracle_crop_box": (ci, [_f32p, ci, ci, _f32p, _f32p, ci, ci, _f32p]),
+        "oracle_residual_image": (None, [_f32p, ci, ci, _f64p, ci, ci, cd, cd, _f32p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -197,6 +198,15 @@ def crop_box(points, box_min, box_max, negative: bool = False, keep_organized: b
     out = np.empty((max(p.shape[0], 1), 4), dtype=np.float32)
     m = lib().oracle_crop_box(p, p.shape[0], p.shape[1], lo, hi, int(negative), int(keep_organized), out)
     return out[:m].copy()
+
+
+def residual_image(points, residuals, width: int = 512, height: int = 512, angle_min: float = -np.pi / 3, angle_max: float = np.pi / 3) -> np.ndarray:
+    """odom.cc:804-827 restated (oracle_gicp.cpp oracle_residual_image): (height, width, 4) float32."""
+    p = _as_points(points)
+    r = np.ascontiguousarray(residuals, dtype=np.float64)
+    out = np.empty((height, width, 4), dtype=np.float32)
+    lib().oracle_residual_image(p, p.shape[0], p.shape[1], r, width, height, float(angle_min), float(angle_max), out.reshape(-1))
+    return out
 
 
 def knn_bruteforce(points, queries, k: int):

@@ -645,3 +645,18 @@ def test_linearize_ragged_source_sizes(rt, oracle, small_pair, ns):
         oc, od = o.correspondences()
         assert np.array_equal(gc, oc) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
         assert rel_err(H, oH) < REL and rel_err(b, ob) < REL and abs(e - oe) <= REL * abs(oe)
+
+
+def test_residual_image_matches_oracle(rt, oracle, small_pair):
+    """the residual cloud of odom.cc:804-827 built on the device from the align's own residuals."""
+    src, tgt = small_pair
+    g = ng.NanoGICP(rt)
+    g.setInputSource(ng.PointCloud(rt, src))
+    g.setInputTarget(ng.PointCloud(rt, tgt))
+    assert g.align().converged
+    res = g.getResiduals()
+    for (w, h) in ((512, 512), (64, 48)):
+        got = g.residualImage(w, h)
+        want = oracle.residual_image(src, res, w, h)
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert (got[..., 3] > 0).any()

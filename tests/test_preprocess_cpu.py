@@ -59,3 +59,21 @@ def test_crop_box(oracle):
     assert np.array_equal(oracle.crop_box(scan, lo, hi, negative=True)[:, :3], scan[~inside, :3])
     org = oracle.crop_box(scan, lo, hi, negative=True, keep_organized=True)
     assert len(org) == len(scan) and np.isnan(org[inside, :3]).all() and np.array_equal(org[~inside, :3], scan[~inside, :3])
+
+
+def test_residual_image_oracle(oracle):
+    """odom.cc:804-827 restated: last point per cell wins, empty cells zero, out-of-view points skipped."""
+    scan = synth.scan(4, 32, 512)
+    res = np.linalg.norm(scan[:, :3], axis=1).astype(np.float64) * 1e-3
+    img = oracle.residual_image(scan, res, 64, 48, -np.pi / 3, np.pi / 3)
+    assert img.shape == (48, 64, 4)
+    # independent numpy statement
+    x, y, z = (scan[:, i].astype(np.float64) for i in range(3))
+    th, ph = np.arctan2(x, z), np.arctan2(y, np.sqrt(x * x + z * z))
+    u = np.trunc((th + np.pi / 3) / (2 * np.pi / 3) * 64).astype(int)
+    v = np.trunc((ph + np.pi / 3) / (2 * np.pi / 3) * 48).astype(int)
+    want = np.zeros((48, 64, 4), np.float32)
+    for i in np.flatnonzero((u >= 0) & (u < 64) & (v >= 0) & (v < 48)):
+        want[v[i], u[i]] = (scan[i, 0], scan[i, 1], scan[i, 2], np.float32(res[i]))
+    assert np.array_equal(img, want)
+    assert (img[..., 3] > 0).any() and (img[..., 3] == 0).any()
