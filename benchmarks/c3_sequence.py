@@ -62,6 +62,9 @@ def main():
         "final_translation_error_vs_truth_m": err_t[-1], "max_translation_error_vs_truth_m": max(err_t),
         "k_correspondences": args.k, "timer": "host wall clock per frame, scan upload and residual read-back included",
         "scan_generation_s": gen_s,
+        "slowest_frames": [{"frame": int(i) + 1, "ms": float(ms[i]), "new_keyframe": bool(loop.records[i].new_keyframe),
+                            "submap_changed": bool(loop.records[i].submap_changed), "submap_points": int(loop.records[i].submap_points)}
+                           for i in np.argsort(-ms)[:6]],
     }
     print(json.dumps(line))
     del loop

@@ -4,6 +4,7 @@
 // knn_cov.cu and gicp.cu; there is no CPU implementation of any of it in this library.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -183,6 +184,20 @@ int ddlo_runtime_create(int device, ddlo_runtime** out) {
   DDLO_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t keep = ~0ull;  // keep freed blocks cached: handle churn must not hit cudaMalloc
   DDLO_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  // Grow the pool once, now, instead of in the middle of a frame: the first allocation of a size the pool has
+  // never held maps new physical memory (tens of milliseconds for the ~100 MB node array of a 650k-point submap).
+  // DDLO_POOL_PREWARM_MB overrides the default of 1 GiB (0 disables).
+  {
+    size_t mb = 1024;
+    if (const char* e = std::getenv("DDLO_POOL_PREWARM_MB")) mb = (size_t)std::max(0L, std::atol(e));
+    if (mb > 0) {
+      void* warm = nullptr;
+      if (cudaMallocAsync(&warm, mb << 20, rt->stream) == cudaSuccess)
+        cudaFreeAsync(warm, rt->stream);
+      else
+        (void)cudaGetLastError();  // not enough memory for the warm-up: carry on without it
+    }
+  }
   DDLO_CUDA(cudaMalloc(&rt->d_scratch, 1u << 20));
   rt->d_scratch_bytes = 1u << 20;
   DDLO_TRY(ensure_pinned(rt, 1u << 16));
@@ -635,13 +650,13 @@ int ddlo_gicp_destroy(ddlo_gicp* g) {
   set_cloud(g->tgt, nullptr);
   set_covs(g->src_cov, nullptr);
   set_covs(g->tgt_cov, nullptr);
-  if (g->corr) cudaFree(g->corr);
-  if (g->nn_seed) cudaFree(g->nn_seed);
-  if (g->tcov_sorted) cudaFree(g->tcov_sorted);
+  if (g->corr) cudaFreeAsync(g->corr, g->rt->stream);
+  if (g->nn_seed) cudaFreeAsync(g->nn_seed, g->rt->stream);
+  if (g->tcov_sorted) cudaFreeAsync(g->tcov_sorted, g->rt->stream);
   set_cloud(g->tcov_for_cloud, nullptr);
   set_covs(g->tcov_for_covs, nullptr);
-  if (g->sqd) cudaFree(g->sqd);
-  if (g->mahal) cudaFree(g->mahal);
+  if (g->sqd) cudaFreeAsync(g->sqd, g->rt->stream);
+  if (g->mahal) cudaFreeAsync(g->mahal, g->rt->stream);
   if (g->partials) cudaFree(g->partials);
   if (g->d_out) cudaFree(g->d_out);
   if (g->d_blk_times) cudaFree(g->d_blk_times);
@@ -786,13 +801,13 @@ static int ensure_sorted_target_covs(ddlo_gicp* g) {
   const size_t n = (size_t)g->tgt->n;
   if (g->tcov_sorted_cap < n) {
     if (g->tcov_sorted) {
-      DDLO_CUDA(cudaStreamSynchronize(g->rt->stream));
-      DDLO_CUDA(cudaFree(g->tcov_sorted));
+      DDLO_CUDA(cudaFreeAsync(g->tcov_sorted, g->rt->stream));
       g->tcov_sorted = nullptr;
       g->tcov_sorted_cap = 0;
     }
-    DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->tcov_sorted), n * kCovStride * sizeof(double)));
-    g->tcov_sorted_cap = n;
+    const size_t cap = n + n / 4;
+    DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&g->tcov_sorted), cap * kCovStride * sizeof(double), g->rt->stream));
+    g->tcov_sorted_cap = cap;
   }
   k_permute_covs<<<(int)((n + 255) / 256), 256, 0, g->rt->stream>>>(g->tgt->spts, (int)n, g->tgt_cov->c, g->tcov_sorted);
   g->rt->launches += 1;
@@ -804,17 +819,19 @@ static int ensure_sorted_target_covs(ddlo_gicp* g) {
 
 static int ensure_workspace(ddlo_gicp* g, int ns) {
   if (g->ws_n >= ns) return DDLO_OK;
-  DDLO_CUDA(cudaStreamSynchronize(g->rt->stream));
-  if (g->corr) cudaFree(g->corr);
-  if (g->nn_seed) cudaFree(g->nn_seed);
-  if (g->sqd) cudaFree(g->sqd);
-  if (g->mahal) cudaFree(g->mahal);
+  // stream-ordered: the frees run behind the kernels that still use the old buffers, the allocations come
+  // from the pool warmed at runtime creation (no cudaMalloc, no synchronisation, in the middle of a frame)
+  cudaStream_t st = g->rt->stream;
+  if (g->corr) cudaFreeAsync(g->corr, st);
+  if (g->nn_seed) cudaFreeAsync(g->nn_seed, st);
+  if (g->sqd) cudaFreeAsync(g->sqd, st);
+  if (g->mahal) cudaFreeAsync(g->mahal, st);
   g->corr = nullptr, g->nn_seed = nullptr, g->sqd = nullptr, g->mahal = nullptr, g->ws_n = 0;
   const size_t cap = (size_t)ns + ns / 4 + 256;
-  DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->corr), cap * sizeof(int)));
-  DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->nn_seed), cap * sizeof(int2)));
-  DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->sqd), cap * sizeof(float)));
-  DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->mahal), cap * kCovStride * sizeof(double)));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&g->corr), cap * sizeof(int), st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&g->nn_seed), cap * sizeof(int2), st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&g->sqd), cap * sizeof(float), st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&g->mahal), cap * kCovStride * sizeof(double), st));
   g->ws_n = (int)cap;
   return DDLO_OK;
 }

@@ -267,20 +267,6 @@ __global__ void __launch_bounds__(256) k_finalize(unsigned* __restrict__ words, 
     if ((w & 63) < 48) words[w] = __float_as_uint(ord2f(words[w]));
 }
 
-static int ensure_scratch(ddlo_runtime* rt, size_t bytes) {
-  if (rt->d_scratch_bytes >= bytes) return DDLO_OK;
-  if (rt->d_scratch) {
-    DDLO_CUDA(cudaStreamSynchronize(rt->stream));
-    DDLO_CUDA(cudaFree(rt->d_scratch));
-    rt->d_scratch = nullptr;
-    rt->d_scratch_bytes = 0;
-  }
-  const size_t want = bytes + bytes / 4 + (1u << 20);
-  DDLO_CUDA(cudaMalloc(&rt->d_scratch, want));
-  rt->d_scratch_bytes = want;
-  return DDLO_OK;
-}
-
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 int build_index(ddlo_cloud* c) {
@@ -291,7 +277,7 @@ int build_index(ddlo_cloud* c) {
   if (n > (1 << 26)) return fail(DDLO_E_UNSUPPORTED, "build_index: cloud too large");
   cudaStream_t st = rt->stream;
 
-  // scratch: bounds (8 u32) | keys | keys_alt | vals | vals_alt | leaf_level | flags[10][n] | cub temp
+  // temporaries: bounds (8 u32) | keys | keys_alt | vals | vals_alt | leaf_level | flags[10][n] | cub temp
   size_t sort_bytes = 0, scan_bytes = 0;
   cub::DoubleBuffer<unsigned> kb0(nullptr, nullptr);
   cub::DoubleBuffer<int> vb0(nullptr, nullptr);
@@ -302,8 +288,9 @@ int build_index(ddlo_cloud* c) {
   const size_t off_keys = 256, sz = align256((size_t)n * 4);
   const size_t off_lvl = off_keys + 4 * sz, off_flags = off_lvl + align256((size_t)n);
   const size_t off_cub = off_flags + align256(n_flags * 4);
-  DDLO_TRY(ensure_scratch(rt, off_cub + align256(cub_bytes)));
-  char* base = static_cast<char*>(rt->d_scratch);
+  // temporaries come from the stream-ordered pool (warmed at runtime creation): no cudaMalloc in a frame
+  char* base = nullptr;
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&base), off_cub + align256(cub_bytes), st));
   unsigned* bounds = reinterpret_cast<unsigned*>(base);
   unsigned* keys = reinterpret_cast<unsigned*>(base + off_keys);
   unsigned* keys_alt = reinterpret_cast<unsigned*>(base + off_keys + sz);
@@ -339,6 +326,7 @@ int build_index(ddlo_cloud* c) {
   k_emit<<<nb, tb, 0, st>>>(kb.Current(), leaf_level, flags, c->spts, n, words, c->meta, c->node_of_point);
   k_finalize<<<gb, tb, 0, st>>>(words, n_nodes_ptr);
   rt->launches += 6;
+  DDLO_CUDA(cudaFreeAsync(base, st));
   DDLO_CUDA(cudaGetLastError());
 
   c->view.spts = c->spts;
