@@ -64,6 +64,7 @@ SIGNATURES = {
     "ddlo_runtime_create": [C.c_int, _vpp],
     "ddlo_runtime_destroy": [_vp],
     "ddlo_runtime_synchronize": [_vp],
+    "ddlo_runtime_set_align_blocks": [_vp, C.c_int],
     "ddlo_runtime_timer_begin": [_vp],
     "ddlo_runtime_timer_end": [_vp, C.POINTER(C.c_float)],
     "ddlo_runtime_launch_count": [_vp, C.POINTER(C.c_longlong)],

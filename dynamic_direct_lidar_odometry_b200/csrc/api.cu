@@ -205,6 +205,7 @@ int ddlo_runtime_create(int device, ddlo_runtime** out) {
   DDLO_TRY(gicp_max_coop_blocks(device, &per_sm));
   rt->max_coop_blocks_align = per_sm * rt->num_sms;
   if (rt->max_coop_blocks_align <= 0) return fail(DDLO_E_CUDA, "align kernel does not fit on this device");
+  rt->align_blocks_limit = rt->max_coop_blocks_align;
   *out = rt;
   return DDLO_OK;
 }
@@ -221,6 +222,12 @@ int ddlo_runtime_destroy(ddlo_runtime* rt) {
   for (auto& e : rt->slots) cudaEventDestroy(e);
   cudaStreamDestroy(rt->stream);
   delete rt;
+  return DDLO_OK;
+}
+
+int ddlo_runtime_set_align_blocks(ddlo_runtime* rt, int max_blocks) {
+  if (!rt) return fail(DDLO_E_INVALID, "runtime is null");
+  rt->align_blocks_limit = max_blocks <= 0 ? rt->max_coop_blocks_align : std::min(max_blocks, rt->max_coop_blocks_align);
   return DDLO_OK;
 }
 
@@ -888,7 +895,7 @@ static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, 
   return DDLO_OK;
 }
 
-static int align_blocks(const ddlo_gicp* g) { return gicp_blocks_for(g->src->n, g->rt->max_coop_blocks_align); }
+static int align_blocks(const ddlo_gicp* g) { return gicp_blocks_for(g->src->n, g->rt->align_blocks_limit); }
 
 static int enqueue_align(ddlo_gicp* g, const float* guess16, int* covs_computed) {
   GicpArgs a;

@@ -92,7 +92,8 @@ struct ddlo_runtime {
   // device scratch reused by the index build (radix sort temp etc.)
   void* d_scratch = nullptr;
   size_t d_scratch_bytes = 0;
-  int max_coop_blocks_align = 0;  // co-resident 256-thread blocks of the align kernel
+  int max_coop_blocks_align = 0;  // co-resident blocks of the align kernel (one 1024-thread block per SM)
+  int align_blocks_limit = 0;     // blocks one align may use (ddlo_runtime_set_align_blocks); default = all
 };
 
 struct ddlo_cloud {

@@ -44,6 +44,10 @@ class Runtime:
             B.load().ddlo_runtime_destroy(self._h)
             self._h = None
 
+    def set_align_blocks(self, max_blocks: int):
+        """limit the align kernel of this runtime to max_blocks SMs (0 = all): lets several runtimes align concurrently"""
+        B.check(B.load().ddlo_runtime_set_align_blocks(self._h, int(max_blocks)))
+
     def synchronize(self):
         B.check(B.load().ddlo_runtime_synchronize(self._h))
 

@@ -100,6 +100,12 @@ int ddlo_device_count(int* count);
 int ddlo_runtime_create(int device, ddlo_runtime** out);
 int ddlo_runtime_destroy(ddlo_runtime* rt);
 int ddlo_runtime_synchronize(ddlo_runtime* rt);
+/* Batched workloads (BASELINE config C5): several runtimes (streams) of one device register independent pairs
+ * concurrently.  The align kernel is a cooperative launch of one block per SM; limiting each runtime to
+ * num_SMs / n_runtimes blocks lets n_runtimes aligns be resident at once instead of queueing behind each other.
+ * max_blocks <= 0 restores the default (all SMs).  The fp64 sums are taken per block and then over the blocks in a
+ * fixed order, so results are reproducible for a given block count and agree to fp64 rounding between counts. */
+int ddlo_runtime_set_align_blocks(ddlo_runtime* rt, int max_blocks);
 /* CUDA-event timer on the runtime's stream (bench.py times kernels with these) */
 int ddlo_runtime_timer_begin(ddlo_runtime* rt);
 int ddlo_runtime_timer_end(ddlo_runtime* rt, float* elapsed_ms); /* synchronises */
