@@ -660,3 +660,23 @@ def test_residual_image_matches_oracle(rt, oracle, small_pair):
         want = oracle.residual_image(src, res, w, h)
         assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert (got[..., 3] > 0).any()
+
+
+def test_align_block_limit_agrees(rt, oracle, small_pair):
+    """ddlo_runtime_set_align_blocks (batched workloads): fewer blocks per align change the fp64 summation
+    order only - same correspondences, same iteration counts, pose within the bar."""
+    src, tgt = small_pair
+    g = ng.NanoGICP(rt)
+    g.setInputSource(ng.PointCloud(rt, src))
+    g.setInputTarget(ng.PointCloud(rt, tgt))
+    full = g.align()
+    c_full = g.correspondences()
+    try:
+        rt.set_align_blocks(5)
+        part = g.align()
+        c_part = g.correspondences()
+    finally:
+        rt.set_align_blocks(0)
+    assert (full.converged, full.iterations) == (part.converged, part.iterations)
+    _check_pose(full, part)
+    assert np.array_equal(c_full[0], c_part[0]) and np.array_equal(c_full[1].view(np.uint32), c_part[1].view(np.uint32))
