@@ -28,11 +28,14 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 
 namespace ddlo {
+
+int morton_sort_cluster(ddlo_runtime* rt, const float4* pts, int n, unsigned* keys_out, int* vals_out, float* lattice);  // cluster_sort.cu
 
 __device__ __forceinline__ unsigned f2ord(float f) {
   const unsigned u = __float_as_uint(f);
@@ -307,25 +310,35 @@ int build_index(ddlo_cloud* c) {
   DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->node_of_point), (size_t)n * sizeof(int), st));
   DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->lattice), 8 * sizeof(float), st));
 
-  DDLO_CUDA(cudaMemsetAsync(bounds, 0xff, 12, st));
-  DDLO_CUDA(cudaMemsetAsync(bounds + 3, 0x00, 16, st));
   const int tb = 256;
   const int nb = (n + tb - 1) / tb;
-  k_bounds<<<std::min(nb, rt->num_sms), tb, 0, st>>>(c->pts, n, bounds);
-  k_morton<<<nb, tb, 0, st>>>(c->pts, n, bounds, keys, vals, c->lattice);
-  cub::DoubleBuffer<unsigned> kb(keys, keys_alt);
-  cub::DoubleBuffer<int> vb(vals, vals_alt);
-  DDLO_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, kb, vb, n, 0, 30, st));
-  // (the radix-sort and scan passes are CUB library kernels and are not counted as ours)
-  k_cells<<<nb, tb, 0, st>>>(kb.Current(), vb.Current(), c->pts, n, leaf_level, flags, c->spts);
+  // Scan-sized clouds: box, Morton keys and the sort in one kernel of a 16-CTA cluster (cluster_sort.cu).
+  // Larger clouds, or a device that refuses the cluster launch: the generic kernels + CUB's radix sort.
+  static const bool cluster_sort_enabled = std::getenv("DDLO_NO_CLUSTER_SORT") == nullptr;
+  const unsigned* skeys = keys;
+  const int* svals = vals;
+  if (!(cluster_sort_enabled && morton_sort_cluster(rt, c->pts, n, keys, vals, c->lattice) == DDLO_OK)) {
+    DDLO_CUDA(cudaMemsetAsync(bounds, 0xff, 12, st));
+    DDLO_CUDA(cudaMemsetAsync(bounds + 3, 0x00, 16, st));
+    k_bounds<<<std::min(nb, rt->num_sms), tb, 0, st>>>(c->pts, n, bounds);
+    k_morton<<<nb, tb, 0, st>>>(c->pts, n, bounds, keys, vals, c->lattice);
+    cub::DoubleBuffer<unsigned> kb(keys, keys_alt);
+    cub::DoubleBuffer<int> vb(vals, vals_alt);
+    DDLO_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, kb, vb, n, 0, 30, st));
+    // (the radix-sort and scan passes are CUB library kernels and are not counted as ours)
+    skeys = kb.Current();
+    svals = vb.Current();
+    rt->launches += 2;
+  }
+  k_cells<<<nb, tb, 0, st>>>(skeys, svals, c->pts, n, leaf_level, flags, c->spts);
   DDLO_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_bytes, flags, flags, (long long)n_flags, st));
   const int* n_nodes_ptr = flags + (n_flags - 1);
   unsigned* words = reinterpret_cast<unsigned*>(c->nodes);
   const int gb = std::min(nb, rt->num_sms * 4);
   k_init_nodes<<<gb, tb, 0, st>>>(words, n_nodes_ptr, c->lattice);
-  k_emit<<<nb, tb, 0, st>>>(kb.Current(), leaf_level, flags, c->spts, n, words, c->meta, c->node_of_point);
+  k_emit<<<nb, tb, 0, st>>>(skeys, leaf_level, flags, c->spts, n, words, c->meta, c->node_of_point);
   k_finalize<<<gb, tb, 0, st>>>(words, n_nodes_ptr);
-  rt->launches += 6;
+  rt->launches += 4;
   DDLO_CUDA(cudaFreeAsync(base, st));
   DDLO_CUDA(cudaGetLastError());
 
