@@ -153,33 +153,55 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_morton_sort_cluster(const flo
   for (int pass = 0; pass < kCsPasses; ++pass) {
     const int shift = pass * kCsBits;
     uint2 e[IPT];
+    int dg[IPT], rk[IPT];  // digit of each element of the chunk, and how many earlier elements of the chunk share it
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) e[j] = chunk[j];
-    // digit counts of the thread's own chunk (private column of cnt: no atomics)
+    for (int j = 0; j < IPT; ++j) {
+      e[j] = chunk[j];
+      dg[j] = (int)((e[j].x >> shift) & (kCsBins - 1));
+    }
+    // digit counts of the thread's own chunk, from registers: the rank of an element inside the chunk is
+    // the number of earlier elements with its digit, and the LAST element of a digit knows the digit's count.
+    // Private column of cnt, plain stores, nothing to wait for.
 #pragma unroll
     for (int b = 0; b < kCsBins; ++b) cnt[b * kCsThreads + t] = 0;
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) cnt[((e[j].x >> shift) & (kCsBins - 1)) * kCsThreads + t] += 1;
+    for (int j = 0; j < IPT; ++j) {
+      int r = 0;
+      bool last = true;
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        if (i < j) r += dg[i] == dg[j] ? 1 : 0;
+        if (i > j) last = last && dg[i] != dg[j];
+      }
+      rk[j] = r;
+      if (last) cnt[dg[j] * kCsThreads + t] = (unsigned short)(r + 1);
+    }
     __syncthreads();
-    // exclusive scan of every digit's counts over the threads of the CTA: warp w takes digits 2w, 2w+1
+    // exclusive scan of every digit's counts over the threads of the CTA: warp w takes digits 2w, 2w+1;
+    // a lane owns 16 consecutive threads' counts = two 128-bit words
     for (int b = 2 * warp; b < 2 * warp + 2; ++b) {
-      unsigned short* row = cnt + b * kCsThreads + lane * (kCsThreads / 32);
+      static_assert(kCsThreads / 32 == 16, "one lane scans 16 counters");
+      uint4* row = reinterpret_cast<uint4*>(cnt + b * kCsThreads + lane * 16);
+      uint4 w0 = row[0], w1 = row[1];
+      unsigned v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};  // 16 counters, two per word (little endian)
       unsigned s = 0;
 #pragma unroll
-      for (int i = 0; i < kCsThreads / 32; ++i) {
-        const unsigned v = row[i];
-        row[i] = (unsigned short)s;
-        s += v;
-      }
+      for (int i = 0; i < 8; ++i) s += (v[i] & 0xffffu) + (v[i] >> 16);
       unsigned inc = s;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += u;
       }
-      const unsigned off = inc - s;
+      unsigned run = inc - s;  // counters of the lanes before this one
 #pragma unroll
-      for (int i = 0; i < kCsThreads / 32; ++i) row[i] = (unsigned short)(row[i] + off);
+      for (int i = 0; i < 8; ++i) {
+        const unsigned a = v[i] & 0xffffu, c = v[i] >> 16;
+        v[i] = run | ((run + a) << 16);
+        run += a + c;
+      }
+      row[0] = make_uint4(v[0], v[1], v[2], v[3]);
+      row[1] = make_uint4(v[4], v[5], v[6], v[7]);
       if (lane == 31) tot[b] = inc;
     }
     __syncthreads();
@@ -194,14 +216,10 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_morton_sort_cluster(const flo
       lbase[lane] = inc - v;
     }
     __syncthreads();
-    // regroup the slice by digit inside the CTA: the chunk in order, so equal digits keep their order
+    // regroup the slice by digit inside the CTA: position = start of the digit's run + elements of the digit in
+    // lower threads + rank inside the chunk, so equal digits keep their order (stable)
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-      const int d = (int)((e[j].x >> shift) & (kCsBins - 1));
-      const unsigned short r = cnt[d * kCsThreads + t];
-      cnt[d * kCsThreads + t] = (unsigned short)(r + 1);
-      B[lbase[d] + r] = e[j];
-    }
+    for (int j = 0; j < IPT; ++j) B[lbase[dg[j]] + cnt[dg[j] * kCsThreads + t] + rk[j]] = e[j];
     cluster.sync();  // every CTA's B and totals are final, and nobody reads its A any more
     {
       const int b = t / kCsCtas, c = t % kCsCtas;  // 512 threads = 32 digits x 16 CTAs
@@ -226,6 +244,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_morton_sort_cluster(const flo
     __syncthreads();
     // the exchange: a digit's run in B is contiguous in the global order too, so consecutive threads store
     // consecutive 8-byte elements into (mostly) one destination CTA's A: wide, coalesced DSMEM traffic
+#pragma unroll
     for (int i = t; i < L::kCap; i += kCsThreads) {
       const uint2 v = B[i];
       const int d = (int)((v.x >> shift) & (kCsBins - 1));
