@@ -28,8 +28,6 @@ namespace cg = cooperative_groups;
 namespace ddlo {
 
 constexpr int kCsCtas = 16;
-constexpr int kCsThreads = 512;
-constexpr int kCsWarps = kCsThreads / 32;
 constexpr int kCsBits = 5;
 constexpr int kCsBins = 1 << kCsBits;
 constexpr int kCsPasses = 6;  // 30 bits
@@ -43,8 +41,9 @@ __device__ __forceinline__ unsigned cs_spread10(unsigned v) {
   return v;
 }
 
-template <int IPT>
+template <int kCsThreads, int IPT>
 struct CsLayout {
+  static constexpr int kCsWarps = kCsThreads / 32;
   static constexpr int kCap = kCsThreads * IPT;       // elements per CTA
   static constexpr int kStride = IPT | 1;             // odd chunk stride (in elements): conflict-free chunk walks
   static constexpr int kPhys = kCsThreads * kStride;  // physical elements of the chunked buffer A
@@ -55,10 +54,13 @@ struct CsLayout {
 };
 
 // lattice: {lo.x, lo.y, lo.z, scale, (int) non-finite count, (int) node count [written later]} as in index.cu
-template <int IPT>
+template <int kCsThreads, int IPT>
 __global__ void __launch_bounds__(kCsThreads, 1) k_morton_sort_cluster(const float4* __restrict__ pts, int n, unsigned* __restrict__ keys_out,
                                                                          int* __restrict__ vals_out, float* __restrict__ lattice) {
-  using L = CsLayout<IPT>;
+  using L = CsLayout<kCsThreads, IPT>;
+  constexpr int kCsWarps = L::kCsWarps;
+  constexpr int kPerLane = kCsThreads / 32;        // counters of one digit a lane scans
+  constexpr int kBinsPerWarp = kCsBins / kCsWarps > 0 ? kCsBins / kCsWarps : 1;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -177,16 +179,20 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_morton_sort_cluster(const flo
       if (last) cnt[dg[j] * kCsThreads + t] = (unsigned short)(r + 1);
     }
     __syncthreads();
-    // exclusive scan of every digit's counts over the threads of the CTA: warp w takes digits 2w, 2w+1;
-    // a lane owns 16 consecutive threads' counts = two 128-bit words
-    for (int b = 2 * warp; b < 2 * warp + 2; ++b) {
-      static_assert(kCsThreads / 32 == 16, "one lane scans 16 counters");
-      uint4* row = reinterpret_cast<uint4*>(cnt + b * kCsThreads + lane * 16);
-      uint4 w0 = row[0], w1 = row[1];
-      unsigned v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};  // 16 counters, two per word (little endian)
+    // exclusive scan of every digit's counts over the threads of the CTA: a warp takes kBinsPerWarp digits,
+    // a lane owns kPerLane consecutive threads' counters = kPerLane / 8 128-bit words
+    for (int b = warp * kBinsPerWarp; b < (warp + 1) * kBinsPerWarp && b < kCsBins; ++b) {
+      static_assert(kPerLane % 8 == 0, "a lane scans whole 128-bit words of 16-bit counters");
+      uint4* row = reinterpret_cast<uint4*>(cnt + b * kCsThreads + lane * kPerLane);
+      unsigned v[kPerLane / 2];  // two counters per word (little endian)
+#pragma unroll
+      for (int q = 0; q < kPerLane / 8; ++q) {
+        const uint4 w = row[q];
+        v[4 * q] = w.x, v[4 * q + 1] = w.y, v[4 * q + 2] = w.z, v[4 * q + 3] = w.w;
+      }
       unsigned s = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += (v[i] & 0xffffu) + (v[i] >> 16);
+      for (int i = 0; i < kPerLane / 2; ++i) s += (v[i] & 0xffffu) + (v[i] >> 16);
       unsigned inc = s;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -195,13 +201,13 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_morton_sort_cluster(const flo
       }
       unsigned run = inc - s;  // counters of the lanes before this one
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kPerLane / 2; ++i) {
         const unsigned a = v[i] & 0xffffu, c = v[i] >> 16;
         v[i] = run | ((run + a) << 16);
         run += a + c;
       }
-      row[0] = make_uint4(v[0], v[1], v[2], v[3]);
-      row[1] = make_uint4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+      for (int q = 0; q < kPerLane / 8; ++q) row[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       if (lane == 31) tot[b] = inc;
     }
     __syncthreads();
@@ -221,8 +227,8 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_morton_sort_cluster(const flo
 #pragma unroll
     for (int j = 0; j < IPT; ++j) B[lbase[dg[j]] + cnt[dg[j] * kCsThreads + t] + rk[j]] = e[j];
     cluster.sync();  // every CTA's B and totals are final, and nobody reads its A any more
-    {
-      const int b = t / kCsCtas, c = t % kCsCtas;  // 512 threads = 32 digits x 16 CTAs
+    if (t < kCsBins * kCsCtas) {
+      const int b = t / kCsCtas, c = t % kCsCtas;  // 32 digits x 16 CTAs
       all[b * kCsCtas + c] = cluster.map_shared_rank(tot, c)[b];
     }
     __syncthreads();
@@ -267,10 +273,10 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_morton_sort_cluster(const flo
   }
 }
 
-template <int IPT>
+template <int kCsThreads, int IPT>
 static int launch_cs(ddlo_runtime* rt, const float4* pts, int n, unsigned* keys_out, int* vals_out, float* lattice) {
-  using L = CsLayout<IPT>;
-  auto kern = k_morton_sort_cluster<IPT>;
+  using L = CsLayout<kCsThreads, IPT>;
+  auto kern = k_morton_sort_cluster<kCsThreads, IPT>;
   static bool configured = false, usable = false;
   if (!configured) {
     configured = true;
@@ -300,12 +306,18 @@ static int launch_cs(ddlo_runtime* rt, const float4* pts, int n, unsigned* keys_
   return DDLO_OK;
 }
 
+#ifndef DDLO_CS_THREADS
+#define DDLO_CS_THREADS 512
+#endif
+
 // DDLO_OK: keys_out / vals_out / lattice are (being) written on the runtime's stream.
 // DDLO_E_UNSUPPORTED (no error text): the cloud is too large or the cluster launch is not possible here.
 int morton_sort_cluster(ddlo_runtime* rt, const float4* pts, int n, unsigned* keys_out, int* vals_out, float* lattice) {
-  if (n <= kCsCtas * kCsThreads * 4) return launch_cs<4>(rt, pts, n, keys_out, vals_out, lattice);
-  if (n <= kCsCtas * kCsThreads * 8) return launch_cs<8>(rt, pts, n, keys_out, vals_out, lattice);
-  if (n <= kCsCtas * kCsThreads * 16) return launch_cs<16>(rt, pts, n, keys_out, vals_out, lattice);
+  constexpr int T = DDLO_CS_THREADS;  // threads per CTA for the smaller clouds (1024 was measured: index 93 -> 105 us, the block barriers cost more than the extra warps hide)
+  if (n <= kCsCtas * T * 2) return launch_cs<T, 2>(rt, pts, n, keys_out, vals_out, lattice);
+  if (n <= kCsCtas * T * 4) return launch_cs<T, 4>(rt, pts, n, keys_out, vals_out, lattice);
+  if (n <= kCsCtas * 512 * 8) return launch_cs<512, 8>(rt, pts, n, keys_out, vals_out, lattice);
+  if (n <= kCsCtas * 512 * 16) return launch_cs<512, 16>(rt, pts, n, keys_out, vals_out, lattice);
   return DDLO_E_UNSUPPORTED;
 }
 
