@@ -16,8 +16,9 @@ its target kd-tree and covariance vector while `submap_hasChanged_` is false, od
              covariances, align, result + residual read-back; host wall clock.
   roofline   the align kernel (k_align): algorithmic bytes / its measured duration.
   cpu_baseline / --impl reference
-             the same step on the host cores: reference's own nanoflann (oracle/_ref) under the
-             restated GICP/LM (oracle/), all OpenMP threads.
+             the same step on the host cores with all OpenMP threads: the reference's OWN nano_gicp engine
+             (oracle/_ref/libnano_gicp_ref.so, its headers compiled unmodified over Eigen/PCL/Boost stand-ins);
+             if that library is missing, the oracle's restatement over the reference's nanoflann.
 
 Multi-GPU (torchrun, one rank per GPU): every rank registers its own scans against its own copy of
 the submap; no data-path collective (independent registrations), weak scaling.
@@ -131,18 +132,30 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_setup(src, tgt):
-    """Host-core arm: oracle GICP/LM over the reference's vendored nanoflann when it was compiled."""
+def cpu_reference_setup(src, tgt, prefer_reference_engine=True):
+    """Host-core arm.  Preferred: the reference's OWN nano_gicp engine (oracle/_ref/libnano_gicp_ref.so: its headers
+    compiled unmodified from /root/reference, over the Eigen/PCL/Boost stand-ins of oracle/stub_include since none of
+    the three is installed) - kind "reference".  Fallback: the oracle's restatement over the reference's vendored
+    nanoflann - kind "port"."""
     from oracle import pyoracle as po
 
-    backend = po.BACKEND_NANOFLANN_REF if po.load_reference_nanoflann() else po.BACKEND_CANONICAL
-    kind = "port"  # GICP/LM layer is the restatement; the kd-tree under it is the reference's own code when available
-    knn = "reference nanoflann 1.3.2 (oracle/_ref)" if backend == po.BACKEND_NANOFLANN_REF else "oracle kd-tree"
-    eng = po.NanoGICP(backend=backend)
-    T = po.Cloud(tgt)
+    mod, kind, what = None, None, None
+    if prefer_reference_engine:
+        from oracle import refgicp
+
+        if refgicp.available():
+            mod, kind = refgicp, "reference"
+            what = "the reference's own nano_gicp sources (oracle/_ref/libnano_gicp_ref.so, Eigen/PCL/Boost stand-ins), OpenMP"
+            eng = refgicp.NanoGICP()
+    if mod is None:
+        backend = po.BACKEND_NANOFLANN_REF if po.load_reference_nanoflann() else po.BACKEND_CANONICAL
+        mod, kind = po, "port"  # GICP/LM layer is the restatement; the kd-tree under it is the reference's own code when available
+        what = "oracle restatement of GICP/LM over " + ("reference nanoflann 1.3.2 (oracle/_ref)" if backend == po.BACKEND_NANOFLANN_REF else "oracle kd-tree")
+        eng = po.NanoGICP(backend=backend)
+    T = mod.Cloud(tgt)
     eng.setInputTarget(T)          # kd-tree over the submap: built once, outside the timed region (steady state)
     eng.calculateTargetCovariances()
-    return po, eng, T, kind, knn
+    return mod, eng, T, kind, what
 
 
 def cpu_step(po, eng, src, guess):
@@ -160,7 +173,9 @@ def run_reference(args):
         return 0
     src, tgt, guess = make_workload(0)
     po, eng, _, kind, knn = cpu_reference_setup(src, tgt)
-    cores = po.max_threads()
+    from oracle import pyoracle as _po
+
+    cores = _po.max_threads()
     for _ in range(max(args.warmup, 0)):
         cpu_step(po, eng, src, guess)
         eng.clearSource()
@@ -171,7 +186,7 @@ def run_reference(args):
         eng.clearSource()
     total = sum(times)
     value = args.steps / total
-    sample = f"{args.steps} full registrations (scan kd-tree + covariances + LM align, {r.n_linearize} linearize / {r.n_compute_error} error passes each); kNN: {knn}"
+    sample = f"{args.steps} full registrations (scan kd-tree + covariances + LM align, {r.iterations + 1} outer iterations each); {knn}"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -323,6 +338,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             po, ceng, _, kind, knn = cpu_reference_setup(src, tgt)
+            from oracle import pyoracle as _po
+            cores = _po.max_threads()
             cpu_step(po, ceng, src, guess)
             ceng.clearSource()
             ct, n = 0.0, 0
@@ -331,9 +348,18 @@ def run_ours(args):
                 ceng.clearSource()
                 ct += dt
                 n += 1
-            line["cpu_baseline"] = {"value": n / ct, "unit": UNIT, "cores": po.max_threads(), "kind": kind,
-                                    "sample": f"{n} full registrations of the same workload in {ct:.1f} s; kNN: {knn}",
+            line["cpu_baseline"] = {"value": n / ct, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{n} full registrations of the same workload in {ct:.1f} s; {knn}",
                                     "ms_per_step": 1e3 * ct / n}
+            if kind == "reference":  # for comparison: the oracle's restatement on the same inputs (a few steps)
+                po2, peng, _, _, _ = cpu_reference_setup(src, tgt, prefer_reference_engine=False)
+                cpu_step(po2, peng, src, guess)
+                peng.clearSource()
+                pts = []
+                for _ in range(5):
+                    pts.append(cpu_step(po2, peng, src, guess)[0])
+                    peng.clearSource()
+                line["cpu_baseline"]["oracle_port_ms_per_step"] = 1e3 * min(pts)
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -19,6 +19,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "_build" / "liboracle_gicp.so"
 REF_LIB_PATH = HERE / "_ref" / "libnanoflann_ref.so"
+REF_GICP_LIB_PATH = HERE / "_ref" / "libnano_gicp_ref.so"  # the reference's own engine, see oracle/refgicp.py
 REFERENCE_ROOT = Path("/root/reference")
 
 BACKEND_CANONICAL = 0
@@ -39,7 +40,10 @@ def build(force: bool = False) -> None:
         subprocess.run(["make", "-C", str(HERE), "-B", "all"], check=True, capture_output=True)
     ref_hdr = REFERENCE_ROOT / "dynamic_direct_lidar_odometry/include/nano_gicp/impl/nanoflann_impl.hpp"
     shim = HERE / "ref_nanoflann_shim.cpp"
-    if ref_hdr.exists() and (force or not REF_LIB_PATH.exists() or REF_LIB_PATH.stat().st_mtime < shim.stat().st_mtime):
+    gicp_shim = HERE / "ref_nano_gicp_shim.cpp"
+    stale = (not REF_LIB_PATH.exists() or REF_LIB_PATH.stat().st_mtime < shim.stat().st_mtime
+             or not REF_GICP_LIB_PATH.exists() or REF_GICP_LIB_PATH.stat().st_mtime < gicp_shim.stat().st_mtime)
+    if ref_hdr.exists() and (force or stale):
         subprocess.run(["make", "-C", str(HERE), "-B", "ref"], check=True, capture_output=True)
 
 
