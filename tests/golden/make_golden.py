@@ -3,8 +3,8 @@
 The reference ships no tests, fixtures or golden vectors, so these are pins made by
 this repository: the oracle's answers on small seeded inputs, frozen so that (a) a change of the
 oracle shows up as a diff and (b) the CUDA path can be checked on the GPU box without trusting a
-freshly built oracle.  Where the reference's own code could run (the vendored nanoflann,
-oracle/_ref) its answers are stored beside the oracle's.
+freshly built oracle.  Where the reference's own code could run (the vendored nanoflann and the nano_gicp
+engine itself, oracle/_ref) its answers are stored too: knn_small.npz ref_* and gicp_reference_engine.npz.
 
     python tests/golden/make_golden.py
 """
@@ -63,6 +63,31 @@ def main():
         res.update({f"{name}_T": r.T, f"{name}_H": r.hessian, f"{name}_meta": np.array([r.converged, r.iterations, r.n_linearize, r.n_compute_error])})
     np.savez_compressed(OUT / "gicp_small.npz", src=src, tgt=tgt, src_covs=eng.getSourceCovariances(), tgt_covs=eng.getTargetCovariances(),
                         T=Tq, err=e, H=H, b=b, corr=corr, sqd=sqd, T2=T2, err2=e2, **res)
+    # ---- the same quantities from the REFERENCE'S OWN ENGINE (oracle/refgicp.py: the reference's nano_gicp headers
+    # compiled unmodified over Eigen/PCL stand-ins), where /root/reference is available to build it
+    from oracle import refgicp as rg
+
+    if rg.available():
+        ref = rg.NanoGICP()
+        ref.setInputSource(rg.Cloud(src))
+        ref.setInputTarget(rg.Cloud(tgt))
+        ref.calculateSourceCovariances()
+        ref.calculateTargetCovariances()
+        re_, rH, rb = ref.linearize(Tq)
+        rcorr, rsqd = ref.correspondences()
+        out = dict(src=src, tgt=tgt, src_covs=ref.getSourceCovariances(), tgt_covs=ref.getTargetCovariances(), T=Tq, err=re_, H=rH, b=rb,
+                   corr=rcorr, sqd=rsqd, T2=T2, err2=ref.compute_error(T2))
+        for m in range(5):
+            rc = rg.NanoGICP()
+            rc.setRegularizationMethod(m)
+            rc.setInputSource(rg.Cloud(tgt))
+            rc.calculateSourceCovariances()
+            out[f"cov_method{m}"] = rc.getSourceCovariances()
+        for name, opt in (("lm", po.OPT_LEVENBERG_MARQUARDT), ("gn", po.OPT_GAUSS_NEWTON)):
+            ref.setOptimizer(opt)
+            r = ref.align()
+            out.update({f"{name}_T": r.T, f"{name}_H": r.hessian, f"{name}_meta": np.array([r.converged, r.iterations])})
+        np.savez_compressed(OUT / "gicp_reference_engine.npz", **out)
     print("golden fixtures written to", OUT)
 
 

@@ -738,3 +738,34 @@ def test_c2_align_matches_reference_engine(rt, ref_engine):
         da = np.linalg.norm(q - tgt[gc[diff], :3], axis=1)
         db = np.linalg.norm(q - tgt[rc[diff], :3], axis=1)
         assert np.allclose(da, db, rtol=1e-4, atol=1e-6)
+
+
+def test_against_reference_engine_fixture(rt):
+    """tests/golden/gicp_reference_engine.npz: outputs of the reference's own nano_gicp engine on a small seeded pair,
+    committed; the CUDA path reproduces them with nothing of oracle/ in the loop."""
+    from pathlib import Path
+
+    s = np.load(Path(__file__).resolve().parent / "golden" / "gicp_reference_engine.npz")
+    eng = ng.NanoGICP(rt)
+    eng.setInputSource(ng.PointCloud(rt, s["src"]))
+    eng.setInputTarget(ng.PointCloud(rt, s["tgt"]))
+    raw = s["cov_method0"][:, :3, :3]
+    w = np.linalg.eigvalsh(raw)
+    ok = (w[:, 1] - w[:, 0]) > 1e-6 * np.maximum(w[:, 2], 1e-30)
+    for m in range(5):
+        covs = ng.Covariances.compute(ng.PointCloud(rt, s["tgt"]), 20, m).to_host()
+        ref = s[f"cov_method{m}"]
+        per_point = np.linalg.norm((covs - ref).reshape(len(ref), -1), axis=1) / np.linalg.norm(ref.reshape(len(ref), -1), axis=1)
+        assert per_point[ok if m in (1, 2, 3) else slice(None)].max() < REL, m
+    eng.setSourceCovariances(s["src_covs"])
+    eng.setTargetCovariances(s["tgt_covs"])
+    e, H, b = eng.linearize(s["T"])
+    corr, sqd = eng.correspondences()
+    assert np.array_equal(corr, s["corr"]) and np.array_equal(sqd.view(np.uint32), s["sqd"].view(np.uint32))
+    assert rel_err(H, s["H"]) < REL and rel_err(b, s["b"]) < REL and abs(e - float(s["err"])) < REL * abs(e)
+    assert abs(eng.compute_error(s["T2"]) - float(s["err2"])) < REL * float(s["err2"])
+    for name, opt in (("lm", ng.OPT_LEVENBERG_MARQUARDT), ("gn", ng.OPT_GAUSS_NEWTON)):
+        eng.setOptimizer(opt)
+        r = eng.align()
+        assert (int(r.converged), r.iterations) == tuple(int(v) for v in s[f"{name}_meta"])
+        assert np.abs(r.T[:3, 3] - s[f"{name}_T"][:3, 3]).max() < POSE_T and rot_angle(r.T[:3, :3], s[f"{name}_T"][:3, :3]) < POSE_R

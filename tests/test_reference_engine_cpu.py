@@ -161,3 +161,34 @@ def test_odomnode_protocol_matches_reference_engine(oracle, ref):
         assert np.abs(o1.T.astype(np.float64) - r1.T).max() < 1e-6
         assert np.abs(o2.T.astype(np.float64) - r2.T).max() < 1e-6
         assert np.allclose(ores, rres, rtol=1e-6, atol=1e-9)
+
+
+def test_oracle_reproduces_reference_engine_fixture(oracle):
+    """tests/golden/gicp_reference_engine.npz holds outputs of the reference's own engine (written by
+    tests/golden/make_golden.py where /root/reference exists); the restatement must reproduce them anywhere."""
+    from pathlib import Path
+
+    f = Path(__file__).resolve().parent / "golden" / "gicp_reference_engine.npz"
+    s = np.load(f)
+    o = oracle.NanoGICP()
+    o.setInputSource(oracle.Cloud(s["src"]))
+    o.setInputTarget(oracle.Cloud(s["tgt"]))
+    o.calculateSourceCovariances(); o.calculateTargetCovariances()
+    raw = oracle.Cloud(s["tgt"]).build_tree().covariances(20, 0)[:, :3, :3]
+    w = np.linalg.eigvalsh(raw)
+    ok = (w[:, 1] - w[:, 0]) > 1e-6 * np.maximum(w[:, 2], 1e-30)
+    for m in range(5):
+        got = oracle.Cloud(s["tgt"]).build_tree().covariances(20, m)
+        sel = ok if m in (1, 2, 3) else np.ones(len(ok), bool)
+        assert rel(got[sel], s[f"cov_method{m}"][sel]) < 1e-9, m
+    o.setSourceCovariances(s["src_covs"]); o.setTargetCovariances(s["tgt_covs"])
+    e, H, b = o.linearize(s["T"])
+    corr, sqd = o.correspondences()
+    assert np.array_equal(corr, s["corr"]) and np.array_equal(sqd.view(np.uint32), s["sqd"].view(np.uint32))
+    assert rel(H, s["H"]) < 1e-10 and rel(b, s["b"]) < 1e-10 and abs(e - float(s["err"])) <= 1e-10 * abs(float(s["err"]))
+    assert abs(o.compute_error(s["T2"]) - float(s["err2"])) <= 1e-10 * abs(float(s["err2"]))
+    for name, opt in (("lm", 1), ("gn", 0)):
+        o.setOptimizer(opt)
+        r = o.align()
+        assert (int(r.converged), r.iterations) == tuple(int(v) for v in s[f"{name}_meta"])
+        assert np.abs(r.T.astype(np.float64) - s[f"{name}_T"]).max() < 1e-6
