@@ -234,6 +234,7 @@ struct TopKRegSub {
   unsigned long long bar;  // candidates must be < bar
   unsigned long long capk; // (cap, sentinel index): admits every index at distance == cap
   int k;
+  int skip_lo = 0, skip_hi = 0;  // Morton positions already in the list (prefill): scans leave them out
   static __device__ __forceinline__ unsigned long long pack(float dist, int oi) {
     return ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)oi;
   }
@@ -245,6 +246,60 @@ struct TopKRegSub {
     bar = capk;
   }
   __device__ __forceinline__ float worst() const { return __uint_as_float((unsigned)(bar >> 32)); }
+  // the bar from the entry at position k-1 (all 32 lanes)
+  __device__ __forceinline__ void refresh_bar(const Sub& sb) {
+    const int kr = (k - 1) % R, kl = sb.base + (k - 1) / R;
+    unsigned long long kth = e[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r) kth = kr == r ? e[r] : kth;
+    kth = __shfl_sync(kFull, kth, kl);
+    bar = min(kth, capk);
+  }
+  // Start from 8R real points of the cloud, the Morton positions [w0, w0 + 8R), instead of an empty list: their
+  // keys are ranked against each other (every lane compares its R keys with the R keys of each other lane) and
+  // moved to their sorted positions through `scratch` (8R words of shared memory owned by the sub-warp).  This
+  // replaces the first k insertions by one pass of compares, and the bar starts at the k-th distance inside the
+  // window.  Scans must skip these positions (skip_lo / skip_hi).  All 32 lanes; `active` uniform per sub-warp.
+  __device__ __forceinline__ void prefill(bool active, const float4* __restrict__ spts, int w0, float qx, float qy, float qz,
+                                          unsigned long long* __restrict__ scratch, const Sub& sb) {
+    unsigned long long key[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      key[r] = pack(FLT_MAX, kIdxSentinel - (sb.sl * R + r));  // (distinct dummies for idle sub-warps)
+      if (active) {
+        const float4 v = __ldg(spts + w0 + sb.sl * R + r);
+        key[r] = pack(sqdist3_rn(qx, qy, qz, v.x, v.y, v.z), __float_as_int(v.w));
+      }
+    }
+    int rank[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      rank[r] = 0;
+#pragma unroll
+      for (int q = 0; q < R; ++q) rank[r] += key[q] < key[r] ? 1 : 0;
+    }
+#pragma unroll
+    for (int d = 1; d < kSubLanes; ++d) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const unsigned long long o = __shfl_sync(kFull, key[q], sb.base + ((sb.sl + d) & (kSubLanes - 1)));
+#pragma unroll
+        for (int r = 0; r < R; ++r) rank[r] += o < key[r] ? 1 : 0;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r) scratch[rank[r]] = key[r];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r) e[r] = scratch[sb.sl * R + r];
+    __syncwarp();
+    if (active) {
+      skip_lo = w0;
+      skip_hi = w0 + kSubLanes * R;
+    }
+    refresh_bar(sb);
+  }
   // all 32 lanes; `c` and `upd` uniform per sub-warp
   __device__ __forceinline__ void insert(bool upd, unsigned long long c, const Sub& sb) {
     unsigned long long left = __shfl_up_sync(kFull, e[R - 1], 1);
@@ -272,7 +327,7 @@ struct TopKRegSub {
     for (int r = 0; __any_sync(kFull, doit && r < count); r += kSubLanes) {
       const int j = r + sb.sl;
       unsigned long long key = ~0ull;
-      if (doit && j < count) {
+      if (doit && j < count && !(start + j >= skip_lo && start + j < skip_hi)) {
         const float4 v = __ldg(spts + start + j);
         const float dist = sqdist3_rn(qx, qy, qz, v.x, v.y, v.z);
         if (dist < FLT_MAX) key = pack(dist, __float_as_int(v.w));

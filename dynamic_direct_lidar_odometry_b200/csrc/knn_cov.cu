@@ -54,10 +54,13 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(IndexView ix, const float4*
     }
   };
   if constexpr (R > 0) {
-    // Self queries know k points of the cloud for free: the k consecutive Morton positions around
-    // the query.  The largest distance among them bounds the k-th neighbour distance from above.
+    // Self queries know points of the cloud for free: the consecutive Morton positions around the query.
+    // With at least 8R of them the result list starts from that window, ranked in one pass (prefill);
+    // otherwise the largest distance among k of them caps the k-th neighbour distance from above.
+    constexpr int kWindow = kSubLanes * R;
+    const bool window_fill = self_mode && ix.n >= kWindow && k <= kWindow;
     float cap = FLT_MAX;
-    if (self_mode && ix.n >= k) {
+    if (self_mode && !window_fill && ix.n >= k) {
       float far = 0.0f;
       if (active) {
         const int w0 = min(max(q - k / 2, 0), ix.n - k);
@@ -72,6 +75,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(IndexView ix, const float4*
     }
     TopKRegSub<R> rs;
     rs.init(k, cap);
+    if (window_fill) rs.prefill(active, ix.spts, min(max(q - kWindow / 2, 0), ix.n - kWindow), v.x, v.y, v.z, stack, sb);
     search(rs);
     if (active) rs.write_sorted(idx_out + row * k, d_out ? d_out + row * k : nullptr, sb);
   } else {
