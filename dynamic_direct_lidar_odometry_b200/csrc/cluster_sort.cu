@@ -277,14 +277,17 @@ template <int kCsThreads, int IPT>
 static int launch_cs(ddlo_runtime* rt, const float4* pts, int n, unsigned* keys_out, int* vals_out, float* lattice) {
   using L = CsLayout<kCsThreads, IPT>;
   auto kern = k_morton_sort_cluster<kCsThreads, IPT>;
-  static bool configured = false, usable = false;
-  if (!configured) {
-    configured = true;
-    usable = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes) == cudaSuccess &&
-             cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
-    if (!usable) (void)cudaGetLastError();
+  // per device (function attributes are per device): bit set in `configured` once tried, in `usable` if it worked
+  static std::atomic<unsigned long long> configured{0}, usable{0};
+  const unsigned long long bit = 1ull << (rt->device & 63);
+  if (!(configured.load() & bit)) {
+    const bool ok = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes) == cudaSuccess &&
+                    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (!ok) (void)cudaGetLastError();
+    if (ok) usable.fetch_or(bit);
+    configured.fetch_or(bit);
   }
-  if (!usable) return DDLO_E_UNSUPPORTED;
+  if (!(usable.load() & bit)) return DDLO_E_UNSUPPORTED;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kCsCtas);
   cfg.blockDim = dim3(kCsThreads);
@@ -299,7 +302,7 @@ static int launch_cs(ddlo_runtime* rt, const float4* pts, int n, unsigned* keys_
   cfg.numAttrs = 1;
   if (cudaLaunchKernelEx(&cfg, kern, pts, n, keys_out, vals_out, lattice) != cudaSuccess) {
     (void)cudaGetLastError();
-    usable = false;  // e.g. no GPC can host a cluster of 16: never try again
+    usable.fetch_and(~bit);  // e.g. no GPC can host a cluster of 16: never try again on this device
     return DDLO_E_UNSUPPORTED;
   }
   rt->launches += 1;

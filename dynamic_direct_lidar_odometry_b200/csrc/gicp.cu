@@ -677,14 +677,18 @@ __global__ void __launch_bounds__(256) k_transform_cloud(const float4* __restric
 }
 
 // ---- launchers ----------------------------------------------------------------------------------
+// function attributes are per device: remember which devices have them (a process may drive several GPUs)
 static int set_smem_attrs() {
-  static bool done = false;
-  if (done) return DDLO_OK;
+  static std::atomic<unsigned long long> done_mask{0};
+  int dev = 0;
+  DDLO_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done_mask.load() & bit) return DDLO_OK;
   const int bytes = (int)sizeof(AlignSmem);
   DDLO_CUDA(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   DDLO_CUDA(cudaFuncSetAttribute(k_linearize_step, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   DDLO_CUDA(cudaFuncSetAttribute(k_error_step, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  done = true;
+  done_mask.fetch_or(bit);
   return DDLO_OK;
 }
 

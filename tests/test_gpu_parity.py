@@ -769,3 +769,21 @@ def test_against_reference_engine_fixture(rt):
         r = eng.align()
         assert (int(r.converged), r.iterations) == tuple(int(v) for v in s[f"{name}_meta"])
         assert np.abs(r.T[:3, 3] - s[f"{name}_T"][:3, 3]).max() < POSE_T and rot_angle(r.T[:3, :3], s[f"{name}_T"][:3, :3]) < POSE_R
+
+
+def test_two_devices_in_one_process(small_pair):
+    """One process driving two GPUs (one runtime each): kernel attributes and pools are per device."""
+    if ng.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    src, tgt = small_pair
+    out = []
+    for dev in (0, 1):
+        r = ng.Runtime(dev)
+        g = ng.NanoGICP(r)
+        g.setInputSource(ng.PointCloud(r, src))
+        g.setInputTarget(ng.PointCloud(r, tgt))
+        out.append(g.align())
+        del g
+        r.close()
+    assert out[0].converged and out[1].converged
+    assert np.array_equal(out[0].T, out[1].T) and np.array_equal(out[0].hessian, out[1].hessian)
