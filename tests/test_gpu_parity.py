@@ -787,3 +787,41 @@ def test_two_devices_in_one_process(small_pair):
         r.close()
     assert out[0].converged and out[1].converged
     assert np.array_equal(out[0].T, out[1].T) and np.array_equal(out[0].hessian, out[1].hessian)
+
+
+def _adversarial_clouds(rng):
+    yield "identical", np.tile(np.array([[1.5, -2.0, 0.25]], np.float32), (300, 1))
+    t = rng.uniform(-50, 50, 4000).astype(np.float32)
+    yield "line", np.stack([t, 2 * t, -t], axis=1).astype(np.float32)
+    yield "plane", np.stack([rng.uniform(-30, 30, 5000), rng.uniform(-30, 30, 5000), np.zeros(5000)], axis=1).astype(np.float32)
+    a = rng.normal(scale=1e-3, size=(3000, 3)) + np.array([1e4, 1e4, 1e4])
+    b = rng.normal(scale=1e-3, size=(3000, 3)) - np.array([1e4, 1e4, 1e4])
+    yield "two far clusters", np.concatenate([a, b]).astype(np.float32)
+    base = rng.normal(size=(700, 3)).astype(np.float32)
+    yield "five-fold duplicates", np.repeat(base, 5, axis=0)[rng.permutation(3500)]
+    g = np.stack(np.meshgrid(np.arange(20), np.arange(20), np.arange(20), indexing="ij"), axis=-1).reshape(-1, 3).astype(np.float32)
+    yield "integer lattice (massive ties)", g
+    yield "dense blob in a huge box", np.concatenate([rng.normal(scale=0.01, size=(20000, 3)), [[1e3, 1e3, 1e3], [-1e3, -1e3, -1e3]]]).astype(np.float32)
+    yield "tiny values", (rng.normal(size=(2000, 3)) * 1e-20).astype(np.float32)
+
+
+def test_knn_adversarial_clouds(rt, oracle):
+    """Exactness on degenerate geometry: zero extent, collinear / coplanar points, far clusters, duplicates, lattices
+    full of ties, a blob deeper than the 10 Morton levels, denormal-scale coordinates - indices and squared distances
+    must equal a brute force with ties broken by index, bit for bit (this also exercises the cluster sort and the
+    octree build on their edge cases)."""
+    rng = np.random.default_rng(11)
+    for name, pts in _adversarial_clouds(rng):
+        cloud = ng.PointCloud(rt, pts).build_index()
+        sel = rng.choice(len(pts), min(len(pts), 64), replace=False)
+        q = np.concatenate([pts[sel], pts[sel] + rng.normal(scale=max(1e-30, float(np.abs(pts).max()) * 1e-3), size=(len(sel), 3)).astype(np.float32)])
+        for k in (1, 6, 20):
+            idx, d2 = cloud.nearestKSearch(q, k)
+            bidx, bd2 = oracle.knn_bruteforce(pts, q, k)
+            assert np.array_equal(idx, bidx), (name, k)
+            assert np.array_equal(d2.view(np.uint32), bd2.view(np.uint32)), (name, k)
+        if len(pts) >= 20:  # the self-kNN path of the covariances (prefill, bottom-up search) on the same clouds
+            covs = ng.Covariances.compute(cloud, 20, ng.REG_NONE).to_host()
+            want = oracle.Cloud(pts).build_tree().covariances(20, oracle.REG_NONE)
+            scale = max(float(np.abs(want).max()), 1e-300)
+            assert np.abs(covs - want).max() <= 1e-6 * scale, name
