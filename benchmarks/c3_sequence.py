@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--frames", type=int, default=100)
     ap.add_argument("--beams", type=int, default=64)
     ap.add_argument("--cols", type=int, default=1024)
+    ap.add_argument("--voxel", type=float, default=0.0, help="leaf size of the scan and keyframe voxel filters on the device (0 = off; the DLO yaml uses 0.25 - 0.5 m)")
     ap.add_argument("--k", type=int, default=20, help="kCorrespondences of both engines (engine default 20; the DLO yaml uses 10)")
     args = ap.parse_args()
 
@@ -42,7 +43,8 @@ def main():
     t0 = time.perf_counter()
     scans = [synth.scan(f, args.beams, args.cols, w) for f in range(args.frames)]
     gen_s = time.perf_counter() - t0
-    cfg = ol.LoopConfig(k_correspondences_s2s=args.k, k_correspondences_s2m=args.k)
+    cfg = ol.LoopConfig(k_correspondences_s2s=args.k, k_correspondences_s2m=args.k,
+                        voxel_leaf_scan=args.voxel or None, voxel_leaf_submap=args.voxel or None)
 
     rt = ng.Runtime(0)
     ol.run_sequence(ol.GpuBackend(rt), scans[: min(8, args.frames)], cfg)  # warm-up: allocator pools, first launches
@@ -60,7 +62,7 @@ def main():
         "s2s_iterations_mean": float(np.mean([r.s2s_iterations + 1 for r in loop.records])),
         "s2m_iterations_mean": float(np.mean([r.s2m_iterations + 1 for r in loop.records])),
         "final_translation_error_vs_truth_m": err_t[-1], "max_translation_error_vs_truth_m": max(err_t),
-        "k_correspondences": args.k, "timer": "host wall clock per frame, scan upload and residual read-back included",
+        "k_correspondences": args.k, "voxel_leaf_m": args.voxel, "timer": "host wall clock per frame, scan upload and residual read-back included",
         "scan_generation_s": gen_s,
         "slowest_frames": [{"frame": int(i) + 1, "ms": float(ms[i]), "new_keyframe": bool(loop.records[i].new_keyframe),
                             "submap_changed": bool(loop.records[i].submap_changed), "submap_points": int(loop.records[i].submap_points)}

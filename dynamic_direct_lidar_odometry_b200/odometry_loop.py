@@ -42,6 +42,12 @@ class GpuBackend:
     def cloud(self, points):
         return self.ng.PointCloud(self.rt, points)
 
+    def voxel_filter(self, cloud, leaf):  # vf_scan_.filter / vf_submap_.filter (odom.cc:469-474, 1133-1137), on the device
+        return cloud.voxel_filtered(leaf)
+
+    def size(self, cloud):
+        return cloud.size()
+
     def transform(self, cloud, T):  # pcl::transformPointCloud
         return cloud.transformed(np.asarray(T, dtype=np.float32))
 
@@ -75,6 +81,8 @@ class LoopConfig:
     keyframe_thresh_dist: float = 1.0   # metres (odom.cc:1169, "rebuilt every 1 m" in SURVEY.md §8d C3)
     keyframe_thresh_rot: float = 15.0   # degrees
     submap_knn: int = 10                # odomNode/submap/keyframe/knn
+    voxel_leaf_scan: Optional[float] = None    # vf_scan_ leaf size (preprocessPoints, odom.cc:469-474); None = off
+    voxel_leaf_submap: Optional[float] = None  # vf_submap_ leaf size applied to every new keyframe (odom.cc:494-499, 1133-1137)
 
 
 @dataclass
@@ -128,9 +136,11 @@ class OdometryLoop:
         self.s2s.setInputTarget(scan_cloud)
         self.s2s.calculateTargetCovariances()
         first = self.b.transform(scan_cloud, self.T)
+        if self.cfg.voxel_leaf_submap:
+            first = self.b.voxel_filter(first, self.cfg.voxel_leaf_submap)
         self.s2s.setInputSource(first)  # temporary storage, overwritten by the next setInputSources()
         self.s2s.calculateSourceCovariances()
-        self.keyframes.append(Keyframe(self.T[:3, 3].copy(), self.T[:3, :3].copy(), first, self.s2s.getSourceCovariances(), n))
+        self.keyframes.append(Keyframe(self.T[:3, 3].copy(), self.T[:3, :3].copy(), first, self.s2s.getSourceCovariances(), self.b.size(first)))
         self._initialised = True
 
     # odom.cc:1215-1315, nearest keyframes only
@@ -154,16 +164,20 @@ class OdometryLoop:
             new = True
         if new:
             kf = self.b.transform(scan_cloud, self.T)
+            if self.cfg.voxel_leaf_submap:
+                kf = self.b.voxel_filter(kf, self.cfg.voxel_leaf_submap)
             self.s2s.setInputSource(kf)
             self.s2s.calculateSourceCovariances()
-            self.keyframes.append(Keyframe(pos.copy(), rot.copy(), kf, self.s2s.getSourceCovariances(), n))
+            self.keyframes.append(Keyframe(pos.copy(), rot.copy(), kf, self.s2s.getSourceCovariances(), self.b.size(kf)))
         return new
 
     def step(self, scan_points: np.ndarray) -> Optional[FrameRecord]:
         """One LiDAR frame (registration scan in the sensor frame, Nx4 float32)."""
         t0 = time.perf_counter()
         cur = self.b.cloud(scan_points)
-        n = len(scan_points)
+        if self.cfg.voxel_leaf_scan:  # preprocessPoints (odom.cc:469-474)
+            cur = self.b.voxel_filter(cur, self.cfg.voxel_leaf_scan)
+        n = self.b.size(cur)
         if not self._initialised:
             self._initialize_input_target(cur, n)
             return None

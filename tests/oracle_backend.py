@@ -13,6 +13,12 @@ class OracleBackend:
     def cloud(self, points):
         return self.po.Cloud(points)
 
+    def voxel_filter(self, cloud, leaf):
+        return self.po.Cloud(self.po.voxel_filter(cloud.points, leaf))
+
+    def size(self, cloud):
+        return cloud.n
+
     def transform(self, cloud, T):
         # float arithmetic of pcl::transformPointCloud as Eigen evaluates it: (r0 x + r1 y) + (r2 z + t)
         T = np.asarray(T, dtype=np.float32)

@@ -825,3 +825,23 @@ def test_knn_adversarial_clouds(rt, oracle):
             want = oracle.Cloud(pts).build_tree().covariances(20, oracle.REG_NONE)
             scale = max(float(np.abs(want).max()), 1e-300)
             assert np.abs(covs - want).max() <= 1e-6 * scale, name
+
+
+def test_sequence_loop_with_voxel_filters_matches_oracle(rt, oracle):
+    """The odometry loop with the scan and keyframe voxel filters of preprocessPoints / updateKeyframes on the device
+    (odom.cc:469-474, 1133-1137) against the same loop on the oracle."""
+    from dynamic_direct_lidar_odometry_b200 import odometry_loop as ol
+    from oracle_backend import OracleBackend
+
+    w = synth.make_world()
+    scans = [synth.scan(f, 32, 512, w) for f in range(8)]
+    cfg = ol.LoopConfig(k_correspondences_s2s=10, k_correspondences_s2m=10, keyframe_thresh_dist=0.3, submap_knn=3,
+                        voxel_leaf_scan=0.5, voxel_leaf_submap=0.5)
+    got = ol.run_sequence(ol.GpuBackend(rt), scans, cfg)
+    want = ol.run_sequence(OracleBackend(oracle), scans, cfg)
+    assert len(got.keyframes) == len(want.keyframes) >= 2
+    for g, o in zip(got.records, want.records):
+        assert (g.s2s_iterations, g.s2m_iterations, g.new_keyframe, g.submap_changed, g.submap_points) == (
+            o.s2s_iterations, o.s2m_iterations, o.new_keyframe, o.submap_changed, o.submap_points)
+        assert np.abs(g.T[:3, 3].astype(np.float64) - o.T[:3, 3]).max() < POSE_T
+        assert rot_angle(g.T[:3, :3], o.T[:3, :3]) < POSE_R
