@@ -300,8 +300,10 @@ struct TopKRegSub {
     }
     refresh_bar(sb);
   }
-  // all 32 lanes; `c` and `upd` uniform per sub-warp
-  __device__ __forceinline__ void insert(bool upd, unsigned long long c, const Sub& sb) {
+  // all 32 lanes; `c` and `upd` uniform per sub-warp.  Puts c at its sorted position (the last entry falls off);
+  // the bar is NOT refreshed: a candidate admitted against a slightly stale bar lands behind position k-1 and
+  // changes nothing among the k nearest, so one refresh per scan step is enough.
+  __device__ __forceinline__ void insert_only(bool upd, unsigned long long c, const Sub& sb) {
     unsigned long long left = __shfl_up_sync(kFull, e[R - 1], 1);
     if (sb.sl == 0) left = 0ull;  // nothing to the left of position 0
     if (upd) {
@@ -315,12 +317,10 @@ struct TopKRegSub {
         gl = gr;
       }
     }
-    const int kr = (k - 1) % R, kl = sb.base + (k - 1) / R;
-    unsigned long long kth = e[0];
-#pragma unroll
-    for (int r = 1; r < R; ++r) kth = kr == r ? e[r] : kth;
-    kth = __shfl_sync(kFull, kth, kl);
-    bar = min(kth, capk);
+  }
+  __device__ __forceinline__ void insert(bool upd, unsigned long long c, const Sub& sb) {
+    insert_only(upd, c, sb);
+    refresh_bar(sb);
   }
   __device__ __forceinline__ void scan(bool doit, const float4* __restrict__ spts, int start, int count, float qx, float qy, float qz,
                                        const Sub& sb) {
@@ -333,12 +333,15 @@ struct TopKRegSub {
         if (dist < FLT_MAX) key = pack(dist, __float_as_int(v.w));
       }
       unsigned cb = sub_ballot(key < bar, sb);
-      while (__any_sync(kFull, cb != 0u)) {
-        const bool act = cb != 0u;
-        const int c = act ? __ffs(cb) - 1 : 0;
-        cb &= cb - 1u;
-        const unsigned long long ck = __shfl_sync(kFull, key, sb.base + c);
-        insert(act && ck < bar, ck, sb);  // the bar may have dropped since the ballot
+      if (__any_sync(kFull, cb != 0u)) {
+        do {
+          const bool act = cb != 0u;
+          const int c = act ? __ffs(cb) - 1 : 0;
+          cb &= cb - 1u;
+          const unsigned long long ck = __shfl_sync(kFull, key, sb.base + c);
+          insert_only(act, ck, sb);
+        } while (__any_sync(kFull, cb != 0u));
+        refresh_bar(sb);
       }
     }
   }
