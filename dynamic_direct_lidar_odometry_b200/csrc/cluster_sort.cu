@@ -28,9 +28,26 @@ namespace cg = cooperative_groups;
 namespace ddlo {
 
 constexpr int kCsCtas = 16;
-constexpr int kCsBits = 5;
+#ifndef DDLO_CS_BITS
+#define DDLO_CS_BITS 5
+#endif
+constexpr int kCsBits = DDLO_CS_BITS;  // 5: six passes over 32 digits; 6: five passes over 64 digits (measured: index 95 vs 97 us, no gain)
 constexpr int kCsBins = 1 << kCsBits;
-constexpr int kCsPasses = 6;  // 30 bits
+constexpr int kCsPasses = (30 + kCsBits - 1) / kCsBits;
+static_assert(kCsBins == 32 || kCsBins == 64, "a warp scans the digit totals: one or two digits per lane");
+
+// exclusive scan of kCsBins values held by warp 0 (value of digit lane, and of digit lane + 32 when there are 64)
+__device__ __forceinline__ void cs_scan_bins(unsigned lo_v, unsigned hi_v, int lane, unsigned& lo_ex, unsigned& hi_ex) {
+  unsigned a = lo_v, b = hi_v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned ua = __shfl_up_sync(0xffffffffu, a, o), ub = __shfl_up_sync(0xffffffffu, b, o);
+    if (lane >= o) a += ua, b += ub;
+  }
+  const unsigned total_lo = __shfl_sync(0xffffffffu, a, 31);
+  lo_ex = a - lo_v;
+  hi_ex = total_lo + b - hi_v;
+}
 
 __device__ __forceinline__ unsigned cs_spread10(unsigned v) {
   v &= 0x3ffu;
@@ -60,7 +77,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_morton_sort_cluster(const flo
   using L = CsLayout<kCsThreads, IPT>;
   constexpr int kCsWarps = L::kCsWarps;
   constexpr int kPerLane = kCsThreads / 32;        // counters of one digit a lane scans
-  constexpr int kBinsPerWarp = kCsBins / kCsWarps > 0 ? kCsBins / kCsWarps : 1;
+  constexpr int kBinsPerWarp = (kCsBins + kCsWarps - 1) / kCsWarps;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -212,14 +229,11 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_morton_sort_cluster(const flo
     }
     __syncthreads();
     if (warp == 0) {  // where each digit's run starts in B
-      const unsigned v = tot[lane];
-      unsigned inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += u;
-      }
-      lbase[lane] = inc - v;
+      const unsigned lo_v = tot[lane], hi_v = kCsBins > 32 ? tot[(lane + 32) % kCsBins] : 0u;
+      unsigned lo_ex, hi_ex;
+      cs_scan_bins(lo_v, hi_v, lane, lo_ex, hi_ex);
+      lbase[lane] = lo_ex;
+      if (kCsBins > 32) lbase[(lane + 32) % kCsBins] = hi_ex;
     }
     __syncthreads();
     // regroup the slice by digit inside the CTA: position = start of the digit's run + elements of the digit in
@@ -227,25 +241,24 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_morton_sort_cluster(const flo
 #pragma unroll
     for (int j = 0; j < IPT; ++j) B[lbase[dg[j]] + cnt[dg[j] * kCsThreads + t] + rk[j]] = e[j];
     cluster.sync();  // every CTA's B and totals are final, and nobody reads its A any more
-    if (t < kCsBins * kCsCtas) {
-      const int b = t / kCsCtas, c = t % kCsCtas;  // 32 digits x 16 CTAs
-      all[b * kCsCtas + c] = cluster.map_shared_rank(tot, c)[b];
+    for (int i = t; i < kCsBins * kCsCtas; i += kCsThreads) {  // every CTA's total of every digit
+      const int b = i / kCsCtas, c = i % kCsCtas;
+      all[i] = cluster.map_shared_rank(tot, c)[b];
     }
     __syncthreads();
     if (warp == 0) {
-      unsigned row = 0, before = 0;
-      for (int c = 0; c < kCsCtas; ++c) {
-        const unsigned v = all[lane * kCsCtas + c];
-        before += c < rank ? v : 0u;
-        row += v;
-      }
-      unsigned inc = row;
+      unsigned row[2] = {0, 0}, before[2] = {0, 0};
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += u;
-      }
-      base[lane] = inc - row + before;  // elements with a smaller digit anywhere + the same digit in lower CTAs
+      for (int hh = 0; hh < (kCsBins > 32 ? 2 : 1); ++hh)
+        for (int c = 0; c < kCsCtas; ++c) {
+          const unsigned v = all[(lane + 32 * hh) * kCsCtas + c];
+          before[hh] += c < rank ? v : 0u;
+          row[hh] += v;
+        }
+      unsigned lo_ex, hi_ex;
+      cs_scan_bins(row[0], row[1], lane, lo_ex, hi_ex);
+      base[lane] = lo_ex + before[0];  // elements with a smaller digit anywhere + the same digit in lower CTAs
+      if (kCsBins > 32) base[(lane + 32) % kCsBins] = hi_ex + before[1];
     }
     __syncthreads();
     // the exchange: a digit's run in B is contiguous in the global order too, so consecutive threads store
