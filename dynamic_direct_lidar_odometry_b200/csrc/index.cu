@@ -203,7 +203,18 @@ __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys,
     o[1] = o[4] = f2ord(p.y);
     o[2] = o[5] = f2ord(p.z);
   }
-  const int Lmax = __reduce_max_sync(0xffffffffu, L);
+  // deepest leaf level inside the block (all warps walk the same number of levels: the loop holds block barriers)
+  __shared__ int s_lmax;
+  __shared__ int s_cell0;
+  __shared__ unsigned s_box[8][6];
+  if (threadIdx.x == 0) s_lmax = 0;
+  __syncthreads();
+  {
+    const int wl = __reduce_max_sync(0xffffffffu, L);
+    if (lane == 0) atomicMax(&s_lmax, wl);
+  }
+  __syncthreads();
+  const int Lmax = s_lmax;
   // the node ids of the point's cells on all its levels, fetched up front (independent loads: one memory
   // latency instead of one per level)
   int nid[kMortonLevels];
@@ -230,6 +241,32 @@ __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys,
       } else {
         pw[48 + 2 * slot] = (unsigned)i;  // leaf start; the count is accumulated below
       }
+    }
+    // High in the tree all 256 points of a block sit in ONE internal cell: then the block folds its box with one
+    // atomic per component instead of one per warp (at the root's children 2048 warps would queue on 48 words).
+    if (threadIdx.x == 0) s_cell0 = cell;
+    __syncthreads();
+    const bool whole_block = __syncthreads_and(in && t < L && cell == s_cell0) != 0;
+    if (whole_block) {
+      const int warp = threadIdx.x >> 5;
+      unsigned r[6];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        r[a] = __reduce_min_sync(0xffffffffu, o[a]);
+        r[3 + a] = __reduce_max_sync(0xffffffffu, o[3 + a]);
+      }
+      if (lane < 6) s_box[warp][lane] = r[lane];
+      __syncthreads();
+      if (threadIdx.x < 6) {
+        unsigned acc = s_box[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) acc = threadIdx.x < 3 ? min(acc, s_box[w][threadIdx.x]) : max(acc, s_box[w][threadIdx.x]);
+        unsigned* pw = nodes + (size_t)parent * 64 + 8 * threadIdx.x + slot;
+        if (threadIdx.x < 3)
+          atomicMin(pw, acc);
+        else
+          atomicMax(pw, acc);
+      }
+      continue;
     }
     // segmented reduction over runs of equal `cell` (runs are contiguous lanes)
     unsigned v[6] = {o[0], o[1], o[2], o[3], o[4], o[5]};
