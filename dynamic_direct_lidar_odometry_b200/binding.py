@@ -123,8 +123,31 @@ SIGNATURES = {
     "ddlo_gicp_get_residuals_async": [_vp, _vp, C.c_int],
     "ddlo_gicp_get_residual_vectors": [_vp, _vp, _vp, C.c_int],
     "ddlo_gicp_residual_image": [_vp, C.c_int, C.c_int, C.c_double, C.c_double, _vp],
+    "ddlo_segment_scan": [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _ip, _vp],
     "ddlo_gicp_align_batch": [_vpp, C.c_int, _vp, C.POINTER(AlignResult)],
 }
+class SegmentationParams(C.Structure):
+    """struct ddlo_segmentation_params (include/ddlo_gicp.h); the defaults are the reference's (detection.cpp:76-105, :520-522)."""
+
+    _fields_ = [(n, C.c_int) for n in ("rows", "cols", "ground_rows", "valid_point_num", "min_line_num", "valid_line_num",
+                                       "window_row_min", "window_row_max", "window_col_min", "window_col_max")] + \
+               [(n, C.c_float) for n in ("ang_bottom", "ground_angle_threshold", "minimum_range", "sensor_mount_angle", "theta",
+                                         "min_delta_z", "max_delta_z", "max_distance", "max_elevation")]
+
+    DEFAULTS = dict(rows=128, cols=1024, ground_rows=30, valid_point_num=15, min_line_num=5, valid_line_num=5,
+                    window_row_min=156, window_row_max=356, window_col_min=156, window_col_max=356,
+                    ang_bottom=45.0, ground_angle_threshold=10.0, minimum_range=10.0, sensor_mount_angle=10.0,
+                    theta=60.0 / 180.0 * 3.14159265358979323846, min_delta_z=0.1, max_delta_z=3.0, max_distance=20.0, max_elevation=2.0)
+
+    def __init__(self, **kw):
+        super().__init__()
+        unknown = set(kw) - set(self.DEFAULTS)
+        if unknown:
+            raise TypeError(f"unknown segmentation parameters: {sorted(unknown)}")
+        for k, v in {**self.DEFAULTS, **kw}.items():
+            setattr(self, k, v)
+
+
 _SPECIAL = {
     "ddlo_abi_version": (C.c_int, []),
     "ddlo_last_error": (C.c_char_p, []),

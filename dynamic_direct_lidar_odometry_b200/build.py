@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libddlo_gicp_b200.so"
-SOURCES = ["api.cu", "index.cu", "knn_cov.cu", "gicp.cu", "preprocess.cu", "cluster_sort.cu"]
+SOURCES = ["api.cu", "index.cu", "knn_cov.cu", "gicp.cu", "preprocess.cu", "cluster_sort.cu", "segmentation.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -30,6 +30,9 @@ int voxel_filter_device(ddlo_runtime* rt, const float4* pts, int n, const float 
 int crop_box_device(ddlo_runtime* rt, const float4* pts, int n, const float lo[3], const float hi[3], int negative, int keep_organized,
                     float4** d_out, int* n_out);
 int residual_image_device(ddlo_runtime* rt, const float4* pts, const float* sqd, int n, int w, int h, double a_min, double a_max, float4* d_out);
+int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, const float* T16, const float* d_scan, int stride_floats,
+                        const float* d_residuals, int* d_label, float* d_range, signed char* d_ground, double* d_avg_by_label,
+                        int* d_label_count);
 
 // raw strided host points -> float4 (x, y, z, 1)
 __global__ void __launch_bounds__(256) k_repack(const unsigned char* __restrict__ raw, int n, int stride, float4* __restrict__ out) {
@@ -1103,6 +1106,59 @@ int ddlo_gicp_residual_image(ddlo_gicp* g, int width, int height, double angle_m
   cudaFreeAsync(d_img, rt->stream);
   if (rc != DDLO_OK) return rc;
   DDLO_CUDA(cudaStreamSynchronize(rt->stream));
+  return DDLO_OK;
+}
+
+int ddlo_segment_scan(ddlo_runtime* rt, const ddlo_segmentation_params* params, const float* scan_t, int stride_bytes, const float* T16,
+                      const float* residuals, int* label_mat, float* range_mat, signed char* ground_mat, double* avg_residuals,
+                      int avg_capacity, int* label_count, float* device_ms) {
+  if (!rt || !params || !scan_t || !T16 || !label_count) return fail(DDLO_E_INVALID, "null argument");
+  const ddlo_segmentation_params& p = *params;
+  if (p.rows < 2 || p.cols < 1 || (long long)p.rows * p.cols > (1 << 24)) return fail(DDLO_E_INVALID, "bad range image geometry");
+  if (stride_bytes < 12 || stride_bytes % 4 != 0) return fail(DDLO_E_INVALID, "stride must be a multiple of 4, at least 12 bytes");
+  if (p.ground_rows < 0 || p.ground_rows >= p.rows) return fail(DDLO_E_INVALID, "ground_rows must be below rows (the reference indexes row -1 otherwise)");
+  if (p.window_col_max >= p.cols)
+    return fail(DDLO_E_UNSUPPORTED, "window_col_max >= cols: the reference's one-directional column wrap (detection.cpp:590-599) is not supported");
+  if (avg_residuals && avg_capacity < 0) return fail(DDLO_E_INVALID, "negative capacity");
+  DDLO_TRY(use_device(rt));
+  cudaStream_t st = rt->stream;
+  const size_t HW = (size_t)p.rows * p.cols;
+  const int stride = stride_bytes / 4;
+  float *d_scan = nullptr, *d_res = nullptr, *d_range = nullptr;
+  int *d_label = nullptr, *d_count = nullptr;
+  signed char* d_ground = nullptr;
+  double* d_avg = nullptr;
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_scan), HW * stride_bytes, st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_range), HW * 4, st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_label), HW * 4 + 16, st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ground), HW, st));
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_avg), (HW + 1) * 8, st));
+  if (residuals) DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_res), HW * 4, st));
+  d_count = d_label + HW;
+  DDLO_CUDA(cudaMemcpyAsync(d_scan, scan_t, HW * stride_bytes, cudaMemcpyHostToDevice, st));
+  if (residuals) DDLO_CUDA(cudaMemcpyAsync(d_res, residuals, HW * 4, cudaMemcpyHostToDevice, st));
+  DDLO_CUDA(cudaMemsetAsync(d_avg, 0, (HW + 1) * 8, st));
+  if (device_ms) DDLO_CUDA(cudaEventRecord(rt->ev0, st));
+  int rc = segment_scan_device(rt, p, T16, d_scan, stride, d_res, d_label, d_range, d_ground, d_avg, d_count);
+  if (device_ms && rc == DDLO_OK) DDLO_CUDA(cudaEventRecord(rt->ev1, st));
+  int count = 0;
+  if (rc == DDLO_OK) {
+    cudaError_t e = cudaMemcpyAsync(&count, d_count, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && label_mat) e = cudaMemcpyAsync(label_mat, d_label, HW * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && range_mat) e = cudaMemcpyAsync(range_mat, d_range, HW * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && ground_mat) e = cudaMemcpyAsync(ground_mat, d_ground, HW, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && avg_residuals && avg_capacity > 0 && count > 0) {
+      e = cudaMemcpyAsync(avg_residuals, d_avg, (size_t)std::min(count, avg_capacity) * 8, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (e != cudaSuccess) rc = fail(DDLO_E_CUDA, cudaGetErrorString(e));
+  }
+  for (void* q : {(void*)d_scan, (void*)d_res, (void*)d_range, (void*)d_label, (void*)d_ground, (void*)d_avg})
+    if (q) cudaFreeAsync(q, st);
+  if (rc != DDLO_OK) return rc;
+  if (device_ms) DDLO_CUDA(cudaEventElapsedTime(device_ms, rt->ev0, rt->ev1));
+  *label_count = count;
   return DDLO_OK;
 }
 

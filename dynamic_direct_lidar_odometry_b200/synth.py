@@ -118,6 +118,35 @@ def scan(frame: int, beams: int = 64, cols: int = 1024, world: World | None = No
     return out
 
 
+def organized_scan(frame: int, beams: int = 64, cols: int = 1024, world: World | None = None, dropout: float = 0.0,
+                   noise_seed: int | None = None) -> np.ndarray:
+    """The same scan kept organised, as the segmentation stage wants it (detection.cpp:296-327): float32
+    (beams, cols, 4), sensor frame, row 0 = the TOP beam (groundRemoval walks up from row H-1), NaN where the ray
+    has no return; `dropout` removes that fraction of the returns at random on top."""
+    world = world or make_world()
+    T = pose(frame)
+    dirs_s = _ray_dirs(beams, cols)
+    rng_hit = _cast(world, T[:3, 3], dirs_s @ T[:3, :3].T)
+    rng = np.random.default_rng(1000 + frame if noise_seed is None else noise_seed)
+    rng_noisy = rng_hit + rng.normal(0.0, RANGE_SIGMA, rng_hit.shape)
+    keep = np.isfinite(rng_noisy) & (rng_noisy > RANGE_MIN) & (rng_noisy < RANGE_MAX)
+    if dropout > 0.0:
+        keep &= rng.random(rng_hit.shape) >= dropout
+    out = np.full((beams * cols, 4), np.nan, dtype=np.float32)
+    out[keep, :3] = (dirs_s * rng_noisy[:, None])[keep].astype(np.float32)
+    out[keep, 3] = 1.0
+    return out.reshape(beams, cols, 4)[::-1].copy()
+
+
+def organized_transform(scan: np.ndarray, T: np.ndarray) -> np.ndarray:
+    """pcl::transformPointCloud on an organised scan: NaN points stay NaN."""
+    flat = scan.reshape(-1, scan.shape[-1])
+    out = np.full_like(flat, np.nan)
+    ok = np.isfinite(flat[:, 0])
+    out[ok] = transform(flat[ok], T)
+    return out.reshape(scan.shape)
+
+
 def transform(points: np.ndarray, T: np.ndarray) -> np.ndarray:
     """Apply a 4x4 pose to (N,4) float32 points (float64 arithmetic, rounded once)."""
     out = np.ones_like(points, dtype=np.float32)

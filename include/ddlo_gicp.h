@@ -225,6 +225,40 @@ int ddlo_gicp_get_residuals_async(ddlo_gicp* g, double* out, int capacity);
  * cell (v, u) holds x, y, z and the residual of the last scan point that falls into it, other cells are zero.
  * out_xyzi: HOST, height * width * 4 floats, row-major. */
 int ddlo_gicp_residual_image(ddlo_gicp* g, int width, int height, double angle_min, double angle_max, float* out_xyzi);
+/* Range-image segmentation of the organised scan: the stage DetectionModule runs on every frame right after the
+ * residual image (OdomNode::applySegmentation, odom.cc:853-857).  One call covers
+ *   projectScan        src/detection/detection.cpp:254-329   range of every return from the sensor position T(:,3)
+ *   projectResiduals   src/detection/detection.cpp:203-252   residual image (the intensity plane of the residual cloud)
+ *   groundRemoval      src/detection/detection.cpp:448-512   slope test between vertical neighbours on the lowest rows
+ *   cloudSegmentation  src/detection/detection.cpp:514-546   raster-order seeds inside the `valid_range` window
+ *   labelComponents    src/detection/detection.cpp:548-724   4-neighbour flood fill on the beam-angle criterion, then the
+ *                                                            segment tests (size, scan lines, distance, height, elevation)
+ * and reproduces the reference's results exactly: segment numbering in raster order of the seeds, the flood fill's
+ * push order (the min_z / max_z update and the float residual sum of :612-634 depend on it), 999999 for rejected
+ * segments, -1 for ground and empty pixels.  Defaults in comments are the reference's (detection.cpp:76-105). */
+typedef struct ddlo_segmentation_params {
+  int rows, cols;                                                     /* H_, W_: 128, 1024 */
+  int ground_rows;                                                    /* groundRows: 30; must be < rows */
+  int valid_point_num, min_line_num, valid_line_num;                  /* 15, 5, 5 */
+  int window_row_min, window_row_max, window_col_min, window_col_max; /* the hard-coded valid_range lambda (:520-522):
+                                                                         156, 356, 156, 356; window_col_max must be < cols
+                                                                         (beyond that the reference wraps one-directionally) */
+  float ang_bottom;                                                   /* 45: vertical resolution = 2 ang_bottom / (rows - 1) */
+  float ground_angle_threshold, minimum_range, sensor_mount_angle, theta; /* 10, 10, 10, 60 deg in rad */
+  float min_delta_z, max_delta_z, max_distance, max_elevation;        /* 0.1, 3.0, 20, 2.0 */
+} ddlo_segmentation_params;
+/* scan_t: HOST, rows * cols points of stride_bytes each (x, y, z floats first; 16 or 32 as for ddlo_cloud_upload), the
+ *         segmentation scan in the world frame, row 0 = top; a non-finite coordinate marks "no return".
+ * T16: column-major 4x4 float pose.  residuals: HOST rows * cols floats or NULL (projectResiduals not called: every
+ *      avg_residuals_ entry is 0, :703-707).
+ * Outputs (HOST): label_mat int32, range_mat float, ground_mat int8 (1 ground, -1 no information, 0), each
+ * rows * cols and any of them NULL to skip; avg_residuals[label] for label < min(*label_count, avg_capacity);
+ * *label_count = label_count_ (labels 1 .. *label_count - 1 are the accepted segments); *device_ms (optional) = time of
+ * the kernels alone, between the uploads and the read-back. */
+int ddlo_segment_scan(ddlo_runtime* rt, const ddlo_segmentation_params* params, const float* scan_t, int stride_bytes, const float* T16,
+                      const float* residuals, int* label_mat, float* range_mat, signed char* ground_mat, double* avg_residuals,
+                      int avg_capacity, int* label_count, float* device_ms);
+
 /* getResiduals(std::vector<Eigen::Vector3f>&, trans) (:199-222) */
 int ddlo_gicp_get_residual_vectors(ddlo_gicp* g, const float* T16, float* out_xyz, int capacity);
 

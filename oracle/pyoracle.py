@@ -33,10 +33,29 @@ _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
+class SegParams(C.Structure):
+    """struct oracle_seg_params (oracle_segmentation.cpp); defaults are the reference's (detection.cpp:76-105, :520-522)."""
+
+    _fields_ = [(n, C.c_int) for n in ("rows", "cols", "ground_rows", "valid_point_num", "min_line_num", "valid_line_num",
+                                       "window_row_min", "window_row_max", "window_col_min", "window_col_max")] + \
+               [(n, C.c_float) for n in ("ang_bottom", "ground_angle_threshold", "minimum_range", "sensor_mount_angle", "theta",
+                                         "min_delta_z", "max_delta_z", "max_distance", "max_elevation")]
+
+    DEFAULTS = dict(rows=128, cols=1024, ground_rows=30, valid_point_num=15, min_line_num=5, valid_line_num=5,
+                    window_row_min=156, window_row_max=356, window_col_min=156, window_col_max=356,
+                    ang_bottom=45.0, ground_angle_threshold=10.0, minimum_range=10.0, sensor_mount_angle=10.0,
+                    theta=60.0 / 180.0 * np.pi, min_delta_z=0.1, max_delta_z=3.0, max_distance=20.0, max_elevation=2.0)
+
+    def __init__(self, **kw):
+        super().__init__()
+        for k, v in {**self.DEFAULTS, **kw}.items():
+            setattr(self, k, v)
+
+
 def build(force: bool = False) -> None:
     """Compile the restatement, and the reference nanoflann when /root/reference is present."""
-    src = HERE / "oracle_gicp.cpp"
-    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+    newest = max((HERE / f).stat().st_mtime for f in ("oracle_gicp.cpp", "oracle_segmentation.cpp"))
+    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < newest:
         subprocess.run(["make", "-C", str(HERE), "-B", "all"], check=True, capture_output=True)
     ref_hdr = REFERENCE_ROOT / "dynamic_direct_lidar_odometry/include/nano_gicp/impl/nanoflann_impl.hpp"
     shim = HERE / "ref_nanoflann_shim.cpp"
@@ -111,6 +130,7 @@ def lib() -> C.CDLL:
         "oracle_voxel_filter": (ci, [_f32p, ci, ci, C.c_float, C.c_float, C.c_float, _f32p]),
         "oracle_crop_box": (ci, [_f32p, ci, ci, _f32p, _f32p, ci, ci, _f32p]),
         "oracle_residual_image": (None, [_f32p, ci, ci, _f64p, ci, ci, cd, cd, _f32p]),
+        "oracle_segment_scan": (ci, [C.POINTER(SegParams), _f32p, ci, _f32p, vp, _i32p, _f32p, vp, _f64p, C.POINTER(ci)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -211,6 +231,26 @@ def residual_image(points, residuals, width: int = 512, height: int = 512, angle
     out = np.empty((height, width, 4), dtype=np.float32)
     lib().oracle_residual_image(p, p.shape[0], p.shape[1], r, width, height, float(angle_min), float(angle_max), out.reshape(-1))
     return out
+
+
+def segment_scan(params: "SegParams", scan_t, T, residuals=None):
+    """DetectionModule projectScan + projectResiduals + groundRemoval + cloudSegmentation restated
+    (oracle_segmentation.cpp).  scan_t: (rows, cols, >=3) float32 organised world-frame scan, NaN = no return;
+    T: 4x4 pose; residuals: (rows, cols) float32 or None.  Returns a dict of label_mat, range_mat, ground_mat,
+    label_count, avg_residuals (indexed by label) and borderline (threshold tests a different libm might flip)."""
+    H, W = params.rows, params.cols
+    s = np.ascontiguousarray(scan_t, dtype=np.float32).reshape(H * W, -1)
+    T16 = _cm(T, np.float32)
+    r = None if residuals is None else np.ascontiguousarray(residuals, dtype=np.float32).reshape(-1)
+    label = np.empty(H * W, dtype=np.int32)
+    rng = np.empty(H * W, dtype=np.float32)
+    ground = np.empty(H * W, dtype=np.int8)
+    avg = np.zeros(H * W, dtype=np.float64)
+    border = C.c_int(0)
+    n = lib().oracle_segment_scan(C.byref(params), s.reshape(-1), s.shape[1], T16, None if r is None else r.ctypes.data, label, rng,
+                                  ground.ctypes.data, avg, C.byref(border))
+    return dict(label_mat=label.reshape(H, W), range_mat=rng.reshape(H, W), ground_mat=ground.reshape(H, W), label_count=n,
+                avg_residuals=avg[:n].copy(), borderline=border.value)
 
 
 def knn_bruteforce(points, queries, k: int):

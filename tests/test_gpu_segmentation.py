@@ -1,0 +1,183 @@
+"""Parity of the range-image segmentation stage with the CPU oracle, through the C ABI.
+
+Everything here is integer / exact-float work: label images, ground flags and the segment count must be identical;
+the range image and the per-segment average residuals bit-exact.  The oracle counts slope tests that land within a few
+ulp of their threshold (`borderline`): a different libm could flip those, so a case is only compared while that count
+is zero (it is for every seed used here).
+"""
+import numpy as np
+import pytest
+
+from dynamic_direct_lidar_odometry_b200 import binding as B
+from dynamic_direct_lidar_odometry_b200 import synth
+from dynamic_direct_lidar_odometry_b200.detection import DetectionModule, INVALID_SEGMENT
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(rt, oracle, params, scan_t, T, residuals):
+    det = DetectionModule(rt, **params)
+    det.projectScan(None, scan_t, T)
+    if residuals is not None:
+        det.projectResiduals(residuals)
+    det.applySegmentation()
+    o = oracle.segment_scan(oracle.SegParams(**params), scan_t, T, residuals)
+    return det, o
+
+
+def assert_same(det, o):
+    assert o["borderline"] == 0, "pick another seed: a slope test sits on its threshold"
+    assert np.array_equal(det.range_mat.view(np.uint32), o["range_mat"].view(np.uint32))
+    assert np.array_equal(det.ground_mat, o["ground_mat"])
+    assert det.label_count_ == o["label_count"]
+    assert np.array_equal(det.label_mat, o["label_mat"])
+    assert np.array_equal(det.avg_residuals[1:].view(np.uint64), o["avg_residuals"][1:].view(np.uint64))
+
+
+def lidar_case(frame, beams, cols, dropout, **over):
+    sc = synth.organized_scan(frame, beams, cols, dropout=dropout)
+    T = synth.pose(frame).astype(np.float32)
+    st = synth.organized_transform(sc, T)
+    params = dict(rows=beams, cols=cols, ground_rows=beams * 3 // 8, window_row_min=0, window_row_max=beams - 1, window_col_min=0,
+                  window_col_max=cols - 1, ang_bottom=22.5, minimum_range=1.0, sensor_mount_angle=0.0, max_distance=40.0)
+    params.update(over)
+    res = np.abs(np.random.default_rng(frame).normal(0.0, 0.05, (beams, cols))).astype(np.float32)
+    res[np.random.default_rng(frame + 1).random((beams, cols)) < 0.3] = 0.0
+    return params, st, T, res
+
+
+@pytest.mark.parametrize("frame,beams,cols,dropout", [(3, 64, 1024, 0.02), (40, 64, 1024, 0.0), (7, 16, 256, 0.1), (12, 128, 2048, 0.01),
+                                                      (5, 33, 255, 0.05)])
+def test_segmentation_matches_oracle(rt, oracle, frame, beams, cols, dropout):
+    params, st, T, res = lidar_case(frame, beams, cols, dropout)
+    det, o = run_both(rt, oracle, params, st, T, res)
+    assert_same(det, o)
+    assert det.getSegmentsCount() > 3                      # the case really has accepted segments,
+    assert (det.label_mat == INVALID_SEGMENT).any()        # rejected ones
+    assert (det.ground_mat == 1).sum() > beams * cols // 20  # and ground
+
+
+def test_segmentation_reference_window_and_defaults(rt, oracle):
+    # the fork's own geometry: a 512 x 512 image and the hard-coded window 156..356 (detection.cpp:520-522)
+    params, st, T, res = lidar_case(9, 512, 512, 0.02, window_row_min=156, window_row_max=356, window_col_min=156, window_col_max=356,
+                                    ground_rows=30)
+    det, o = run_both(rt, oracle, params, st, T, res)
+    assert_same(det, o)
+    lm = det.label_mat
+    outside = np.ones_like(lm, dtype=bool)
+    outside[156:357, 156:357] = False
+    assert not ((lm[outside] > 0)).any()  # nothing outside the window is ever labelled
+
+
+def test_segmentation_without_residuals(rt, oracle):
+    params, st, T, _ = lidar_case(3, 64, 1024, 0.02)
+    det, o = run_both(rt, oracle, params, st, T, None)
+    assert_same(det, o)
+    assert not det.avg_residuals.any()
+
+
+def test_segmentation_residual_cloud_input(rt, oracle):
+    # projectResiduals takes the residual cloud itself: intensity where the point is finite, zero elsewhere (:240-249)
+    params, st, T, res = lidar_case(3, 32, 512, 0.05)
+    cloud = np.zeros((32, 512, 4), dtype=np.float32)
+    cloud[..., 3] = res
+    cloud[::7, ::5, 0] = np.nan
+    expect = res.copy()
+    expect[::7, ::5] = 0.0
+    det = DetectionModule(rt, **params)
+    det.projectScan(None, st, T)
+    det.projectResiduals(cloud)
+    det.applySegmentation()
+    o = oracle.segment_scan(oracle.SegParams(**params), st, T, expect)
+    assert_same(det, o)
+
+
+def sphere_image(H, W, radius=10.0):
+    """every pixel at the same range: one component covering the whole image, the widest flood-fill fronts"""
+    el = np.linspace(0.6, -0.6, H)[:, None]
+    az = np.linspace(-1.2, 1.2, W)[None, :]
+    s = np.empty((H, W, 4), dtype=np.float32)
+    s[..., 0] = radius * np.cos(el) * np.cos(az)
+    s[..., 1] = radius * np.cos(el) * np.sin(az)
+    s[..., 2] = radius * np.sin(el) * np.ones_like(az)
+    s[..., 3] = 1.0
+    return s
+
+
+@pytest.mark.parametrize("ring", [None, "64"])
+def test_segmentation_one_huge_component(rt, oracle, monkeypatch, ring):
+    # 540 x 540 pixels in a single segment; with a 64-entry ring most queue reads come back from global memory
+    if ring:
+        monkeypatch.setenv("DDLO_SEG_RING", ring)
+    H = W = 540
+    s = sphere_image(H, W)
+    rng = np.random.default_rng(1)
+    s[..., :3] *= (1.0 + 0.001 * rng.standard_normal((H, W, 1))).astype(np.float32)
+    T = np.eye(4, dtype=np.float32)
+    params = dict(rows=H, cols=W, ground_rows=0, window_row_min=0, window_row_max=H - 1, window_col_min=0, window_col_max=W - 1,
+                  ang_bottom=34.0, minimum_range=1.0, theta=0.2, max_distance=50.0, max_delta_z=20.0, max_elevation=20.0)
+    res = rng.random((H, W)).astype(np.float32)
+    det, o = run_both(rt, oracle, params, s, T, res)
+    assert_same(det, o)
+    assert det.getSegmentsCount() == 1 and (det.label_mat == 1).sum() > H * W * 0.99
+
+
+def test_segmentation_edge_cases(rt, oracle):
+    T = np.eye(4, dtype=np.float32)
+    base = dict(rows=8, cols=16, ground_rows=3, window_row_min=0, window_row_max=7, window_col_min=0, window_col_max=15, ang_bottom=10.0,
+                minimum_range=1.0, valid_point_num=2, valid_line_num=1, min_line_num=1, min_delta_z=-10.0, max_delta_z=10.0)
+    # no return at all
+    s = np.full((8, 16, 4), np.nan, dtype=np.float32)
+    det, o = run_both(rt, oracle, base, s, T, None)
+    assert_same(det, o)
+    assert det.label_count_ == 1 and (det.label_mat == -1).all()
+    # a point with x == 0 exactly is "no info" for the ground test (:476-481); a z of exactly 0 never becomes min_z (:612)
+    s = sphere_image(8, 16, 5.0)
+    s[6, 3, 0] = 0.0
+    s[2, 5:9, 2] = 0.0
+    det, o = run_both(rt, oracle, base, s, T, np.ones((8, 16), dtype=np.float32))
+    assert_same(det, o)
+    assert (det.ground_mat == -1).any()
+    # everything closer than minimum_range
+    det, o = run_both(rt, oracle, {**base, "minimum_range": 100.0}, s, T, None)
+    assert_same(det, o)
+    assert (det.range_mat == 0).all()
+    # an empty window
+    det, o = run_both(rt, oracle, {**base, "window_row_min": 156, "window_row_max": 356}, s, T, None)
+    assert_same(det, o)
+    assert det.label_count_ == 1
+    # 32-byte points (pcl::PointXYZI) give the same result as packed ones
+    wide = np.zeros((8, 16, 8), dtype=np.float32)
+    wide[..., :4] = s
+    det2, _ = run_both(rt, oracle, base, wide, T, None)
+    det1, _ = run_both(rt, oracle, base, s, T, None)
+    assert np.array_equal(det1.label_mat, det2.label_mat)
+
+
+def test_segmentation_argument_errors(rt):
+    s = np.zeros((8, 16, 4), dtype=np.float32)
+    det = DetectionModule(rt, rows=8, cols=16, ground_rows=3, window_col_max=16)
+    det.projectScan(None, s, np.eye(4))
+    with pytest.raises(B.DdloError) as e:
+        det.applySegmentation()
+    assert e.value.code == -8  # DDLO_E_UNSUPPORTED
+    det = DetectionModule(rt, rows=8, cols=16, ground_rows=8, window_col_max=15)
+    det.projectScan(None, s, np.eye(4))
+    with pytest.raises(B.DdloError) as e:
+        det.applySegmentation()
+    assert e.value.code == -1  # DDLO_E_INVALID
+    with pytest.raises(ValueError):
+        det.projectScan(None, np.zeros((5, 4), dtype=np.float32), np.eye(4))
+
+
+def test_segmentation_is_deterministic(rt):
+    params, st, T, res = lidar_case(3, 64, 1024, 0.02)
+    outs = []
+    for _ in range(3):
+        det = DetectionModule(rt, **params)
+        det.projectScan(None, st, T)
+        det.projectResiduals(res)
+        det.applySegmentation()
+        outs.append((det.label_mat.copy(), det.avg_residuals.copy()))
+    for lm, avg in outs[1:]:
+        assert np.array_equal(lm, outs[0][0]) and np.array_equal(avg.view(np.uint64), outs[0][1].view(np.uint64))
