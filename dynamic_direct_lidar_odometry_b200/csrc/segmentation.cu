@@ -214,17 +214,16 @@ __global__ void __launch_bounds__(kFillThreads) k_seg_fill(SegDev p, const unsig
   extern __shared__ __align__(16) unsigned char seg_smem[];
   const int nib_bytes = ((p.HW + 1) / 2 + 15) & ~15;
   const int vis_words = (p.HW + 31) / 32;
-  const int row_words = (p.H + 31) / 32;
   unsigned char* snib = seg_smem;
   unsigned* vis = reinterpret_cast<unsigned*>(seg_smem + nib_bytes);
   int* rings = reinterpret_cast<int*>(vis + ((vis_words + 3) & ~3));
-  unsigned* rowbits_all = reinterpret_cast<unsigned*>(rings + kFillWarps * kRing);
   for (int i = threadIdx.x; i < nib_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(snib)[i] = reinterpret_cast<const uint4*>(nib)[i];
   for (int i = threadIdx.x; i < vis_words; i += blockDim.x) vis[i] = 0u;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pl = lane >> 2, n = lane & 3;  // flood fill: slot = (queue entry of the step, direction)
+  const int step_n = n == 0 ? -p.W : (n == 1 ? 1 : (n == 2 ? -1 : p.W));
   int* ring = rings + warp * kRing;
-  unsigned* rowbits = rowbits_all + warp * row_words;
   const int total = *n_seeds;
   const int W = p.W;
   while (true) {
@@ -244,20 +243,19 @@ __global__ void __launch_bounds__(kFillThreads) k_seg_fill(SegDev p, const unsig
     __syncwarp();
     while (head < tail) {
       const int cnt = min(8, tail - head);
-      const int pl = lane >> 2, n = lane & 3;
       bool cand = false;
       int v = 0;
       if (pl < cnt) {
         const int q = head + pl;
         const int u = (tail - q <= ring_size) ? ring[q & (ring_size - 1)] : (int)(__ldcg(order + beg + q) & 0x3fffffffu);
-        const unsigned nb = ((unsigned)snib[u >> 1] >> ((u & 1) * 4)) & 15u;
-        if ((nb >> n) & 1u) {
-          v = u + (n == 0 ? -W : (n == 1 ? 1 : (n == 2 ? -1 : W)));
+        if (((unsigned)snib[u >> 1] >> ((u & 1) * 4 + n)) & 1u) {
+          v = u + step_n;
           cand = ((vis[v >> 5] >> (v & 31)) & 1u) == 0u;
         }
       }
-      // a pixel wanted by several (entry, direction) slots of this step goes to the first of them
-      const unsigned same = __match_any_sync(kFullMask, cand ? v : -1 - lane);
+      // A pixel wanted by several (entry, direction) slots of this step goes to the first of them.  (The match costs
+      // one round per distinct value: every slot without a candidate shares one dummy.)
+      const unsigned same = __match_any_sync(kFullMask, cand ? v : -1);
       const bool win = cand && (int)(__ffs(same) - 1) == lane;
       const unsigned wins = __ballot_sync(kFullMask, win);
       if (win) {
@@ -270,25 +268,40 @@ __global__ void __launch_bounds__(kFillThreads) k_seg_fill(SegDev p, const unsig
       head += cnt;
       __syncwarp();
     }
-    // ---- statistics over the pushed pixels in push order (the seed itself only counts for the size, :556-569)
-    for (int w = lane; w < row_words; w += 32) rowbits[w] = 0u;
-    __syncwarp();
+    // ---- statistics over the pushed pixels in push order (the seed itself only counts for the size, :556-569).
+    // The gathers of a 32-pixel group are issued one group ahead of their use.
     float min_z = 1e6f, max_z = -1e6f, max_dist = -1e6f, total_res = 0.0f;
-    int res_count = 0;
-    for (int base = 1; base < tail; base += 32) {
+    int res_count = 0, row_lo = 0x7fffffff, row_hi = -1;
+    auto fetch = [&](int base) -> unsigned {
       const int i = base + lane;
-      const bool active = i < tail;
-      float z = 0.0f, r = 0.0f;
-      if (active) {
-        const unsigned e = __ldcg(order + beg + i);
-        const int v = (int)(e & 0x3fffffffu), n = (int)(e >> 30);
-        const int u = v - (n == 0 ? -W : (n == 1 ? 1 : (n == 2 ? -1 : W)));
-        max_dist = fmaxf(max_dist, fmaxf(range[u], range[v]));
-        const int row = v / W;
-        atomicOr(rowbits + (row >> 5), 1u << (row & 31));
-        z = scan[(size_t)v * stride + 2];
-        if (p.have_residuals) r = residuals[v];
+      return i < tail ? __ldcg(order + beg + i) : 0xffffffffu;
+    };
+    struct Pushed {
+      float z, r, d;
+      int row;
+      bool active;
+    };
+    auto gather = [&](unsigned e) -> Pushed {
+      Pushed g{0.0f, 0.0f, -1e6f, 0, e != 0xffffffffu};
+      if (g.active) {
+        const int v = (int)(e & 0x3fffffffu), dir = (int)(e >> 30);
+        const int u = v - (dir == 0 ? -W : (dir == 1 ? 1 : (dir == 2 ? -1 : W)));
+        g.d = fmaxf(range[u], range[v]);
+        g.z = scan[(size_t)v * stride + 2];
+        if (p.have_residuals) g.r = residuals[v];
+        g.row = v / W;
       }
+      return g;
+    };
+    Pushed cur = gather(fetch(1));
+    unsigned e_ahead = fetch(33);
+    for (int base = 1; base < tail; base += 32) {
+      const Pushed nxt = gather(e_ahead);
+      e_ahead = fetch(base + 64);
+      const bool active = cur.active;
+      const float z = cur.z;
+      max_dist = fmaxf(max_dist, cur.d);
+      if (active) row_lo = min(row_lo, cur.row), row_hi = max(row_hi, cur.row);
       // `if (z < min_z && z != 0) min_z = z; else if (z > max_z) max_z = z;` (:612-616): min_z before pixel i is the
       // minimum of the non-zero z pushed before it
       const float val = (active && z != 0.0f && !isnan(z)) ? z : INFINITY;
@@ -304,24 +317,28 @@ __global__ void __launch_bounds__(kFillThreads) k_seg_fill(SegDev p, const unsig
       const bool new_min = active && z != 0.0f && z < before;
       if (active && !new_min && z > max_z) max_z = z;
       min_z = fminf(min_z, __shfl_sync(kFullMask, incl, 31));
-      // total_residuum += residual, in push order (:632-634): a lane-ordered chain, the zeros of skipped pixels change nothing
-      const bool counted = active && r > 0.0f;
+      // total_residuum += residual, in push order (:632-634): a lane-ordered chain; the zeros of skipped pixels and of
+      // the lanes behind the end change nothing
+      const bool counted = active && cur.r > 0.0f;
       res_count += counted ? 1 : 0;
-      const float rv = counted ? r : 0.0f;
-      const int lanes = min(32, tail - base);
-      for (int j = 0; j < lanes; ++j) total_res = __fadd_rn(total_res, __shfl_sync(kFullMask, rv, j));
+      const float rv = counted ? cur.r : 0.0f;
+      if (__any_sync(kFullMask, counted)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) total_res = __fadd_rn(total_res, __shfl_sync(kFullMask, rv, j));
+      }
+      cur = nxt;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       max_z = fmaxf(max_z, __shfl_xor_sync(kFullMask, max_z, o));
       max_dist = fmaxf(max_dist, __shfl_xor_sync(kFullMask, max_dist, o));
       res_count += __shfl_xor_sync(kFullMask, res_count, o);
+      row_lo = min(row_lo, __shfl_xor_sync(kFullMask, row_lo, o));
+      row_hi = max(row_hi, __shfl_xor_sync(kFullMask, row_hi, o));
     }
-    __syncwarp();
-    int line_count = 0;
-    for (int w = lane; w < row_words; w += 32) line_count += __popc(rowbits[w]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) line_count += __shfl_xor_sync(kFullMask, line_count, o);
+    // line_count (:640-644): the rows of a 4-connected segment are consecutive, and so are those of its pushed pixels
+    // (the seed lies in the top row; without it that row either stays or goes as a whole)
+    const int line_count = row_hi >= row_lo ? row_hi - row_lo + 1 : 0;
     // ---- the segment tests (:640-685)
     bool feasible = false;
     if (tail >= 50 && line_count >= p.min_line_num)
@@ -392,7 +409,7 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   const int HW = p.HW;
   const size_t nib_bytes = (((size_t)HW + 1) / 2 + 15) & ~(size_t)15;
   const size_t vis_words = (((size_t)HW + 31) / 32 + 3) & ~(size_t)3;
-  const size_t smem = nib_bytes + vis_words * 4 + (size_t)kFillWarps * kRing * 4 + (size_t)kFillWarps * ((p.H + 31) / 32) * 4;
+  const size_t smem = nib_bytes + vis_words * 4 + (size_t)kFillWarps * kRing * 4;
   if (smem > 227 * 1024) return fail(DDLO_E_UNSUPPORTED, "range image too large for the shared-memory flood fill (rows * cols <= ~300000)");
   static std::atomic<unsigned long long> configured{0};
   if (!((configured.load() >> rt->device) & 1ull)) {
