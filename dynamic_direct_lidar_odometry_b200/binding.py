@@ -124,6 +124,7 @@ SIGNATURES = {
     "ddlo_gicp_get_residual_vectors": [_vp, _vp, _vp, C.c_int],
     "ddlo_gicp_residual_image": [_vp, C.c_int, C.c_int, C.c_double, C.c_double, _vp],
     "ddlo_segment_scan": [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _ip, _vp],
+    "ddlo_gicp_segment_scan": [_vp, _vp, _vp, C.c_int, _vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, C.c_int, _ip, _vp],
     "ddlo_gicp_align_batch": [_vpp, C.c_int, _vp, C.POINTER(AlignResult)],
 }
 class SegmentationParams(C.Structure):

@@ -31,7 +31,7 @@ int crop_box_device(ddlo_runtime* rt, const float4* pts, int n, const float lo[3
                     float4** d_out, int* n_out);
 int residual_image_device(ddlo_runtime* rt, const float4* pts, const float* sqd, int n, int w, int h, double a_min, double a_max, float4* d_out);
 int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, const float* T16, const float* d_scan, int stride_floats,
-                        const float* d_residuals, int* d_label, float* d_range, signed char* d_ground, double* d_avg_by_label,
+                        const float* d_residuals, int res_stride, int* d_label, float* d_range, signed char* d_ground, double* d_avg_by_label,
                         int* d_label_count);
 
 // raw strided host points -> float4 (x, y, z, 1)
@@ -1109,9 +1109,10 @@ int ddlo_gicp_residual_image(ddlo_gicp* g, int width, int height, double angle_m
   return DDLO_OK;
 }
 
-int ddlo_segment_scan(ddlo_runtime* rt, const ddlo_segmentation_params* params, const float* scan_t, int stride_bytes, const float* T16,
-                      const float* residuals, int* label_mat, float* range_mat, signed char* ground_mat, double* avg_residuals,
-                      int avg_capacity, int* label_count, float* device_ms) {
+// residuals: host plane, or (engine != null) the residual image of the engine's last align built on the device
+static int segment_scan_impl(ddlo_runtime* rt, const ddlo_segmentation_params* params, const float* scan_t, int stride_bytes, const float* T16,
+                             const float* residuals, ddlo_gicp* engine, double angle_min, double angle_max, int* label_mat, float* range_mat,
+                             signed char* ground_mat, double* avg_residuals, int avg_capacity, int* label_count, float* device_ms) {
   if (!rt || !params || !scan_t || !T16 || !label_count) return fail(DDLO_E_INVALID, "null argument");
   const ddlo_segmentation_params& p = *params;
   if (p.rows < 2 || p.cols < 1 || (long long)p.rows * p.cols > (1 << 24)) return fail(DDLO_E_INVALID, "bad range image geometry");
@@ -1134,12 +1135,17 @@ int ddlo_segment_scan(ddlo_runtime* rt, const ddlo_segmentation_params* params, 
   DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ground), HW, st));
   DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_avg), (HW + 1) * 8, st));
   if (residuals) DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_res), HW * 4, st));
+  if (engine) DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_res), HW * sizeof(float4), st));
   d_count = d_label + HW;
   DDLO_CUDA(cudaMemcpyAsync(d_scan, scan_t, HW * stride_bytes, cudaMemcpyHostToDevice, st));
   if (residuals) DDLO_CUDA(cudaMemcpyAsync(d_res, residuals, HW * 4, cudaMemcpyHostToDevice, st));
   DDLO_CUDA(cudaMemsetAsync(d_avg, 0, (HW + 1) * 8, st));
   if (device_ms) DDLO_CUDA(cudaEventRecord(rt->ev0, st));
-  int rc = segment_scan_device(rt, p, T16, d_scan, stride, d_res, d_label, d_range, d_ground, d_avg, d_count);
+  int rc = DDLO_OK;
+  if (engine)  // the residual cloud of odom.cc:804-827, cols x rows cells; its intensity channel is the residual plane (:240-249)
+    rc = residual_image_device(rt, engine->src->pts, engine->sqd, engine->corr_n, p.cols, p.rows, angle_min, angle_max, reinterpret_cast<float4*>(d_res));
+  if (rc == DDLO_OK)
+    rc = segment_scan_device(rt, p, T16, d_scan, stride, engine ? d_res + 3 : d_res, engine ? 4 : 1, d_label, d_range, d_ground, d_avg, d_count);
   if (device_ms && rc == DDLO_OK) DDLO_CUDA(cudaEventRecord(rt->ev1, st));
   int count = 0;
   if (rc == DDLO_OK) {
@@ -1160,6 +1166,23 @@ int ddlo_segment_scan(ddlo_runtime* rt, const ddlo_segmentation_params* params, 
   if (device_ms) DDLO_CUDA(cudaEventElapsedTime(device_ms, rt->ev0, rt->ev1));
   *label_count = count;
   return DDLO_OK;
+}
+
+int ddlo_segment_scan(ddlo_runtime* rt, const ddlo_segmentation_params* params, const float* scan_t, int stride_bytes, const float* T16,
+                      const float* residuals, int* label_mat, float* range_mat, signed char* ground_mat, double* avg_residuals,
+                      int avg_capacity, int* label_count, float* device_ms) {
+  return segment_scan_impl(rt, params, scan_t, stride_bytes, T16, residuals, nullptr, 0.0, 0.0, label_mat, range_mat, ground_mat, avg_residuals,
+                           avg_capacity, label_count, device_ms);
+}
+
+int ddlo_gicp_segment_scan(ddlo_gicp* g, const ddlo_segmentation_params* params, const float* scan_t, int stride_bytes, const float* T16,
+                           double angle_min, double angle_max, int* label_mat, float* range_mat, signed char* ground_mat, double* avg_residuals,
+                           int avg_capacity, int* label_count, float* device_ms) {
+  if (!g) return fail(DDLO_E_INVALID, "null argument");
+  if (!(angle_max > angle_min)) return fail(DDLO_E_INVALID, "bad image geometry");
+  if (!g->src || g->corr_n != g->src->n) return fail(DDLO_E_NOT_READY, "no residuals: run align first");
+  return segment_scan_impl(g->rt, params, scan_t, stride_bytes, T16, nullptr, g, angle_min, angle_max, label_mat, range_mat, ground_mat,
+                           avg_residuals, avg_capacity, label_count, device_ms);
 }
 
 int ddlo_gicp_get_residual_vectors(ddlo_gicp* g, const float* T16, float* out_xyz, int capacity) {

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) k_seg_seeds(SegDev p, const int* __restri
 __global__ void __launch_bounds__(kFillThreads) k_seg_fill(SegDev p, const unsigned char* __restrict__ nib, const int* __restrict__ seeds,
                                                            const int* __restrict__ n_seeds, const unsigned long long* __restrict__ pre,
                                                            const float* __restrict__ scan, int stride, const float* __restrict__ range,
-                                                           const float* __restrict__ residuals, unsigned* __restrict__ order,
+                                                           const float* __restrict__ residuals, int res_stride, unsigned* __restrict__ order,
                                                            int* __restrict__ next_seed, int* __restrict__ accepted, double* __restrict__ seg_avg,
                                                            int ring_size) {
   extern __shared__ __align__(16) unsigned char seg_smem[];
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kFillThreads) k_seg_fill(SegDev p, const unsig
         const int u = v - (dir == 0 ? -W : (dir == 1 ? 1 : (dir == 2 ? -1 : W)));
         g.d = fmaxf(range[u], range[v]);
         g.z = scan[(size_t)v * stride + 2];
-        if (p.have_residuals) g.r = residuals[v];
+        if (p.have_residuals) g.r = residuals[(size_t)v * res_stride];
         g.row = v / W;
       }
       return g;
@@ -387,9 +387,10 @@ int pool_alloc(ddlo_runtime* rt, T** ptr, size_t count) {
 
 }  // namespace
 
-// All pointers are device pointers; d_label doubles as the initial label image.  Enqueues only.
+// All pointers are device pointers; d_label doubles as the initial label image; the residual of pixel i is
+// d_residuals[i * res_stride] (1 for a plane, 4 for the w channel of a residual image).  Enqueues only.
 int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, const float* T16, const float* d_scan, int stride_floats,
-                        const float* d_residuals, int* d_label, float* d_range, signed char* d_ground, double* d_avg_by_label,
+                        const float* d_residuals, int res_stride, int* d_label, float* d_range, signed char* d_ground, double* d_avg_by_label,
                         int* d_label_count) {
   SegDev p{};
   p.H = prm.rows, p.W = prm.cols, p.HW = prm.rows * prm.cols;
@@ -460,7 +461,7 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
     const int v = std::atoi(e);
     if (v >= 64 && v <= kRing && (v & (v - 1)) == 0) ring_size = v;
   }
-  k_seg_fill<<<rt->num_sms * per_sm, kFillThreads, smem, st>>>(p, nib, seeds, small, keys, d_scan, stride_floats, d_range, d_residuals, order,
+  k_seg_fill<<<rt->num_sms * per_sm, kFillThreads, smem, st>>>(p, nib, seeds, small, keys, d_scan, stride_floats, d_range, d_residuals, res_stride, order,
                                                               small + 1, accepted, seg_avg, ring_size);
   tb = tmp_bytes;
   DDLO_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, accepted, rank, HW, st));

@@ -32,6 +32,7 @@ class DetectionModule:
         self._scan_t: Optional[np.ndarray] = None
         self._T = np.eye(4, dtype=np.float32)
         self._residuals: Optional[np.ndarray] = None
+        self._engine = None
         self.icp_residuals_set_ = False
         self.label_mat = self.range_mat = self.ground_mat = None
         self.avg_residuals = np.zeros(0)
@@ -47,7 +48,7 @@ class DetectionModule:
             raise ValueError(f"the segmentation scan must be organised: {self.H_} x {self.W_} points of >= 3 floats")
         self._scan_t = s
         self._T = np.asarray(T, dtype=np.float32).reshape(4, 4)
-        self.icp_residuals_set_ = self.icp_residuals_set_ and self._residuals is not None
+        self.icp_residuals_set_ = self.icp_residuals_set_ and (self._residuals is not None or self._engine is not None)
 
     # detection.cpp:203-252: residuals_cloud is the (rows, cols, 4) residual image (NanoGICP.residualImage), or just its intensity plane
     def projectResiduals(self, residuals_cloud):
@@ -58,6 +59,14 @@ class DetectionModule:
         if r.size != self.H_ * self.W_:
             raise ValueError("the residual image must have rows x cols pixels")
         self._residuals = np.ascontiguousarray(r, dtype=np.float32).reshape(self.H_, self.W_)
+        self._engine = None
+        self.icp_residuals_set_ = True
+
+    def projectResidualsFrom(self, engine, angle_min: float = -np.pi / 3, angle_max: float = np.pi / 3):
+        """projectResiduals without the host round trip: the residual cloud of `engine`'s last align (odom.cc:804-827) is
+        built on the device with rows x cols cells and its intensity channel used directly (ddlo_gicp_segment_scan)."""
+        self._engine = (engine, float(angle_min), float(angle_max))
+        self._residuals = None
         self.icp_residuals_set_ = True
 
     # detection.cpp:191-199 (groundRemoval + cloudSegmentation; icp_residuals_set_ is cleared at the end)
@@ -72,9 +81,16 @@ class DetectionModule:
         count, ms = C.c_int(0), C.c_float(0)
         T16 = np.ascontiguousarray(self._T.T)
         res = self._residuals if self.icp_residuals_set_ else None
-        B.check(B.load().ddlo_segment_scan(self.rt._h, C.byref(self.params), B.ptr(self._scan_t), self._scan_t.shape[1] * 4, B.ptr(T16),
-                                           None if res is None else B.ptr(res), B.ptr(label), B.ptr(rng), B.ptr(ground), B.ptr(avg),
-                                           avg.size, C.byref(count), C.byref(ms)))
+        eng = self._engine if self.icp_residuals_set_ else None
+        if eng is not None:
+            B.check(B.load().ddlo_gicp_segment_scan(eng[0]._g, C.byref(self.params), B.ptr(self._scan_t), self._scan_t.shape[1] * 4, B.ptr(T16),
+                                                    eng[1], eng[2], B.ptr(label), B.ptr(rng), B.ptr(ground), B.ptr(avg), avg.size,
+                                                    C.byref(count), C.byref(ms)))
+        else:
+            B.check(B.load().ddlo_segment_scan(self.rt._h, C.byref(self.params), B.ptr(self._scan_t), self._scan_t.shape[1] * 4, B.ptr(T16),
+                                               None if res is None else B.ptr(res), B.ptr(label), B.ptr(rng), B.ptr(ground), B.ptr(avg),
+                                               avg.size, C.byref(count), C.byref(ms)))
+        self._engine = None
         self.label_mat, self.range_mat, self.ground_mat = label, rng, ground
         self.label_count_ = count.value
         self.avg_residuals = avg[: count.value].copy()

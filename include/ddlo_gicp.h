@@ -259,6 +259,13 @@ int ddlo_segment_scan(ddlo_runtime* rt, const ddlo_segmentation_params* params, 
                       const float* residuals, int* label_mat, float* range_mat, signed char* ground_mat, double* avg_residuals,
                       int avg_capacity, int* label_count, float* device_ms);
 
+/* The same with projectResiduals fed on the device: the residual cloud of the engine's last align (odom.cc:804-827, as
+ * ddlo_gicp_residual_image builds it, width = cols and height = rows, angles in [angle_min, angle_max)) never leaves
+ * the GPU; its intensity channel is the residual plane (detection.cpp:240-249).  DDLO_E_NOT_READY before an align. */
+int ddlo_gicp_segment_scan(ddlo_gicp* g, const ddlo_segmentation_params* params, const float* scan_t, int stride_bytes, const float* T16,
+                           double angle_min, double angle_max, int* label_mat, float* range_mat, signed char* ground_mat,
+                           double* avg_residuals, int avg_capacity, int* label_count, float* device_ms);
+
 /* getResiduals(std::vector<Eigen::Vector3f>&, trans) (:199-222) */
 int ddlo_gicp_get_residual_vectors(ddlo_gicp* g, const float* T16, float* out_xyz, int capacity);
 

@@ -181,3 +181,41 @@ def test_segmentation_is_deterministic(rt):
         outs.append((det.label_mat.copy(), det.avg_residuals.copy()))
     for lm, avg in outs[1:]:
         assert np.array_equal(lm, outs[0][0]) and np.array_equal(avg.view(np.uint64), outs[0][1].view(np.uint64))
+
+
+def test_segmentation_residuals_straight_from_the_engine(rt, oracle):
+    # projectResidualsFrom(engine): the residual cloud of the last align is built on the device and never read back;
+    # it must give exactly what residualImage() -> host -> projectResiduals() gives, and what the oracle gives for it
+    from dynamic_direct_lidar_odometry_b200 import nano_gicp as ng
+
+    w = synth.make_world()
+    src, tgt = synth.scan(1, 16, 256, w), synth.scan(0, 16, 256, w)
+    g = ng.NanoGICP(rt)
+    g.setInputSource(ng.PointCloud(rt, src))
+    g.setInputTarget(ng.PointCloud(rt, tgt))
+    g.align()
+    params, st, T, _ = lidar_case(3, 64, 1024, 0.02)
+    a0, a1 = -np.pi / 2, np.pi / 2
+    img = g.residualImage(1024, 64, a0, a1)
+    assert (img[..., 3] > 0).sum() > 100  # the test really feeds residuals
+    two_step = DetectionModule(rt, **params)
+    two_step.projectScan(None, st, T)
+    two_step.projectResiduals(img)
+    two_step.applySegmentation()
+    fused = DetectionModule(rt, **params)
+    fused.projectScan(None, st, T)
+    fused.projectResidualsFrom(g, a0, a1)
+    fused.applySegmentation()
+    assert np.array_equal(fused.label_mat, two_step.label_mat)
+    assert np.array_equal(fused.avg_residuals.view(np.uint64), two_step.avg_residuals.view(np.uint64))
+    assert fused.avg_residuals.any()
+    o = oracle.segment_scan(oracle.SegParams(**params), st, T, img[..., 3])
+    assert_same(fused, o)
+    # before any align the engine has no residuals to give
+    fresh = ng.NanoGICP(rt)
+    det = DetectionModule(rt, **params)
+    det.projectScan(None, st, T)
+    det.projectResidualsFrom(fresh)
+    with pytest.raises(B.DdloError) as e:
+        det.applySegmentation()
+    assert e.value.code == -5  # DDLO_E_NOT_READY
