@@ -11,8 +11,9 @@
 //                   bottom-up loop of groundRemoval collapses to a function of two vertical pixel pairs)
 //   k_seg_edges     the flood fill's admission test for the 4 neighbours of every pixel -> 4 bits per pixel.
 //                   The test is symmetric, so segments are the connected components of an undirected graph:
-//   k_ccl_*         union-find labelling; the root of a component is its smallest raster index = the seed the
-//                   reference starts it from.  Component sizes give every segment its slice of the push list.
+//   k_ccl_*         union-find labelling (horizontal runs are joined by a ballot inside each warp first); the root of a
+//                   component is its smallest raster index = the seed the reference starts it from.  Component sizes
+//                   give every segment its slice of the push list.
 //   k_seg_fill      one warp per segment replays the queue: 8 queue entries x 4 neighbours per step, a neighbour
 //                   wanted twice in a step goes to the earlier (entry, direction) -- which is what the queue order
 //                   means -- and the survivors are appended in lane order.  The edge bits of the whole image and the
@@ -129,26 +130,28 @@ __device__ unsigned seg_edge_bits(const SegDev& p, const float* __restrict__ ran
   return bits;
 }
 
-// two pixels per thread -> one byte; parent[] initialised for the union-find
+// One pixel per thread: the edge nibbles (two pixels per byte) and the start of the union-find.  Pixels joined by
+// left/right edges form runs of consecutive raster indices (edge bits are clear at the row ends); inside a warp's 32
+// pixels every pixel is hung directly under the first pixel of its run (or of the warp's part of it), so only the
+// links between warps and between rows are left for k_ccl_union.
 __global__ void __launch_bounds__(256) k_seg_edges(SegDev p, const float* __restrict__ range, const int* __restrict__ label0,
                                                    unsigned char* __restrict__ nib, int* __restrict__ parent) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i0 = 2 * t, i1 = 2 * t + 1;
-  if (i0 >= p.HW) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   unsigned b = 0u;
-  {
-    const int y = i0 / p.W, x = i0 - y * p.W;
-    const bool ok = label0[i0] == 0 && seg_in_window(p, y, x);
-    parent[i0] = ok ? i0 : -1;
-    b = seg_edge_bits(p, range, label0, i0);
+  bool ok = false;
+  if (i < p.HW) {
+    const int y = i / p.W, x = i - y * p.W;
+    ok = label0[i] == 0 && seg_in_window(p, y, x);
+    b = seg_edge_bits(p, range, label0, i);
   }
-  if (i1 < p.HW) {
-    const int y = i1 / p.W, x = i1 - y * p.W;
-    const bool ok = label0[i1] == 0 && seg_in_window(p, y, x);
-    parent[i1] = ok ? i1 : -1;
-    b |= seg_edge_bits(p, range, label0, i1) << 4;
+  const unsigned hi = __shfl_down_sync(kFullMask, b, 1);
+  if (i < p.HW && (lane & 1) == 0) nib[i >> 1] = (unsigned char)(b | (hi << 4));
+  const unsigned starts = __ballot_sync(kFullMask, ok && (b & 4u) == 0u);  // pixels without a left edge open a run
+  if (i < p.HW) {
+    const unsigned upto = starts & (0xffffffffu >> (31 - lane));
+    parent[i] = !ok ? -1 : (i - lane + (upto ? 31 - __clz(upto) : 0));
   }
-  nib[t] = (unsigned char)b;
 }
 
 __device__ __forceinline__ int ccl_find(const int* parent, int x) {
@@ -170,12 +173,18 @@ __device__ void ccl_union(int* parent, int a, int b) {
     a = old;  // somebody moved a meanwhile: merge what it points to now
   }
 }
+__device__ __forceinline__ unsigned seg_nibble(const unsigned char* __restrict__ nib, int i) { return ((unsigned)nib[i >> 1] >> ((i & 1) * 4)) & 15u; }
 __global__ void __launch_bounds__(256) k_ccl_union(SegDev p, const unsigned char* __restrict__ nib, int* __restrict__ parent) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.HW) return;
-  const unsigned b = (nib[i >> 1] >> ((i & 1) * 4)) & 15u;
-  if (b & 2u) ccl_union(parent, i, i + 1);
-  if (b & 8u) ccl_union(parent, i, i + p.W);
+  const unsigned b = seg_nibble(nib, i);
+  // a run that continues across the warp boundary
+  if ((threadIdx.x & 31) == 0 && (b & 4u)) ccl_union(parent, i, i - 1);
+  // a link to the row below, unless the left neighbour makes the same link between the same two runs
+  if (b & 8u) {
+    const bool repeated = (b & 4u) && (seg_nibble(nib, i - 1) & 8u) && (seg_nibble(nib, i + p.W) & 4u);
+    if (!repeated) ccl_union(parent, i, i + p.W);
+  }
 }
 // root[] = smallest raster index of the pixel's component (-1 outside), size[root] = pixels of the component
 __global__ void __launch_bounds__(256) k_ccl_flatten(SegDev p, const int* __restrict__ parent, int* __restrict__ root, int* __restrict__ size) {
@@ -448,7 +457,7 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
 
   const int pb = (HW + 255) / 256;
   k_seg_project<<<pb, 256, 0, st>>>(p, d_scan, stride_floats, d_range, d_ground, d_label);
-  k_seg_edges<<<((HW + 1) / 2 + 255) / 256, 256, 0, st>>>(p, d_range, d_label, nib, parent);
+  k_seg_edges<<<pb, 256, 0, st>>>(p, d_range, d_label, nib, parent);
   k_ccl_union<<<pb, 256, 0, st>>>(p, nib, parent);
   k_ccl_flatten<<<pb, 256, 0, st>>>(p, parent, root, size);
   k_seg_seed_keys<<<pb, 256, 0, st>>>(p, root, size, keys);
