@@ -271,6 +271,9 @@ class NanoGICP {
   NanoGICP(const NanoGICP&) = delete;
   NanoGICP& operator=(const NanoGICP&) = delete;
 
+  // the C-ABI engine behind this object (for the calls that take an engine, e.g. ddlo_gicp_segment_scan)
+  ddlo_gicp* handle() const { return g_; }
+
   // ---- knobs (nano_gicp.hpp:83-85, lsq_registration.hpp:89-91, pcl::Registration) -------------
   void setNumThreads(int) {}  // OpenMP threads: no meaning on the device
   void setCorrespondenceRandomness(int k) { p_.k_correspondences = k; }

@@ -219,3 +219,41 @@ def test_segmentation_residuals_straight_from_the_engine(rt, oracle):
     with pytest.raises(B.DdloError) as e:
         det.applySegmentation()
     assert e.value.code == -5  # DDLO_E_NOT_READY
+
+
+def test_cpp_detection_shim_matches(rt, oracle, tmp_path):
+    """tests/cpp/segmentation_protocol.cpp drives ddlo_shim::DetectionModule (the C++ header with the reference's
+    method and member names) through OdomNode::applySegmentation's calls; it must write exactly what the Python mirror
+    and the oracle give for the same scan."""
+    import subprocess
+    from pathlib import Path
+
+    exe = Path(__file__).resolve().parent / "cpp" / "_build" / "segmentation_protocol"
+    if not exe.exists():
+        import __graft_entry__ as ge
+
+        ge.build_cpp_tests()
+    params, st, T, res = lidar_case(3, 64, 1024, 0.02)
+    H, W = params["rows"], params["cols"]
+    src, dst = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(src, "wb") as fh:
+        fh.write(np.array([H, W, params["ground_rows"]], dtype=np.int32).tobytes())
+        fh.write(np.array([params["ang_bottom"], params["minimum_range"], params["sensor_mount_angle"], params["max_distance"]],
+                          dtype=np.float32).tobytes())
+        fh.write(np.ascontiguousarray(T.T, dtype=np.float32).tobytes())  # column-major
+        fh.write(np.ascontiguousarray(st, dtype=np.float32).tobytes())
+        fh.write(np.ascontiguousarray(res, dtype=np.float32).tobytes())
+    out = subprocess.run([str(exe), str(src), str(dst)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    raw = dst.read_bytes()
+    count = int(np.frombuffer(raw, dtype=np.int32, count=1)[0])
+    labels = np.frombuffer(raw, dtype=np.int32, count=H * W, offset=4).reshape(H, W)
+    ground = np.frombuffer(raw, dtype=np.int8, count=H * W, offset=4 + 4 * H * W).reshape(H, W)
+    avg = np.frombuffer(raw, dtype=np.float64, count=count, offset=4 + 5 * H * W)
+    det, o = run_both(rt, oracle, params, st, T, res)
+    assert_same(det, o)
+    assert count == det.label_count_ and np.array_equal(labels, det.label_mat) and np.array_equal(ground, det.ground_mat)
+    assert np.array_equal(avg[1:].view(np.uint64), det.avg_residuals[1:].view(np.uint64))
+    f = out.stdout.split()
+    assert int(f[1]) == det.getSegmentsCount() and int(f[3]) == len(det.getGroundIndices())
+    assert int(f[5]) == int(((det.label_mat > 0) & (det.label_mat != INVALID_SEGMENT)).sum())
