@@ -1125,44 +1125,53 @@ static int segment_scan_impl(ddlo_runtime* rt, const ddlo_segmentation_params* p
   cudaStream_t st = rt->stream;
   const size_t HW = (size_t)p.rows * p.cols;
   const int stride = stride_bytes / 4;
-  float *d_scan = nullptr, *d_res = nullptr, *d_range = nullptr;
-  int *d_label = nullptr, *d_count = nullptr;
-  signed char* d_ground = nullptr;
-  double* d_avg = nullptr;
-  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_scan), HW * stride_bytes, st));
-  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_range), HW * 4, st));
-  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_label), HW * 4 + 16, st));
-  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ground), HW, st));
-  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_avg), (HW + 1) * 8, st));
-  if (residuals) DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_res), HW * 4, st));
-  if (engine) DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_res), HW * sizeof(float4), st));
-  d_count = d_label + HW;
+  // stream-ordered pool buffers, returned to the pool on every exit path
+  struct PoolBuf {
+    void* p = nullptr;
+    cudaStream_t st;
+    explicit PoolBuf(cudaStream_t s) : st(s) {}
+    ~PoolBuf() {
+      if (p) cudaFreeAsync(p, st);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, st); }
+  };
+  PoolBuf b_scan(st), b_res(st), b_range(st), b_label(st), b_ground(st), b_avg(st);
+  DDLO_CUDA(b_scan.alloc(HW * stride_bytes));
+  DDLO_CUDA(b_range.alloc(HW * 4));
+  DDLO_CUDA(b_label.alloc(HW * 4 + 16));
+  DDLO_CUDA(b_ground.alloc(HW));
+  DDLO_CUDA(b_avg.alloc((HW + 1) * 8));
+  if (residuals) DDLO_CUDA(b_res.alloc(HW * 4));
+  if (engine) DDLO_CUDA(b_res.alloc(HW * sizeof(float4)));
+  float *d_scan = static_cast<float*>(b_scan.p), *d_res = static_cast<float*>(b_res.p), *d_range = static_cast<float*>(b_range.p);
+  int* d_label = static_cast<int*>(b_label.p);
+  int* d_count = d_label + HW;
+  signed char* d_ground = static_cast<signed char*>(b_ground.p);
+  double* d_avg = static_cast<double*>(b_avg.p);
   DDLO_CUDA(cudaMemcpyAsync(d_scan, scan_t, HW * stride_bytes, cudaMemcpyHostToDevice, st));
   if (residuals) DDLO_CUDA(cudaMemcpyAsync(d_res, residuals, HW * 4, cudaMemcpyHostToDevice, st));
   DDLO_CUDA(cudaMemsetAsync(d_avg, 0, (HW + 1) * 8, st));
   if (device_ms) DDLO_CUDA(cudaEventRecord(rt->ev0, st));
-  int rc = DDLO_OK;
   if (engine)  // the residual cloud of odom.cc:804-827, cols x rows cells; its intensity channel is the residual plane (:240-249)
-    rc = residual_image_device(rt, engine->src->pts, engine->sqd, engine->corr_n, p.cols, p.rows, angle_min, angle_max, reinterpret_cast<float4*>(d_res));
-  if (rc == DDLO_OK)
-    rc = segment_scan_device(rt, p, T16, d_scan, stride, engine ? d_res + 3 : d_res, engine ? 4 : 1, d_label, d_range, d_ground, d_avg, d_count);
-  if (device_ms && rc == DDLO_OK) DDLO_CUDA(cudaEventRecord(rt->ev1, st));
+    DDLO_TRY(residual_image_device(rt, engine->src->pts, engine->sqd, engine->corr_n, p.cols, p.rows, angle_min, angle_max,
+                                   reinterpret_cast<float4*>(d_res)));
+  DDLO_TRY(segment_scan_device(rt, p, T16, d_scan, stride, engine ? d_res + 3 : d_res, engine ? 4 : 1, d_label, d_range, d_ground, d_avg, d_count));
+  if (device_ms) DDLO_CUDA(cudaEventRecord(rt->ev1, st));
+  // One synchronisation in the common case: the segment count travels together with the first kAvgFirst averages.
+  constexpr int kAvgFirst = 1024;
+  const int first = avg_residuals ? std::min<long long>(std::min(avg_capacity, kAvgFirst), (long long)HW + 1) : 0;
   int count = 0;
-  if (rc == DDLO_OK) {
-    cudaError_t e = cudaMemcpyAsync(&count, d_count, 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && label_mat) e = cudaMemcpyAsync(label_mat, d_label, HW * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && range_mat) e = cudaMemcpyAsync(range_mat, d_range, HW * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && ground_mat) e = cudaMemcpyAsync(ground_mat, d_ground, HW, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess && avg_residuals && avg_capacity > 0 && count > 0) {
-      e = cudaMemcpyAsync(avg_residuals, d_avg, (size_t)std::min(count, avg_capacity) * 8, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    }
-    if (e != cudaSuccess) rc = fail(DDLO_E_CUDA, cudaGetErrorString(e));
+  DDLO_CUDA(cudaMemcpyAsync(&count, d_count, 4, cudaMemcpyDeviceToHost, st));
+  if (first > 0) DDLO_CUDA(cudaMemcpyAsync(avg_residuals, d_avg, (size_t)first * 8, cudaMemcpyDeviceToHost, st));
+  if (label_mat) DDLO_CUDA(cudaMemcpyAsync(label_mat, d_label, HW * 4, cudaMemcpyDeviceToHost, st));
+  if (range_mat) DDLO_CUDA(cudaMemcpyAsync(range_mat, d_range, HW * 4, cudaMemcpyDeviceToHost, st));
+  if (ground_mat) DDLO_CUDA(cudaMemcpyAsync(ground_mat, d_ground, HW, cudaMemcpyDeviceToHost, st));
+  DDLO_CUDA(cudaStreamSynchronize(st));
+  const int wanted = avg_residuals ? std::min(count, avg_capacity) : 0;
+  if (wanted > first) {
+    DDLO_CUDA(cudaMemcpyAsync(avg_residuals + first, d_avg + first, (size_t)(wanted - first) * 8, cudaMemcpyDeviceToHost, st));
+    DDLO_CUDA(cudaStreamSynchronize(st));
   }
-  for (void* q : {(void*)d_scan, (void*)d_res, (void*)d_range, (void*)d_label, (void*)d_ground, (void*)d_avg})
-    if (q) cudaFreeAsync(q, st);
-  if (rc != DDLO_OK) return rc;
   if (device_ms) DDLO_CUDA(cudaEventElapsedTime(device_ms, rt->ev0, rt->ev1));
   *label_count = count;
   return DDLO_OK;

@@ -252,7 +252,8 @@ typedef struct ddlo_segmentation_params {
  * T16: column-major 4x4 float pose.  residuals: HOST rows * cols floats or NULL (projectResiduals not called: every
  *      avg_residuals_ entry is 0, :703-707).
  * Outputs (HOST): label_mat int32, range_mat float, ground_mat int8 (1 ground, -1 no information, 0), each
- * rows * cols and any of them NULL to skip; avg_residuals[label] for label < min(*label_count, avg_capacity);
+ * rows * cols and any of them NULL to skip; avg_residuals[label] for label < min(*label_count, avg_capacity) (entries
+ * behind *label_count, up to 1024, may be overwritten with zeros);
  * *label_count = label_count_ (labels 1 .. *label_count - 1 are the accepted segments); *device_ms (optional) = time of
  * the kernels alone, between the uploads and the read-back. */
 int ddlo_segment_scan(ddlo_runtime* rt, const ddlo_segmentation_params* params, const float* scan_t, int stride_bytes, const float* T16,
