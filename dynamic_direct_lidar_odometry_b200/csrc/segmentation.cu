@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(kFillThreads) k_seg_fill(SegDev p, const unsig
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pl = lane >> 2, n = lane & 3;  // flood fill: slot = (queue entry of the step, direction)
   const int step_n = n == 0 ? -p.W : (n == 1 ? 1 : (n == 2 ? -1 : p.W));
+  const unsigned lanes_below = (1u << lane) - 1u;
   int* ring = rings + warp * kRing;
   const int total = *n_seeds;
   const int W = p.W;
@@ -265,10 +266,10 @@ __global__ void __launch_bounds__(kFillThreads) k_seg_fill(SegDev p, const unsig
       // A pixel wanted by several (entry, direction) slots of this step goes to the first of them.  (The match costs
       // one round per distinct value: every slot without a candidate shares one dummy.)
       const unsigned same = __match_any_sync(kFullMask, cand ? v : -1);
-      const bool win = cand && (int)(__ffs(same) - 1) == lane;
+      const bool win = cand && (same & lanes_below) == 0u;
       const unsigned wins = __ballot_sync(kFullMask, win);
       if (win) {
-        const int pos = tail + __popc(wins & ((1u << lane) - 1u));
+        const int pos = tail + __popc(wins & lanes_below);
         ring[pos & (ring_size - 1)] = v;
         order[beg + pos] = (unsigned)v | ((unsigned)n << 30);  // the direction recovers the pixel it was pushed from
         atomicOr(vis + (v >> 5), 1u << (v & 31));
