@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--beams", type=int, default=64)
     ap.add_argument("--cols", type=int, default=1024)
     ap.add_argument("--voxel", type=float, default=0.0, help="leaf size of the scan and keyframe voxel filters on the device (0 = off; the DLO yaml uses 0.25 - 0.5 m)")
+    ap.add_argument("--segmentation", action="store_true",
+                    help="also run the range-image segmentation stage (OdomNode::applySegmentation, odom.cc:853-857) on every frame")
     ap.add_argument("--k", type=int, default=20, help="kCorrespondences of both engines (engine default 20; the DLO yaml uses 10)")
     args = ap.parse_args()
 
@@ -41,7 +43,12 @@ def main():
 
     w = synth.make_world()
     t0 = time.perf_counter()
-    scans = [synth.scan(f, args.beams, args.cols, w) for f in range(args.frames)]
+    organized = None
+    if args.segmentation:  # the registration scan is the organised scan without its empty pixels
+        organized = [synth.organized_scan(f, args.beams, args.cols, w) for f in range(args.frames)]
+        scans = [np.ascontiguousarray(o.reshape(-1, 4)[np.isfinite(o[..., 0]).reshape(-1)]) for o in organized]
+    else:
+        scans = [synth.scan(f, args.beams, args.cols, w) for f in range(args.frames)]
     gen_s = time.perf_counter() - t0
     cfg = ol.LoopConfig(k_correspondences_s2s=args.k, k_correspondences_s2m=args.k,
                         voxel_leaf_scan=args.voxel or None, voxel_leaf_submap=args.voxel or None)
@@ -49,7 +56,32 @@ def main():
     rt = ng.Runtime(0)
     ol.run_sequence(ol.GpuBackend(rt), scans[: min(8, args.frames)], cfg)  # warm-up: allocator pools, first launches
     rt.synchronize()
-    loop = ol.run_sequence(ol.GpuBackend(rt), scans, cfg)
+    seg_ms, seg_dev_ms, seg_counts = [], [], []
+    if not args.segmentation:
+        loop = ol.run_sequence(ol.GpuBackend(rt), scans, cfg)
+    else:
+        from dynamic_direct_lidar_odometry_b200.detection import DetectionModule
+
+        det = DetectionModule(rt, rows=args.beams, cols=args.cols, ground_rows=args.beams * 3 // 8, window_row_min=0, window_row_max=args.beams - 1,
+                              window_col_min=0, window_col_max=args.cols - 1, ang_bottom=22.5, minimum_range=1.0, sensor_mount_angle=0.0,
+                              max_distance=40.0)
+        loop = ol.OdometryLoop(ol.GpuBackend(rt), cfg)
+        for f, scan in enumerate(scans):
+            rec = loop.step(scan)
+            if rec is None:
+                continue
+            # segmentation_scan_t_ = the organised scan moved by the frame's pose (odom.cc:957-963; host side, not timed)
+            scan_t = synth.organized_transform(organized[f], rec.T)
+            residuals = loop.s2m.getResiduals()
+            t1 = time.perf_counter()
+            plane = np.zeros(args.beams * args.cols, dtype=np.float32)  # residual per pixel of the organised scan (odom.cc:804-827)
+            plane[np.isfinite(organized[f][..., 0]).reshape(-1)] = residuals
+            det.projectScan(None, scan_t, rec.T)
+            det.projectResiduals(plane)
+            det.applySegmentation()
+            seg_ms.append((time.perf_counter() - t1) * 1e3)
+            seg_dev_ms.append(det.device_ms)
+            seg_counts.append(det.getSegmentsCount())
     ms = np.array([r.seconds for r in loop.records]) * 1e3
     inv0 = np.linalg.inv(synth.pose(0))
     err_t = [float(np.abs(r.T[:3, 3].astype(np.float64) - (inv0 @ synth.pose(f))[:3, 3]).max()) for f, r in enumerate(loop.records, start=1)]
@@ -64,6 +96,10 @@ def main():
         "final_translation_error_vs_truth_m": err_t[-1], "max_translation_error_vs_truth_m": max(err_t),
         "k_correspondences": args.k, "voxel_leaf_m": args.voxel, "timer": "host wall clock per frame, scan upload and residual read-back included",
         "scan_generation_s": gen_s,
+        **({"segmentation_ms_per_frame_mean": float(np.mean(seg_ms)), "segmentation_ms_per_frame_p99": float(np.percentile(seg_ms, 99)),
+            "segmentation_device_ms_mean": float(np.mean(seg_dev_ms)), "segments_per_frame_mean": float(np.mean(seg_counts)),
+            "segmentation_timer": "host wall clock around projectScan + projectResiduals + applySegmentation (host buffers both sides)"}
+           if seg_ms else {}),
         "slowest_frames": [{"frame": int(i) + 1, "ms": float(ms[i]), "new_keyframe": bool(loop.records[i].new_keyframe),
                             "submap_changed": bool(loop.records[i].submap_changed), "submap_points": int(loop.records[i].submap_points)}
                            for i in np.argsort(-ms)[:6]],
