@@ -85,6 +85,25 @@ __device__ int seg_pair_state(const float* __restrict__ scan, int stride, const 
   return fabsf(__fsub_rn(angle, p.mount)) <= p.ground_thr ? 1 : 0;
 }
 
+// OdomNode::transformScans for the segmentation scan (odom.cc:957-963): pcl::transformPointCloud in float,
+// (r0 x + r1 y) + (r2 z + t) per row; points with a non-finite coordinate are left as they are.  T: column-major 4x4.
+struct SegPose {
+  float m[16];
+};
+__global__ void __launch_bounds__(256) k_seg_transform(int n, const float* __restrict__ scan, int stride, SegPose T, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* q = scan + (size_t)i * stride;
+  const float x = q[0], y = q[1], z = q[2];
+  float4 o = make_float4(x, y, z, 1.0f);
+  if (isfinite(x) && isfinite(y) && isfinite(z)) {
+    o.x = __fadd_rn(__fadd_rn(__fmul_rn(T.m[0], x), __fmul_rn(T.m[4], y)), __fadd_rn(__fmul_rn(T.m[8], z), T.m[12]));
+    o.y = __fadd_rn(__fadd_rn(__fmul_rn(T.m[1], x), __fmul_rn(T.m[5], y)), __fadd_rn(__fmul_rn(T.m[9], z), T.m[13]));
+    o.z = __fadd_rn(__fadd_rn(__fmul_rn(T.m[2], x), __fmul_rn(T.m[6], y)), __fadd_rn(__fmul_rn(T.m[10], z), T.m[14]));
+  }
+  out[i] = o;
+}
+
 __global__ void __launch_bounds__(256) k_seg_project(SegDev p, const float* __restrict__ scan, int stride, float* __restrict__ range,
                                                      signed char* __restrict__ ground, int* __restrict__ label0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -457,6 +476,16 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   DDLO_CUDA(cudaMemsetAsync(nib, 0, nib_bytes, st));
 
   const int pb = (HW + 255) / 256;
+  float4* moved = nullptr;
+  if (prm.scan_in_sensor_frame) {
+    DDLO_TRY(pool_alloc(rt, &moved, HW));
+    SegPose pose;
+    for (int i = 0; i < 16; ++i) pose.m[i] = T16[i];
+    k_seg_transform<<<pb, 256, 0, st>>>(HW, d_scan, stride_floats, pose, moved);
+    rt->launches += 1;
+    d_scan = reinterpret_cast<const float*>(moved);
+    stride_floats = 4;
+  }
   k_seg_project<<<pb, 256, 0, st>>>(p, d_scan, stride_floats, d_range, d_ground, d_label);
   k_seg_edges<<<pb, 256, 0, st>>>(p, d_range, d_label, nib, parent);
   k_ccl_union<<<pb, 256, 0, st>>>(p, nib, parent);
@@ -479,8 +508,8 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   rt->launches += 8 + 4;  // ours + the two scans' kernels
   DDLO_CUDA(cudaGetLastError());
   for (void* q : {(void*)nib, (void*)parent, (void*)root, (void*)size, (void*)seeds, (void*)accepted, (void*)rank, (void*)small, (void*)keys,
-                  (void*)order, (void*)seg_avg, tmp})
-    cudaFreeAsync(q, st);
+                  (void*)order, (void*)seg_avg, tmp, (void*)moved})
+    if (q) cudaFreeAsync(q, st);
   return DDLO_OK;
 }
 

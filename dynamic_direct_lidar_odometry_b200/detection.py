@@ -39,9 +39,11 @@ class DetectionModule:
         self.label_count_ = 1
         self.device_ms = 0.0
 
-    # detection.cpp:254-329: only the transformed scan and the pose enter the range image
+    # detection.cpp:254-329: only the transformed scan and the pose enter the range image.  With cloud_in_t = None the
+    # sensor-frame scan cloud_in is moved by T on the device first (OdomNode::transformScans, odom.cc:957-963).
     def projectScan(self, cloud_in, cloud_in_t, T, T_s2s=None):
-        s = np.ascontiguousarray(cloud_in_t, dtype=np.float32)
+        self.params.scan_in_sensor_frame = 1 if cloud_in_t is None else 0
+        s = np.ascontiguousarray(cloud_in if cloud_in_t is None else cloud_in_t, dtype=np.float32)
         if s.ndim == 3:
             s = s.reshape(-1, s.shape[-1])
         if s.ndim != 2 or s.shape[0] != self.H_ * self.W_ or s.shape[1] < 3:

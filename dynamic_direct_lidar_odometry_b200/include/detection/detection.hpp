@@ -33,6 +33,7 @@ public:
     params_.rows = 128, params_.cols = 1024, params_.ground_rows = 30;
     params_.valid_point_num = 15, params_.min_line_num = 5, params_.valid_line_num = 5;
     params_.window_row_min = 156, params_.window_row_max = 356, params_.window_col_min = 156, params_.window_col_max = 356;
+    params_.scan_in_sensor_frame = 0;
     params_.ang_bottom = 45.0f, params_.ground_angle_threshold = 10.0f, params_.minimum_range = 10.0f, params_.sensor_mount_angle = 10.0f;
     params_.theta = static_cast<float>(60.0 / 180.0 * M_PI);
     params_.min_delta_z = 0.1f, params_.max_delta_z = 3.0f, params_.max_distance = 20.0f, params_.max_elevation = 2.0f;
@@ -43,10 +44,13 @@ public:
   }
 
   // :254-329 — only the transformed scan and the pose enter the range image
-  void projectScan(const CloudPtr& /*cloud_in*/, const CloudPtr& cloud_in_t, const Matrix4f& T, const Matrix4f& T_s2s = identity4f()) {
-    if (!cloud_in_t || cloud_in_t->size() != (size_t)H_ * W_) throw std::invalid_argument("DetectionModule: the segmentation scan must be organised (H_ x W_ points)");
+  // (a null cloud_in_t: the sensor-frame scan cloud_in is moved by T on the device, OdomNode::transformScans, odom.cc:957-963)
+  void projectScan(const CloudPtr& cloud_in, const CloudPtr& cloud_in_t, const Matrix4f& T, const Matrix4f& T_s2s = identity4f()) {
+    const CloudPtr& scan = cloud_in_t ? cloud_in_t : cloud_in;
+    if (!scan || scan->size() != (size_t)H_ * W_) throw std::invalid_argument("DetectionModule: the segmentation scan must be organised (H_ x W_ points)");
     resetParameters();
-    cloud_in_t_ = cloud_in_t;
+    params_.scan_in_sensor_frame = cloud_in_t ? 0 : 1;
+    cloud_in_t_ = scan;
     T_ = T, T_s2s_ = T_s2s;
   }
 

@@ -243,6 +243,10 @@ typedef struct ddlo_segmentation_params {
   int window_row_min, window_row_max, window_col_min, window_col_max; /* the hard-coded valid_range lambda (:520-522):
                                                                          156, 356, 156, 356; window_col_max must be < cols
                                                                          (beyond that the reference wraps one-directionally) */
+  int scan_in_sensor_frame;                                           /* 0: scan_t is segmentation_scan_t_ (world frame), as projectScan gets it.
+                                                                         1: scan_t is segmentation_scan_ (sensor frame) and is first moved by T16
+                                                                         on the device like pcl::transformPointCloud in OdomNode::transformScans
+                                                                         (odom.cc:957-963): float (r0 x + r1 y) + (r2 z + t), non-finite points kept */
   float ang_bottom;                                                   /* 45: vertical resolution = 2 ang_bottom / (rows - 1) */
   float ground_angle_threshold, minimum_range, sensor_mount_angle, theta; /* 10, 10, 10, 60 deg in rad */
   float min_delta_z, max_delta_z, max_distance, max_elevation;        /* 0.1, 3.0, 20, 2.0 */

@@ -34,6 +34,7 @@ struct oracle_seg_params {  // same layout as ddlo_segmentation_params (include/
   int ground_rows;
   int valid_point_num, min_line_num, valid_line_num;
   int window_row_min, window_row_max, window_col_min, window_col_max;
+  int scan_in_sensor_frame;
   float ang_bottom;
   float ground_angle_threshold, minimum_range, sensor_mount_angle, theta;
   float min_delta_z, max_delta_z, max_distance, max_elevation;
@@ -62,6 +63,22 @@ int oracle_segment_scan(const oracle_seg_params* p, const float* scan_t, int str
   std::fill(ground_mat, ground_mat + HW, (signed char)0);
   std::fill(range_mat, range_mat + HW, 0.0f);
   std::vector<float> full(HW * 3, nan);
+  // OdomNode::transformScans (odom.cc:957-963) when the caller hands over the sensor-frame scan: pcl::transformPointCloud,
+  // float (r0 x + r1 y) + (r2 z + t) as Eigen evaluates the 4x4 product; non-finite points are left alone
+  std::vector<float> moved;
+  if (p->scan_in_sensor_frame) {
+    moved.resize(HW * 3);
+    for (size_t i = 0; i < HW; ++i) {
+      const float* q = scan_t + i * stride_floats;
+      const float x = q[0], y = q[1], z = q[2];
+      float* o = &moved[i * 3];
+      o[0] = x, o[1] = y, o[2] = z;
+      if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z))
+        for (int r = 0; r < 3; ++r) o[r] = (T16[r] * x + T16[4 + r] * y) + (T16[8 + r] * z + T16[12 + r]);
+    }
+    scan_t = moved.data();
+    stride_floats = 3;
+  }
   auto pt = [&](size_t i) { return scan_t + i * stride_floats; };
 
   // projectScan (:296-327)

@@ -257,3 +257,25 @@ def test_cpp_detection_shim_matches(rt, oracle, tmp_path):
     f = out.stdout.split()
     assert int(f[1]) == det.getSegmentsCount() and int(f[3]) == len(det.getGroundIndices())
     assert int(f[5]) == int(((det.label_mat > 0) & (det.label_mat != INVALID_SEGMENT)).sum())
+
+
+def test_segmentation_transforms_sensor_frame_scan_on_device(rt, oracle):
+    # projectScan(cloud_in, None, T): OdomNode::transformScans (odom.cc:957-963) happens on the device, in the float
+    # arithmetic of pcl::transformPointCloud; NaN pixels stay NaN
+    frame = 3
+    sc = synth.organized_scan(frame, 64, 1024, dropout=0.02)
+    T = synth.pose(frame).astype(np.float32)
+    params, _, _, res = lidar_case(frame, 64, 1024, 0.02)
+    det = DetectionModule(rt, **params)
+    det.projectScan(sc, None, T)
+    det.projectResiduals(res)
+    det.applySegmentation()
+    o = oracle.segment_scan(oracle.SegParams(**{**params, "scan_in_sensor_frame": 1}), sc, T, res)
+    assert_same(det, o)
+    assert det.getSegmentsCount() > 3
+    # and it is the same scene as the host-transformed one: ranges agree to float rounding of the transform
+    _, st, _, _ = lidar_case(frame, 64, 1024, 0.02)
+    det2 = DetectionModule(rt, **params)
+    det2.projectScan(None, st, T)
+    det2.applySegmentation()
+    assert np.allclose(det.range_mat, det2.range_mat, rtol=0, atol=1e-4)
