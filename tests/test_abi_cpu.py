@@ -155,3 +155,57 @@ def test_shard_range():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
             sizes = [e - b for b, e in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_segmentation_params_layout_matches_header():
+    """ddlo_segmentation_params is mirrored three times (ctypes for the product, ctypes for the oracle, the oracle's own
+    C struct): all of them must list the header's fields in the header's order and types."""
+    import ctypes as C
+    import re
+
+    from dynamic_direct_lidar_odometry_b200 import binding as B
+    from oracle import pyoracle
+
+    def fields_of(text, name_open, name_close):
+        body = text[text.index(name_open) + len(name_open): text.index(name_close)]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        body = re.sub(r"//[^\n]*", "", body)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            ctype, names = decl.split(None, 1)
+            out += [(n.strip(), ctype) for n in names.split(",")]
+        return out
+
+    header = fields_of((ROOT / "include" / "ddlo_gicp.h").read_text(), "typedef struct ddlo_segmentation_params {", "} ddlo_segmentation_params;")
+    oracle_c = fields_of((ROOT / "oracle" / "oracle_segmentation.cpp").read_text(), "struct oracle_seg_params {", "};\n\n// scan_t")
+    assert header == oracle_c and len(header) == 20
+    ctype = {"int": C.c_int, "float": C.c_float}
+    want = [(n, ctype[t]) for n, t in header]
+    assert list(B.SegmentationParams._fields_) == want
+    assert list(pyoracle.SegParams._fields_) == want
+    assert set(B.SegmentationParams.DEFAULTS) == {n for n, _ in header} == set(pyoracle.SegParams.DEFAULTS)
+    assert B.SegmentationParams.DEFAULTS.keys() == pyoracle.SegParams.DEFAULTS.keys()
+    for k, v in B.SegmentationParams.DEFAULTS.items():
+        assert abs(v - pyoracle.SegParams.DEFAULTS[k]) < 1e-12
+
+
+def test_detection_module_argument_checks_need_no_gpu():
+    # the host mirror validates shapes before anything reaches the library
+    from dynamic_direct_lidar_odometry_b200.detection import DetectionModule
+
+    det = DetectionModule(None, rows=8, cols=16, ground_rows=3)
+    with pytest.raises(ValueError):
+        det.projectScan(None, np.zeros((7, 16, 4), dtype=np.float32), np.eye(4))
+    with pytest.raises(ValueError):
+        det.projectResiduals(np.zeros((8, 15), dtype=np.float32))
+    with pytest.raises(RuntimeError):
+        det.applySegmentation()
+    with pytest.raises(TypeError):
+        DetectionModule(None, rowz=8)
+    det.projectScan(np.zeros((8, 16, 4), dtype=np.float32), None, np.eye(4))
+    assert det.params.scan_in_sensor_frame == 1
+    det.projectScan(None, np.zeros((8, 16, 4), dtype=np.float32), np.eye(4))
+    assert det.params.scan_in_sensor_frame == 0
