@@ -8,8 +8,13 @@
 //   cloudSegmentation  src/detection/detection.cpp:514-546   raster-order seeds
 //   labelComponents    src/detection/detection.cpp:548-724   queue flood fill + segment feasibility
 //
-// PARITY UNPINNED for this stage: the reference's detection.cpp needs ROS, OpenCV and PCL, none of which is
-// installed here, so it cannot be compiled beside this file, and the reference ships no fixtures for it.
+// PIN: the reference's detection.cpp as a whole needs ROS, OpenCV, PCL and the tracking module and cannot be compiled
+// here, and the reference ships no fixtures for it.  Its class declaration (include/detection/detection.h, unmodified)
+// and the definitions of exactly the member functions restated below are compiled from /root/reference over stand-in
+// headers into oracle/_ref/libdetection_ref.so (ref_detection_shim.cpp, extract_detection.py, refdet.py);
+// tests/test_reference_detection_cpu.py requires this file to reproduce that code bit for bit (labels, ground flags,
+// ranges, average residuals), and the outputs of that code are committed as tests/golden/segmentation_reference.npz.
+// Not covered by the pin: windows other than the reference's hard-coded 156..356 and the scan_in_sensor_frame option.
 //
 // Arithmetic notes (what the reference's build, -O2 without -march, evaluates):
 //   * all members are float (include/detection/detection.h:60-86); products and sums are rounded one by one

@@ -20,6 +20,7 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "_build" / "liboracle_gicp.so"
 REF_LIB_PATH = HERE / "_ref" / "libnanoflann_ref.so"
 REF_GICP_LIB_PATH = HERE / "_ref" / "libnano_gicp_ref.so"  # the reference's own engine, see oracle/refgicp.py
+REF_DETECTION_LIB_PATH = HERE / "_ref" / "libdetection_ref.so"  # the reference's own segmentation code, see oracle/refdet.py
 REFERENCE_ROOT = Path("/root/reference")
 
 BACKEND_CANONICAL = 0
@@ -60,8 +61,10 @@ def build(force: bool = False) -> None:
     ref_hdr = REFERENCE_ROOT / "dynamic_direct_lidar_odometry/include/nano_gicp/impl/nanoflann_impl.hpp"
     shim = HERE / "ref_nanoflann_shim.cpp"
     gicp_shim = HERE / "ref_nano_gicp_shim.cpp"
+    det_newest = max((HERE / f).stat().st_mtime for f in ("ref_detection_shim.cpp", "extract_detection.py", "stub_include/tracking/tracking.h"))
     stale = (not REF_LIB_PATH.exists() or REF_LIB_PATH.stat().st_mtime < shim.stat().st_mtime
-             or not REF_GICP_LIB_PATH.exists() or REF_GICP_LIB_PATH.stat().st_mtime < gicp_shim.stat().st_mtime)
+             or not REF_GICP_LIB_PATH.exists() or REF_GICP_LIB_PATH.stat().st_mtime < gicp_shim.stat().st_mtime
+             or not REF_DETECTION_LIB_PATH.exists() or REF_DETECTION_LIB_PATH.stat().st_mtime < det_newest)
     if ref_hdr.exists() and (force or stale):
         subprocess.run(["make", "-C", str(HERE), "-B", "ref"], check=True, capture_output=True)
 

@@ -88,6 +88,19 @@ def main():
             r = ref.align()
             out.update({f"{name}_T": r.T, f"{name}_H": r.hessian, f"{name}_meta": np.array([r.converged, r.iterations])})
         np.savez_compressed(OUT / "gicp_reference_engine.npz", **out)
+    # ---- the segmentation stage from the REFERENCE'S OWN DetectionModule code (oracle/refdet.py), inputs included
+    from oracle import refdet
+
+    if refdet.available():
+        sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+        import segmentation_cases as cases
+
+        params, st, T, res = cases.golden_case()
+        r = refdet.segment(params, st, T, res)
+        np.savez_compressed(OUT / "segmentation_reference.npz", scan_t=st[..., :3].astype(np.float32), T=T, residuals=res,
+                            param_names=np.array(list(params.keys())), param_values=np.array([float(v) for v in params.values()]),
+                            label_mat=r["label_mat"], ground_mat=r["ground_mat"], range_mat=r["range_mat"], avg_residuals=r["avg_residuals"],
+                            label_count=np.int32(r["label_count"]))
     print("golden fixtures written to", OUT)
 
 

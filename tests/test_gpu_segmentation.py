@@ -279,3 +279,52 @@ def test_segmentation_transforms_sensor_frame_scan_on_device(rt, oracle):
     det2.projectScan(None, st, T)
     det2.applySegmentation()
     assert np.allclose(det.range_mat, det2.range_mat, rtol=0, atol=1e-4)
+
+
+# ------------------------------------------------------------------ against the reference's own DetectionModule code
+@pytest.fixture(scope="module")
+def refdet(oracle):
+    from oracle import refdet as rd
+
+    if not rd.available():
+        pytest.skip("oracle/_ref/libdetection_ref.so not built (needs /root/reference)")
+    rd.lib()
+    return rd
+
+
+def assert_same_as_reference(det, r):
+    assert det.label_count_ == r["label_count"]
+    assert np.array_equal(det.label_mat, r["label_mat"])
+    assert np.array_equal(det.ground_mat, r["ground_mat"])
+    assert np.array_equal(det.range_mat.view(np.uint32), r["range_mat"].view(np.uint32))
+    assert np.array_equal(det.avg_residuals[1:].view(np.uint64), r["avg_residuals"][1:].view(np.uint64))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_segmentation_matches_reference_detection_code(rt, oracle, refdet, variant):
+    """the CUDA stage against the reference's own groundRemoval / cloudSegmentation / labelComponents (oracle/refdet.py),
+    bit for bit; the oracle's borderline count guards against a slope test that a different atan2 could flip"""
+    import segmentation_cases as cases
+
+    params, st, T, res = cases.reference_case(variant)
+    assert oracle.segment_scan(oracle.SegParams(**params), st, T, res)["borderline"] == 0 or variant == 1
+    det = DetectionModule(rt, **params)
+    det.projectScan(None, st, T)
+    det.projectResiduals(res)
+    det.applySegmentation()
+    assert_same_as_reference(det, refdet.segment(params, st, T, res))
+
+
+def test_segmentation_matches_reference_golden_fixture(rt):
+    """the committed answers of the reference's code (tests/golden/segmentation_reference.npz): needs neither the oracle
+    nor /root/reference"""
+    from pathlib import Path
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "segmentation_reference.npz")
+    params = {k: (float(v) if k in ("theta", "max_delta_z", "max_elevation") else int(v)) for k, v in zip(g["param_names"], g["param_values"])}
+    det = DetectionModule(rt, **params)
+    det.projectScan(None, g["scan_t"], g["T"])
+    det.projectResiduals(g["residuals"])
+    det.applySegmentation()
+    assert_same_as_reference(det, dict(label_count=int(g["label_count"]), label_mat=g["label_mat"], ground_mat=g["ground_mat"],
+                                       range_mat=g["range_mat"], avg_residuals=g["avg_residuals"]))

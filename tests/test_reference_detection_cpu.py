@@ -1,0 +1,81 @@
+"""Pins the segmentation oracle (oracle/oracle_segmentation.cpp) to the REFERENCE'S OWN DetectionModule code: the class
+declaration of include/detection/detection.h unmodified, and the definitions of loadParams, allocateMemory,
+resetParameters, projectResiduals, projectScan, groundRemoval, cloudSegmentation and labelComponents extracted from
+src/detection/detection.cpp at build time (oracle/extract_detection.py), compiled over stand-ins for ROS / OpenCV / PCL /
+Eigen (oracle/stub_include/tracking/tracking.h) into oracle/_ref/libdetection_ref.so (oracle/refdet.py).  Every output of
+this stage is integer or exact-float work, so the two must agree bit for bit.
+
+The library is prebuilt where /root/reference exists and travels to the GPU box; where it is absent the comparison
+tests skip and the committed fixture of its outputs (tests/golden/segmentation_reference.npz) still pins the oracle.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import segmentation_cases as cases
+
+GOLDEN = Path(__file__).resolve().parent / "golden" / "segmentation_reference.npz"
+
+
+@pytest.fixture(scope="module")
+def refdet(oracle):
+    from oracle import refdet as rd
+
+    if not rd.available():
+        pytest.skip("oracle/_ref/libdetection_ref.so not built (needs /root/reference)")
+    rd.lib()
+    return rd
+
+
+def same(a, b):
+    assert a["label_count"] == b["label_count"]
+    assert np.array_equal(a["label_mat"], b["label_mat"])
+    assert np.array_equal(a["ground_mat"], b["ground_mat"])
+    assert np.array_equal(a["range_mat"].view(np.uint32), b["range_mat"].view(np.uint32))
+    assert np.array_equal(a["avg_residuals"][1:].view(np.uint64), b["avg_residuals"][1:].view(np.uint64))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("with_residuals", [True, False])
+def test_oracle_matches_reference_detection_code(oracle, refdet, variant, with_residuals):
+    params, st, T, res = cases.reference_case(variant)
+    r = refdet.segment(params, st, T, res if with_residuals else None)
+    o = oracle.segment_scan(oracle.SegParams(**params), st, T, res if with_residuals else None)
+    same(o, r)
+    if variant > 0:
+        assert r["label_count"] > 4 and (r["label_mat"] == 999999).any() and ((r["ground_mat"] == 1).any() or params["ground_rows"] == 0)
+    if not with_residuals:
+        assert not r["avg_residuals"].any()
+
+
+@pytest.mark.parametrize("frame,dropout", [(2, 0.0), (35, 0.2), (60, 0.05)])
+def test_oracle_matches_reference_detection_code_other_frames(oracle, refdet, frame, dropout):
+    params, st, T, res = cases.reference_case(1, frame=frame, size=400, dropout=dropout)
+    same(oracle.segment_scan(oracle.SegParams(**params), st, T, res), refdet.segment(params, st, T, res))
+
+
+def test_reference_detection_defaults_are_the_documented_ones(refdet):
+    # no overrides but the image size: loadParams' own defaults (detection.cpp:76-105) drive the result; an empty scan
+    # gives an all -1 label image and label_count_ 1
+    params = dict(rows=360, cols=360)
+    s = np.full((360, 360, 4), np.nan, dtype=np.float32)
+    r = refdet.segment(params, s, np.eye(4, dtype=np.float32))
+    assert r["label_count"] == 1 and (r["label_mat"] == -1).all() and not r["range_mat"].any()
+
+
+def test_golden_fixture_is_current(oracle, refdet):
+    params, st, T, res = cases.golden_case()
+    g = np.load(GOLDEN)
+    r = refdet.segment(params, st, T, res)
+    assert int(g["label_count"]) == r["label_count"] and np.array_equal(g["label_mat"], r["label_mat"])
+
+
+def test_oracle_matches_golden_fixture_of_the_reference(oracle):
+    """runs everywhere: the stored answers of the reference's code for the stored inputs"""
+    g = np.load(GOLDEN)
+    params = {k: (float(v) if k in ("theta", "max_delta_z", "max_elevation") else int(v)) for k, v in zip(g["param_names"], g["param_values"])}
+    o = oracle.segment_scan(oracle.SegParams(**params), g["scan_t"], g["T"], g["residuals"])
+    same(o, dict(label_count=int(g["label_count"]), label_mat=g["label_mat"], ground_mat=g["ground_mat"], range_mat=g["range_mat"],
+                 avg_residuals=g["avg_residuals"]))
+    assert int(g["label_count"]) > 3

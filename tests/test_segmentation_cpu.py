@@ -1,8 +1,8 @@
 """The segmentation oracle (oracle/oracle_segmentation.cpp) against hand-made known answers and against an
 independent pure-Python restatement of detection.cpp:254-329, 448-724 on small images.  CPU only.
 
-The reference ships no fixtures for this stage and its detection.cpp cannot be compiled here (ROS, OpenCV, PCL):
-parity of this stage is unpinned, these tests only guard the restatement against itself."""
+The pin to the reference's own code is tests/test_reference_detection_cpu.py (the reference hard-codes the window
+156..356); these tests cover what that pin cannot reach: small images, other windows, hand-made known answers."""
 import math
 from collections import deque
 
