@@ -293,17 +293,19 @@ int crop_box_device(ddlo_runtime* rt, const float4* pts, int n, const float lo[3
 // theta = atan2(x, z), phi = atan2(y, sqrt(x^2 + z^2)), u = int((theta - a_min) / (a_max - a_min) * W), v alike
 // with H (C++ int conversion: truncation toward zero), and cell (v, u) keeps x, y, z and the GICP residual
 // (as intensity) of the LAST scan point that falls into it; the other cells stay zero.  The reference's
-// sequential loop makes "last" the largest point index; here an atomicMax per cell elects it.  Angles are
-// evaluated in double (the reference's float arguments make its overload depend on its include set; the two
-// differ only for points within ~1e-7 rad of a cell border).
+// sequential loop makes "last" the largest point index; here an atomicMax per cell elects it.  The angles are
+// FLOAT: `atan2(pt.x, pt.z)` and `sqrt(pt.x * pt.x + pt.z * pt.z)` have float arguments, and odom.cc sees
+// `using namespace std;` (odom.h -> detection/detection.h -> tracking/tracking.h -> tracking/hungarian.h:42), so the
+// float overloads are chosen and only their results are widened to double.  atan2 is evaluated in double and
+// rounded to float here, i.e. the correctly rounded float value.
 struct ResidualImageSpec {
   int w, h;
   double a_min, a_span;
 };
 __device__ __forceinline__ int residual_cell(const float4 p, const ResidualImageSpec& g) {
-  const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
-  const double theta = atan2(x, z);
-  const double phi = atan2(y, sqrt(x * x + z * z));
+  const double theta = (double)(float)atan2((double)p.x, (double)p.z);
+  const float rxz = __fsqrt_rn(__fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.z, p.z)));
+  const double phi = (double)(float)atan2((double)p.y, (double)rxz);
   const int u = (int)((theta - g.a_min) / g.a_span * (double)g.w);
   const int v = (int)((phi - g.a_min) / g.a_span * (double)g.h);
   if (u < 0 || u >= g.w || v < 0 || v >= g.h) return -1;

@@ -1108,18 +1108,18 @@ int oracle_crop_box(const float* xyz, int n, int stride_floats, const float* lo,
 
 // The residual cloud of OdomNode::scanMatching (odom.cc:804-827): sequential loop, later points overwrite
 // earlier ones.  residuals: one double per point (getResiduals).  out: h*w*4 floats, zero-initialised here.
-// The angles are evaluated in double.  (In the reference `atan2(pt.x, pt.z)` has float arguments, so whether
-// the float or the double overload runs depends on which of <cmath> / <math.h> its include set pulls in;
-// the two differ only for points within ~1e-7 rad of a cell border.)
+// The angles are evaluated in FLOAT and widened: `atan2(pt.x, pt.z)` and `sqrt(pt.x * pt.x + pt.z * pt.z)` have
+// float arguments, and odom.cc sees `using namespace std;` (odom.h -> detection/detection.h -> tracking/tracking.h ->
+// tracking/hungarian.h:42), which makes the float overloads the best match.
 void oracle_residual_image(const float* xyz, int n, int stride_floats, const double* residuals, int w, int h, double a_min, double a_max,
                            float* out_xyzi) {
   std::fill(out_xyzi, out_xyzi + (size_t)w * h * 4, 0.0f);
   for (int i = 0; i < n; ++i) {
     const float* pt = xyz + (size_t)i * stride_floats;
     if (!std::isfinite(pt[0]) || !std::isfinite(pt[1]) || !std::isfinite(pt[2])) continue;
-    const double x = pt[0], y = pt[1], z = pt[2];
-    const double theta = atan2(x, z);
-    const double phi = atan2(y, sqrt(x * x + z * z));
+    const float x = pt[0], y = pt[1], z = pt[2];
+    const double theta = std::atan2(x, z);                         // float overload
+    const double phi = std::atan2(y, std::sqrt(x * x + z * z));    // float overloads
     const int u = static_cast<int>((theta - a_min) / (a_max - a_min) * w);
     const int v = static_cast<int>((phi - a_min) / (a_max - a_min) * h);
     if (u < 0 || u >= w || v < 0 || v >= h) continue;

@@ -19,7 +19,8 @@
 // Arithmetic notes (what the reference's build, -O2 without -march, evaluates):
 //   * all members are float (include/detection/detection.h:60-86); products and sums are rounded one by one
 //     (no FMA, this file is compiled with -ffp-contract=off);
-//   * atan2 / sqrt / abs on float arguments resolve to the float overloads (<cmath> is in the include set);
+//   * atan2 / sqrt / abs on float arguments resolve to the float overloads: detection.cpp sees `using namespace std;`
+//     (detection.h -> tracking/tracking.h -> tracking/hungarian.h:42);
 //   * groundRemoval keeps its loop temporaries outside the `omp parallel for` (a data race in the reference);
 //     the sequential meaning is restated;
 //   * the `valid_range` window is hard-coded to rows/cols 156..356 in the reference (:520-522, :565-567); here it

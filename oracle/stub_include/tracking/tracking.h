@@ -4,8 +4,9 @@
 // the segmentation path (oracle/extract_detection.py) touch, so that the reference's own text compiles unmodified:
 // cv::Mat / Scalar / Vec3b, pcl::PointXYZI / PointCloud / isFinite / copyPointCloud, Eigen::Matrix4f::coeff,
 // ros::NodeHandle::param (with an override table the shim fills), the ROS_* log macros, and empty shells for the rest.
-// <math.h> and <stdlib.h> are included on purpose: with them the unqualified abs / atan2 / sqrt calls of the reference
-// resolve to the float overloads, as they do in its real include set.
+// The real tracking.h pulls in tracking/hungarian.h, whose `using namespace std;` (hungarian.h:42) makes the unqualified
+// abs / atan2 / sqrt calls of the reference resolve to the float overloads; the same directive is repeated here (and
+// <math.h> / <stdlib.h> are included, which has the same effect with libstdc++).
 #ifndef DDLO_ORACLE_TRACKING_STUB
 #define DDLO_ORACLE_TRACKING_STUB
 #include <math.h>
@@ -23,6 +24,8 @@
 #include <unordered_map>
 #include <utility>
 #include <vector>
+
+using namespace std;  // tracking/hungarian.h:42
 
 #define ROS_INFO(...) ((void)0)
 #define ROS_WARN(...) ((void)0)
