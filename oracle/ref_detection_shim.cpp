@@ -18,6 +18,8 @@
 #include <detection/detection.h>
 #undef private
 
+typedef pcl::PointXYZI PointType;  // odometry/ddlo.h:90, for the loop taken from odom.cc
+
 #include "_ref/detection_extract.inc"
 
 DetectionModule::DetectionModule() : initialized_(false), icp_residuals_set_(false), it_(nh_) {
@@ -70,6 +72,23 @@ int refdet_segment(const char* const* names, const double* values, int n_params,
     }
   for (int i = 0; i < det.label_count_ && i < avg_capacity; ++i) avg_residuals[i] = det.avg_residuals_[i];
   return det.label_count_;
+}
+
+// The residual cloud of OdomNode::scanMatching (odom.cc:804-827), the reference's own loop: 512 x 512 cells, +-60 degrees.
+// scan: n points (x y z w floats); residuals: n doubles (getResiduals).  out_xyzi: 512*512*4 floats (x, y, z, intensity).
+void refdet_residual_cloud(const float* scan, int n, const double* residuals_in, float* out_xyzi) {
+  using Cloud = pcl::PointCloud<pcl::PointXYZI>;
+  Cloud::Ptr registration_scan_(new Cloud), residuals_cloud_(new Cloud);
+  registration_scan_->points.resize((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    registration_scan_->points[i].x = scan[4 * i], registration_scan_->points[i].y = scan[4 * i + 1], registration_scan_->points[i].z = scan[4 * i + 2];
+  }
+  std::vector<double> residuals(residuals_in, residuals_in + n);
+  ref_residual_cloud_body(registration_scan_, residuals, residuals_cloud_);
+  for (size_t c = 0; c < residuals_cloud_->points.size(); ++c) {
+    const pcl::PointXYZI& p = residuals_cloud_->points[c];
+    out_xyzi[4 * c] = p.x, out_xyzi[4 * c + 1] = p.y, out_xyzi[4 * c + 2] = p.z, out_xyzi[4 * c + 3] = p.intensity;
+  }
 }
 
 }  // extern "C"

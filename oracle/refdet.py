@@ -41,6 +41,8 @@ def lib() -> C.CDLL:
         L.refdet_segment.restype = C.c_int
         L.refdet_segment.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.refdet_residual_cloud.restype = None
+        L.refdet_residual_cloud.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -72,3 +74,14 @@ def segment(params: dict, scan_t, T, residuals=None):
         raise ValueError("image size does not match rows x cols")
     return dict(label_mat=label.reshape(H, W), range_mat=rng.reshape(H, W), ground_mat=ground.reshape(H, W), label_count=n,
                 avg_residuals=avg[:n].copy())
+
+
+def residual_cloud(points, residuals) -> np.ndarray:
+    """the reference's own residual-cloud loop (odom.cc:804-827): (512, 512, 4) float32, angles +-60 degrees"""
+    p = np.ascontiguousarray(np.asarray(points, dtype=np.float32)[:, :4])
+    if p.shape[1] < 4:
+        p = np.ascontiguousarray(np.concatenate([p, np.ones((len(p), 4 - p.shape[1]), dtype=np.float32)], axis=1))
+    r = np.ascontiguousarray(residuals, dtype=np.float64)
+    out = np.empty((512, 512, 4), dtype=np.float32)
+    lib().refdet_residual_cloud(p.ctypes.data, len(p), r.ctypes.data, out.ctypes.data)
+    return out

@@ -662,6 +662,29 @@ def test_residual_image_matches_oracle(rt, oracle, small_pair):
     assert (got[..., 3] > 0).any()
 
 
+def test_residual_image_matches_reference_loop(rt, oracle):
+    """the same against the reference's own loop (odom.cc:804-827 extracted into oracle/_ref/libdetection_ref.so): a
+    camera-like cloud so that tens of thousands of cells are filled and many are contested"""
+    from oracle import refdet
+
+    if not refdet.available():
+        pytest.skip("oracle/_ref/libdetection_ref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(5)
+    n = 60_000
+    th, ph, r = rng.uniform(-1.2, 1.2, n), rng.uniform(-1.2, 1.2, n), rng.uniform(2.0, 30.0, n)
+    tgt = np.stack([r * np.sin(th) * np.cos(ph), r * np.sin(ph), r * np.cos(th) * np.cos(ph), np.ones(n)], 1).astype(np.float32)
+    src = tgt[::2].copy()
+    src[:, :3] += rng.normal(0.0, 0.01, (len(src), 3)).astype(np.float32)
+    g = ng.NanoGICP(rt)
+    g.setInputSource(ng.PointCloud(rt, src))
+    g.setInputTarget(ng.PointCloud(rt, tgt))
+    g.align()
+    got = g.residualImage(512, 512)
+    want = refdet.residual_cloud(src, g.getResiduals())
+    assert (want[..., 3] > 0).sum() > 10_000
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 def test_align_block_limit_agrees(rt, oracle, small_pair):
     """ddlo_runtime_set_align_blocks (batched workloads): fewer blocks per align change the fp64 summation
     order only - same correspondences, same iteration counts, pose within the bar."""

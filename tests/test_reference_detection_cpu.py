@@ -14,6 +14,7 @@ import numpy as np
 import pytest
 
 import segmentation_cases as cases
+from dynamic_direct_lidar_odometry_b200 import synth
 
 GOLDEN = Path(__file__).resolve().parent / "golden" / "segmentation_reference.npz"
 
@@ -79,3 +80,22 @@ def test_oracle_matches_golden_fixture_of_the_reference(oracle):
     same(o, dict(label_count=int(g["label_count"]), label_mat=g["label_mat"], ground_mat=g["ground_mat"], range_mat=g["range_mat"],
                  avg_residuals=g["avg_residuals"]))
     assert int(g["label_count"]) > 3
+
+
+def test_residual_cloud_matches_reference_loop(oracle, refdet):
+    """oracle_residual_image against the reference's own loop of OdomNode::scanMatching (odom.cc:804-827), extracted and
+    compiled like the DetectionModule functions: every cell bit for bit, including which point wins a shared cell and
+    the float atan2 / sqrt overloads the reference's `using namespace std;` selects"""
+    rng = np.random.default_rng(0)
+    n = 150_000
+    th, ph, r = rng.uniform(-1.2, 1.2, n), rng.uniform(-1.2, 1.2, n), rng.uniform(0.5, 30.0, n)
+    pts = np.stack([r * np.sin(th) * np.cos(ph), r * np.sin(ph), r * np.cos(th) * np.cos(ph), np.ones(n)], 1).astype(np.float32)
+    res = rng.uniform(0.0, 1.0, n)
+    want = refdet.residual_cloud(pts, res)
+    got = oracle.residual_image(pts, res)
+    assert (want[..., 3] != 0).sum() > 50_000
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # a spinning-LiDAR scan: most points outside the +-60 degree image, still identical
+    scan = synth.scan(3, 32, 512)
+    res = np.linalg.norm(scan[:, :3], axis=1) * 1e-3
+    assert np.array_equal(oracle.residual_image(scan, res).view(np.uint32), refdet.residual_cloud(scan, res).view(np.uint32))
