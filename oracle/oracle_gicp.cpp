@@ -10,11 +10,19 @@
 //     (oracle/ref_nanoflann_shim.cpp -> oracle/_ref/libnanoflann_ref.so) and tests/ check this
 //     file's canonical kNN against it (bit-identical d^2 everywhere, identical indices wherever
 //     the k+1 smallest distances are distinct).
-//   * GICP / LM layer: PARITY UNPINNED by the reference itself.  The reference ships no tests,
-//     golden vectors or fixtures, and nano_gicp_impl.hpp / lsq_registration_impl.hpp need Eigen,
-//     PCL and Boost, none of which exist in this image, so they cannot be compiled here.  The
-//     restatement below follows those files line by line (citations at each function) and its
-//     linear algebra is cross-checked against numpy in tests/test_oracle_math.py.
+//   * GICP / LM / covariance layer: PINNED to the reference's own sources, with one caveat.  The reference ships no
+//     tests, golden vectors or fixtures, and nano_gicp_impl.hpp / lsq_registration_impl.hpp need Eigen, PCL and Boost,
+//     none of which exist in this image.  oracle/ref_nano_gicp_shim.cpp compiles those headers UNMODIFIED from
+//     /root/reference against stand-in headers (oracle/stub_include/) into oracle/_ref/libnano_gicp_ref.so, so the
+//     reference's control flow and formulas run as written and only Eigen's dense arithmetic is a stand-in (the
+//     caveat).  tests/test_reference_engine_cpu.py requires this file to reproduce that engine (correspondences and
+//     squared distances bit-exact, iteration counts identical, covariances 1e-9, H / b / error 1e-10, poses 1e-6); its
+//     outputs are committed as tests/golden/gicp_reference_engine.npz.  The linear algebra is additionally cross-checked
+//     against numpy in tests/test_oracle_cpu.py.
+//   * Filters (voxel grid, crop box): UNPINNED - they are PCL's, and PCL is not under /root/reference; restated from
+//     the published algorithm and checked against an independent numpy statement (tests/test_preprocess_cpu.py).
+//   * Residual cloud (oracle_residual_image): PINNED to the reference's own loop, extracted from odom.cc:804-827 into
+//     oracle/_ref/libdetection_ref.so (tests/test_reference_detection_cpu.py).
 //
 // Reference files restated (R = /root/reference/dynamic_direct_lidar_odometry/include/nano_gicp):
 //   R/impl/nano_gicp_impl.hpp:98-106,133-196,199-441   NanoGICP state, covariances, linearize
