@@ -798,18 +798,29 @@ def test_two_devices_in_one_process(small_pair):
     """One process driving two GPUs (one runtime each): kernel attributes and pools are per device."""
     if ng.device_count() < 2:
         pytest.skip("needs two GPUs")
+    from dynamic_direct_lidar_odometry_b200.detection import DetectionModule
+
     src, tgt = small_pair
-    out = []
+    T = synth.pose(3).astype(np.float32)
+    st = synth.organized_transform(synth.organized_scan(3, 32, 512, dropout=0.05), T)
+    seg = dict(rows=32, cols=512, ground_rows=12, window_row_min=0, window_row_max=31, window_col_min=0, window_col_max=511, ang_bottom=22.5,
+               minimum_range=1.0, sensor_mount_angle=0.0, max_distance=40.0)
+    out, labels = [], []
     for dev in (0, 1):
         r = ng.Runtime(dev)
         g = ng.NanoGICP(r)
         g.setInputSource(ng.PointCloud(r, src))
         g.setInputTarget(ng.PointCloud(r, tgt))
         out.append(g.align())
+        det = DetectionModule(r, **seg)  # the segmentation stage's kernels carry per-device attributes too
+        det.projectScan(None, st, T)
+        det.applySegmentation()
+        labels.append((det.label_count_, det.label_mat))
         del g
         r.close()
     assert out[0].converged and out[1].converged
     assert np.array_equal(out[0].T, out[1].T) and np.array_equal(out[0].hessian, out[1].hessian)
+    assert labels[0][0] == labels[1][0] > 1 and np.array_equal(labels[0][1], labels[1][1])
 
 
 def _adversarial_clouds(rng):
