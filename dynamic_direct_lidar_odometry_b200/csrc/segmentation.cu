@@ -205,14 +205,56 @@ __global__ void __launch_bounds__(256) k_ccl_union(SegDev p, const unsigned char
     if (!repeated) ccl_union(parent, i, i + p.W);
   }
 }
-// root[] = smallest raster index of the pixel's component (-1 outside), size[root] = pixels of the component
-__global__ void __launch_bounds__(256) k_ccl_flatten(SegDev p, const int* __restrict__ parent, int* __restrict__ root, int* __restrict__ size) {
+// order-preserving map float -> unsigned (and back), for atomicMin / atomicMax on floats of either sign
+__device__ __forceinline__ unsigned seg_f2ord(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u ^ 0x80000000u);
+}
+__device__ __forceinline__ float seg_ord2f(unsigned o) { return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o); }
+
+// Per-segment statistics that do not depend on the flood fill's order, cstat[k * HW + root]:
+//   0 largest range of any pixel (float bits; ranges are positive)      3 largest z of the pushed pixels (ordered, 0 = none)
+//   1 smallest row of the pushed pixels (0xffffffff = none)             4 smallest non-zero z of the pushed pixels (ordered,
+//   2 largest row + 1 of the pushed pixels (0 = none)                     0xffffffff = none)
+//   5 largest z of the pushed pixels other than the FIRST pushed one (ordered, 0 = none)
+// "pushed" = every pixel of the segment but its seed (the seed is popped, never pushed: :556-569); the first pushed pixel
+// is the seed's first neighbour in direction order.
+constexpr int kStatRange = 0, kStatRowMin = 1, kStatRowMax = 2, kStatZMax = 3, kStatZMin = 4, kStatZMaxRest = 5, kStatCount = 6;
+__device__ __forceinline__ int seg_step(int d, int W) { return d == 0 ? -W : (d == 1 ? 1 : (d == 2 ? -1 : W)); }
+
+// root[] = smallest raster index of the pixel's component (-1 outside), size[root] = pixels of the component, and the
+// statistics above, folded per warp over the lanes that share a root before they go to memory
+__global__ void __launch_bounds__(256) k_ccl_flatten(SegDev p, const int* __restrict__ parent, const float* __restrict__ scan, int stride,
+                                                     const float* __restrict__ range, const unsigned char* __restrict__ nib,
+                                                     int* __restrict__ root, int* __restrict__ size, unsigned* __restrict__ cstat) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int r = -1;
   if (i < p.HW && parent[i] >= 0) r = ccl_find(parent, i);
   if (i < p.HW) root[i] = r;
+  const bool member = r >= 0, pushed = member && r != i;
+  const float z = pushed ? scan[(size_t)i * stride + 2] : 0.0f;
+  const unsigned row = (unsigned)(i / p.W);
+  bool first_pushed = false;
+  if (pushed) {
+    const unsigned nb = seg_nibble(nib, r);  // not empty: the seed has company
+    first_pushed = i == r + seg_step(__ffs(nb) - 1, p.W);
+  }
   const unsigned m = __match_any_sync(kFullMask, r);
-  if (r >= 0 && (int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) atomicAdd(size + r, __popc(m));
+  const unsigned s_range = __reduce_max_sync(m, member ? __float_as_uint(range[i]) : 0u);
+  const unsigned s_rmin = __reduce_min_sync(m, pushed ? row : 0xffffffffu);
+  const unsigned s_rmax = __reduce_max_sync(m, pushed ? row + 1u : 0u);
+  const unsigned s_zmax = __reduce_max_sync(m, pushed ? seg_f2ord(z) : 0u);
+  const unsigned s_zmin = __reduce_min_sync(m, (pushed && z != 0.0f) ? seg_f2ord(z) : 0xffffffffu);
+  const unsigned s_zrest = __reduce_max_sync(m, (pushed && !first_pushed) ? seg_f2ord(z) : 0u);
+  if (member && (int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) {
+    atomicAdd(size + r, __popc(m));
+    atomicMax(cstat + (size_t)kStatRange * p.HW + r, s_range);
+    atomicMin(cstat + (size_t)kStatRowMin * p.HW + r, s_rmin);
+    atomicMax(cstat + (size_t)kStatRowMax * p.HW + r, s_rmax);
+    atomicMax(cstat + (size_t)kStatZMax * p.HW + r, s_zmax);
+    atomicMin(cstat + (size_t)kStatZMin * p.HW + r, s_zmin);
+    atomicMax(cstat + (size_t)kStatZMaxRest * p.HW + r, s_zrest);
+  }
 }
 // per pixel (size << 32 | 1) at the seeds, 0 elsewhere; its exclusive sum gives every seed the start of its push list
 // (high word) and its ordinal among the seeds in raster order (low word)
@@ -238,7 +280,8 @@ __global__ void __launch_bounds__(kFillThreads) k_seg_fill(SegDev p, const unsig
                                                            const float* __restrict__ scan, int stride, const float* __restrict__ range,
                                                            const float* __restrict__ residuals, int res_stride, unsigned* __restrict__ order,
                                                            int* __restrict__ next_seed, int* __restrict__ accepted, double* __restrict__ seg_avg,
-                                                           int ring_size) {
+                                                           int ring_size, const int* __restrict__ size, const unsigned* __restrict__ cstat,
+                                                           int shortcut) {
   extern __shared__ __align__(16) unsigned char seg_smem[];
   const int nib_bytes = ((p.HW + 1) / 2 + 15) & ~15;
   const int vis_words = (p.HW + 31) / 32;
@@ -262,6 +305,74 @@ __global__ void __launch_bounds__(kFillThreads) k_seg_fill(SegDev p, const unsig
     if (si >= total) break;
     const int seed = seeds[si];
     const unsigned beg = (unsigned)(pre[seed] >> 32);
+    // ---- Most segments are decided without replaying the queue.  Of the segment tests (:640-685) only max_z depends on the
+    // push order: it is the largest z among the pushed pixels that did not set a new minimum when they were pushed
+    // (:612-616).  A pixel sets a new (strict) minimum only if every non-zero z pushed before it is larger, so
+    //   * the highest pixel counts unless it is the first pushed pixel p1 (the seed's first neighbour in direction order);
+    //   * if p1 is the highest, the highest of the others counts if it ties with p1, or if it is not the second pushed
+    //     pixel p2 (p2 came before it with a smaller z);
+    // anything else (a zero z in p1 or p2, p2 the unique runner-up) is left to the replay.  Size, scan lines, max_dist (= the
+    // largest range of the segment once anything was pushed: the seed enters through its children), min_z and the
+    // elevation never depend on the order.  A segment that fails a test is rejected here; one that passes still needs the
+    // replay when residuals are summed in push order.
+    if (shortcut) {
+      const int sz = size[seed];
+      const unsigned rmin = cstat[(size_t)kStatRowMin * p.HW + seed], rmax = cstat[(size_t)kStatRowMax * p.HW + seed];
+      const unsigned ozmax = cstat[(size_t)kStatZMax * p.HW + seed], ozmin = cstat[(size_t)kStatZMin * p.HW + seed];
+      const unsigned ozrest = cstat[(size_t)kStatZMaxRest * p.HW + seed];
+      const int lines = rmax > rmin ? (int)(rmax - rmin) : 0;
+      const float max_dist = sz >= 2 ? __uint_as_float(cstat[(size_t)kStatRange * p.HW + seed]) : -1e6f;
+      const float min_z = ozmin == 0xffffffffu ? 1e6f : seg_ord2f(ozmin);
+      const float top_z = ozmax == 0u ? -1e6f : seg_ord2f(ozmax);
+      bool pass = (sz >= 50 && lines >= p.min_line_num) || (sz >= p.valid_point_num && lines >= p.valid_line_num);
+      pass = pass && max_dist <= p.max_distance && __fsub_rn(min_z, p.height) <= p.max_elevation;
+      bool decided = !pass;
+      const unsigned nb = ((unsigned)snib[seed >> 1] >> ((seed & 1) * 4)) & 15u;
+      if (pass && nb != 0u) {
+        const int d1 = __ffs(nb) - 1;
+        const int p1 = seed + seg_step(d1, W);
+        const float z1 = scan[(size_t)p1 * stride + 2];
+        float max_z = 0.0f;
+        bool known = false;
+        if (z1 != 0.0f && z1 != top_z) {
+          max_z = top_z, known = true;
+        } else if (z1 != 0.0f) {  // p1 is the highest pixel and sets the first minimum: it never counts
+          if (ozrest == 0u) {
+            max_z = -1e6f, known = true;  // nothing else was pushed
+          } else {
+            const float t = seg_ord2f(ozrest);
+            if (t == z1) {
+              max_z = t, known = true;  // as high as p1 and pushed later: not a strict minimum
+            } else {
+              const unsigned nb_rest = nb & (nb - 1u);
+              int p2 = -1;
+              if (nb_rest != 0u) {
+                p2 = seed + seg_step(__ffs(nb_rest) - 1, W);  // the seed's second neighbour
+              } else {
+                const unsigned nb1 = (((unsigned)snib[p1 >> 1] >> ((p1 & 1) * 4)) & 15u) & ~(1u << (3 - d1));  // p1's neighbours but the seed
+                if (nb1 != 0u) p2 = p1 + seg_step(__ffs(nb1) - 1, W);
+              }
+              if (p2 >= 0) {
+                const float z2 = scan[(size_t)p2 * stride + 2];
+                if (z2 != 0.0f && z2 != t) max_z = t, known = true;  // p2 came first with a smaller z: the runner-up counts
+              }
+            }
+          }
+        }
+        if (known) {
+          const float delta_z = __fsub_rn(max_z, min_z);
+          pass = p.min_delta_z <= delta_z && delta_z <= p.max_delta_z;
+          decided = !pass || !p.have_residuals;
+        }
+      }
+      if (decided) {
+        if (lane == 0) {
+          accepted[si] = pass ? 1 : 0;
+          seg_avg[si] = 0.0;
+        }
+        continue;
+      }
+    }
     // ---- the queue: entries [head, tail) wait to be popped; entry 0 is the seed
     int head = 0, tail = 1;
     if (lane == 0) {
@@ -451,7 +562,7 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   unsigned char* nib = nullptr;
   int *parent = nullptr, *root = nullptr, *size = nullptr, *seeds = nullptr, *accepted = nullptr, *rank = nullptr, *small = nullptr;
   unsigned long long* keys = nullptr;
-  unsigned* order = nullptr;
+  unsigned *order = nullptr, *cstat = nullptr;
   double* seg_avg = nullptr;
   void* tmp = nullptr;
   size_t tmp_a = 0, tmp_b = 0;
@@ -468,12 +579,16 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   DDLO_TRY(pool_alloc(rt, &small, 4));  // [0] seeds found, [1] next seed to fill
   DDLO_TRY(pool_alloc(rt, &keys, HW));
   DDLO_TRY(pool_alloc(rt, &order, HW));
+  DDLO_TRY(pool_alloc(rt, &cstat, (size_t)kStatCount * HW));
   DDLO_TRY(pool_alloc(rt, &seg_avg, HW));
   DDLO_TRY(pool_alloc(rt, reinterpret_cast<unsigned char**>(&tmp), tmp_bytes));
   DDLO_CUDA(cudaMemsetAsync(size, 0, (size_t)HW * 4, st));
   DDLO_CUDA(cudaMemsetAsync(accepted, 0, (size_t)HW * 4, st));
   DDLO_CUDA(cudaMemsetAsync(small, 0, 16, st));
   DDLO_CUDA(cudaMemsetAsync(nib, 0, nib_bytes, st));
+  DDLO_CUDA(cudaMemsetAsync(cstat, 0, (size_t)kStatCount * HW * 4, st));  // "none" of the max statistics ...
+  DDLO_CUDA(cudaMemsetAsync(cstat + (size_t)kStatRowMin * HW, 0xff, (size_t)HW * 4, st));  // ... and of the two min statistics
+  DDLO_CUDA(cudaMemsetAsync(cstat + (size_t)kStatZMin * HW, 0xff, (size_t)HW * 4, st));
 
   const int pb = (HW + 255) / 256;
   float4* moved = nullptr;
@@ -489,7 +604,7 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   k_seg_project<<<pb, 256, 0, st>>>(p, d_scan, stride_floats, d_range, d_ground, d_label);
   k_seg_edges<<<pb, 256, 0, st>>>(p, d_range, d_label, nib, parent);
   k_ccl_union<<<pb, 256, 0, st>>>(p, nib, parent);
-  k_ccl_flatten<<<pb, 256, 0, st>>>(p, parent, root, size);
+  k_ccl_flatten<<<pb, 256, 0, st>>>(p, parent, d_scan, stride_floats, d_range, nib, root, size, cstat);
   k_seg_seed_keys<<<pb, 256, 0, st>>>(p, root, size, keys);
   size_t tb = tmp_bytes;
   DDLO_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, keys, keys, HW, st));
@@ -500,15 +615,16 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
     const int v = std::atoi(e);
     if (v >= 64 && v <= kRing && (v & (v - 1)) == 0) ring_size = v;
   }
+  const int shortcut = std::getenv("DDLO_SEG_NO_SHORTCUT") ? 0 : 1;  // testing aid: replay the queue of every segment
   k_seg_fill<<<rt->num_sms * per_sm, kFillThreads, smem, st>>>(p, nib, seeds, small, keys, d_scan, stride_floats, d_range, d_residuals, res_stride, order,
-                                                              small + 1, accepted, seg_avg, ring_size);
+                                                              small + 1, accepted, seg_avg, ring_size, size, cstat, shortcut);
   tb = tmp_bytes;
   DDLO_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, accepted, rank, HW, st));
   k_seg_labels<<<pb, 256, 0, st>>>(p, root, keys, accepted, rank, seg_avg, small, d_label, d_avg_by_label, d_label_count);
   rt->launches += 8 + 4;  // ours + the two scans' kernels
   DDLO_CUDA(cudaGetLastError());
   for (void* q : {(void*)nib, (void*)parent, (void*)root, (void*)size, (void*)seeds, (void*)accepted, (void*)rank, (void*)small, (void*)keys,
-                  (void*)order, (void*)seg_avg, tmp, (void*)moved})
+                  (void*)order, (void*)cstat, (void*)seg_avg, tmp, (void*)moved})
     if (q) cudaFreeAsync(q, st);
   return DDLO_OK;
 }

@@ -328,3 +328,40 @@ def test_segmentation_matches_reference_golden_fixture(rt):
     det.applySegmentation()
     assert_same_as_reference(det, dict(label_count=int(g["label_count"]), label_mat=g["label_mat"], ground_mat=g["ground_mat"],
                                        range_mat=g["range_mat"], avg_residuals=g["avg_residuals"]))
+
+
+@pytest.mark.parametrize("with_residuals", [True, False])
+def test_segmentation_early_decisions_equal_full_replay(rt, oracle, monkeypatch, with_residuals):
+    """Segments whose fate cannot depend on the push order are decided without replaying the queue; with
+    DDLO_SEG_NO_SHORTCUT every segment is replayed.  Both must give the same images, on inputs that are hard for the
+    shortcut: exact zeros in z, equal maxima, tiny segments, thresholds that split the segments about evenly."""
+    rng = np.random.default_rng(17)
+    cases = []
+    for frame, over in ((3, {}), (40, dict(max_delta_z=1.0, max_distance=15.0)), (21, dict(max_elevation=0.3, min_delta_z=0.5)),
+                        (8, dict(valid_point_num=3, valid_line_num=1, min_line_num=1, theta=0.4))):
+        params, st, T, res = lidar_case(frame, 64, 1024, 0.05, **over)
+        st = st.copy()
+        flat = st.reshape(-1, 4)
+        pick = rng.choice(len(flat), 3000, replace=False)
+        flat[pick[:1500], 2] = 0.0                                   # exact zeros: never a minimum, always a maximum candidate
+        flat[pick[1500:], 2] = np.round(flat[pick[1500:], 2], 1)     # many exactly equal heights
+        cases.append((params, st, T, res))
+    for params, st, T, res in cases:
+        outs = []
+        for no_shortcut in (False, True):
+            if no_shortcut:
+                monkeypatch.setenv("DDLO_SEG_NO_SHORTCUT", "1")
+            else:
+                monkeypatch.delenv("DDLO_SEG_NO_SHORTCUT", raising=False)
+            det = DetectionModule(rt, **params)
+            det.projectScan(None, st, T)
+            if with_residuals:
+                det.projectResiduals(res)
+            det.applySegmentation()
+            outs.append(det)
+        monkeypatch.delenv("DDLO_SEG_NO_SHORTCUT", raising=False)
+        assert outs[0].label_count_ == outs[1].label_count_ and np.array_equal(outs[0].label_mat, outs[1].label_mat)
+        assert np.array_equal(outs[0].avg_residuals.view(np.uint64), outs[1].avg_residuals.view(np.uint64))
+        o = oracle.segment_scan(oracle.SegParams(**params), st, T, res if with_residuals else None)
+        if o["borderline"] == 0:
+            assert_same(outs[0], o)
