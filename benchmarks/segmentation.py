@@ -51,11 +51,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--repeats", type=int, default=50)
     ap.add_argument("--json", type=str, default=None)
+    ap.add_argument("--unordered", action="store_true", help="opt-in unordered_residual_sums mode (averages to float rounding, no queue replay)")
     a = ap.parse_args()
     rt = ng.Runtime(0)
     rows = []
     for name, (frame, beams, cols, over) in CASES.items():
         params, st, T, res = case(frame, beams, cols, **over)
+        if a.unordered:
+            params["unordered_residual_sums"] = 1
         det = DetectionModule(rt, **params)
         dev, e2e = [], []
         for i in range(a.repeats + 5):
@@ -67,7 +70,7 @@ def main():
             if i >= 5:
                 dev.append(det.device_ms)
                 e2e.append((t1 - t0) * 1e3)
-        row = {"case": name, "pixels": beams * cols, "segments": det.getSegmentsCount(),
+        row = {"case": name, "unordered_residual_sums": bool(a.unordered), "pixels": beams * cols, "segments": det.getSegmentsCount(),
                "largest_segment_px": int(np.bincount(det.label_mat[(det.label_mat > 0) & (det.label_mat < 999999)].ravel()).max()) if det.getSegmentsCount() else 0,
                "rejected_px": int((det.label_mat == 999999).sum()),
                "device_ms_median": statistics.median(dev), "device_ms_min": min(dev), "e2e_ms_median": statistics.median(e2e),

@@ -52,6 +52,7 @@ struct SegDev {
   float x0, y0, z0, height;
   float min_delta_z, max_delta_z, max_distance, max_elevation;
   int have_residuals;
+  int unordered_sums;
 };
 
 __device__ __forceinline__ bool seg_in_window(const SegDev& p, int y, int x) { return y >= p.wr0 && y <= p.wr1 && x >= p.wc0 && x <= p.wc1; }
@@ -226,7 +227,9 @@ __device__ __forceinline__ int seg_step(int d, int W) { return d == 0 ? -W : (d 
 // statistics above, folded per warp over the lanes that share a root before they go to memory
 __global__ void __launch_bounds__(256) k_ccl_flatten(SegDev p, const int* __restrict__ parent, const float* __restrict__ scan, int stride,
                                                      const float* __restrict__ range, const unsigned char* __restrict__ nib,
-                                                     int* __restrict__ root, int* __restrict__ size, unsigned* __restrict__ cstat) {
+                                                     int* __restrict__ root, int* __restrict__ size, unsigned* __restrict__ cstat,
+                                                     const float* __restrict__ residuals, int res_stride, double* __restrict__ res_sum,
+                                                     int* __restrict__ res_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int r = -1;
   if (i < p.HW && parent[i] >= 0) r = ccl_find(parent, i);
@@ -255,6 +258,13 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(SegDev p, const int* __rest
     atomicMin(cstat + (size_t)kStatZMin * p.HW + r, s_zmin);
     atomicMax(cstat + (size_t)kStatZMaxRest * p.HW + r, s_zrest);
   }
+  if (p.unordered_sums && p.have_residuals && pushed) {  // opt-in: total_residuum without the push order (:632-634)
+    const float rv = residuals[(size_t)i * res_stride];
+    if (rv > 0.0f) {
+      atomicAdd(res_sum + r, (double)rv);
+      atomicAdd(res_count + r, 1);
+    }
+  }
 }
 // per pixel (size << 32 | 1) at the seeds, 0 elsewhere; its exclusive sum gives every seed the start of its push list
 // (high word) and its ordinal among the seeds in raster order (low word)
@@ -281,7 +291,7 @@ __global__ void __launch_bounds__(kFillThreads) k_seg_fill(SegDev p, const unsig
                                                            const float* __restrict__ residuals, int res_stride, unsigned* __restrict__ order,
                                                            int* __restrict__ next_seed, int* __restrict__ accepted, double* __restrict__ seg_avg,
                                                            int ring_size, const int* __restrict__ size, const unsigned* __restrict__ cstat,
-                                                           int shortcut) {
+                                                           int shortcut, const double* __restrict__ res_sum, const int* __restrict__ res_count) {
   extern __shared__ __align__(16) unsigned char seg_smem[];
   const int nib_bytes = ((p.HW + 1) / 2 + 15) & ~15;
   const int vis_words = (p.HW + 31) / 32;
@@ -362,13 +372,16 @@ __global__ void __launch_bounds__(kFillThreads) k_seg_fill(SegDev p, const unsig
         if (known) {
           const float delta_z = __fsub_rn(max_z, min_z);
           pass = p.min_delta_z <= delta_z && delta_z <= p.max_delta_z;
-          decided = !pass || !p.have_residuals;
+          decided = !pass || !p.have_residuals || p.unordered_sums;
         }
       }
       if (decided) {
         if (lane == 0) {
           accepted[si] = pass ? 1 : 0;
-          seg_avg[si] = 0.0;
+          double avg = 0.0;
+          if (pass && p.have_residuals && p.unordered_sums && res_count[seed] > 0)
+            avg = (double)__fdiv_rn((float)res_sum[seed], (float)res_count[seed]);  // float total / count, as :697
+          seg_avg[si] = avg;
         }
         continue;
       }
@@ -546,6 +559,7 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   p.x0 = -T16[12], p.y0 = -T16[13], p.z0 = -T16[14], p.height = T16[14];
   p.min_delta_z = prm.min_delta_z, p.max_delta_z = prm.max_delta_z, p.max_distance = prm.max_distance, p.max_elevation = prm.max_elevation;
   p.have_residuals = d_residuals ? 1 : 0;
+  p.unordered_sums = prm.unordered_residual_sums ? 1 : 0;
 
   const int HW = p.HW;
   const size_t nib_bytes = (((size_t)HW + 1) / 2 + 15) & ~(size_t)15;
@@ -563,7 +577,8 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   int *parent = nullptr, *root = nullptr, *size = nullptr, *seeds = nullptr, *accepted = nullptr, *rank = nullptr, *small = nullptr;
   unsigned long long* keys = nullptr;
   unsigned *order = nullptr, *cstat = nullptr;
-  double* seg_avg = nullptr;
+  double *seg_avg = nullptr, *res_sum = nullptr;
+  int* res_count = nullptr;
   void* tmp = nullptr;
   size_t tmp_a = 0, tmp_b = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_a, keys, keys, HW, st);
@@ -580,6 +595,12 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   DDLO_TRY(pool_alloc(rt, &keys, HW));
   DDLO_TRY(pool_alloc(rt, &order, HW));
   DDLO_TRY(pool_alloc(rt, &cstat, (size_t)kStatCount * HW));
+  if (p.unordered_sums && p.have_residuals) {
+    DDLO_TRY(pool_alloc(rt, &res_sum, HW));
+    DDLO_TRY(pool_alloc(rt, &res_count, HW));
+    DDLO_CUDA(cudaMemsetAsync(res_sum, 0, (size_t)HW * 8, st));
+    DDLO_CUDA(cudaMemsetAsync(res_count, 0, (size_t)HW * 4, st));
+  }
   DDLO_TRY(pool_alloc(rt, &seg_avg, HW));
   DDLO_TRY(pool_alloc(rt, reinterpret_cast<unsigned char**>(&tmp), tmp_bytes));
   DDLO_CUDA(cudaMemsetAsync(size, 0, (size_t)HW * 4, st));
@@ -604,7 +625,7 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   k_seg_project<<<pb, 256, 0, st>>>(p, d_scan, stride_floats, d_range, d_ground, d_label);
   k_seg_edges<<<pb, 256, 0, st>>>(p, d_range, d_label, nib, parent);
   k_ccl_union<<<pb, 256, 0, st>>>(p, nib, parent);
-  k_ccl_flatten<<<pb, 256, 0, st>>>(p, parent, d_scan, stride_floats, d_range, nib, root, size, cstat);
+  k_ccl_flatten<<<pb, 256, 0, st>>>(p, parent, d_scan, stride_floats, d_range, nib, root, size, cstat, d_residuals, res_stride, res_sum, res_count);
   k_seg_seed_keys<<<pb, 256, 0, st>>>(p, root, size, keys);
   size_t tb = tmp_bytes;
   DDLO_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, keys, keys, HW, st));
@@ -617,14 +638,14 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   }
   const int shortcut = std::getenv("DDLO_SEG_NO_SHORTCUT") ? 0 : 1;  // testing aid: replay the queue of every segment
   k_seg_fill<<<rt->num_sms * per_sm, kFillThreads, smem, st>>>(p, nib, seeds, small, keys, d_scan, stride_floats, d_range, d_residuals, res_stride, order,
-                                                              small + 1, accepted, seg_avg, ring_size, size, cstat, shortcut);
+                                                              small + 1, accepted, seg_avg, ring_size, size, cstat, shortcut, res_sum, res_count);
   tb = tmp_bytes;
   DDLO_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, accepted, rank, HW, st));
   k_seg_labels<<<pb, 256, 0, st>>>(p, root, keys, accepted, rank, seg_avg, small, d_label, d_avg_by_label, d_label_count);
   rt->launches += 8 + 4;  // ours + the two scans' kernels
   DDLO_CUDA(cudaGetLastError());
   for (void* q : {(void*)nib, (void*)parent, (void*)root, (void*)size, (void*)seeds, (void*)accepted, (void*)rank, (void*)small, (void*)keys,
-                  (void*)order, (void*)cstat, (void*)seg_avg, tmp, (void*)moved})
+                  (void*)order, (void*)cstat, (void*)seg_avg, tmp, (void*)moved, (void*)res_sum, (void*)res_count})
     if (q) cudaFreeAsync(q, st);
   return DDLO_OK;
 }

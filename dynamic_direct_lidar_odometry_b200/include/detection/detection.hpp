@@ -33,7 +33,7 @@ public:
     params_.rows = 128, params_.cols = 1024, params_.ground_rows = 30;
     params_.valid_point_num = 15, params_.min_line_num = 5, params_.valid_line_num = 5;
     params_.window_row_min = 156, params_.window_row_max = 356, params_.window_col_min = 156, params_.window_col_max = 356;
-    params_.scan_in_sensor_frame = 0;
+    params_.scan_in_sensor_frame = 0, params_.unordered_residual_sums = 0;
     params_.ang_bottom = 45.0f, params_.ground_angle_threshold = 10.0f, params_.minimum_range = 10.0f, params_.sensor_mount_angle = 10.0f;
     params_.theta = static_cast<float>(60.0 / 180.0 * M_PI);
     params_.min_delta_z = 0.1f, params_.max_delta_z = 3.0f, params_.max_distance = 20.0f, params_.max_elevation = 2.0f;

@@ -247,6 +247,11 @@ typedef struct ddlo_segmentation_params {
                                                                          1: scan_t is segmentation_scan_ (sensor frame) and is first moved by T16
                                                                          on the device like pcl::transformPointCloud in OdomNode::transformScans
                                                                          (odom.cc:957-963): float (r0 x + r1 y) + (r2 z + t), non-finite points kept */
+  int unordered_residual_sums;                                        /* 0: avg_residuals_ are float sums in the flood fill's push order, bit for
+                                                                         bit the reference's (:632-634, :697).  1 (opt-in): the residuals of a segment
+                                                                         are summed in double in no particular order; labels are unchanged, the
+                                                                         averages agree with the reference's to float rounding of its own sum
+                                                                         (~1e-6 relative), and almost no segment has to replay its queue */
   float ang_bottom;                                                   /* 45: vertical resolution = 2 ang_bottom / (rows - 1) */
   float ground_angle_threshold, minimum_range, sensor_mount_angle, theta; /* 10, 10, 10, 60 deg in rad */
   float min_delta_z, max_delta_z, max_distance, max_elevation;        /* 0.1, 3.0, 20, 2.0 */

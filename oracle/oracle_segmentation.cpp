@@ -41,6 +41,7 @@ struct oracle_seg_params {  // same layout as ddlo_segmentation_params (include/
   int valid_point_num, min_line_num, valid_line_num;
   int window_row_min, window_row_max, window_col_min, window_col_max;
   int scan_in_sensor_frame;
+  int unordered_residual_sums;  // ignored here: the restatement always sums in push order
   float ang_bottom;
   float ground_angle_threshold, minimum_range, sensor_mount_angle, theta;
   float min_delta_z, max_delta_z, max_distance, max_elevation;

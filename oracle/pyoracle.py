@@ -38,12 +38,13 @@ class SegParams(C.Structure):
     """struct oracle_seg_params (oracle_segmentation.cpp); defaults are the reference's (detection.cpp:76-105, :520-522)."""
 
     _fields_ = [(n, C.c_int) for n in ("rows", "cols", "ground_rows", "valid_point_num", "min_line_num", "valid_line_num",
-                                       "window_row_min", "window_row_max", "window_col_min", "window_col_max", "scan_in_sensor_frame")] + \
+                                       "window_row_min", "window_row_max", "window_col_min", "window_col_max", "scan_in_sensor_frame",
+                                       "unordered_residual_sums")] + \
                [(n, C.c_float) for n in ("ang_bottom", "ground_angle_threshold", "minimum_range", "sensor_mount_angle", "theta",
                                          "min_delta_z", "max_delta_z", "max_distance", "max_elevation")]
 
     DEFAULTS = dict(rows=128, cols=1024, ground_rows=30, valid_point_num=15, min_line_num=5, valid_line_num=5,
-                    window_row_min=156, window_row_max=356, window_col_min=156, window_col_max=356, scan_in_sensor_frame=0,
+                    window_row_min=156, window_row_max=356, window_col_min=156, window_col_max=356, scan_in_sensor_frame=0, unordered_residual_sums=0,
                     ang_bottom=45.0, ground_angle_threshold=10.0, minimum_range=10.0, sensor_mount_angle=10.0,
                     theta=60.0 / 180.0 * np.pi, min_delta_z=0.1, max_delta_z=3.0, max_distance=20.0, max_elevation=2.0)
 

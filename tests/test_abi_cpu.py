@@ -181,7 +181,7 @@ def test_segmentation_params_layout_matches_header():
 
     header = fields_of((ROOT / "include" / "ddlo_gicp.h").read_text(), "typedef struct ddlo_segmentation_params {", "} ddlo_segmentation_params;")
     oracle_c = fields_of((ROOT / "oracle" / "oracle_segmentation.cpp").read_text(), "struct oracle_seg_params {", "};\n\n// scan_t")
-    assert header == oracle_c and len(header) == 20
+    assert header == oracle_c and len(header) == 21
     ctype = {"int": C.c_int, "float": C.c_float}
     want = [(n, ctype[t]) for n, t in header]
     assert list(B.SegmentationParams._fields_) == want

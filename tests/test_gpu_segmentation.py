@@ -365,3 +365,21 @@ def test_segmentation_early_decisions_equal_full_replay(rt, oracle, monkeypatch,
         o = oracle.segment_scan(oracle.SegParams(**params), st, T, res if with_residuals else None)
         if o["borderline"] == 0:
             assert_same(outs[0], o)
+
+
+def test_segmentation_unordered_residual_sums_mode(rt, oracle):
+    """opt-in unordered_residual_sums: same label image, averages equal to the push-order float sums up to the rounding
+    of those sums (1e-5 relative is generous for a few thousand terms)"""
+    for frame in (3, 40):
+        params, st, T, res = lidar_case(frame, 64, 1024, 0.02)
+        exact = DetectionModule(rt, **params)
+        exact.projectScan(None, st, T)
+        exact.projectResiduals(res)
+        exact.applySegmentation()
+        fast = DetectionModule(rt, **{**params, "unordered_residual_sums": 1})
+        fast.projectScan(None, st, T)
+        fast.projectResiduals(res)
+        fast.applySegmentation()
+        assert fast.label_count_ == exact.label_count_ > 4 and np.array_equal(fast.label_mat, exact.label_mat)
+        assert np.allclose(fast.avg_residuals, exact.avg_residuals, rtol=1e-5, atol=0.0)
+        assert fast.avg_residuals[1:].all()
