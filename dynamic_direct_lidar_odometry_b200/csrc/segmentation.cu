@@ -105,10 +105,16 @@ __global__ void __launch_bounds__(256) k_seg_transform(int n, const float* __res
   out[i] = o;
 }
 
+// (also clears the per-pixel work arrays of the later kernels: one launch instead of five memsets)
 __global__ void __launch_bounds__(256) k_seg_project(SegDev p, const float* __restrict__ scan, int stride, float* __restrict__ range,
-                                                     signed char* __restrict__ ground, int* __restrict__ label0) {
+                                                     signed char* __restrict__ ground, int* __restrict__ label0, int* __restrict__ size,
+                                                     int* __restrict__ accepted, unsigned* __restrict__ cstat) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.HW) return;
+  size[i] = 0;
+  accepted[i] = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) cstat[(size_t)k * p.HW + i] = (k == 1 || k == 4) ? 0xffffffffu : 0u;  // "none" of the min / max statistics
   const int row = i / p.W, col = i - row * p.W;
   float x, y, z, r;
   seg_full_point(scan, stride, p, i, x, y, z, r);
@@ -603,13 +609,8 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   }
   DDLO_TRY(pool_alloc(rt, &seg_avg, HW));
   DDLO_TRY(pool_alloc(rt, reinterpret_cast<unsigned char**>(&tmp), tmp_bytes));
-  DDLO_CUDA(cudaMemsetAsync(size, 0, (size_t)HW * 4, st));
-  DDLO_CUDA(cudaMemsetAsync(accepted, 0, (size_t)HW * 4, st));
   DDLO_CUDA(cudaMemsetAsync(small, 0, 16, st));
-  DDLO_CUDA(cudaMemsetAsync(nib, 0, nib_bytes, st));
-  DDLO_CUDA(cudaMemsetAsync(cstat, 0, (size_t)kStatCount * HW * 4, st));  // "none" of the max statistics ...
-  DDLO_CUDA(cudaMemsetAsync(cstat + (size_t)kStatRowMin * HW, 0xff, (size_t)HW * 4, st));  // ... and of the two min statistics
-  DDLO_CUDA(cudaMemsetAsync(cstat + (size_t)kStatZMin * HW, 0xff, (size_t)HW * 4, st));
+  DDLO_CUDA(cudaMemsetAsync(nib + nib_bytes - 16, 0, 16, st));  // the padding behind the last pixel pair
 
   const int pb = (HW + 255) / 256;
   float4* moved = nullptr;
@@ -622,7 +623,8 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
     d_scan = reinterpret_cast<const float*>(moved);
     stride_floats = 4;
   }
-  k_seg_project<<<pb, 256, 0, st>>>(p, d_scan, stride_floats, d_range, d_ground, d_label);
+  static_assert(kStatCount == 6 && kStatRowMin == 1 && kStatZMin == 4, "k_seg_project initialises the statistics by index");
+  k_seg_project<<<pb, 256, 0, st>>>(p, d_scan, stride_floats, d_range, d_ground, d_label, size, accepted, cstat);
   k_seg_edges<<<pb, 256, 0, st>>>(p, d_range, d_label, nib, parent);
   k_ccl_union<<<pb, 256, 0, st>>>(p, nib, parent);
   k_ccl_flatten<<<pb, 256, 0, st>>>(p, parent, d_scan, stride_floats, d_range, nib, root, size, cstat, d_residuals, res_stride, res_sum, res_count);
