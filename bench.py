@@ -132,6 +132,15 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must run on all the cores it can use.  Has to happen
+    before the OpenMP runtime is loaded (the oracle / reference libraries bring it in)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    return n
+
+
 def cpu_reference_setup(src, tgt, prefer_reference_engine=True):
     """Host-core arm.  Preferred: the reference's OWN nano_gicp engine (oracle/_ref/libnano_gicp_ref.so: its headers
     compiled unmodified from /root/reference, over the Eigen/PCL/Boost stand-ins of oracle/stub_include since none of
@@ -171,6 +180,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    use_all_host_cores()
     src, tgt, guess = make_workload(0)
     po, eng, _, kind, knn = cpu_reference_setup(src, tgt)
     from oracle import pyoracle as _po
@@ -394,6 +404,7 @@ def run_ours(args):
                                "note": "independent registrations of the same workload driven concurrently from S host threads per GPU "
                                        "(own stream, engine and submap copy each); `value` above is one stream, i.e. 1000 / ms_per_scan"}
         if world == 1 and not args.no_cpu_baseline:
+            use_all_host_cores()
             po, ceng, _, kind, knn = cpu_reference_setup(src, tgt)
             from oracle import pyoracle as _po
             cores = _po.max_threads()
