@@ -315,44 +315,50 @@ def run_ours(args):
     if S > 0:
         import threading
 
-        per_thread = max(8, min(args.steps, 200) // S)
         workers = []
-        for _ in range(S):
-            brt = ng.Runtime(local_rank)
-            brt.set_align_blocks(max(1, 148 // S))
-            beng = ng.NanoGICP(brt)
-            beng.setCorrespondenceRandomness(K_COV)
-            btarget = ng.PointCloud(brt, tgt)
-            beng.setInputTarget(btarget)
-            beng.calculateTargetCovariances()
-            bres = ng.PointCloud(brt, src)
-            brt.synchronize()
-            workers.append((brt, beng, btarget, bres))
+        try:  # an extra leg: whatever happens here must not cost the main line (no barrier inside: a failing rank cannot hang the others)
+            per_thread = max(8, min(args.steps, 200) // S)
+            for _ in range(S):
+                brt = ng.Runtime(local_rank)
+                brt.set_align_blocks(max(1, 148 // S))
+                beng = ng.NanoGICP(brt)
+                beng.setCorrespondenceRandomness(K_COV)
+                btarget = ng.PointCloud(brt, tgt)
+                beng.setInputTarget(btarget)
+                beng.calculateTargetCovariances()
+                bres = ng.PointCloud(brt, src)
+                brt.synchronize()
+                workers.append((brt, beng, btarget, bres))
+            errors = []
 
-        def batched_worker(w, count):
-            brt, beng, _, bres = w
-            for _ in range(count):
-                fresh = bres.transformed(np.eye(4, dtype=np.float32))
-                beng.setInputSource(fresh)
-                beng.calculateSourceCovariances()
-                beng.align(guess)
-                beng.clearSource()
-            brt.synchronize()
+            def batched_worker(w, count):
+                try:
+                    brt, beng, _, bres = w
+                    for _ in range(count):
+                        fresh = bres.transformed(np.eye(4, dtype=np.float32))
+                        beng.setInputSource(fresh)
+                        beng.calculateSourceCovariances()
+                        beng.align(guess)
+                        beng.clearSource()
+                    brt.synchronize()
+                except Exception as exc:  # noqa: BLE001
+                    errors.append(exc)
 
-        def run_batched(count):
-            th = [threading.Thread(target=batched_worker, args=(w, count)) for w in workers]
-            for t_ in th:
-                t_.start()
-            for t_ in th:
-                t_.join()
+            def run_batched(count):
+                th = [threading.Thread(target=batched_worker, args=(w, count)) for w in workers]
+                for t_ in th:
+                    t_.start()
+                for t_ in th:
+                    t_.join()
 
-        run_batched(3)
-        barrier()
-        t0 = time.perf_counter()
-        run_batched(per_thread)
-        batched_s = time.perf_counter() - t0
-        barrier()
-        batched_n = per_thread * S
+            run_batched(3)
+            t0 = time.perf_counter()
+            run_batched(per_thread)
+            if not errors:
+                batched_s = time.perf_counter() - t0
+                batched_n = per_thread * S
+        except Exception:  # noqa: BLE001
+            batched_s, batched_n = 0.0, 0
         for brt, beng, btarget, bres in workers:
             del beng, btarget, bres
             brt.close()
@@ -361,9 +367,11 @@ def run_ours(args):
     if dist is not None:
         import torch
 
-        t = torch.tensor([total_ms, e2e_total, batched_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([total_ms, e2e_total, batched_s, 0.0 if batched_n else 1.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_total, batched_s = float(t[0]), float(t[1]), float(t[2])
+        if float(t[3]) > 0.0:  # some rank has no batched result
+            batched_n = 0
 
     if rank == 0:
         align_ms = statistics.mean(t[2] for t in stage)
