@@ -383,3 +383,51 @@ def test_segmentation_unordered_residual_sums_mode(rt, oracle):
         assert fast.label_count_ == exact.label_count_ > 4 and np.array_equal(fast.label_mat, exact.label_mat)
         assert np.allclose(fast.avg_residuals, exact.avg_residuals, rtol=1e-5, atol=0.0)
         assert fast.avg_residuals[1:].all()
+
+
+def test_segmentation_fuzz_against_oracle(rt, oracle):
+    """random small range images (piecewise-smooth depth with steps, holes, exact zeros and repeated heights) and random
+    parameters: the early decisions, the queue replay and the statistics must agree with the oracle on every one"""
+    rng = np.random.default_rng(2024)
+    compared = accepted_total = 0
+    for trial in range(40):
+        H, W = int(rng.integers(6, 48)), int(rng.integers(12, 160))
+        el = np.linspace(0.35, -0.35, H)[:, None]
+        az = np.linspace(-1.0, 1.0, W)[None, :]
+        depth = 6.0 + 3.0 * np.sin(az * rng.uniform(1, 5) + rng.uniform(0, 6)) + 2.0 * np.cos(el * rng.uniform(2, 9))
+        for _ in range(int(rng.integers(0, 6))):  # foreground blobs: range steps
+            r0, c0 = int(rng.integers(0, H)), int(rng.integers(0, W))
+            hh, ww = int(rng.integers(2, max(3, H // 2))), int(rng.integers(2, max(3, W // 3)))
+            depth[r0:r0 + hh, c0:c0 + ww] -= rng.uniform(1.0, 4.0)
+        depth = np.maximum(depth, 0.6) + rng.normal(0.0, 0.004, (H, W))
+        s = np.empty((H, W, 4), dtype=np.float32)
+        s[..., 0] = depth * np.cos(el) * np.cos(az)
+        s[..., 1] = depth * np.cos(el) * np.sin(az)
+        s[..., 2] = depth * np.sin(el)
+        s[..., 3] = 1.0
+        s[rng.random((H, W)) < rng.uniform(0.0, 0.15)] = np.nan
+        zero = rng.random((H, W)) < 0.02
+        s[zero, 2] = 0.0
+        if rng.random() < 0.5:
+            s[..., 2] = np.round(s[..., 2], 1)  # many equal heights: ties at the maximum and at the minimum
+        T = np.eye(4, dtype=np.float32)
+        T[:3, 3] = rng.uniform(-0.2, 0.2, 3).astype(np.float32)
+        params = dict(rows=H, cols=W, ground_rows=int(rng.integers(0, H)), window_row_min=int(rng.integers(0, 3)), window_row_max=H - 1 - int(rng.integers(0, 3)),
+                      window_col_min=int(rng.integers(0, 4)), window_col_max=W - 1 - int(rng.integers(0, 4)), ang_bottom=float(rng.uniform(5, 30)),
+                      minimum_range=float(rng.uniform(0.3, 2.0)), sensor_mount_angle=float(rng.uniform(-5, 5)), ground_angle_threshold=float(rng.uniform(2, 15)),
+                      theta=float(rng.uniform(0.05, 1.2)), valid_point_num=int(rng.integers(1, 12)), valid_line_num=int(rng.integers(0, 4)),
+                      min_line_num=int(rng.integers(0, 4)), min_delta_z=float(rng.uniform(-0.5, 0.3)), max_delta_z=float(rng.uniform(0.2, 4.0)),
+                      max_distance=float(rng.uniform(4.0, 12.0)), max_elevation=float(rng.uniform(-0.5, 3.0)))
+        res = (rng.random((H, W)) * (rng.random((H, W)) < 0.8)).astype(np.float32) if rng.random() < 0.8 else None
+        o = oracle.segment_scan(oracle.SegParams(**params), s, T, res)
+        if o["borderline"]:
+            continue
+        det = DetectionModule(rt, **params)
+        det.projectScan(None, s, T)
+        if res is not None:
+            det.projectResiduals(res)
+        det.applySegmentation()
+        assert_same(det, o)
+        compared += 1
+        accepted_total += det.getSegmentsCount()
+    assert compared >= 25 and accepted_total >= 40
