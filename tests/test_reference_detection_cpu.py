@@ -99,3 +99,40 @@ def test_residual_cloud_matches_reference_loop(oracle, refdet):
     scan = synth.scan(3, 32, 512)
     res = np.linalg.norm(scan[:, :3], axis=1) * 1e-3
     assert np.array_equal(oracle.residual_image(scan, res).view(np.uint32), refdet.residual_cloud(scan, res).view(np.uint32))
+
+
+def test_oracle_matches_reference_detection_code_fuzz(oracle, refdet):
+    """random 360 x 360 range images (steps, holes, exact zeros, repeated heights) and random parameters within what the
+    reference can express (its window, integer values for its int-typed parameters)"""
+    rng = np.random.default_rng(77)
+    accepted = 0
+    for trial in range(12):
+        H = W = 360
+        el = np.linspace(0.5, -0.5, H)[:, None]
+        az = np.linspace(-1.0, 1.0, W)[None, :]
+        depth = 7.0 + 3.0 * np.sin(az * rng.uniform(1, 6) + rng.uniform(0, 6)) + 2.0 * np.cos(el * rng.uniform(2, 9))
+        for _ in range(int(rng.integers(2, 14))):
+            r0, c0 = int(rng.integers(140, 350)), int(rng.integers(140, 350))
+            depth[r0:r0 + int(rng.integers(3, 60)), c0:c0 + int(rng.integers(3, 60))] -= rng.uniform(1.0, 4.0)
+        depth = np.maximum(depth, 0.6) + rng.normal(0.0, 0.004, (H, W))
+        s = np.empty((H, W, 4), dtype=np.float32)
+        s[..., 0] = depth * np.cos(el) * np.cos(az)
+        s[..., 1] = depth * np.cos(el) * np.sin(az)
+        s[..., 2] = depth * np.sin(el)
+        s[..., 3] = 1.0
+        s[rng.random((H, W)) < rng.uniform(0.0, 0.1)] = np.nan
+        s[rng.random((H, W)) < 0.01, 2] = 0.0
+        if trial % 2:
+            s[..., 2] = np.round(s[..., 2], 1)
+        T = np.eye(4, dtype=np.float32)
+        T[:3, 3] = rng.uniform(-0.2, 0.2, 3).astype(np.float32)
+        params = dict(rows=H, cols=W, ground_rows=int(rng.integers(0, 120)), ang_bottom=int(rng.integers(10, 40)), minimum_range=int(rng.integers(0, 3)),
+                      sensor_mount_angle=int(rng.integers(-5, 6)), ground_angle_threshold=int(rng.integers(2, 15)), max_distance=int(rng.integers(6, 14)),
+                      theta=float(rng.uniform(0.05, 1.2)), valid_point_num=int(rng.integers(1, 12)), valid_line_num=int(rng.integers(0, 4)),
+                      min_line_num=int(rng.integers(0, 4)), min_delta_z=float(rng.uniform(0.0, 0.3)), max_delta_z=float(rng.uniform(0.3, 4.0)),
+                      max_elevation=float(rng.uniform(-0.5, 3.0)), **cases.WINDOW)
+        res = (rng.random((H, W)) * (rng.random((H, W)) < 0.8)).astype(np.float32) if trial % 4 else None
+        r = refdet.segment(params, s, T, res)
+        same(oracle.segment_scan(oracle.SegParams(**params), s, T, res), r)
+        accepted += r["label_count"] - 1
+    assert accepted >= 30
