@@ -57,6 +57,51 @@ def make_workload(rank: int):
     return src, tgt, guess
 
 
+def kernel_source_sha16() -> str:
+    """fingerprint of the sources of the align kernel: profiles/align_traffic.json is only quoted while it matches"""
+    import hashlib
+
+    h = hashlib.sha256()
+    for name in ("gicp.cu", "gicp.cuh", "knn.cuh", "knn_pair.cuh", "math.cuh", "common.cuh"):
+        h.update((ROOT / "dynamic_direct_lidar_odometry_b200" / "csrc" / name).read_bytes())
+    return h.hexdigest()[:16]
+
+
+def percentiles(xs):
+    a = np.sort(np.asarray(xs, dtype=np.float64))
+    return {"n": int(a.size), "mean": float(a.mean()), "p50": float(np.percentile(a, 50)), "p99": float(np.percentile(a, 99)), "max": float(a[-1])}
+
+
+class HostGroup:
+    """Barrier and max-over-ranks between the ranks of one node over gloo (host side).  The registrations of different
+    ranks never exchange data, so no device collective exists anywhere in this benchmark."""
+
+    def __init__(self, world: int):
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("gloo")
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def reduce_max(self, values):
+        if self.dist is None:
+            return [float(v) for v in values]
+        import torch
+
+        t = torch.tensor([float(v) for v in values], dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
 def config_dict(n_src: int, extra=None):
     cfg = {
         "workload": "C2: S2M registration, 64x1024 synthetic scan vs 500k-point synthetic keyframe submap",
@@ -216,13 +261,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    group = HostGroup(world)
 
     src, tgt, guess = make_workload(rank)
     rt = ng.Runtime(local_rank)
@@ -275,8 +314,8 @@ def run_ours(args):
     rt.synchronize()
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
+        rt.synchronize()
+        group.barrier()
         rt.synchronize()
 
     sampler = ClockSampler(local_rank)
@@ -306,72 +345,39 @@ def run_ours(args):
     clocks = sampler.stop(first_sample) if rank == 0 else None
     e2e_total = sum(e2e_times)
 
-    # Batched throughput (the second half of BASELINE's metric): the same step for independent scans, S host threads
-    # per GPU, each with its own runtime (stream), engine and copy of the submap; every stream's align kernel is limited
-    # to 148 // S SMs so that the cooperative launches of all streams are resident side by side.  No L2 flush here: the
-    # S working sets together (S x ~50 MB of submap points, covariances and index) exceed the L2.
-    batched_s, batched_n = 0.0, 0
+    # Latency distribution (median + p99 of >= 100 repeats): the K timed steps when K >= 100, else an
+    # extra leg of 100 steps that does not enter `value`.
+    lat_steps = [t[3] for t in stage]
+    if len(lat_steps) < 100:
+        lat_steps = [device_step(True)[0][3] for _ in range(100)]
+    latency = percentiles(lat_steps)
+
+    # C1 (BASELINE configs[0], the reference's CPU-runnable case): S2S of two 64x1024 scans, raw and 0.25 m voxel-filtered,
+    # full pipeline per registration (two indexes, two covariance passes, align), device-timed, L2 flushed.
+    c1 = None
+    if rank == 0 and not args.no_c1:
+        try:
+            c1 = run_c1(ng, rt)
+        except Exception as exc:  # noqa: BLE001  (an extra leg must not cost the main line)
+            c1 = {"error": repr(exc)}
+
+    # Batched throughput (the second half of BASELINE's metric), driven by the C++ batch driver (ddlo_batch_*): the same
+    # C2 step for a stream of independent scans against ONE resident submap shared by S lanes (stream + engine each,
+    # align kernels limited to 148 // S SMs so that they are resident side by side).  >= 512 registrations per GPU over
+    # >= 64 distinct scans; no L2 flush here: consecutive units are different scans and S of them are in flight at once.
+    batched = None
     S = args.batched_streams
     if S > 0:
-        import threading
+        try:
+            batched = run_batched(ng, group, local_rank, rank, world, tgt, args)
+        except Exception as exc:  # noqa: BLE001
+            batched = {"error": repr(exc)}
+            try:
+                group.barrier()
+            except Exception:  # noqa: BLE001
+                pass
 
-        workers = []
-        try:  # an extra leg: whatever happens here must not cost the main line (no barrier inside: a failing rank cannot hang the others)
-            per_thread = max(8, min(args.steps, 200) // S)
-            for _ in range(S):
-                brt = ng.Runtime(local_rank)
-                brt.set_align_blocks(max(1, 148 // S))
-                beng = ng.NanoGICP(brt)
-                beng.setCorrespondenceRandomness(K_COV)
-                btarget = ng.PointCloud(brt, tgt)
-                beng.setInputTarget(btarget)
-                beng.calculateTargetCovariances()
-                bres = ng.PointCloud(brt, src)
-                brt.synchronize()
-                workers.append((brt, beng, btarget, bres))
-            errors = []
-
-            def batched_worker(w, count):
-                try:
-                    brt, beng, _, bres = w
-                    for _ in range(count):
-                        fresh = bres.transformed(np.eye(4, dtype=np.float32))
-                        beng.setInputSource(fresh)
-                        beng.calculateSourceCovariances()
-                        beng.align(guess)
-                        beng.clearSource()
-                    brt.synchronize()
-                except Exception as exc:  # noqa: BLE001
-                    errors.append(exc)
-
-            def run_batched(count):
-                th = [threading.Thread(target=batched_worker, args=(w, count)) for w in workers]
-                for t_ in th:
-                    t_.start()
-                for t_ in th:
-                    t_.join()
-
-            run_batched(3)
-            t0 = time.perf_counter()
-            run_batched(per_thread)
-            if not errors:
-                batched_s = time.perf_counter() - t0
-                batched_n = per_thread * S
-        except Exception:  # noqa: BLE001
-            batched_s, batched_n = 0.0, 0
-        for brt, beng, btarget, bres in workers:
-            del beng, btarget, bres
-            brt.close()
-        workers = []
-
-    if dist is not None:
-        import torch
-
-        t = torch.tensor([total_ms, e2e_total, batched_s, 0.0 if batched_n else 1.0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_total, batched_s = float(t[0]), float(t[1]), float(t[2])
-        if float(t[3]) > 0.0:  # some rank has no batched result
-            batched_n = 0
+    total_ms, e2e_total = group.reduce_max([total_ms, e2e_total])
 
     if rank == 0:
         align_ms = statistics.mean(t[2] for t in stage)
@@ -383,34 +389,41 @@ def run_ours(args):
         except Exception:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = align_bytes / (align_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM bytes of one k_align launch from the last `ncu --set full` capture; only quoted while the kernel's
+        # sources are the ones that capture was taken from
+        traffic, traffic_note = None, "no ncu capture for this build of the kernel (profiles/align_traffic.json is from another source state)"
         tfile = ROOT / "profiles" / "align_traffic.json"
         if tfile.exists():
             try:
-                traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+                tj = json.load(open(tfile))
+                if tj.get("kernel_source_sha16") == kernel_source_sha16():
+                    traffic, traffic_note = tj.get("dram_bytes_per_launch"), f"ncu --set full, {tj.get('captured', '?')}"
             except Exception:
-                traffic = None
+                pass
+        from dynamic_direct_lidar_odometry_b200 import binding as _B
         line = {
             "metric": METRIC, "value": world * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 kNN / f64 GICP", "data": "synthetic",
-            "config": config_dict(n_src, {"parallelism": f"{world} independent replica(s), no collective"}),
+            "config": config_dict(n_src),
+            "parallelism": f"{world} independent replica(s), one process per GPU, no collective (host-side gloo barrier only)",
             "stages_ms": {"source_index": statistics.mean(t[0] for t in stage), "source_covariances": statistics.mean(t[1] for t in stage),
                           "align": align_ms},
+            "latency_ms": latency,
             "align": {"converged": info.converged, "outer_iterations": info.iterations + 1, "n_linearize": L, "n_compute_error": E},
             "roofline": {"bound": "hbm", "kernel": "k_align (1 cooperative launch per align)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": align_bytes, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "algorithmic_bytes": align_bytes, "peak_source": peak_src,
                          "note": "latency-bound by construction: 65k points x ~100 MB of algorithmic traffic per align (SURVEY.md finding 6)"},
             "e2e": {"value": world * args.steps / e2e_total, "unit": UNIT, "ms_per_step": 1e3 * e2e_total / args.steps,
-                    "h2d_bytes_per_step": int(src_pinned.nbytes), "d2h_bytes_per_step": int(232 + res.nbytes), "timer": "host wall clock"},
+                    "h2d_bytes_per_step": int(src_pinned.nbytes), "d2h_bytes_per_step": int(_B.load().ddlo_align_d2h_bytes() + res.nbytes),
+                    "latency_ms": percentiles([1e3 * x for x in e2e_times]), "timer": "host wall clock"},
             "gpu_launches": int(launches1 - launches0),
             "clocks": clocks,
         }
-        if batched_n:
-            line["batched"] = {"value": world * batched_n / batched_s, "unit": UNIT, "streams_per_gpu": S, "align_sms_per_stream": max(1, 148 // S),
-                               "registrations": world * batched_n, "timer": "host wall clock, max over ranks",
-                               "note": "independent registrations of the same workload driven concurrently from S host threads per GPU "
-                                       "(own stream, engine and submap copy each); `value` above is one stream, i.e. 1000 / ms_per_scan"}
+        if batched is not None:
+            line["batched"] = batched
+        if c1 is not None:
+            line["c1"] = c1
         if world == 1 and not args.no_cpu_baseline:
             use_all_host_cores()
             po, ceng, _, kind, knn = cpu_reference_setup(src, tgt)
@@ -436,12 +449,101 @@ def run_ours(args):
                     pts.append(cpu_step(po2, peng, src, guess)[0])
                     peng.clearSource()
                 line["cpu_baseline"]["oracle_port_ms_per_step"] = 1e3 * min(pts)
+                line["cpu_baseline"]["note"] = ("reference sources on stand-in Eigen (no vectorised fixed-size kernels): the dependency-free "
+                                                "restatement on the same inputs is oracle_port_ms_per_step")
         print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    group.close()
     del eng, target, resident
     rt.close()
     return 0
+
+
+def run_c1(ng, rt):
+    from dynamic_direct_lidar_odometry_b200 import synth
+
+    out = {"workload": "C1: S2S registration of two 64x1024 synthetic scans, guess = I, k = 20; per step: 2 index builds, 2 covariance passes, LM align",
+           "timer": "CUDA events on the library's stream, L2 flushed before every step", "repeats": 100}
+    src, tgt, guess = synth.workload_c1(NS_BEAMS, NS_COLS)
+    for name, leaf in (("raw", 0.0), ("voxel_0.25m", 0.25)):
+        S, T = ng.PointCloud(rt, src), ng.PointCloud(rt, tgt)
+        if leaf > 0.0:
+            S, T = S.voxel_filtered(leaf), T.voxel_filtered(leaf)
+        eng = ng.NanoGICP(rt)
+        eng.setCorrespondenceRandomness(K_COV)
+        eye = np.eye(4, dtype=np.float32)
+        times, info = [], None
+        for i in range(105):
+            s, t = S.transformed(eye), T.transformed(eye)  # fresh, index-less handles
+            rt.flush_l2(L2_FLUSH_BYTES)
+            rt.event_record(4)
+            eng.setInputSource(s)
+            eng.setInputTarget(t)
+            eng.align_async(guess)
+            rt.event_record(5)
+            info = eng.align_finish()
+            if i >= 5:
+                times.append(rt.event_elapsed(4, 5))
+            eng.clearSource()
+            eng.clearTarget()
+        out[name] = {"source_points": len(S), "target_points": len(T), "ms": percentiles(times), "converged": info.converged,
+                     "outer_iterations": info.iterations + 1}
+        del eng, S, T
+    return out
+
+
+def run_batched(ng, group, local_rank, rank, world, tgt, args):
+    from dynamic_direct_lidar_odometry_b200 import synth
+
+    S = args.batched_streams
+    n_units = max(512, args.batched_units)
+    n_distinct = 64
+    w = synth.make_world()
+    frames = [40 + ((rank * n_distinct + i) % 160) for i in range(n_distinct)]
+    batch = ng.Batch(local_rank, lanes=S, host_threads=args.batched_host_threads)
+    batch.set_params(k_correspondences=K_COV)
+    sub_id = batch.stage(tgt)
+    batch.set_shared_target(sub_id)
+    ids, guesses = [], []
+    for f in frames:
+        ids.append(batch.stage(synth.scan(f, NS_BEAMS, NS_COLS, w)))
+        guesses.append(synth.perturbed_guess(synth.pose(f)))
+    jobs = ng.Batch.jobs([(ids[i % n_distinct], -1, guesses[i % n_distinct]) for i in range(n_units)])
+    batch.run(ng.Batch.jobs([(ids[i % n_distinct], -1, guesses[i % n_distinct]) for i in range(8 * S)]))  # warm-up
+
+    def timed():
+        t0 = time.perf_counter()
+        res = batch.run(jobs, raw=True)
+        return time.perf_counter() - t0, res
+
+    solo = None
+    if world > 1:
+        # this GPU alone (the other ranks idle at the barrier), then all ranks together: the ratio is the scaling
+        # efficiency of the batched workload on this box, measured inside this run
+        group.barrier()
+        if rank == 0:
+            solo, _ = timed()
+        group.barrier()
+    launches0 = batch.launch_count()
+    group.barrier()
+    dt, res = timed()
+    group.barrier()
+    launches1 = batch.launch_count()
+    ok = all(res[i].flags & 1 for i in range(n_units))
+    iters = statistics.mean(res[i].nr_iterations + 1 for i in range(n_units))
+    (dt_max,) = group.reduce_max([dt])
+    (bad,) = group.reduce_max([0.0 if ok else 1.0])
+    out = {"value": world * n_units / dt_max, "unit": UNIT, "registrations_per_gpu": n_units, "distinct_scans_per_gpu": n_distinct,
+           "lanes_per_gpu": batch.lanes, "align_sms_per_lane": batch.align_blocks, "host_threads_per_gpu": batch.host_threads,
+           "seconds": dt_max, "all_converged": bad == 0.0, "mean_outer_iterations": iters, "gpu_launches": int(launches1 - launches0),
+           "driver": "ddlo_batch_submit / ddlo_batch_wait (C++; Python passes the job table only)",
+           "timer": "host wall clock around submit + wait, max over ranks",
+           "l2": "not flushed: 64 distinct scans cycled, S units in flight; the 500k-point submap (shared by the lanes) stays resident",
+           "note": "`value` at the top of the line is one stream, i.e. 1000 / ms_per_scan"}
+    if solo is not None:
+        out["one_gpu_alone"] = n_units / solo
+        out["scaling_efficiency"] = (world * n_units / dt_max) / (world * n_units / solo)
+    batch.close()
+    return out
 
 
 def main():
@@ -451,7 +553,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batched-streams", type=int, default=4, help="host threads / streams per GPU for the batched-throughput leg (0 = skip)")
+    ap.add_argument("--batched-streams", type=int, default=4, help="lanes (stream + engine) per GPU of the batched-throughput leg (0 = skip)")
+    ap.add_argument("--batched-units", type=int, default=1024, help="registrations per GPU in the batched leg (at least 512)")
+    ap.add_argument("--batched-host-threads", type=int, default=2, help="C++ host threads that enqueue the batched leg")
+    ap.add_argument("--no-c1", action="store_true", help="skip the C1 (S2S) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -1,17 +1,15 @@
 #!/usr/bin/env python
 """BASELINE config C5: batched, independent S2S registrations (64x1024 scan pairs) sharded over GPUs.
 
-    python benchmarks/c5_batch.py --pairs 256 [--threads 4]                       # one GPU
-    python -m torch.distributed.run --nproc-per-node N benchmarks/c5_batch.py ...  # N GPUs, one rank each
+    python benchmarks/c5_batch.py --pairs 4096 [--lanes 8]                          # one GPU
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 benchmarks/c5_batch.py ...  # N GPUs, one rank each
 
-Every unit is a full registration from raw clouds: two index builds, two covariance passes (k=20) and
-the LM align, exactly what `NanoGICP::align` does for a fresh pair.  Units are independent, so ranks get
-contiguous shards (sharding.shard_range) and no collective touches the data; inside a rank several host
-threads drive their own runtime (stream) so that the small index kernels of one pair overlap the search
-kernels of another; each stream's align kernel is limited to a slice of the SMs (--align-blocks), so that the
-cooperative launches of different streams are resident side by side instead of waiting for the whole GPU
-(measured on B200: 1 stream 1 340 pairs/s, 8 streams x 24 SMs 2 680 pairs/s).  Inputs are staged in HBM before the clock starts.  Prints one JSON
-line with registrations/s over all ranks (max-over-ranks time).
+Every unit is a full registration from raw clouds: two index builds, two covariance passes (k = 20) and the LM align,
+exactly what `NanoGICP::align` does for a fresh pair.  Units are independent, so ranks get contiguous shards
+(sharding.shard_range) and no collective touches the data.  Inside a rank the C++ batch driver (ddlo_batch_*,
+csrc/batch.cu) owns S lanes (CUDA stream + engine, align kernel limited to 148 // S SMs) and deals the units to them;
+Python stages the inputs in HBM before the clock starts and hands over the job table.  Prints one JSON
+line with registrations/s over all ranks (max-over-ranks time, strong scaling: the pair count is fixed).
 """
 from __future__ import annotations
 
@@ -19,7 +17,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -28,13 +25,17 @@ import numpy as np
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 
+B_REG_C1 = 100.9e6  # algorithmic bytes of one C1 registration (2 indexes, 2 covariance passes, L = E = 5)
+
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--pairs", type=int, default=256, help="registrations over ALL ranks")
-    ap.add_argument("--unique", type=int, default=8, help="distinct synthetic scan pairs that are cycled")
-    ap.add_argument("--threads", type=int, default=8, help="host threads (= runtimes/streams) per rank")
-    ap.add_argument("--align-blocks", type=int, default=24, help="SMs one align may use (0 = all); e.g. 148 // threads lets the aligns of all streams be resident at once")
+    ap.add_argument("--pairs", type=int, default=4096, help="registrations over ALL ranks")
+    ap.add_argument("--unique", type=int, default=64, help="distinct synthetic scan pairs (frames f, f+1) that are cycled")
+    ap.add_argument("--lanes", type=int, default=8, help="lanes (stream + engine) per GPU")
+    ap.add_argument("--align-blocks", type=int, default=0, help="SMs one align may use (0 = 148 // lanes)")
+    ap.add_argument("--host-threads", type=int, default=2, help="C++ threads that enqueue the units")
+    ap.add_argument("--out", type=str, default="", help="also write the JSON line to this file (rank 0)")
     args = ap.parse_args()
 
     from dynamic_direct_lidar_odometry_b200 import nano_gicp as ng
@@ -45,67 +46,55 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
-    dev = None
     if world > 1:
-        import torch
         import torch.distributed as dist
 
-        torch.cuda.set_device(local_rank)
-        dev = torch.device("cuda", local_rank)
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("gloo")  # host-side barrier / max only: the shards never exchange data
 
     begin, end = shard_range(args.pairs, rank, world)
     w = synth.make_world()
     scans = [synth.scan(f, 64, 1024, w) for f in range(args.unique + 1)]
 
-    results = [None] * (end - begin)
-    runtimes = [ng.Runtime(local_rank) for _ in range(args.threads)]
-    for r_ in runtimes:
-        r_.set_align_blocks(args.align_blocks)
-    staged = [[(ng.PointCloud(rt, scans[u + 1]), ng.PointCloud(rt, scans[u])) for u in range(args.unique)] for rt in runtimes]
-    for rt in runtimes:
-        rt.synchronize()
-    eye = np.eye(4, dtype=np.float32)
+    batch = ng.Batch(local_rank, lanes=args.lanes, align_blocks=args.align_blocks, host_threads=args.host_threads)
+    ids = [batch.stage(s) for s in scans]
+    units = [(ids[p % args.unique + 1], ids[p % args.unique], None) for p in range(begin, end)]  # source = frame f+1, target = frame f
+    jobs = ng.Batch.jobs(units)
+    batch.run(ng.Batch.jobs(units[: 4 * args.lanes]))  # warm-up (allocator pools, first-touch)
 
-    def worker(t: int):
-        rt = runtimes[t]
-        eng = ng.NanoGICP(rt)
-        for p in range(begin + t, end, args.threads):
-            s, g = staged[t][p % args.unique]
-            eng.clearSource()
-            eng.clearTarget()
-            eng.setInputSource(s.transformed(eye))  # fresh handles: nothing cached from an earlier unit
-            eng.setInputTarget(g.transformed(eye))
-            r = eng.align()
-            results[p - begin] = (r.converged, r.iterations, r.T)
-
-    def run_all():
-        th = [threading.Thread(target=worker, args=(t,)) for t in range(args.threads)]
-        for x in th:
-            x.start()
-        for x in th:
-            x.join()
-        for rt in runtimes:
-            rt.synchronize()
-
-    run_all()  # warm-up (allocator pools, first-touch)
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
-    run_all()
+    res = batch.run(jobs, raw=True)
     dt = time.perf_counter() - t0
-    (tmax,) = max_over_ranks([dt], dist, dev)
-    (total,) = sum_over_ranks([end - begin], dist, dev)
-    ok = all(r is not None and r[0] for r in results)
-    gt = np.linalg.inv(synth.pose(0)) @ synth.pose(1)
-    err = max(float(np.abs(r[2][:3, 3] - (np.linalg.inv(synth.pose(i % args.unique)) @ synth.pose(i % args.unique + 1))[:3, 3]).max())
-              for i, r in zip(range(begin, end), results))
+    (tmax,) = max_over_ranks([dt], dist)
+    (total,) = sum_over_ranks([end - begin], dist)
+    ok = all(res[i].flags & 1 for i in range(end - begin))
+    err = 0.0
+    for i, p in enumerate(range(begin, end)):
+        u = p % args.unique
+        gt = np.linalg.inv(synth.pose(u)) @ synth.pose(u + 1)
+        T = np.array(res[i].final_transformation, dtype=np.float64).reshape(4, 4).T
+        err = max(err, float(np.abs(T[:3, 3] - gt[:3, 3]).max()))
+    (err, bad) = max_over_ranks([err, 0.0 if ok else 1.0], dist)
     if rank == 0:
-        print(json.dumps({"metric": "gicp_s2s_batched_registrations_per_s", "value": total / tmax, "unit": "registrations/s", "n_gpus": world,
-                          "pairs": int(total), "seconds": tmax, "host_threads_per_gpu": args.threads, "align_blocks": args.align_blocks, "all_converged": bool(ok),
-                          "max_translation_error_vs_truth_m": err, "scaling": "strong (fixed pair count)",
-                          "config": {"workload": "C5: independent S2S registrations of 64x1024 synthetic scan pairs, full pipeline per pair",
-                                     "unique_pairs_cycled": args.unique}}))
+        try:
+            peak = float(json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"])
+        except Exception:
+            peak = 6650.0
+        value = total / tmax
+        line = {"metric": "gicp_s2s_batched_registrations_per_s", "value": value, "unit": "registrations/s", "n_gpus": world,
+                "pairs": int(total), "seconds": tmax, "lanes_per_gpu": batch.lanes, "align_sms_per_lane": batch.align_blocks,
+                "host_threads_per_gpu": batch.host_threads, "all_converged": bad == 0.0, "max_translation_error_vs_truth_m": err,
+                "scaling": "strong (fixed pair count)", "driver": "ddlo_batch_submit / ddlo_batch_wait (C++)",
+                "roofline": {"bound": "hbm", "algorithmic_bytes_per_registration": B_REG_C1, "achieved": value / world * B_REG_C1 / 1e9,
+                             "peak": peak, "unit": "GB/s per GPU", "frac": value / world * B_REG_C1 / 1e9 / peak},
+                "config": {"workload": "C5: independent S2S registrations of 64x1024 synthetic scan pairs, full pipeline per pair",
+                           "unique_pairs_cycled": args.unique}}
+        print(json.dumps(line))
+        if args.out:
+            Path(args.out).parent.mkdir(parents=True, exist_ok=True)
+            Path(args.out).write_text(json.dumps(line) + "\n")
+    batch.close()
     if dist is not None:
         dist.destroy_process_group()
 

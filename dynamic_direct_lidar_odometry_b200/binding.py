@@ -126,7 +126,27 @@ SIGNATURES = {
     "ddlo_segment_scan": [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _ip, _vp],
     "ddlo_gicp_segment_scan": [_vp, _vp, _vp, C.c_int, _vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, C.c_int, _ip, _vp],
     "ddlo_gicp_align_batch": [_vpp, C.c_int, _vp, C.POINTER(AlignResult)],
+    "ddlo_cloud_share": [_vp],
+    "ddlo_covs_share": [_vp, _vp],
+    "ddlo_batch_create": [C.c_int, C.c_int, C.c_int, C.c_int, _vpp],
+    "ddlo_batch_destroy": [_vp],
+    "ddlo_batch_info": [_vp, _ip, _ip, _ip],
+    "ddlo_batch_set_params": [_vp, C.POINTER(Params)],
+    "ddlo_batch_stage_cloud": [_vp, _vp, C.c_int, C.c_int, _ip],
+    "ddlo_batch_staged_count": [_vp, _ip],
+    "ddlo_batch_set_shared_target": [_vp, C.c_int, _vp],
+    "ddlo_batch_submit": [_vp, _vp, C.c_int, _vp],
+    "ddlo_batch_wait": [_vp],
+    "ddlo_batch_run": [_vp, _vp, C.c_int, _vp],
+    "ddlo_batch_launch_count": [_vp, C.POINTER(C.c_longlong)],
 }
+
+
+class BatchJob(C.Structure):
+    """struct ddlo_batch_job (include/ddlo_gicp.h)"""
+
+    _fields_ = [("source", C.c_int), ("target", C.c_int), ("guess", C.c_float * 16)]
+
 class SegmentationParams(C.Structure):
     """struct ddlo_segmentation_params (include/ddlo_gicp.h); the defaults are the reference's (detection.cpp:76-105, :520-522)."""
 
@@ -202,6 +222,10 @@ def load() -> C.CDLL:
     L.ddlo_gicp_debug_visits.argtypes = [_vp, _vp, C.c_int]
     L.ddlo_gicp_debug_timeline.restype = C.c_int
     L.ddlo_gicp_debug_timeline.argtypes = [_vp, _vp, C.c_int]
+    L.ddlo_align_d2h_bytes.restype = C.c_int
+    L.ddlo_align_d2h_bytes.argtypes = []
+    L.ddlo_gicp_debug_enable.restype = C.c_int
+    L.ddlo_gicp_debug_enable.argtypes = [_vp, C.c_int]
     _lib = L
     return L
 

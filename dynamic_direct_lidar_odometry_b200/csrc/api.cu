@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "gicp.cuh"
+#include "engine.cuh"
 
 namespace ddlo {
 
@@ -74,12 +75,12 @@ __global__ void __launch_bounds__(256) k_fill(float4* p, size_t n4) {
     p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-static int use_device(const ddlo_runtime* rt) {
+int use_device(const ddlo_runtime* rt) {
   DDLO_CUDA(cudaSetDevice(rt->device));
   return DDLO_OK;
 }
 
-static int ensure_pinned(ddlo_runtime* rt, size_t bytes) {
+int ensure_pinned(ddlo_runtime* rt, size_t bytes) {
   if (rt->h_pinned_bytes >= bytes) return DDLO_OK;
   if (rt->h_pinned) {
     DDLO_CUDA(cudaStreamSynchronize(rt->stream));
@@ -107,54 +108,74 @@ static void cloud_free(ddlo_cloud* c) {
 static void covs_free(ddlo_covs* v) {
   cudaSetDevice(v->rt->device);
   if (v->c) cudaFreeAsync(v->c, v->rt->stream);
+  if (v->sorted) cudaFreeAsync(v->sorted, v->rt->stream);
+  if (v->sorted_for && v->sorted_for->refs.fetch_sub(1) == 1) cloud_free(v->sorted_for);
   delete v;
+}
+
+void cloud_set(ddlo_cloud*& slot, ddlo_cloud* c) {
+  if (c) c->refs.fetch_add(1);
+  if (slot && slot->refs.fetch_sub(1) == 1) cloud_free(slot);
+  slot = c;
+}
+void covs_set(ddlo_covs*& slot, ddlo_covs* v) {
+  if (v) v->refs.fetch_add(1);
+  if (slot && slot->refs.fetch_sub(1) == 1) covs_free(slot);
+  slot = v;
 }
 
 }  // namespace ddlo
 
 using namespace ddlo;
 
-struct ddlo_gicp {
-  ddlo_runtime* rt = nullptr;
-  ddlo_params p{};
-  ddlo_cloud* src = nullptr;
-  ddlo_cloud* tgt = nullptr;
-  ddlo_covs* src_cov = nullptr;
-  ddlo_covs* tgt_cov = nullptr;
-  // per-source-point workspace (correspondences_, sq_distances_, mahalanobis_)
-  int ws_n = 0;
-  int* corr = nullptr;
-  int2* nn_seed = nullptr;
-  // target covariances permuted into the Morton order of the target index (cache keyed by the two handles)
-  double* tcov_sorted = nullptr;
-  size_t tcov_sorted_cap = 0;
-  ddlo_cloud* tcov_for_cloud = nullptr;
-  ddlo_covs* tcov_for_covs = nullptr;
-  float* sqd = nullptr;
-  double* mahal = nullptr;
-  int corr_n = 0;  // number of valid entries (0 after swap/clear: correspondences_.clear())
-  double* partials = nullptr;
-  int partial_stride = 0;
-  AlignOut* d_out = nullptr;
-  int4* d_dbg = nullptr;  // DDLO_VISIT_STATS builds only
-  int d_dbg_n = 0;
-  unsigned long long* d_blk_times = nullptr;  // [8][partial_stride][4]
-  float last_T[16];
-  bool has_last_T = false;
-  bool align_pending = false;
-  int pending_covs_computed = 0;
-};
+static inline void set_cloud(ddlo_cloud*& slot, ddlo_cloud* c) { cloud_set(slot, c); }
+static inline void set_covs(ddlo_covs*& slot, ddlo_covs* v) { covs_set(slot, v); }
 
-static void set_cloud(ddlo_cloud*& slot, ddlo_cloud* c) {
-  if (c) c->refs.fetch_add(1);
-  if (slot && slot->refs.fetch_sub(1) == 1) cloud_free(slot);
-  slot = c;
+namespace ddlo {
+
+int cloud_new(ddlo_runtime* rt, int n, ddlo_cloud** out) {
+  ddlo_cloud* c = new (std::nothrow) ddlo_cloud();
+  if (!c) return fail(DDLO_E_INVALID, "out of host memory");
+  c->rt = rt;
+  c->n = n;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&c->pts), std::max<size_t>(1, (size_t)n) * sizeof(float4), rt->stream);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(DDLO_E_CUDA, std::string("cudaMallocAsync(cloud): ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return DDLO_OK;
 }
-static void set_covs(ddlo_covs*& slot, ddlo_covs* v) {
-  if (v) v->refs.fetch_add(1);
-  if (slot && slot->refs.fetch_sub(1) == 1) covs_free(slot);
-  slot = v;
+
+// a cloud handle around a device buffer that is already filled (takes ownership)
+int cloud_adopt(ddlo_runtime* rt, float4* pts, int n, ddlo_cloud** out) {
+  ddlo_cloud* c = new (std::nothrow) ddlo_cloud();
+  if (!c) {
+    cudaFreeAsync(pts, rt->stream);
+    return fail(DDLO_E_INVALID, "out of host memory");
+  }
+  c->rt = rt;
+  c->n = n;
+  c->pts = pts;
+  *out = c;
+  return DDLO_OK;
 }
+
+int covs_new(ddlo_runtime* rt, int n, ddlo_covs** out) {
+  ddlo_covs* v = new (std::nothrow) ddlo_covs();
+  if (!v) return fail(DDLO_E_INVALID, "out of host memory");
+  v->rt = rt;
+  v->n = n;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&v->c), std::max<size_t>(1, (size_t)n) * kCovStride * sizeof(double), rt->stream);
+  if (e != cudaSuccess) {
+    delete v;
+    return fail(DDLO_E_CUDA, std::string("cudaMallocAsync(covs): ") + cudaGetErrorString(e));
+  }
+  *out = v;
+  return DDLO_OK;
+}
+
+}  // namespace ddlo
 
 extern "C" {
 
@@ -168,6 +189,7 @@ int ddlo_device_count(int* count) {
 }
 
 // ---- runtime --------------------------------------------------------------------------------------
+static int runtime_init(ddlo_runtime* rt, int device);
 int ddlo_runtime_create(int device, ddlo_runtime** out) {
   if (!out) return fail(DDLO_E_INVALID, "out is null");
   *out = nullptr;
@@ -178,6 +200,17 @@ int ddlo_runtime_create(int device, ddlo_runtime** out) {
   ddlo_runtime* rt = new (std::nothrow) ddlo_runtime();
   if (!rt) return fail(DDLO_E_INVALID, "out of host memory");
   rt->device = device;
+  const int rc = runtime_init(rt, device);
+  if (rc != DDLO_OK) {
+    const std::string why = g_err;
+    ddlo_runtime_destroy(rt);  // releases whatever was created
+    return fail(rc, why);
+  }
+  *out = rt;
+  return DDLO_OK;
+}
+
+static int runtime_init(ddlo_runtime* rt, int device) {
   DDLO_CUDA(cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking));
   DDLO_CUDA(cudaEventCreate(&rt->ev0));
   DDLO_CUDA(cudaEventCreate(&rt->ev1));
@@ -209,21 +242,21 @@ int ddlo_runtime_create(int device, ddlo_runtime** out) {
   rt->max_coop_blocks_align = per_sm * rt->num_sms;
   if (rt->max_coop_blocks_align <= 0) return fail(DDLO_E_CUDA, "align kernel does not fit on this device");
   rt->align_blocks_limit = rt->max_coop_blocks_align;
-  *out = rt;
   return DDLO_OK;
 }
 
 int ddlo_runtime_destroy(ddlo_runtime* rt) {
   if (!rt) return DDLO_OK;
   cudaSetDevice(rt->device);
-  cudaStreamSynchronize(rt->stream);
+  if (rt->stream) cudaStreamSynchronize(rt->stream);
   if (rt->d_scratch) cudaFree(rt->d_scratch);
   if (rt->flush_buf) cudaFree(rt->flush_buf);
   if (rt->h_pinned) cudaFreeHost(rt->h_pinned);
-  cudaEventDestroy(rt->ev0);
-  cudaEventDestroy(rt->ev1);
-  for (auto& e : rt->slots) cudaEventDestroy(e);
-  cudaStreamDestroy(rt->stream);
+  if (rt->ev0) cudaEventDestroy(rt->ev0);
+  if (rt->ev1) cudaEventDestroy(rt->ev1);
+  for (auto& e : rt->slots)
+    if (e) cudaEventDestroy(e);
+  if (rt->stream) cudaStreamDestroy(rt->stream);
   delete rt;
   return DDLO_OK;
 }
@@ -306,21 +339,8 @@ int ddlo_host_free(void* p) {
   return DDLO_OK;
 }
 
-// ---- clouds ---------------------------------------------------------------------------------------
-static int cloud_new(ddlo_runtime* rt, int n, ddlo_cloud** out) {
-  ddlo_cloud* c = new (std::nothrow) ddlo_cloud();
-  if (!c) return fail(DDLO_E_INVALID, "out of host memory");
-  c->rt = rt;
-  c->n = n;
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&c->pts), std::max<size_t>(1, (size_t)n) * sizeof(float4), rt->stream);
-  if (e != cudaSuccess) {
-    delete c;
-    return fail(DDLO_E_CUDA, std::string("cudaMallocAsync(cloud): ") + cudaGetErrorString(e));
-  }
-  *out = c;
-  return DDLO_OK;
-}
 
+// ---- clouds ---------------------------------------------------------------------------------------
 int ddlo_cloud_create(ddlo_runtime* rt, const float* xyz, int n, int stride_bytes, ddlo_cloud** out) {
   if (!rt || !out || (n > 0 && !xyz)) return fail(DDLO_E_INVALID, "null argument");
   if (n < 0 || stride_bytes < 12 || (stride_bytes & 3)) return fail(DDLO_E_INVALID, "bad n or stride");
@@ -331,12 +351,18 @@ int ddlo_cloud_create(ddlo_runtime* rt, const float* xyz, int n, int stride_byte
   if (n > 0) {
     const size_t raw_bytes = (size_t)(n - 1) * stride_bytes + 12;
     unsigned char* d_raw = nullptr;
-    DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_raw), raw_bytes, rt->stream));
-    DDLO_CUDA(cudaMemcpyAsync(d_raw, xyz, raw_bytes, cudaMemcpyHostToDevice, rt->stream));
-    k_repack<<<(n + 255) / 256, 256, 0, rt->stream>>>(d_raw, n, stride_bytes, c->pts);
-    rt->launches += 1;
-    DDLO_CUDA(cudaGetLastError());
-    DDLO_CUDA(cudaFreeAsync(d_raw, rt->stream));
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&d_raw), raw_bytes, rt->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_raw, xyz, raw_bytes, cudaMemcpyHostToDevice, rt->stream);
+    if (e == cudaSuccess) {
+      k_repack<<<(n + 255) / 256, 256, 0, rt->stream>>>(d_raw, n, stride_bytes, c->pts);
+      rt->launches += 1;
+      e = cudaGetLastError();
+    }
+    if (d_raw) cudaFreeAsync(d_raw, rt->stream);
+    if (e != cudaSuccess) {
+      cloud_free(c);
+      return fail(DDLO_E_CUDA, std::string("cloud upload: ") + cudaGetErrorString(e));
+    }
   }
   *out = c;
   return DDLO_OK;
@@ -352,7 +378,11 @@ int ddlo_cloud_create_from_device(ddlo_runtime* rt, const void* d_xyzw, int n, d
   if (n > 0) {
     k_repack<<<(n + 255) / 256, 256, 0, rt->stream>>>(static_cast<const unsigned char*>(d_xyzw), n, 16, c->pts);
     rt->launches += 1;
-    DDLO_CUDA(cudaGetLastError());
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      cloud_free(c);
+      return fail(DDLO_E_CUDA, std::string("cloud copy: ") + cudaGetErrorString(e));
+    }
   }
   *out = c;
   return DDLO_OK;
@@ -448,19 +478,6 @@ int ddlo_cloud_transform(ddlo_cloud* c, const float* T16, ddlo_cloud** out) {
   return DDLO_OK;
 }
 
-// a cloud handle around a device buffer that is already filled (takes ownership)
-static int cloud_adopt(ddlo_runtime* rt, float4* pts, int n, ddlo_cloud** out) {
-  ddlo_cloud* c = new (std::nothrow) ddlo_cloud();
-  if (!c) {
-    cudaFreeAsync(pts, rt->stream);
-    return fail(DDLO_E_INVALID, "out of host memory");
-  }
-  c->rt = rt;
-  c->n = n;
-  c->pts = pts;
-  *out = c;
-  return DDLO_OK;
-}
 
 int ddlo_cloud_voxel_filter(ddlo_cloud* c, float leaf_x, float leaf_y, float leaf_z, ddlo_cloud** out) {
   if (!c || !out) return fail(DDLO_E_INVALID, "null argument");
@@ -505,21 +522,19 @@ int ddlo_cloud_concat(ddlo_runtime* rt, ddlo_cloud* const* parts, int m, ddlo_cl
   return DDLO_OK;
 }
 
-// ---- covariances ------------------------------------------------------------------------------------
-static int covs_new(ddlo_runtime* rt, int n, ddlo_covs** out) {
-  ddlo_covs* v = new (std::nothrow) ddlo_covs();
-  if (!v) return fail(DDLO_E_INVALID, "out of host memory");
-  v->rt = rt;
-  v->n = n;
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&v->c), std::max<size_t>(1, (size_t)n) * kCovStride * sizeof(double), rt->stream);
-  if (e != cudaSuccess) {
-    delete v;
-    return fail(DDLO_E_CUDA, std::string("cudaMallocAsync(covs): ") + cudaGetErrorString(e));
-  }
-  *out = v;
+
+// Make a finished cloud (points uploaded, index built) readable from other runtimes (streams) of the same device:
+// synchronises the owner's stream once; from then on the handle is immutable.
+int ddlo_cloud_share(ddlo_cloud* c) {
+  if (!c) return fail(DDLO_E_INVALID, "cloud is null");
+  DDLO_TRY(use_device(c->rt));
+  if (c->n > 0) DDLO_TRY(build_index(c));
+  DDLO_CUDA(cudaStreamSynchronize(c->rt->stream));
+  c->shared = true;
   return DDLO_OK;
 }
 
+// ---- covariances ------------------------------------------------------------------------------------
 int ddlo_covs_compute(ddlo_cloud* c, int k, int regularization_method, ddlo_covs** out) {
   if (!c || !out) return fail(DDLO_E_INVALID, "null argument");
   *out = nullptr;
@@ -550,12 +565,18 @@ int ddlo_covs_from_host(ddlo_runtime* rt, const double* mat4x4, int n, ddlo_covs
   DDLO_TRY(covs_new(rt, n, &v));
   if (n > 0) {
     double* d_m = nullptr;
-    DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_m), (size_t)n * 16 * sizeof(double), rt->stream));
-    DDLO_CUDA(cudaMemcpyAsync(d_m, mat4x4, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, rt->stream));
-    k_cov_pack<<<(n + 255) / 256, 256, 0, rt->stream>>>(d_m, n, v->c);
-    rt->launches += 1;
-    DDLO_CUDA(cudaGetLastError());
-    DDLO_CUDA(cudaFreeAsync(d_m, rt->stream));
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&d_m), (size_t)n * 16 * sizeof(double), rt->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_m, mat4x4, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, rt->stream);
+    if (e == cudaSuccess) {
+      k_cov_pack<<<(n + 255) / 256, 256, 0, rt->stream>>>(d_m, n, v->c);
+      rt->launches += 1;
+      e = cudaGetLastError();
+    }
+    if (d_m) cudaFreeAsync(d_m, rt->stream);
+    if (e != cudaSuccess) {
+      covs_free(v);
+      return fail(DDLO_E_CUDA, std::string("covariance upload: ") + cudaGetErrorString(e));
+    }
   }
   *out = v;
   return DDLO_OK;
@@ -590,6 +611,22 @@ int ddlo_covs_retain(ddlo_covs* v) {
 int ddlo_covs_release(ddlo_covs* v) {
   if (!v) return DDLO_OK;
   if (v->refs.fetch_sub(1) == 1) covs_free(v);
+  return DDLO_OK;
+}
+
+// The same for a covariance vector; `target` (optional) is the cloud it will be the target covariances of: the
+// Morton-ordered copy the align kernel reads is prepared here, once, for all engines that share the pair.
+int ddlo_covs_share(ddlo_covs* v, ddlo_cloud* target) {
+  if (!v) return fail(DDLO_E_INVALID, "covs is null");
+  if (target && (target->rt->device != v->rt->device || target->n != v->n)) return fail(DDLO_E_SIZE, "covs_share: cloud of another device or size");
+  DDLO_TRY(use_device(v->rt));
+  if (target) {
+    if (!target->has_index) return fail(DDLO_E_NOT_READY, "covs_share: the target cloud has no index yet");
+    if (target->rt != v->rt) DDLO_CUDA(cudaStreamSynchronize(target->rt->stream));
+    DDLO_TRY(ensure_sorted_covs(v, target, v->rt->stream));
+  }
+  DDLO_CUDA(cudaStreamSynchronize(v->rt->stream));
+  v->shared = true;
   return DDLO_OK;
 }
 
@@ -643,8 +680,9 @@ int ddlo_gicp_create(ddlo_runtime* rt, ddlo_gicp** out) {
   g->partial_stride = std::max(rt->max_coop_blocks_align, 64);
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&g->partials), (size_t)2 * kNumSums * g->partial_stride * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->d_out), sizeof(AlignOut));
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->d_blk_times), (size_t)8 * g->partial_stride * 8 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
+    if (g->partials) cudaFree(g->partials);
+    if (g->d_out) cudaFree(g->d_out);
     delete g;
     return fail(DDLO_E_CUDA, std::string("cudaMalloc(engine): ") + cudaGetErrorString(e));
   }
@@ -662,14 +700,11 @@ int ddlo_gicp_destroy(ddlo_gicp* g) {
   set_covs(g->tgt_cov, nullptr);
   if (g->corr) cudaFreeAsync(g->corr, g->rt->stream);
   if (g->nn_seed) cudaFreeAsync(g->nn_seed, g->rt->stream);
-  if (g->tcov_sorted) cudaFreeAsync(g->tcov_sorted, g->rt->stream);
-  set_cloud(g->tcov_for_cloud, nullptr);
-  set_covs(g->tcov_for_covs, nullptr);
   if (g->sqd) cudaFreeAsync(g->sqd, g->rt->stream);
   if (g->mahal) cudaFreeAsync(g->mahal, g->rt->stream);
   if (g->partials) cudaFree(g->partials);
   if (g->d_out) cudaFree(g->d_out);
-  if (g->d_blk_times) cudaFree(g->d_blk_times);
+  if (g->d_prof) cudaFree(g->d_prof);
   delete g;
   return DDLO_OK;
 }
@@ -691,12 +726,21 @@ int ddlo_gicp_get_params(const ddlo_gicp* g, ddlo_params* p) {
   return DDLO_OK;
 }
 
+// a handle of another runtime is accepted only once it has been shared (complete, synchronised, read-only)
+static int check_foreign(const ddlo_gicp* g, const ddlo_runtime* owner, bool shared, const char* what) {
+  if (owner == g->rt) return DDLO_OK;
+  if (owner->device != g->rt->device) return fail(DDLO_E_INVALID, std::string(what) + " lives on another device");
+  if (!shared) return fail(DDLO_E_INVALID, std::string(what) + " belongs to another runtime (ddlo_cloud_share / ddlo_covs_share make it usable from other streams)");
+  return DDLO_OK;
+}
+
 int ddlo_gicp_set_input_source(ddlo_gicp* g, ddlo_cloud* c, int build) {
   if (!g || !c) return fail(DDLO_E_INVALID, "null argument");
-  if (c->rt != g->rt) return fail(DDLO_E_INVALID, "cloud belongs to another runtime");
+  DDLO_TRY(check_foreign(g, c->rt, c->shared, "cloud"));
   if (g->src == c) return DDLO_OK;  // if (input_ == cloud) return;
   DDLO_TRY(use_device(g->rt));
   set_cloud(g->src, c);
+  g->corr_n = 0;  // the stored correspondences index the previous source
   if (build) {
     if (c->n > 0) DDLO_TRY(build_index(c));
     set_covs(g->src_cov, nullptr);
@@ -706,10 +750,11 @@ int ddlo_gicp_set_input_source(ddlo_gicp* g, ddlo_cloud* c, int build) {
 
 int ddlo_gicp_set_input_target(ddlo_gicp* g, ddlo_cloud* c) {
   if (!g || !c) return fail(DDLO_E_INVALID, "null argument");
-  if (c->rt != g->rt) return fail(DDLO_E_INVALID, "cloud belongs to another runtime");
+  DDLO_TRY(check_foreign(g, c->rt, c->shared, "cloud"));
   if (g->tgt == c) return DDLO_OK;
   DDLO_TRY(use_device(g->rt));
   set_cloud(g->tgt, c);
+  g->corr_n = 0;  // the stored correspondences index points of the previous target
   if (c->n > 0) DDLO_TRY(build_index(c));
   set_covs(g->tgt_cov, nullptr);
   return DDLO_OK;
@@ -719,24 +764,26 @@ int ddlo_gicp_clear_source(ddlo_gicp* g) {
   if (!g) return fail(DDLO_E_INVALID, "engine is null");
   set_cloud(g->src, nullptr);
   set_covs(g->src_cov, nullptr);
+  g->corr_n = 0;
   return DDLO_OK;
 }
 int ddlo_gicp_clear_target(ddlo_gicp* g) {
   if (!g) return fail(DDLO_E_INVALID, "engine is null");
   set_cloud(g->tgt, nullptr);
   set_covs(g->tgt_cov, nullptr);
+  g->corr_n = 0;
   return DDLO_OK;
 }
 
 int ddlo_gicp_set_source_covariances(ddlo_gicp* g, ddlo_covs* v) {
   if (!g) return fail(DDLO_E_INVALID, "engine is null");
-  if (v && v->rt != g->rt) return fail(DDLO_E_INVALID, "covariances belong to another runtime");
+  if (v) DDLO_TRY(check_foreign(g, v->rt, v->shared, "covariance vector"));
   set_covs(g->src_cov, v);
   return DDLO_OK;
 }
 int ddlo_gicp_set_target_covariances(ddlo_gicp* g, ddlo_covs* v) {
   if (!g) return fail(DDLO_E_INVALID, "engine is null");
-  if (v && v->rt != g->rt) return fail(DDLO_E_INVALID, "covariances belong to another runtime");
+  if (v) DDLO_TRY(check_foreign(g, v->rt, v->shared, "covariance vector"));
   set_covs(g->tgt_cov, v);
   return DDLO_OK;
 }
@@ -790,6 +837,8 @@ int ddlo_gicp_swap_source_and_target(ddlo_gicp* g) {
   return DDLO_OK;
 }
 
+}  // extern "C"
+
 // covs_sorted[p] = covs[original index of the p-th point in Morton order]
 __global__ void __launch_bounds__(256) k_permute_covs(const float4* __restrict__ spts, int n, const double* __restrict__ covs,
                                                       double* __restrict__ covs_sorted) {
@@ -805,25 +854,22 @@ __global__ void __launch_bounds__(256) k_permute_covs(const float4* __restrict__
 
 // The kernels gather the matched target covariance by the match's position in the Morton order, so
 // that neighbouring source points (whose matches are neighbours too) touch the same DRAM pages.
-// The permuted copy is rebuilt only when the target cloud or its covariance vector changes.
-static int ensure_sorted_target_covs(ddlo_gicp* g) {
-  if (g->tcov_for_cloud == g->tgt && g->tcov_for_covs == g->tgt_cov && g->tcov_sorted) return DDLO_OK;
-  const size_t n = (size_t)g->tgt->n;
-  if (g->tcov_sorted_cap < n) {
-    if (g->tcov_sorted) {
-      DDLO_CUDA(cudaFreeAsync(g->tcov_sorted, g->rt->stream));
-      g->tcov_sorted = nullptr;
-      g->tcov_sorted_cap = 0;
-    }
-    const size_t cap = n + n / 4;
-    DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&g->tcov_sorted), cap * kCovStride * sizeof(double), g->rt->stream));
-    g->tcov_sorted_cap = cap;
+// The permuted copy lives on the covariance handle and is rebuilt only when it is paired with another
+// cloud; engines that share a target (S2S -> S2M hand-over, the lanes of a batch) share the copy.
+int ddlo::ensure_sorted_covs(ddlo_covs* v, ddlo_cloud* cloud, cudaStream_t st) {
+  if (v->sorted && v->sorted_for == cloud) return DDLO_OK;
+  if (v->shared) return fail(DDLO_E_NOT_READY, "shared covariances were prepared for another target cloud (ddlo_covs_share)");
+  const size_t n = (size_t)cloud->n;
+  if (v->sorted) {
+    DDLO_CUDA(cudaFreeAsync(v->sorted, st));
+    v->sorted = nullptr;
   }
-  k_permute_covs<<<(int)((n + 255) / 256), 256, 0, g->rt->stream>>>(g->tgt->spts, (int)n, g->tgt_cov->c, g->tcov_sorted);
-  g->rt->launches += 1;
+  cloud_set(v->sorted_for, nullptr);
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&v->sorted), n * kCovStride * sizeof(double), st));
+  k_permute_covs<<<(int)((n + 255) / 256), 256, 0, st>>>(cloud->spts, (int)n, v->c, v->sorted);
+  v->rt->launches += 1;
   DDLO_CUDA(cudaGetLastError());
-  set_cloud(g->tcov_for_cloud, g->tgt);  // retained: the key can not be recycled while cached
-  set_covs(g->tcov_for_covs, g->tgt_cov);
+  cloud_set(v->sorted_for, cloud);  // retained: the key can not be recycled while cached
   return DDLO_OK;
 }
 
@@ -863,13 +909,13 @@ static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, 
     if (covs_computed) *covs_computed = 1;
   }
   DDLO_TRY(ensure_workspace(g, g->src->n));
-  DDLO_TRY(ensure_sorted_target_covs(g));
+  DDLO_TRY(ensure_sorted_covs(g->tgt_cov, g->tgt, g->rt->stream));
   a->tgt = g->tgt->view;
   a->src_pts = g->src->pts;
   a->src_lattice = g->src->has_index ? g->src->lattice : nullptr;
   a->src_cov = g->src_cov->c;
   a->tgt_pts = g->tgt->pts;
-  a->tgt_cov = g->tcov_sorted;
+  a->tgt_cov = g->tgt_cov->sorted;
   a->ns = g->src->n;
   a->corr = g->corr;
   a->nn_seed = g->nn_seed;
@@ -885,7 +931,15 @@ static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, 
   a->rot_eps = g->p.rotation_epsilon;
   a->lm_init_lambda_factor = g->p.lm_init_lambda_factor;
   a->out = g->d_out;
-  a->blk_times = g->d_blk_times;
+  a->blk_times = nullptr;
+  a->stamps = nullptr;
+  if (g->profile) {
+    const size_t words = (size_t)8 * g->partial_stride * 8 + kStampCap + 1;
+    if (!g->d_prof) DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->d_prof), words * sizeof(unsigned long long)));
+    DDLO_CUDA(cudaMemsetAsync(g->d_prof, 0, words * sizeof(unsigned long long), g->rt->stream));
+    a->blk_times = g->d_prof;
+    a->stamps = g->d_prof + (size_t)8 * g->partial_stride * 8;
+  }
   a->dbg_visits = nullptr;
 #ifdef DDLO_VISIT_STATS
   if (g->d_dbg_n < g->src->n) {
@@ -900,19 +954,18 @@ static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, 
 
 static int align_blocks(const ddlo_gicp* g) { return gicp_blocks_for(g->src->n, g->rt->align_blocks_limit); }
 
-static int enqueue_align(ddlo_gicp* g, const float* guess16, int* covs_computed) {
+int ddlo::enqueue_align(ddlo_gicp* g, const float* guess16, int* covs_computed) {
   GicpArgs a;
   DDLO_TRY(prepare(g, true, covs_computed, &a));
   static const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   std::memcpy(a.guess, guess16 ? guess16 : I16, sizeof(a.guess));
   std::memset(a.T_step, 0, sizeof(a.T_step));
-  DDLO_CUDA(cudaMemsetAsync(g->d_blk_times, 0, (size_t)8 * g->partial_stride * 8 * sizeof(unsigned long long), g->rt->stream));
   DDLO_TRY(launch_align(g->rt, a, align_blocks(g)));
   g->corr_n = g->p.max_iterations > 0 ? g->src->n : g->corr_n;
   return DDLO_OK;
 }
 
-static void fill_result(const AlignOut* o, int covs_computed, ddlo_align_result* r) {
+void ddlo::fill_result(const AlignOut* o, int covs_computed, ddlo_align_result* r) {
   std::memcpy(r->final_transformation, o->final_transformation, sizeof(r->final_transformation));
   std::memcpy(r->final_hessian, o->final_hessian, sizeof(r->final_hessian));
   r->flags = o->flags | (covs_computed ? DDLO_FLAG_COVS_COMPUTED : 0);
@@ -922,6 +975,8 @@ static void fill_result(const AlignOut* o, int covs_computed, ddlo_align_result*
   r->final_error = o->final_error;
   r->lm_lambda = o->lm_lambda;
 }
+
+extern "C" {
 
 int ddlo_gicp_align_async(ddlo_gicp* g, const float* guess16) {
   if (!g) return fail(DDLO_E_INVALID, "engine is null");
@@ -960,20 +1015,26 @@ int ddlo_gicp_align_batch(ddlo_gicp* const* engines, int m, const float* guesses
   if (!rt) return fail(DDLO_E_INVALID, "null engine");
   for (int i = 0; i < m; ++i)
     if (!engines[i] || engines[i]->rt != rt) return fail(DDLO_E_INVALID, "batch engines must share one runtime");
+  DDLO_TRY(use_device(rt));
   DDLO_TRY(ensure_pinned(rt, sizeof(AlignOut) * (size_t)m));
   std::vector<int> covs_computed(m, 0);
   AlignOut* h = static_cast<AlignOut*>(rt->h_pinned);
-  for (int i = 0; i < m; ++i) {
-    DDLO_TRY(enqueue_align(engines[i], guesses16 ? guesses16 + 16 * (size_t)i : nullptr, &covs_computed[i]));
-    DDLO_CUDA(cudaMemcpyAsync(h + i, engines[i]->d_out, sizeof(AlignOut), cudaMemcpyDeviceToHost, rt->stream));
+  int rc = DDLO_OK, done = 0;
+  for (; done < m && rc == DDLO_OK; ++done) {
+    rc = enqueue_align(engines[done], guesses16 ? guesses16 + 16 * (size_t)done : nullptr, &covs_computed[done]);
+    if (rc == DDLO_OK && cudaMemcpyAsync(h + done, engines[done]->d_out, sizeof(AlignOut), cudaMemcpyDeviceToHost, rt->stream) != cudaSuccess)
+      rc = fail(DDLO_E_CUDA, "align_batch: result copy failed");
+    if (rc != DDLO_OK) break;
   }
-  DDLO_CUDA(cudaStreamSynchronize(rt->stream));
-  for (int i = 0; i < m; ++i) {
+  // whatever was enqueued completes before this call returns, also on failure
+  if (cudaStreamSynchronize(rt->stream) != cudaSuccess && rc == DDLO_OK) rc = fail(DDLO_E_CUDA, "align_batch: synchronisation failed");
+  for (int i = 0; i < done; ++i) {
     fill_result(h + i, covs_computed[i], results + i);
     std::memcpy(engines[i]->last_T, results[i].final_transformation, sizeof(engines[i]->last_T));
     engines[i]->has_last_T = true;
+    if (rc == DDLO_OK && (results[i].flags & DDLO_FLAG_NONFINITE)) rc = fail(DDLO_E_NONFINITE, "align_batch: an input cloud holds NaN or Inf coordinates");
   }
-  return DDLO_OK;
+  return rc;
 }
 
 int ddlo_gicp_aligned_cloud(ddlo_gicp* g, ddlo_cloud** out) {
@@ -1210,26 +1271,38 @@ int ddlo_gicp_get_residual_vectors(ddlo_gicp* g, const float* T16, float* out_xy
   return DDLO_OK;
 }
 
-// debugging aid (declared in ddlo_gicp_testing.h): the phase timeline block 0 recorded during the last
-// align; entries are tag << 56 | globaltimer ns.  Returns the number of entries written.
+// debugging aids (declared in ddlo_gicp_testing.h).  Profiling is off by default: the align kernel then takes no
+// timestamps and touches no profiling memory.
+int ddlo_gicp_debug_enable(ddlo_gicp* g, int on) {
+  if (!g) return fail(DDLO_E_INVALID, "engine is null");
+  g->profile = on != 0;
+  return DDLO_OK;
+}
+
+// the phase timeline block 0 recorded during the last align; entries are tag << 56 | globaltimer ns.
+// Returns the number of entries written.
 int ddlo_gicp_debug_timeline(ddlo_gicp* g, unsigned long long* out, int capacity) {
   if (!g || !out) return fail(DDLO_E_INVALID, "null argument");
-  AlignOut o;
-  if (read_out(g, &o) != DDLO_OK) return DDLO_E_CUDA;
-  const int n = std::min(std::min(o.n_stamps, 128), capacity);
-  for (int i = 0; i < n; ++i) out[i] = o.stamps[i];
+  if (!g->profile || !g->d_prof) return 0;
+  if (cudaStreamSynchronize(g->rt->stream) != cudaSuccess) return DDLO_E_CUDA;
+  std::vector<unsigned long long> h(kStampCap + 1);
+  if (cudaMemcpy(h.data(), g->d_prof + (size_t)8 * g->partial_stride * 8, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return DDLO_E_CUDA;
+  const int n = std::min(std::min((int)h[0], kStampCap), capacity);
+  for (int i = 0; i < n; ++i) out[i] = h[1 + i];
   return n;
 }
 
-// debugging aid: per-block phase times of the first 8 linearize passes of the last align,
-// out[pass][block][4] in ns; returns the number of blocks the kernel ran with.
+// per-block phase times of the first 8 linearize passes of the last align,
+// out[pass][block][8] in ns; returns the number of blocks the kernel ran with (0 when profiling is off).
 int ddlo_gicp_debug_block_times(ddlo_gicp* g, unsigned long long* out, int capacity_blocks) {
   if (!g || !out || !g->src) return fail(DDLO_E_INVALID, "null argument");
+  if (!g->profile || !g->d_prof) return 0;
   const int nb = align_blocks(g);
   if (capacity_blocks < nb) return fail(DDLO_E_SIZE, "capacity too small");
   DDLO_CUDA(cudaStreamSynchronize(g->rt->stream));
   for (int p = 0; p < 8; ++p)
-    DDLO_CUDA(cudaMemcpy(out + (size_t)p * capacity_blocks * 8, g->d_blk_times + (size_t)p * nb * 8, (size_t)nb * 8 * sizeof(unsigned long long),
+    DDLO_CUDA(cudaMemcpy(out + (size_t)p * capacity_blocks * 8, g->d_prof + (size_t)p * nb * 8, (size_t)nb * 8 * sizeof(unsigned long long),
                          cudaMemcpyDeviceToHost));
   return nb;
 }
@@ -1247,6 +1320,9 @@ int ddlo_gicp_debug_visits(ddlo_gicp* g, int* out, int capacity_points) {
   return 0;
 #endif
 }
+
+// size of the record one align copies back to the host (bench.py's d2h_bytes_per_step)
+int ddlo_align_d2h_bytes(void) { return (int)sizeof(AlignOut); }
 
 // ---- host-callable copies of the device math (CPU tests of the exact code the kernels run) --------------
 void ddlo_math_sym3_eig(const double* sym6, double* w3, double* V9) {

@@ -1,0 +1,280 @@
+// Batched registrations behind the C ABI (BASELINE config C5): many independent
+// (source, target, guess) units on ONE device, driven from C++.
+//
+// The reference has no batched entry point: OdomNode calls one engine from one callback
+// (src/odometry/odom.cc:745-793).  A single registration is 65k points of latency-bound work and leaves most
+// of a B200 idle, so the batch owns S LANES, each a runtime (CUDA stream) + a NanoGICP engine whose align kernel
+// is limited to num_SMs / S blocks: the cooperative launches of all lanes are resident side by side and the
+// small index kernels of one unit overlap the searches of another.  Units are dealt to the lanes round-robin
+// and every unit runs the whole path on its lane's stream without a host synchronisation:
+//     fresh source (and target) handles -> index build(s) -> covariances -> LM align -> result copy
+// `ddlo_batch_submit` only enqueues (optionally from a few C++ host threads, one group of lanes each);
+// `ddlo_batch_wait` is the one synchronisation of the batch.  Results are bit-identical to what a single
+// engine with the same align-block limit returns for the same unit (same kernels, same fixed-order sums).
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "engine.cuh"
+
+using namespace ddlo;
+
+struct ddlo_batch {
+  int device = 0;
+  int align_blocks = 0;
+  int host_threads = 1;
+  struct Lane {
+    ddlo_runtime* rt = nullptr;
+    ddlo_gicp* eng = nullptr;
+    bool has_shared_target = false;
+  };
+  std::vector<Lane> lanes;
+  std::vector<ddlo_cloud*> staged;  // inputs resident in HBM (owned by lane 0's runtime), index-less
+  bool staging_dirty = false;
+  ddlo_cloud* shared_tgt = nullptr;
+  ddlo_covs* shared_cov = nullptr;
+  // the submission in flight
+  AlignOut* h_out = nullptr;  // pinned, one slot per unit
+  size_t h_cap = 0;
+  std::vector<int> covs_computed;
+  std::vector<int> unit_rc;
+  ddlo_align_result* results = nullptr;
+  int pending = 0;
+};
+
+static void batch_free(ddlo_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  for (auto& l : b->lanes)
+    if (l.rt) cudaStreamSynchronize(l.rt->stream);
+  for (auto& l : b->lanes)
+    if (l.eng) ddlo_gicp_destroy(l.eng);
+  for (ddlo_cloud* c : b->staged) ddlo_cloud_release(c);
+  if (b->shared_cov) ddlo_covs_release(b->shared_cov);
+  if (b->shared_tgt) ddlo_cloud_release(b->shared_tgt);
+  for (auto& l : b->lanes)
+    if (l.rt) ddlo_runtime_destroy(l.rt);
+  if (b->h_out) cudaFreeHost(b->h_out);
+  delete b;
+}
+
+// one unit, enqueued on its lane's stream; nothing here waits for the device
+static int enqueue_unit(ddlo_batch* b, ddlo_batch::Lane& lane, const ddlo_batch_job& job, int slot) {
+  const int n_staged = (int)b->staged.size();
+  if (job.source < 0 || job.source >= n_staged) return fail(DDLO_E_INVALID, "batch job: unknown source cloud id");
+  if (job.target >= n_staged) return fail(DDLO_E_INVALID, "batch job: unknown target cloud id");
+  if (job.target < 0 && !b->shared_tgt) return fail(DDLO_E_NOT_READY, "batch job: target < 0 needs ddlo_batch_set_shared_target");
+  ddlo_gicp* g = lane.eng;
+  ddlo_cloud *src = nullptr, *tgt = nullptr;
+  // fresh handles: every unit builds its own indexes and covariances, nothing is cached from an earlier unit
+  DDLO_TRY(ddlo_cloud_create_from_device(lane.rt, b->staged[job.source]->pts, b->staged[job.source]->n, &src));
+  int rc = DDLO_OK;
+  if (job.target >= 0) rc = ddlo_cloud_create_from_device(lane.rt, b->staged[job.target]->pts, b->staged[job.target]->n, &tgt);
+  if (rc == DDLO_OK) rc = ddlo_gicp_clear_source(g);
+  if (rc == DDLO_OK) rc = ddlo_gicp_set_input_source(g, src, 1);
+  if (rc == DDLO_OK) {
+    if (job.target >= 0) {
+      rc = ddlo_gicp_set_input_target(g, tgt);
+      lane.has_shared_target = false;
+    } else if (!lane.has_shared_target) {
+      rc = ddlo_gicp_set_input_target(g, b->shared_tgt);
+      if (rc == DDLO_OK) rc = ddlo_gicp_set_target_covariances(g, b->shared_cov);
+      lane.has_shared_target = rc == DDLO_OK;
+    }
+  }
+  if (rc == DDLO_OK) rc = enqueue_align(g, job.guess, &b->covs_computed[slot]);
+  if (rc == DDLO_OK && cudaMemcpyAsync(b->h_out + slot, g->d_out, sizeof(AlignOut), cudaMemcpyDeviceToHost, lane.rt->stream) != cudaSuccess)
+    rc = fail(DDLO_E_CUDA, "batch: result copy failed");
+  ddlo_cloud_release(src);  // the engine holds them until the lane's next unit
+  if (tgt) ddlo_cloud_release(tgt);
+  return rc;
+}
+
+extern "C" {
+
+int ddlo_batch_create(int device, int n_lanes, int align_blocks_per_lane, int host_threads, ddlo_batch** out) {
+  if (!out) return fail(DDLO_E_INVALID, "out is null");
+  *out = nullptr;
+  if (n_lanes < 1 || n_lanes > 64 || host_threads < 0 || host_threads > 64) return fail(DDLO_E_INVALID, "batch: 1..64 lanes, 0..64 host threads");
+  ddlo_batch* b = new (std::nothrow) ddlo_batch();
+  if (!b) return fail(DDLO_E_INVALID, "out of host memory");
+  b->device = device;
+  b->host_threads = std::max(1, std::min(host_threads, n_lanes));
+  b->lanes.resize(n_lanes);
+  for (auto& l : b->lanes) {
+    int rc = ddlo_runtime_create(device, &l.rt);
+    if (rc == DDLO_OK) rc = ddlo_gicp_create(l.rt, &l.eng);
+    if (rc != DDLO_OK) {
+      const std::string why = ddlo_last_error();
+      batch_free(b);
+      return fail(rc, why);
+    }
+  }
+  const int sms = b->lanes[0].rt->num_sms;
+  b->align_blocks = align_blocks_per_lane > 0 ? align_blocks_per_lane : std::max(1, sms / n_lanes);
+  for (auto& l : b->lanes) ddlo_runtime_set_align_blocks(l.rt, b->align_blocks);
+  b->align_blocks = b->lanes[0].rt->align_blocks_limit;
+  *out = b;
+  return DDLO_OK;
+}
+
+int ddlo_batch_destroy(ddlo_batch* b) {
+  batch_free(b);
+  return DDLO_OK;
+}
+
+int ddlo_batch_info(const ddlo_batch* b, int* n_lanes, int* align_blocks_per_lane, int* host_threads) {
+  if (!b) return fail(DDLO_E_INVALID, "batch is null");
+  if (n_lanes) *n_lanes = (int)b->lanes.size();
+  if (align_blocks_per_lane) *align_blocks_per_lane = b->align_blocks;
+  if (host_threads) *host_threads = b->host_threads;
+  return DDLO_OK;
+}
+
+int ddlo_batch_set_params(ddlo_batch* b, const ddlo_params* p) {
+  if (!b || !p) return fail(DDLO_E_INVALID, "null argument");
+  if (b->pending) return fail(DDLO_E_NOT_READY, "batch: a submission is in flight");
+  for (auto& l : b->lanes) DDLO_TRY(ddlo_gicp_set_params(l.eng, p));
+  return DDLO_OK;
+}
+
+int ddlo_batch_stage_cloud(ddlo_batch* b, const float* xyz, int n, int stride_bytes, int* id) {
+  if (!b || !id) return fail(DDLO_E_INVALID, "null argument");
+  if (b->pending) return fail(DDLO_E_NOT_READY, "batch: a submission is in flight");
+  ddlo_cloud* c = nullptr;
+  DDLO_TRY(ddlo_cloud_create(b->lanes[0].rt, xyz, n, stride_bytes, &c));
+  b->staged.push_back(c);
+  b->staging_dirty = true;
+  *id = (int)b->staged.size() - 1;
+  return DDLO_OK;
+}
+
+int ddlo_batch_staged_count(const ddlo_batch* b, int* count) {
+  if (!b || !count) return fail(DDLO_E_INVALID, "null argument");
+  *count = (int)b->staged.size();
+  return DDLO_OK;
+}
+
+int ddlo_batch_set_shared_target(ddlo_batch* b, int cloud_id, const double* covs_mat4x4) {
+  if (!b) return fail(DDLO_E_INVALID, "batch is null");
+  if (b->pending) return fail(DDLO_E_NOT_READY, "batch: a submission is in flight");
+  if (cloud_id < 0 || cloud_id >= (int)b->staged.size()) return fail(DDLO_E_INVALID, "batch: unknown cloud id");
+  ddlo_runtime* rt = b->lanes[0].rt;
+  for (auto& l : b->lanes) {  // nobody may still read the previous shared target
+    DDLO_TRY(ddlo_runtime_synchronize(l.rt));
+    if (l.has_shared_target) DDLO_TRY(ddlo_gicp_clear_target(l.eng));
+    l.has_shared_target = false;
+  }
+  if (b->shared_cov) ddlo_covs_release(b->shared_cov);
+  if (b->shared_tgt) ddlo_cloud_release(b->shared_tgt);
+  b->shared_cov = nullptr, b->shared_tgt = nullptr;
+  ddlo_cloud* t = nullptr;
+  ddlo_covs* v = nullptr;
+  DDLO_TRY(ddlo_cloud_create_from_device(rt, b->staged[cloud_id]->pts, b->staged[cloud_id]->n, &t));
+  int rc = ddlo_cloud_build_index(t);
+  if (rc == DDLO_OK) {
+    ddlo_params p;
+    ddlo_gicp_get_params(b->lanes[0].eng, &p);
+    rc = covs_mat4x4 ? ddlo_covs_from_host(rt, covs_mat4x4, t->n, &v) : ddlo_covs_compute(t, p.k_correspondences, p.regularization_method, &v);
+  }
+  if (rc == DDLO_OK) rc = ddlo_cloud_share(t);
+  if (rc == DDLO_OK) rc = ddlo_covs_share(v, t);
+  if (rc != DDLO_OK) {
+    if (v) ddlo_covs_release(v);
+    ddlo_cloud_release(t);
+    return rc;
+  }
+  b->shared_tgt = t;
+  b->shared_cov = v;
+  return DDLO_OK;
+}
+
+int ddlo_batch_submit(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_result* results) {
+  if (!b || m < 0 || (m > 0 && (!jobs || !results))) return fail(DDLO_E_INVALID, "null argument");
+  if (b->pending) return fail(DDLO_E_NOT_READY, "batch: the previous submission has not been waited for");
+  if (m == 0) return DDLO_OK;
+  DDLO_CUDA(cudaSetDevice(b->device));
+  if (b->staging_dirty) {  // uploads run on lane 0's stream; every lane reads them
+    DDLO_CUDA(cudaStreamSynchronize(b->lanes[0].rt->stream));
+    b->staging_dirty = false;
+  }
+  if (b->h_cap < (size_t)m) {
+    if (b->h_out) DDLO_CUDA(cudaFreeHost(b->h_out));
+    b->h_out = nullptr, b->h_cap = 0;
+    const size_t cap = std::max<size_t>(m, 64);
+    DDLO_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_out), cap * sizeof(AlignOut)));
+    b->h_cap = cap;
+  }
+  b->covs_computed.assign(m, 0);
+  b->unit_rc.assign(m, DDLO_OK);
+  b->results = results;
+  b->pending = m;
+  const int S = (int)b->lanes.size();
+  const int T = std::min(b->host_threads, S);
+  std::vector<std::string> errs(T);
+  auto drive = [&](int t) {
+    cudaSetDevice(b->device);
+    // thread t owns the lanes t, t + T, ...; unit i runs on lane i % S, units of one lane stay in submission order
+    for (int i = 0; i < m; ++i) {
+      const int lane = i % S;
+      if (lane % T != t) continue;
+      const int rc = enqueue_unit(b, b->lanes[lane], jobs[i], i);
+      b->unit_rc[i] = rc;
+      if (rc != DDLO_OK && errs[t].empty()) errs[t] = ddlo_last_error();
+    }
+  };
+  if (T <= 1) {
+    drive(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(drive, t);
+    drive(0);
+    for (auto& x : th) x.join();
+  }
+  for (int i = 0; i < m; ++i)
+    if (b->unit_rc[i] != DDLO_OK) {
+      for (int t = 0; t < T; ++t)
+        if (!errs[t].empty()) return fail(b->unit_rc[i], errs[t]);  // ddlo_batch_wait still has to be called
+      return fail(b->unit_rc[i], "batch: a unit could not be enqueued");
+    }
+  return DDLO_OK;
+}
+
+int ddlo_batch_wait(ddlo_batch* b) {
+  if (!b) return fail(DDLO_E_INVALID, "batch is null");
+  if (!b->pending) return DDLO_OK;
+  DDLO_CUDA(cudaSetDevice(b->device));
+  int rc = DDLO_OK;
+  for (auto& l : b->lanes)
+    if (cudaStreamSynchronize(l.rt->stream) != cudaSuccess && rc == DDLO_OK) rc = fail(DDLO_E_CUDA, "batch: synchronisation failed");
+  const int m = b->pending;
+  b->pending = 0;
+  for (int i = 0; i < m; ++i) {
+    if (b->unit_rc[i] != DDLO_OK) {
+      std::memset(b->results + i, 0, sizeof(ddlo_align_result));
+      if (rc == DDLO_OK) rc = fail(b->unit_rc[i], "batch: a unit could not be enqueued (see the status of ddlo_batch_submit)");
+      continue;
+    }
+    fill_result(b->h_out + i, b->covs_computed[i], b->results + i);
+    if (rc == DDLO_OK && (b->results[i].flags & DDLO_FLAG_NONFINITE)) rc = fail(DDLO_E_NONFINITE, "batch: an input cloud holds NaN or Inf coordinates");
+  }
+  b->results = nullptr;
+  return rc;
+}
+
+int ddlo_batch_run(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_result* results) {
+  const int rc = ddlo_batch_submit(b, jobs, m, results);
+  const int rw = ddlo_batch_wait(b);
+  return rc != DDLO_OK ? rc : rw;
+}
+
+int ddlo_batch_launch_count(ddlo_batch* b, long long* count) {
+  if (!b || !count) return fail(DDLO_E_INVALID, "null argument");
+  long long n = 0;
+  for (auto& l : b->lanes) n += l.rt->launches;
+  *count = n;
+  return DDLO_OK;
+}
+
+}  // extern "C"

@@ -109,6 +109,9 @@ struct ddlo_cloud {
   int* node_of_point = nullptr;
   float* lattice = nullptr;  // 4 floats + the node count (int) behind them
   ddlo::IndexView view{};
+  // ddlo_cloud_share: the handle's work is complete and synchronised; engines of other runtimes (streams) of the
+  // same device may read it, nobody may add an index to it any more
+  bool shared = false;
 };
 
 struct ddlo_covs {
@@ -116,4 +119,9 @@ struct ddlo_covs {
   ddlo_runtime* rt = nullptr;
   int n = 0;
   double* c = nullptr;  // n * 6
+  // the same covariances permuted into the Morton order of one cloud's index (target role: the align kernel gathers
+  // the matched target covariance by Morton position); cached here, keyed by the retained cloud handle
+  double* sorted = nullptr;
+  ddlo_cloud* sorted_for = nullptr;
+  bool shared = false;  // see ddlo_cloud::shared
 };

@@ -351,7 +351,7 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
     // ---- phase B: one thread per point of the round
     if (threadIdx.x < nround) {
       const int i = dl.point(base + threadIdx.x);
-      const unsigned long long t0 = globaltimer_ns();
+      const unsigned long long t0 = bt ? globaltimer_ns() : 0ull;
       lin_point(a, sm.lm, i < a.ns, i, sm.nn_d[threadIdx.x], sm.nn_idx[threadIdx.x], sm.nn_pos[threadIdx.x], sm.contrib + threadIdx.x);
       if (bt && lane == 0) {
         const unsigned long long dt = globaltimer_ns() - t0;
@@ -458,12 +458,12 @@ __device__ __noinline__ void lm_solve(LmShared& s, double lambda) {
   for (int i = 0; i < 3; ++i) s.delta.t[i] = s.d[3 + i];
 }
 
-// phase tags of the timeline block 0 leaves in AlignOut::stamps
+// phase tags of the timeline block 0 leaves in GicpArgs::stamps (profiling runs only)
 enum { kTagSearchDone = 10, kTagStart = 1, kTagLinDone = 2, kTagLinSynced = 3, kTagLinSummed = 4, kTagSolved = 5, kTagErrDone = 6, kTagErrSynced = 7, kTagDecided = 8, kTagEnd = 9 };
 #define DDLO_STAMP(tag)                                                                                         \
   do {                                                                                                          \
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n_stamps < 128)                                                  \
-      a.out->stamps[n_stamps++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00ffffffffffffffull); \
+    if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0 && n_stamps < 128)                                      \
+      a.stamps[1 + n_stamps++] = ((unsigned long long)(tag) << 56) | (globaltimer_ns() & 0x00ffffffffffffffull); \
   } while (0)
 
 __global__ void __launch_bounds__(kAlignThreads, kAlignBlocksPerSM) k_align(const GicpArgs a) {
@@ -507,8 +507,8 @@ __global__ void __launch_bounds__(kAlignThreads, kAlignBlocksPerSM) k_align(cons
       bt[1] = sm.t_search;
       bt[2] = globaltimer_ns();
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n_stamps < 128)
-      a.out->stamps[n_stamps++] = ((unsigned long long)kTagSearchDone << 56) | (sm.t_search & 0x00ffffffffffffffull);
+    if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0 && n_stamps < 128)
+      a.stamps[1 + n_stamps++] = ((unsigned long long)kTagSearchDone << 56) | (sm.t_search & 0x00ffffffffffffffull);
     DDLO_STAMP(kTagLinDone);
     grid.sync();
     if (bt && threadIdx.x == 0) bt[3] = globaltimer_ns();
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(kAlignThreads, kAlignBlocksPerSM) k_align(cons
     o->final_error = s.final_error;
     o->lm_lambda = s.lambda;
     DDLO_STAMP(kTagEnd);
-    o->n_stamps = n_stamps;
+    if (a.stamps) a.stamps[0] = (unsigned long long)n_stamps;
   }
 }
 

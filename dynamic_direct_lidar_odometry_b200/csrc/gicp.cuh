@@ -17,9 +17,6 @@ struct AlignOut {
   double final_error;
   double lm_lambda;
   double sums[kNumSums];  // stepwise hooks: H upper / b / error of the last reduction
-  // phase timeline of the last align (block 0, %globaltimer ns): tag << 56 | time
-  unsigned long long stamps[128];
-  int n_stamps;
 };
 
 struct GicpArgs {
@@ -45,7 +42,9 @@ struct GicpArgs {
   double T_step[16];        // stepwise hooks: transform to evaluate at (column-major)
   AlignOut* out;
   int4* dbg_visits;         // DDLO_VISIT_STATS builds only: [pass < 4][ns] {node visits, leaf scans, warp steps, 0}
-  unsigned long long* blk_times;  // profiling: [pass < 8][block][8] %globaltimer at pass start / search done / phase B done / after grid sync, then max and (2^32-1 - min) lin_point duration
+  // profiling, both null unless ddlo_gicp_debug_enable was called:
+  unsigned long long* blk_times;  // [pass < 8][block][8] %globaltimer at pass start / search done / phase B done / after grid sync, then max and (2^32-1 - min) lin_point duration
+  unsigned long long* stamps;     // [0] = count, then the phase timeline of block 0: tag << 56 | %globaltimer ns
 };
 
 int gicp_max_coop_blocks(int device, int* blocks_per_sm);

@@ -13,6 +13,7 @@ ABI's column-major (Eigen) layout here.  Covariances are (n, 4, 4) float64 (`Eig
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Sequence
 
 import numpy as np
@@ -21,7 +22,7 @@ from . import binding as B
 from .binding import (FLAG_CONVERGED, FLAG_COVS_COMPUTED, FLAG_LM_FAILED, OPT_GAUSS_NEWTON, OPT_LEVENBERG_MARQUARDT, REG_FROBENIUS,
                       REG_MIN_EIG, REG_NONE, REG_NORMALIZED_MIN_EIG, REG_PLANE, DdloError)
 
-__all__ = ["Runtime", "PointCloud", "Covariances", "NanoGICP", "AlignInfo", "DdloError", "REG_NONE", "REG_MIN_EIG",
+__all__ = ["Runtime", "PointCloud", "Covariances", "NanoGICP", "AlignInfo", "Batch", "DdloError", "REG_NONE", "REG_MIN_EIG",
            "REG_NORMALIZED_MIN_EIG", "REG_PLANE", "REG_FROBENIUS", "OPT_GAUSS_NEWTON", "OPT_LEVENBERG_MARQUARDT"]
 
 
@@ -84,11 +85,17 @@ def pinned_array(shape, dtype=np.float32) -> np.ndarray:
     B.check(B.load().ddlo_host_alloc(nbytes, C.byref(p)))
     buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
-    _PINNED[id(buf)] = (buf, p)
+    # the page-locked block lives exactly as long as some array still views it: ddlo_host_free runs when the ctypes
+    # buffer (the base object of every view) is collected
+    weakref.finalize(buf, _free_pinned, p.value)
     return arr
 
 
-_PINNED = {}
+def _free_pinned(address: int) -> None:
+    try:
+        B.load().ddlo_host_free(C.c_void_p(address))
+    except Exception:  # interpreter shutdown
+        pass
 
 
 class PointCloud:
@@ -122,6 +129,11 @@ class PointCloud:
         out = np.empty((self.size(), 4), dtype=np.float32)
         B.check(B.load().ddlo_cloud_download(self._h, B.ptr(out)))
         return out
+
+    def share(self) -> "PointCloud":
+        """ddlo_cloud_share: index built, owner stream synchronised, handle usable from other runtimes of the device"""
+        B.check(B.load().ddlo_cloud_share(self._h))
+        return self
 
     def build_index(self) -> "PointCloud":
         B.check(B.load().ddlo_cloud_build_index(self._h))
@@ -195,6 +207,11 @@ class Covariances:
         h = C.c_void_p()
         B.check(B.load().ddlo_covs_compute(cloud._h, k, method, C.byref(h)))
         return Covariances(cloud.rt, _handle=h)
+
+    def share(self, target: Optional[PointCloud] = None) -> "Covariances":
+        """ddlo_covs_share: usable from other runtimes of the device; `target` = the cloud these are the target covariances of"""
+        B.check(B.load().ddlo_covs_share(self._h, target._h if target is not None else None))
+        return self
 
     def size(self) -> int:
         n = C.c_int()
@@ -404,6 +421,10 @@ class NanoGICP:
 
     TIMELINE_TAGS = {1: "start", 2: "lin_done", 3: "lin_synced", 4: "lin_summed", 5: "solved", 6: "err_done", 7: "err_synced", 8: "decided", 9: "end", 10: "search_done"}
 
+    def debug_enable(self, on: bool = True):
+        """profiling of the align kernel (timeline, block times) is off unless enabled here"""
+        B.check(B.load().ddlo_gicp_debug_enable(self._g, int(on)))
+
     def debug_timeline(self):
         """[(tag, microseconds since kernel start)] recorded by block 0 during the last align (profiling aid)."""
         buf = np.zeros(128, dtype=np.uint64)
@@ -518,3 +539,84 @@ def align_batch(engines: Sequence[NanoGICP], guesses=None):
     for e, o in zip(engines, out):
         e._last = o
     return out
+
+
+class Batch:
+    """ddlo_batch_*: many independent registrations on one device, driven from C++ (BASELINE config C5).
+
+    S lanes (stream + engine each, align kernels limited to num_SMs / S blocks) work through the submitted units
+    concurrently; Python only hands over the job table.  Units are (source id, target id or -1, guess) over clouds
+    staged in HBM with `stage`."""
+
+    def __init__(self, device: int = 0, lanes: int = 4, align_blocks: int = 0, host_threads: int = 1):
+        self._b = C.c_void_p()
+        B.check(B.load().ddlo_batch_create(device, lanes, align_blocks, host_threads, C.byref(self._b)))
+        self.device = device
+        a, c, t = C.c_int(), C.c_int(), C.c_int()
+        B.check(B.load().ddlo_batch_info(self._b, C.byref(a), C.byref(c), C.byref(t)))
+        self.lanes, self.align_blocks, self.host_threads = a.value, c.value, t.value
+        self._res = None
+        self._m = 0
+
+    def close(self):
+        if getattr(self, "_b", None):
+            B.load().ddlo_batch_destroy(self._b)
+            self._b = None
+
+    __del__ = close
+
+    def set_params(self, **kw):
+        p = B.Params()
+        B.check(B.load().ddlo_params_default(C.byref(p)))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise TypeError(f"unknown engine parameter {k}")
+            setattr(p, k, v)
+        B.check(B.load().ddlo_batch_set_params(self._b, C.byref(p)))
+
+    def stage(self, points) -> int:
+        p = np.ascontiguousarray(points, dtype=np.float32)
+        if p.ndim != 2 or p.shape[1] < 3:
+            raise ValueError("points must be (n, >=3) float32")
+        i = C.c_int()
+        B.check(B.load().ddlo_batch_stage_cloud(self._b, B.ptr(p), p.shape[0], p.strides[0] if p.shape[0] else 4 * p.shape[1], C.byref(i)))
+        return i.value
+
+    def set_shared_target(self, cloud_id: int, covariances=None):
+        m = None if covariances is None else np.ascontiguousarray(covariances, dtype=np.float64)
+        B.check(B.load().ddlo_batch_set_shared_target(self._b, cloud_id, None if m is None else B.ptr(m)))
+
+    @staticmethod
+    def jobs(units) -> "C.Array":
+        """units: iterable of (source id, target id or -1, guess 4x4 or None) -> ddlo_batch_job[]"""
+        units = list(units)
+        arr = (B.BatchJob * len(units))()
+        eye = np.eye(4, dtype=np.float32)
+        for j, (s, t, g) in zip(arr, units):
+            j.source, j.target = int(s), int(t)
+            gm = eye if g is None else np.asarray(g, dtype=np.float32)
+            j.guess[:] = np.ascontiguousarray(gm.T).ravel().tolist()
+        return arr
+
+    def submit(self, jobs) -> None:
+        if not isinstance(jobs, C.Array):
+            jobs = self.jobs(jobs)
+        self._m = len(jobs)
+        self._res = (B.AlignResult * max(self._m, 1))()
+        self._jobs = jobs
+        B.check(B.load().ddlo_batch_submit(self._b, jobs, self._m, self._res))
+
+    def wait(self, raw: bool = False):
+        B.check(B.load().ddlo_batch_wait(self._b))
+        if raw:
+            return self._res
+        return [AlignInfo(self._res[i]) for i in range(self._m)]
+
+    def run(self, jobs, raw: bool = False):
+        self.submit(jobs)
+        return self.wait(raw)
+
+    def launch_count(self) -> int:
+        n = C.c_longlong()
+        B.check(B.load().ddlo_batch_launch_count(self._b, C.byref(n)))
+        return n.value

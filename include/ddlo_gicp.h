@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DDLO_ABI_VERSION 1
+#define DDLO_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -141,6 +141,13 @@ int ddlo_cloud_knn(ddlo_cloud* c, const float* queries, int nq, int qstride_byte
 int ddlo_cloud_transform(ddlo_cloud* c, const float* T16, ddlo_cloud** out);
 /* concatenation of m clouds (device-side `*submap_cloud_ += *keyframe`, odom.cc:1298-1313) */
 int ddlo_cloud_concat(ddlo_runtime* rt, ddlo_cloud* const* parts, int m, ddlo_cloud** out);
+
+/* Handles are bound to their runtime (stream).  ddlo_cloud_share builds the index if missing, synchronises the owner's
+ * stream once and marks the cloud immutable; engines of OTHER runtimes of the same device may then take it as input
+ * (the lanes of a batch share one submap this way).  ddlo_covs_share does the same for a covariance vector and, given
+ * the cloud it is the target covariances of, prepares the Morton-ordered copy the align kernel reads. */
+int ddlo_cloud_share(ddlo_cloud* c);
+int ddlo_covs_share(ddlo_covs* v, ddlo_cloud* target /* or NULL */);
 
 /* Scan preprocessing on the device (the filters OdomNode::preprocessPoints runs right
  * before this path, odom.cc:442-478, and on every new keyframe, odom.cc:494-499, 1133-1137).
@@ -279,9 +286,42 @@ int ddlo_gicp_segment_scan(ddlo_gicp* g, const ddlo_segmentation_params* params,
 /* getResiduals(std::vector<Eigen::Vector3f>&, trans) (:199-222) */
 int ddlo_gicp_get_residual_vectors(ddlo_gicp* g, const float* T16, float* out_xyz, int capacity);
 
-/* Batched registrations (BASELINE.json config C5): m independent engines of one runtime, aligned
- * back to back on the device with a single host synchronisation at the end. */
+/* m engines of one runtime aligned back to back on that runtime's stream with a single host synchronisation at the
+ * end (kept from ABI 1; the batched workload proper is ddlo_batch_* below). */
 int ddlo_gicp_align_batch(ddlo_gicp* const* engines, int m, const float* guesses16 /* m*16 or NULL */, ddlo_align_result* results);
+
+/* ---- batched registrations: BASELINE.json config C5 ------------------------------------------
+ * The reference has no batched entry point (OdomNode drives one engine from one callback, odom.cc:745-793); this is
+ * the contract of SURVEY.md §8e: many independent (source, target, guess) units on one device, no collective.
+ * A batch owns S lanes = S runtimes (CUDA streams) + S engines; each lane's align kernel is limited to
+ * align_blocks_per_lane SMs (0: num_SMs / S) so that the lanes' cooperative launches are resident side by side.
+ * Units are dealt to the lanes round-robin and run entirely on the device: fresh handles, index build(s),
+ * covariances, LM align, result copy; the host only enqueues.  host_threads C++ threads (0 or 1: the calling thread)
+ * share the enqueueing, each owning a group of lanes.  One process per GPU (or one batch per device in one process)
+ * shards a workload over several GPUs; there is nothing to exchange between them. */
+typedef struct ddlo_batch ddlo_batch;
+typedef struct ddlo_batch_job {
+  int source;      /* id of a staged cloud */
+  int target;      /* id of a staged cloud (scan-to-scan unit: its index and covariances are built per unit), or -1 = the
+                      batch's shared target (scan-to-map unit) */
+  float guess[16]; /* column-major initial guess, as align(output, guess) */
+} ddlo_batch_job;
+int ddlo_batch_create(int device, int n_lanes, int align_blocks_per_lane, int host_threads, ddlo_batch** out);
+int ddlo_batch_destroy(ddlo_batch* b);
+int ddlo_batch_info(const ddlo_batch* b, int* n_lanes, int* align_blocks_per_lane, int* host_threads);
+int ddlo_batch_set_params(ddlo_batch* b, const ddlo_params* p); /* all lanes */
+/* Stage an input cloud in HBM (as ddlo_cloud_create; SURVEY.md §8d: inputs are pre-staged per GPU before timing). */
+int ddlo_batch_stage_cloud(ddlo_batch* b, const float* xyz, int n, int stride_bytes, int* id);
+int ddlo_batch_staged_count(const ddlo_batch* b, int* count);
+/* One target for all units with target == -1 (a keyframe submap): index and covariances are prepared once
+ * (covs_mat4x4 == NULL: computed with the batch's k and regularisation) and shared by the lanes. */
+int ddlo_batch_set_shared_target(ddlo_batch* b, int cloud_id, const double* covs_mat4x4);
+/* Enqueue m units; returns once everything is enqueued.  results[i] (HOST, m entries) is valid after
+ * ddlo_batch_wait, which synchronises all lanes and returns the first error.  _run = submit + wait. */
+int ddlo_batch_submit(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_result* results);
+int ddlo_batch_wait(ddlo_batch* b);
+int ddlo_batch_run(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_result* results);
+int ddlo_batch_launch_count(ddlo_batch* b, long long* count); /* kernels launched by all lanes since creation */
 
 #ifdef __cplusplus
 }

@@ -15,8 +15,13 @@ void ddlo_math_ldlt6_solve(const double* A36, const double* rhs6, double* x6); /
 void ddlo_math_ldlt6_solve_fast(const double* A36, const double* rhs6, double* x6); /* register-resident SPD path of the kernel */
 void ddlo_math_so3_exp(const double* omega3, double* R9);                       /* gicp/so3.hpp:101-124 */
 void ddlo_math_sym3_inverse(const double* sym6, double* out6);
-/* phase timeline of the last align (block 0): entries are tag << 56 | %globaltimer ns; returns the count */
 struct ddlo_gicp;
+/* bytes of the result record one align copies device -> host */
+int ddlo_align_d2h_bytes(void);
+/* Profiling of the align kernel is OFF by default (no timestamps taken, no profiling memory touched); on != 0 makes
+ * the following aligns of this engine record the two tables below. */
+int ddlo_gicp_debug_enable(struct ddlo_gicp* g, int on);
+/* phase timeline of the last align (block 0): entries are tag << 56 | %globaltimer ns; returns the count */
 /* per-block phase times (ns) of the first 8 linearize passes: out[pass][capacity_blocks][8]; returns block count */
 int ddlo_gicp_debug_block_times(struct ddlo_gicp* g, unsigned long long* out, int capacity_blocks);
 int ddlo_gicp_debug_timeline(struct ddlo_gicp* g, unsigned long long* out, int capacity);

@@ -12,6 +12,7 @@ reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 src, tgt, guess = synth.workload_c2()
 rt = ng.Runtime(0)
 eng = ng.NanoGICP(rt)
+eng.debug_enable(True)  # the kernel records its phase timeline only when asked to
 target = ng.PointCloud(rt, tgt)
 eng.setInputTarget(target)
 eng.calculateTargetCovariances()

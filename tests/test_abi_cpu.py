@@ -22,7 +22,7 @@ def test_exports_every_declared_symbol(ddlo_lib):
     assert len(names) > 55
     missing = [n for n in names if not hasattr(ddlo_lib, n)]
     assert not missing, missing
-    assert ddlo_lib.ddlo_abi_version() == 1
+    assert ddlo_lib.ddlo_abi_version() == 2
 
 
 def test_binding_covers_header():

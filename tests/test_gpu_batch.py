@@ -1,0 +1,149 @@
+"""The C++ batch driver (ddlo_batch_*, BASELINE config C5) and handle sharing between runtimes.  B200 box."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from dynamic_direct_lidar_odometry_b200 import binding as B
+from dynamic_direct_lidar_odometry_b200 import nano_gicp as ng
+from dynamic_direct_lidar_odometry_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scans():
+    w = synth.make_world()
+    return [synth.scan(f, 16, 256, w) for f in range(7)]
+
+
+def single_align(device, blocks, src, tgt, guess=None, shared=None):
+    rt = ng.Runtime(device)
+    rt.set_align_blocks(blocks)
+    g = ng.NanoGICP(rt)
+    g.setInputSource(ng.PointCloud(rt, src))
+    if shared is None:
+        g.setInputTarget(ng.PointCloud(rt, tgt))
+    else:
+        g.setInputTarget(shared[0])
+        g.setTargetCovariances(shared[1])
+    r = g.align(guess)
+    del g
+    rt.close()
+    return r
+
+
+def test_batch_s2s_bit_identical_to_single_align(scans):
+    """every unit of a batch returns the pose, Hessian and iteration counts a single ddlo_gicp_align gives with the
+    same align-block limit - bit for bit, whatever lane it ran on"""
+    b = ng.Batch(0, lanes=3, host_threads=2)
+    ids = [b.stage(s) for s in scans]
+    rng = np.random.default_rng(3)
+    units = []
+    for u in range(11):
+        s = u % 6
+        guess = np.eye(4, dtype=np.float32)
+        guess[:3, 3] = rng.normal(0, 0.02, 3)
+        units.append((ids[s + 1], ids[s], guess))
+    res = b.run(units)
+    res2 = b.run(units)  # lanes are reused: nothing of the first run may leak into the second
+    for (s, t, guess), r, r2 in zip(units, res, res2):
+        ref = single_align(0, b.align_blocks, scans[s], scans[t], guess)
+        assert r.converged and ref.converged
+        assert (r.iterations, r.n_linearize, r.n_compute_error) == (ref.iterations, ref.n_linearize, ref.n_compute_error)
+        assert np.array_equal(r.T, ref.T) and np.array_equal(r.hessian, ref.hessian) and r.final_error == ref.final_error
+        assert r.covs_computed
+        assert np.array_equal(r.T, r2.T) and np.array_equal(r.hessian, r2.hessian)
+    assert b.launch_count() > 0
+    b.close()
+
+
+def test_batch_shared_target_matches_single_engine(scans):
+    """scan-to-map units (target = -1) against one submap whose index and covariances are shared by all lanes"""
+    submap = np.concatenate([synth.transform(scans[f], synth.pose(f)) for f in (0, 2, 4)])
+    b = ng.Batch(0, lanes=4, host_threads=1)
+    sub_id = b.stage(submap)
+    ids = [b.stage(scans[f]) for f in (1, 3, 5)]
+    b.set_shared_target(sub_id)
+    guesses = [synth.pose(f).astype(np.float32) for f in (1, 3, 5)]
+    units = [(ids[i % 3], -1, guesses[i % 3]) for i in range(9)]
+    res = b.run(units)
+    # the same on one ordinary engine
+    rt = ng.Runtime(0)
+    tgt = ng.PointCloud(rt, submap).share()
+    cov = ng.Covariances.compute(tgt, 20).share(tgt)
+    for i, r in enumerate(res):
+        ref = single_align(0, b.align_blocks, scans[(1, 3, 5)[i % 3]], None, guesses[i % 3], shared=(tgt, cov))
+        assert r.converged == ref.converged and r.iterations == ref.iterations
+        assert np.array_equal(r.T, ref.T) and np.array_equal(r.hessian, ref.hessian)
+        assert r.covs_computed  # source covariances are computed inside the unit
+    # mixing unit kinds on the same lanes: S2S after S2M and back
+    mixed = [(ids[0], -1, guesses[0]), (ids[1], ids[0], None), (ids[2], -1, guesses[2]), (ids[0], ids[2], None), (ids[1], -1, guesses[1])]
+    rm = b.run(mixed)
+    assert np.array_equal(rm[0].T, res[0].T) and np.array_equal(rm[2].T, res[2].T) and np.array_equal(rm[4].T, res[1].T)
+    del tgt, cov
+    rt.close()
+    b.close()
+
+
+def test_batch_errors(scans):
+    b = ng.Batch(0, lanes=2)
+    i0 = b.stage(scans[0])
+    with pytest.raises(ng.DdloError) as e:
+        b.run([(i0, -1, None)])  # no shared target
+    assert e.value.code == -5
+    with pytest.raises(ng.DdloError) as e:
+        b.run([(7, i0, None)])
+    assert e.value.code == -1
+    r = b.run([(i0, i0, None)])  # still usable afterwards
+    assert r[0].converged
+    assert b.run([]) == []
+    b.close()
+    with pytest.raises(ng.DdloError):
+        ng.Batch(0, lanes=0)
+
+
+def test_foreign_handles_need_share(rt, scans):
+    """a cloud of another runtime is refused until it has been shared; shared handles are read-only inputs"""
+    rt2 = ng.Runtime(0)
+    c = ng.PointCloud(rt2, scans[0])
+    g = ng.NanoGICP(rt)
+    with pytest.raises(ng.DdloError) as e:
+        g.setInputTarget(c)
+    assert e.value.code == -1
+    c.share()
+    g.setInputTarget(c)
+    g.setInputSource(ng.PointCloud(rt, scans[1]))
+    r = g.align()
+    g2 = ng.NanoGICP(rt2)
+    g2.setInputTarget(c)
+    g2.setInputSource(ng.PointCloud(rt2, scans[1]))
+    r2 = g2.align()
+    assert r.converged and np.array_equal(r.T, r2.T)
+    del g, g2, c
+    rt2.close()
+
+
+def test_new_input_invalidates_stored_correspondences(rt, scans):
+    """after setInputTarget / setInputSource with another cloud the correspondences of the previous align
+    must not be readable (they index the old clouds); the reference throws from at() in that situation"""
+    g = ng.NanoGICP(rt)
+    src = ng.PointCloud(rt, scans[1])
+    g.setInputSource(src)
+    g.setInputTarget(ng.PointCloud(rt, scans[0]))
+    g.align()
+    assert len(g.getResiduals()) == len(scans[1])
+    g.setInputTarget(ng.PointCloud(rt, scans[0][:50]))  # a much smaller target: stale indices would point behind it
+    for call in (lambda: g.getResiduals(), lambda: g.getResidualVectors(np.eye(4)), lambda: g.compute_error(np.eye(4)), lambda: g.correspondences()):
+        with pytest.raises(ng.DdloError) as e:
+            call()
+        assert e.value.code == -5
+    g.align()
+    g.getResiduals()
+    other = ng.PointCloud(rt, scans[1].copy())  # same size, another handle
+    g.registerInputSource(other)
+    with pytest.raises(ng.DdloError):
+        g.getResiduals()
+    g.clearTarget()
+    with pytest.raises(ng.DdloError):
+        g.getResiduals()
