@@ -362,9 +362,10 @@ def run_ours(args):
             c1 = {"error": repr(exc)}
 
     # Batched throughput (the second half of BASELINE's metric), driven by the C++ batch driver (ddlo_batch_*): the same
-    # C2 step for a stream of independent scans against ONE resident submap shared by S lanes (stream + engine each,
-    # align kernels limited to 148 // S SMs so that they are resident side by side).  >= 512 registrations per GPU over
-    # >= 64 distinct scans; no L2 flush here: consecutive units are different scans and S of them are in flight at once.
+    # C2 step for a stream of independent scans against ONE resident submap shared by S lanes (streams).  The lanes
+    # prepare the units (index, covariances); the aligns run wave by wave in the batched round kernels (or, in lanes
+    # mode, as one cooperative launch each on 148 // S SMs).  >= 512 registrations per GPU over >= 64 distinct scans; no
+    # L2 flush here: consecutive units are different scans and many of them are in flight at once.
     batched = None
     S = args.batched_streams
     if S > 0:
@@ -499,7 +500,7 @@ def run_batched(ng, group, local_rank, rank, world, tgt, args):
     n_distinct = 64
     w = synth.make_world()
     frames = [40 + ((rank * n_distinct + i) % 160) for i in range(n_distinct)]
-    batch = ng.Batch(local_rank, lanes=S, host_threads=args.batched_host_threads)
+    batch = ng.Batch(local_rank, lanes=S, host_threads=args.batched_host_threads, mode=args.batched_mode, wave_units=args.batched_wave)
     batch.set_params(k_correspondences=K_COV)
     sub_id = batch.stage(tgt)
     batch.set_shared_target(sub_id)
@@ -533,7 +534,8 @@ def run_batched(ng, group, local_rank, rank, world, tgt, args):
     (dt_max,) = group.reduce_max([dt])
     (bad,) = group.reduce_max([0.0 if ok else 1.0])
     out = {"value": world * n_units / dt_max, "unit": UNIT, "registrations_per_gpu": n_units, "distinct_scans_per_gpu": n_distinct,
-           "lanes_per_gpu": batch.lanes, "align_sms_per_lane": batch.align_blocks, "host_threads_per_gpu": batch.host_threads,
+           "mode": batch.mode, "wave_units": args.batched_wave if batch.mode == "waves" else None, "lanes_per_gpu": batch.lanes,
+           "align_sms_per_lane": batch.align_blocks if batch.mode == "lanes" else None, "host_threads_per_gpu": batch.host_threads,
            "seconds": dt_max, "all_converged": bad == 0.0, "mean_outer_iterations": iters, "gpu_launches": int(launches1 - launches0),
            "driver": "ddlo_batch_submit / ddlo_batch_wait (C++; Python passes the job table only)",
            "timer": "host wall clock around submit + wait, max over ranks",
@@ -556,6 +558,8 @@ def main():
     ap.add_argument("--batched-streams", type=int, default=4, help="lanes (stream + engine) per GPU of the batched-throughput leg (0 = skip)")
     ap.add_argument("--batched-units", type=int, default=1024, help="registrations per GPU in the batched leg (at least 512)")
     ap.add_argument("--batched-host-threads", type=int, default=2, help="C++ host threads that enqueue the batched leg")
+    ap.add_argument("--batched-mode", choices=["waves", "lanes"], default="waves", help="align stage of the batched leg (ddlo_batch_set_mode)")
+    ap.add_argument("--batched-wave", type=int, default=32, help="units per wave in waves mode")
     ap.add_argument("--no-c1", action="store_true", help="skip the C1 (S2S) leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=8, help="lanes (stream + engine) per GPU")
     ap.add_argument("--align-blocks", type=int, default=0, help="SMs one align may use (0 = 148 // lanes)")
     ap.add_argument("--host-threads", type=int, default=2, help="C++ threads that enqueue the units")
+    ap.add_argument("--mode", choices=["waves", "lanes"], default="waves", help="align stage: batched round kernels over waves of units, or one cooperative launch per unit on its lane")
+    ap.add_argument("--wave", type=int, default=32, help="units per wave (waves mode)")
     ap.add_argument("--out", type=str, default="", help="also write the JSON line to this file (rank 0)")
     args = ap.parse_args()
 
@@ -55,7 +57,7 @@ def main():
     w = synth.make_world()
     scans = [synth.scan(f, 64, 1024, w) for f in range(args.unique + 1)]
 
-    batch = ng.Batch(local_rank, lanes=args.lanes, align_blocks=args.align_blocks, host_threads=args.host_threads)
+    batch = ng.Batch(local_rank, lanes=args.lanes, align_blocks=args.align_blocks, host_threads=args.host_threads, mode=args.mode, wave_units=args.wave)
     ids = [batch.stage(s) for s in scans]
     units = [(ids[p % args.unique + 1], ids[p % args.unique], None) for p in range(begin, end)]  # source = frame f+1, target = frame f
     jobs = ng.Batch.jobs(units)
@@ -83,7 +85,8 @@ def main():
             peak = 6650.0
         value = total / tmax
         line = {"metric": "gicp_s2s_batched_registrations_per_s", "value": value, "unit": "registrations/s", "n_gpus": world,
-                "pairs": int(total), "seconds": tmax, "lanes_per_gpu": batch.lanes, "align_sms_per_lane": batch.align_blocks,
+                "pairs": int(total), "seconds": tmax, "mode": batch.mode, "wave_units": args.wave if batch.mode == "waves" else None,
+                "lanes_per_gpu": batch.lanes, "align_sms_per_lane": batch.align_blocks if batch.mode == "lanes" else None, "lm_rounds_and_polls": batch.stats(),
                 "host_threads_per_gpu": batch.host_threads, "all_converged": bad == 0.0, "max_translation_error_vs_truth_m": err,
                 "scaling": "strong (fixed pair count)", "driver": "ddlo_batch_submit / ddlo_batch_wait (C++)",
                 "roofline": {"bound": "hbm", "algorithmic_bytes_per_registration": B_REG_C1, "achieved": value / world * B_REG_C1 / 1e9,

@@ -16,6 +16,7 @@ OK = 0
 REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = range(5)
 OPT_GAUSS_NEWTON, OPT_LEVENBERG_MARQUARDT = 0, 1
 FLAG_CONVERGED, FLAG_LM_FAILED, FLAG_COVS_COMPUTED = 1, 2, 4
+BATCH_LANES, BATCH_WAVES = 0, 1
 
 ERROR_NAMES = {-1: "INVALID", -2: "CUDA", -3: "EMPTY", -4: "TOO_FEW", -5: "NOT_READY", -6: "SIZE", -7: "NONFINITE", -8: "UNSUPPORTED"}
 
@@ -132,6 +133,8 @@ SIGNATURES = {
     "ddlo_batch_destroy": [_vp],
     "ddlo_batch_info": [_vp, _ip, _ip, _ip],
     "ddlo_batch_set_params": [_vp, C.POINTER(Params)],
+    "ddlo_batch_set_mode": [_vp, C.c_int, C.c_int],
+    "ddlo_batch_stats": [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
     "ddlo_batch_stage_cloud": [_vp, _vp, C.c_int, C.c_int, _ip],
     "ddlo_batch_staged_count": [_vp, _ip],
     "ddlo_batch_set_shared_target": [_vp, C.c_int, _vp],

@@ -954,14 +954,23 @@ static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, 
 
 static int align_blocks(const ddlo_gicp* g) { return gicp_blocks_for(g->src->n, g->rt->align_blocks_limit); }
 
+// the argument record of one align (missing covariances are computed first, on the engine's stream) and the number
+// of blocks / chunks it runs with
+int ddlo::prepare_align(ddlo_gicp* g, const float* guess16, int* covs_computed, GicpArgs* a, int* nblocks) {
+  DDLO_TRY(prepare(g, true, covs_computed, a));
+  static const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  std::memcpy(a->guess, guess16 ? guess16 : I16, sizeof(a->guess));
+  std::memset(a->T_step, 0, sizeof(a->T_step));
+  *nblocks = align_blocks(g);
+  g->corr_n = g->p.max_iterations > 0 ? g->src->n : g->corr_n;
+  return DDLO_OK;
+}
+
 int ddlo::enqueue_align(ddlo_gicp* g, const float* guess16, int* covs_computed) {
   GicpArgs a;
-  DDLO_TRY(prepare(g, true, covs_computed, &a));
-  static const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-  std::memcpy(a.guess, guess16 ? guess16 : I16, sizeof(a.guess));
-  std::memset(a.T_step, 0, sizeof(a.T_step));
-  DDLO_TRY(launch_align(g->rt, a, align_blocks(g)));
-  g->corr_n = g->p.max_iterations > 0 ? g->src->n : g->corr_n;
+  int blocks = 0;
+  DDLO_TRY(prepare_align(g, guess16, covs_computed, &a, &blocks));
+  DDLO_TRY(launch_align(g->rt, a, blocks));
   return DDLO_OK;
 }
 

@@ -8,11 +8,20 @@
 // small index kernels of one unit overlap the searches of another.  Units are dealt to the lanes round-robin
 // and every unit runs the whole path on its lane's stream without a host synchronisation:
 //     fresh source (and target) handles -> index build(s) -> covariances -> LM align -> result copy
-// `ddlo_batch_submit` only enqueues (optionally from a few C++ host threads, one group of lanes each);
-// `ddlo_batch_wait` is the one synchronisation of the batch.  Results are bit-identical to what a single
-// engine with the same align-block limit returns for the same unit (same kernels, same fixed-order sums).
+// Two ways to run the align stage (ddlo_batch_set_mode):
+//   WAVES (default)  the units are taken W at a time.  The lanes prepare a wave (handles, indexes, covariances)
+//                    while the previous wave is being aligned by the batched round kernels of batch_align.cu: three
+//                    ordinary launches per LM round over ALL problems of the wave, 256-thread blocks scheduled freely
+//                    over the SMs, no cooperative launch, no grid barrier.  A C++ driver thread owned by the batch
+//                    feeds the rounds and polls one counter per round once the typical iteration count is through.
+//   LANES            every unit's align is the single-registration kernel k_align (one cooperative launch) on its
+//                    lane's stream, limited to num_SMs / S blocks so that the lanes' launches are resident side by side.
+// In both modes the host only enqueues; `ddlo_batch_wait` is the synchronisation of the batch.  Results are
+// bit-identical to a single engine's (WAVES: with the default block count; LANES: with the same align-block limit),
+// because chunks, groups and summation orders are shared (gicp_dev.cuh).
 #include <algorithm>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -30,6 +39,28 @@ struct ddlo_batch {
     bool has_shared_target = false;
   };
   std::vector<Lane> lanes;
+  // WAVES mode: two wave buffers of W slots (engine on lane slot % S + its "prepared" event), a stream for the rounds
+  int mode = DDLO_BATCH_WAVES;
+  int wave_units = 32;
+  struct Slot {
+    ddlo_gicp* eng = nullptr;
+    cudaEvent_t ready = nullptr;
+    bool has_shared_target = false;
+  };
+  struct WaveBuf {
+    std::vector<Slot> slots;
+    void* d_probs = nullptr;
+    void* h_probs = nullptr;  // pinned
+    AlignOut* d_outs = nullptr;
+    int* d_active = nullptr;
+    int* h_active = nullptr;  // pinned
+  };
+  WaveBuf wb[2];
+  ddlo_runtime* align_rt = nullptr;
+  std::thread driver;
+  int driver_rc = DDLO_OK;
+  std::string driver_err;
+  long long wave_rounds = 0, wave_polls = 0;
   std::vector<ddlo_cloud*> staged;  // inputs resident in HBM (owned by lane 0's runtime), index-less
   bool staging_dirty = false;
   ddlo_cloud* shared_tgt = nullptr;
@@ -43,11 +74,31 @@ struct ddlo_batch {
   int pending = 0;
 };
 
+static void waves_free(ddlo_batch* b) {
+  for (auto& w : b->wb) {
+    for (auto& s : w.slots) {
+      if (s.eng) ddlo_gicp_destroy(s.eng);
+      if (s.ready) cudaEventDestroy(s.ready);
+    }
+    w.slots.clear();
+    if (w.d_probs) cudaFree(w.d_probs);
+    if (w.h_probs) cudaFreeHost(w.h_probs);
+    if (w.d_outs) cudaFree(w.d_outs);
+    if (w.d_active) cudaFree(w.d_active);
+    if (w.h_active) cudaFreeHost(w.h_active);
+    w = ddlo_batch::WaveBuf();
+  }
+}
+
 static void batch_free(ddlo_batch* b) {
   if (!b) return;
+  if (b->driver.joinable()) b->driver.join();
   cudaSetDevice(b->device);
   for (auto& l : b->lanes)
     if (l.rt) cudaStreamSynchronize(l.rt->stream);
+  if (b->align_rt) cudaStreamSynchronize(b->align_rt->stream);
+  waves_free(b);
+  if (b->align_rt) ddlo_runtime_destroy(b->align_rt);
   for (auto& l : b->lanes)
     if (l.eng) ddlo_gicp_destroy(l.eng);
   for (ddlo_cloud* c : b->staged) ddlo_cloud_release(c);
@@ -59,36 +110,154 @@ static void batch_free(ddlo_batch* b) {
   delete b;
 }
 
-// one unit, enqueued on its lane's stream; nothing here waits for the device
-static int enqueue_unit(ddlo_batch* b, ddlo_batch::Lane& lane, const ddlo_batch_job& job, int slot) {
+// one unit, enqueued on its lane's stream; nothing here waits for the device.  args == nullptr: the unit's align is
+// enqueued too (k_align, LANES mode); else only the preparation is, and *args / *nchunks describe the align to be run.
+static int enqueue_unit(ddlo_batch* b, ddlo_runtime* rt, ddlo_gicp* g, bool& has_shared_target, const ddlo_batch_job& job, int slot,
+                        GicpArgs* args, int* nchunks) {
   const int n_staged = (int)b->staged.size();
   if (job.source < 0 || job.source >= n_staged) return fail(DDLO_E_INVALID, "batch job: unknown source cloud id");
   if (job.target >= n_staged) return fail(DDLO_E_INVALID, "batch job: unknown target cloud id");
   if (job.target < 0 && !b->shared_tgt) return fail(DDLO_E_NOT_READY, "batch job: target < 0 needs ddlo_batch_set_shared_target");
-  ddlo_gicp* g = lane.eng;
   ddlo_cloud *src = nullptr, *tgt = nullptr;
   // fresh handles: every unit builds its own indexes and covariances, nothing is cached from an earlier unit
-  DDLO_TRY(ddlo_cloud_create_from_device(lane.rt, b->staged[job.source]->pts, b->staged[job.source]->n, &src));
+  DDLO_TRY(ddlo_cloud_create_from_device(rt, b->staged[job.source]->pts, b->staged[job.source]->n, &src));
   int rc = DDLO_OK;
-  if (job.target >= 0) rc = ddlo_cloud_create_from_device(lane.rt, b->staged[job.target]->pts, b->staged[job.target]->n, &tgt);
+  if (job.target >= 0) rc = ddlo_cloud_create_from_device(rt, b->staged[job.target]->pts, b->staged[job.target]->n, &tgt);
   if (rc == DDLO_OK) rc = ddlo_gicp_clear_source(g);
   if (rc == DDLO_OK) rc = ddlo_gicp_set_input_source(g, src, 1);
   if (rc == DDLO_OK) {
     if (job.target >= 0) {
       rc = ddlo_gicp_set_input_target(g, tgt);
-      lane.has_shared_target = false;
-    } else if (!lane.has_shared_target) {
+      has_shared_target = false;
+    } else if (!has_shared_target) {
       rc = ddlo_gicp_set_input_target(g, b->shared_tgt);
       if (rc == DDLO_OK) rc = ddlo_gicp_set_target_covariances(g, b->shared_cov);
-      lane.has_shared_target = rc == DDLO_OK;
+      has_shared_target = rc == DDLO_OK;
     }
   }
-  if (rc == DDLO_OK) rc = enqueue_align(g, job.guess, &b->covs_computed[slot]);
-  if (rc == DDLO_OK && cudaMemcpyAsync(b->h_out + slot, g->d_out, sizeof(AlignOut), cudaMemcpyDeviceToHost, lane.rt->stream) != cudaSuccess)
-    rc = fail(DDLO_E_CUDA, "batch: result copy failed");
+  if (args) {
+    if (rc == DDLO_OK) rc = prepare_align(g, job.guess, &b->covs_computed[slot], args, nchunks);
+  } else {
+    if (rc == DDLO_OK) rc = enqueue_align(g, job.guess, &b->covs_computed[slot]);
+    if (rc == DDLO_OK && cudaMemcpyAsync(b->h_out + slot, g->d_out, sizeof(AlignOut), cudaMemcpyDeviceToHost, rt->stream) != cudaSuccess)
+      rc = fail(DDLO_E_CUDA, "batch: result copy failed");
+  }
   ddlo_cloud_release(src);  // the engine holds them until the lane's next unit
   if (tgt) ddlo_cloud_release(tgt);
   return rc;
+}
+
+// ---- WAVES mode -----------------------------------------------------------------------------------------------------
+static int waves_setup(ddlo_batch* b) {
+  const int W = b->wave_units;
+  if (!b->align_rt) DDLO_TRY(ddlo_runtime_create(b->device, &b->align_rt));
+  for (auto& w : b->wb) {
+    if ((int)w.slots.size() == W) continue;
+    if (!w.slots.empty()) return fail(DDLO_E_INVALID, "batch: wave size can not change once used");
+    w.slots.resize(W);
+    for (int s = 0; s < W; ++s) {
+      DDLO_TRY(ddlo_gicp_create(b->lanes[s % b->lanes.size()].rt, &w.slots[s].eng));
+      DDLO_TRY(ddlo_gicp_set_params(w.slots[s].eng, &b->lanes[0].eng->p));
+      DDLO_CUDA(cudaEventCreateWithFlags(&w.slots[s].ready, cudaEventDisableTiming));
+    }
+    DDLO_CUDA(cudaMalloc(&w.d_probs, batch_prob_bytes() * W));
+    DDLO_CUDA(cudaMallocHost(&w.h_probs, batch_prob_bytes() * W));
+    DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.d_outs), sizeof(AlignOut) * W));
+    DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.d_active), sizeof(int)));
+    DDLO_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w.h_active), sizeof(int)));
+  }
+  return DDLO_OK;
+}
+
+// prepare the units [u0, u1) of a wave on the lanes' streams (handles, indexes, covariances, argument records)
+static void wave_prepare(ddlo_batch* b, ddlo_batch::WaveBuf& w, const ddlo_batch_job* jobs, int u0, int u1, std::vector<std::string>& errs) {
+  const int S = (int)b->lanes.size();
+  const int T = std::min(b->host_threads, S);
+  auto drive = [&](int t) {
+    cudaSetDevice(b->device);
+    for (int u = u0; u < u1; ++u) {
+      const int slot = u - u0, lane = slot % S;
+      if (lane % T != t) continue;
+      ddlo_batch::Slot& sl = w.slots[slot];
+      GicpArgs a;
+      int nchunks = 0;
+      int rc = enqueue_unit(b, b->lanes[lane].rt, sl.eng, sl.has_shared_target, jobs[u], u, &a, &nchunks);
+      if (rc == DDLO_OK) {
+        a.out = w.d_outs + slot;
+        batch_prob_fill(w.h_probs, slot, &a, nchunks);
+        if (cudaEventRecord(sl.ready, b->lanes[lane].rt->stream) != cudaSuccess) rc = fail(DDLO_E_CUDA, "batch: event record failed");
+      }
+      if (rc != DDLO_OK) {
+        batch_prob_fill(w.h_probs, slot, nullptr, 0);
+        if (errs[t].empty()) errs[t] = ddlo_last_error();
+      }
+      b->unit_rc[u] = rc;
+    }
+  };
+  if (T <= 1) {
+    drive(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(drive, t);
+    drive(0);
+    for (auto& x : th) x.join();
+  }
+}
+
+// align the prepared wave: rounds of the batched kernels until every problem is done; blocks until then
+static int wave_align(ddlo_batch* b, ddlo_batch::WaveBuf& w, int u0, int u1) {
+  const int n = u1 - u0;
+  cudaStream_t st = b->align_rt->stream;
+  int max_chunks = 0;
+  for (int s = 0; s < n; ++s)
+    if (b->unit_rc[u0 + s] == DDLO_OK) DDLO_CUDA(cudaStreamWaitEvent(st, w.slots[s].ready, 0));
+  DDLO_CUDA(cudaMemcpyAsync(w.d_probs, w.h_probs, batch_prob_bytes() * n, cudaMemcpyHostToDevice, st));
+  max_chunks = b->lanes[0].rt->max_coop_blocks_align;  // no problem has more chunks than a full-size align has blocks
+  DDLO_TRY(batch_align_begin(st, w.d_probs, n, w.d_active, &b->align_rt->launches));
+  const ddlo_params& p = b->lanes[0].eng->p;
+  const long long cap = (long long)std::max(p.max_iterations, 0) * (1 + std::max(p.lm_max_iterations, 0)) + 2;
+  long long rounds = 0;
+  // a registration of consecutive scans typically takes 3-5 outer iterations of one linearize + one accepted trial
+  // each: enqueue that many rounds blind, then poll the number of unfinished problems after every further round
+  for (int r = 0; r < 4 && rounds < cap; ++r, ++rounds) DDLO_TRY(batch_align_round(st, w.d_probs, n, max_chunks, w.d_active, &b->align_rt->launches));
+  for (;;) {
+    DDLO_CUDA(cudaMemcpyAsync(w.h_active, w.d_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DDLO_CUDA(cudaStreamSynchronize(st));
+    b->wave_polls += 1;
+    if (*w.h_active <= 0 || rounds >= cap) break;
+    DDLO_TRY(batch_align_round(st, w.d_probs, n, max_chunks, w.d_active, &b->align_rt->launches));
+    ++rounds;
+  }
+  b->wave_rounds += rounds;
+  DDLO_CUDA(cudaMemcpyAsync(b->h_out + u0, w.d_outs, sizeof(AlignOut) * n, cudaMemcpyDeviceToHost, st));
+  DDLO_CUDA(cudaStreamSynchronize(st));
+  if (*w.h_active > 0) return fail(DDLO_E_CUDA, "batch: problems still active after the round limit");
+  return DDLO_OK;
+}
+
+static void waves_run(ddlo_batch* b, const ddlo_batch_job* jobs, int m) {
+  cudaSetDevice(b->device);
+  const int W = b->wave_units;
+  const int nw = (m + W - 1) / W;
+  std::vector<std::string> errs(std::max(1, b->host_threads));
+  int rc = DDLO_OK;
+  wave_prepare(b, b->wb[0], jobs, 0, std::min(m, W), errs);
+  for (int w = 0; w < nw && rc == DDLO_OK; ++w) {
+    if (w + 1 < nw) wave_prepare(b, b->wb[(w + 1) & 1], jobs, (w + 1) * W, std::min(m, (w + 2) * W), errs);
+    rc = wave_align(b, b->wb[w & 1], w * W, std::min(m, (w + 1) * W));
+  }
+  if (rc != DDLO_OK) {
+    b->driver_rc = rc;
+    b->driver_err = ddlo_last_error();
+    return;
+  }
+  for (int i = 0; i < m; ++i)
+    if (b->unit_rc[i] != DDLO_OK) {
+      b->driver_rc = b->unit_rc[i];
+      for (auto& e : errs)
+        if (!e.empty()) b->driver_err = e;
+      return;
+    }
 }
 
 extern "C" {
@@ -136,6 +305,8 @@ int ddlo_batch_set_params(ddlo_batch* b, const ddlo_params* p) {
   if (!b || !p) return fail(DDLO_E_INVALID, "null argument");
   if (b->pending) return fail(DDLO_E_NOT_READY, "batch: a submission is in flight");
   for (auto& l : b->lanes) DDLO_TRY(ddlo_gicp_set_params(l.eng, p));
+  for (auto& w : b->wb)
+    for (auto& sl : w.slots) DDLO_TRY(ddlo_gicp_set_params(sl.eng, p));
   return DDLO_OK;
 }
 
@@ -166,6 +337,11 @@ int ddlo_batch_set_shared_target(ddlo_batch* b, int cloud_id, const double* covs
     if (l.has_shared_target) DDLO_TRY(ddlo_gicp_clear_target(l.eng));
     l.has_shared_target = false;
   }
+  for (auto& w : b->wb)
+    for (auto& sl : w.slots) {
+      if (sl.has_shared_target) DDLO_TRY(ddlo_gicp_clear_target(sl.eng));
+      sl.has_shared_target = false;
+    }
   if (b->shared_cov) ddlo_covs_release(b->shared_cov);
   if (b->shared_tgt) ddlo_cloud_release(b->shared_tgt);
   b->shared_cov = nullptr, b->shared_tgt = nullptr;
@@ -210,6 +386,17 @@ int ddlo_batch_submit(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_ali
   b->unit_rc.assign(m, DDLO_OK);
   b->results = results;
   b->pending = m;
+  b->driver_rc = DDLO_OK;
+  b->driver_err.clear();
+  if (b->mode == DDLO_BATCH_WAVES) {
+    const int rc = waves_setup(b);
+    if (rc != DDLO_OK) {
+      b->pending = 0;
+      return rc;
+    }
+    b->driver = std::thread(waves_run, b, jobs, m);  // `jobs` must stay valid until ddlo_batch_wait
+    return DDLO_OK;
+  }
   const int S = (int)b->lanes.size();
   const int T = std::min(b->host_threads, S);
   std::vector<std::string> errs(T);
@@ -219,7 +406,7 @@ int ddlo_batch_submit(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_ali
     for (int i = 0; i < m; ++i) {
       const int lane = i % S;
       if (lane % T != t) continue;
-      const int rc = enqueue_unit(b, b->lanes[lane], jobs[i], i);
+      const int rc = enqueue_unit(b, b->lanes[lane].rt, b->lanes[lane].eng, b->lanes[lane].has_shared_target, jobs[i], i, nullptr, nullptr);
       b->unit_rc[i] = rc;
       if (rc != DDLO_OK && errs[t].empty()) errs[t] = ddlo_last_error();
     }
@@ -246,6 +433,10 @@ int ddlo_batch_wait(ddlo_batch* b) {
   if (!b->pending) return DDLO_OK;
   DDLO_CUDA(cudaSetDevice(b->device));
   int rc = DDLO_OK;
+  if (b->driver.joinable()) {
+    b->driver.join();
+    if (b->driver_rc != DDLO_OK) rc = fail(b->driver_rc, b->driver_err.empty() ? "batch: a unit failed" : b->driver_err);
+  }
   for (auto& l : b->lanes)
     if (cudaStreamSynchronize(l.rt->stream) != cudaSuccess && rc == DDLO_OK) rc = fail(DDLO_E_CUDA, "batch: synchronisation failed");
   const int m = b->pending;
@@ -269,9 +460,34 @@ int ddlo_batch_run(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_
   return rc != DDLO_OK ? rc : rw;
 }
 
+int ddlo_batch_set_mode(ddlo_batch* b, int mode, int wave_units) {
+  if (!b) return fail(DDLO_E_INVALID, "batch is null");
+  if (b->pending) return fail(DDLO_E_NOT_READY, "batch: a submission is in flight");
+  if (mode != DDLO_BATCH_WAVES && mode != DDLO_BATCH_LANES) return fail(DDLO_E_INVALID, "batch: unknown mode");
+  if (mode == DDLO_BATCH_WAVES) {
+    if (wave_units <= 0) wave_units = b->wave_units;
+    if (wave_units > 4096) return fail(DDLO_E_INVALID, "batch: at most 4096 units per wave");
+    if (!b->wb[0].slots.empty() && (int)b->wb[0].slots.size() != wave_units) {
+      cudaSetDevice(b->device);
+      for (auto& l : b->lanes) cudaStreamSynchronize(l.rt->stream);
+      waves_free(b);
+    }
+    b->wave_units = wave_units;
+  }
+  b->mode = mode;
+  return DDLO_OK;
+}
+
+int ddlo_batch_stats(ddlo_batch* b, long long* wave_rounds, long long* wave_polls) {
+  if (!b) return fail(DDLO_E_INVALID, "batch is null");
+  if (wave_rounds) *wave_rounds = b->wave_rounds;
+  if (wave_polls) *wave_polls = b->wave_polls;
+  return DDLO_OK;
+}
+
 int ddlo_batch_launch_count(ddlo_batch* b, long long* count) {
   if (!b || !count) return fail(DDLO_E_INVALID, "null argument");
-  long long n = 0;
+  long long n = b->align_rt ? b->align_rt->launches : 0;
   for (auto& l : b->lanes) n += l.rt->launches;
   *count = n;
   return DDLO_OK;

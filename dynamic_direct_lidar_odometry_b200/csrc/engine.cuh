@@ -46,7 +46,13 @@ int use_device(const ddlo_runtime* rt);
 int ensure_pinned(ddlo_runtime* rt, size_t bytes);
 // enqueue one align on the engine's stream (missing covariances are computed first); nothing is read back
 int enqueue_align(ddlo_gicp* g, const float* guess16, int* covs_computed);
+int prepare_align(ddlo_gicp* g, const float* guess16, int* covs_computed, GicpArgs* a, int* nblocks);
 void fill_result(const AlignOut* o, int covs_computed, ddlo_align_result* r);
+// batch_align.cu: a wave of problems advanced together (device array of BatchProb records, opaque here)
+size_t batch_prob_bytes();
+void batch_prob_fill(void* h_probs, int slot, const GicpArgs* args, int nchunks);  // args == nullptr: empty slot
+int batch_align_begin(cudaStream_t st, void* d_probs, int n, int* d_active, long long* launches);
+int batch_align_round(cudaStream_t st, void* d_probs, int n, int max_chunks, int* d_active, long long* launches);
 // the target covariances permuted into the Morton order of `cloud`'s index (cached on the covariance handle)
 int ensure_sorted_covs(ddlo_covs* v, ddlo_cloud* cloud, cudaStream_t st);
 

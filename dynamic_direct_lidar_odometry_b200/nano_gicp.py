@@ -548,10 +548,12 @@ class Batch:
     concurrently; Python only hands over the job table.  Units are (source id, target id or -1, guess) over clouds
     staged in HBM with `stage`."""
 
-    def __init__(self, device: int = 0, lanes: int = 4, align_blocks: int = 0, host_threads: int = 1):
+    def __init__(self, device: int = 0, lanes: int = 4, align_blocks: int = 0, host_threads: int = 1, mode: str = "waves", wave_units: int = 0):
         self._b = C.c_void_p()
         B.check(B.load().ddlo_batch_create(device, lanes, align_blocks, host_threads, C.byref(self._b)))
         self.device = device
+        self.mode = mode
+        B.check(B.load().ddlo_batch_set_mode(self._b, {"lanes": B.BATCH_LANES, "waves": B.BATCH_WAVES}[mode], wave_units))
         a, c, t = C.c_int(), C.c_int(), C.c_int()
         B.check(B.load().ddlo_batch_info(self._b, C.byref(a), C.byref(c), C.byref(t)))
         self.lanes, self.align_blocks, self.host_threads = a.value, c.value, t.value
@@ -603,8 +605,18 @@ class Batch:
             jobs = self.jobs(jobs)
         self._m = len(jobs)
         self._res = (B.AlignResult * max(self._m, 1))()
-        self._jobs = jobs
-        B.check(B.load().ddlo_batch_submit(self._b, jobs, self._m, self._res))
+        self._jobs = jobs  # the job table must outlive the submission
+        rc = B.load().ddlo_batch_submit(self._b, jobs, self._m, self._res)
+        if rc != B.OK:
+            text = B.load().ddlo_last_error().decode(errors="replace")
+            B.load().ddlo_batch_wait(self._b)  # whatever was enqueued completes; the batch stays usable
+            raise DdloError(rc, text)
+
+    def stats(self):
+        """(LM rounds launched, completion polls) by the waves driver since creation"""
+        r, p = C.c_longlong(), C.c_longlong()
+        B.check(B.load().ddlo_batch_stats(self._b, C.byref(r), C.byref(p)))
+        return r.value, p.value
 
     def wait(self, raw: bool = False):
         B.check(B.load().ddlo_batch_wait(self._b))

@@ -310,14 +310,27 @@ int ddlo_batch_create(int device, int n_lanes, int align_blocks_per_lane, int ho
 int ddlo_batch_destroy(ddlo_batch* b);
 int ddlo_batch_info(const ddlo_batch* b, int* n_lanes, int* align_blocks_per_lane, int* host_threads);
 int ddlo_batch_set_params(ddlo_batch* b, const ddlo_params* p); /* all lanes */
+/* How the align stage of the units runs.
+ *   DDLO_BATCH_WAVES (default): the units are taken wave_units at a time (<= 0: keep, default 32).  While the lanes
+ *     prepare one wave (handles, indexes, covariances), the previous one is aligned by batched kernels that advance ALL
+ *     its problems by one LM round per three ordinary launches (no cooperative launch, no grid barrier; problems at
+ *     different iterations share the launches).  A C++ thread owned by the batch drives the rounds between
+ *     ddlo_batch_submit and ddlo_batch_wait.  Results are bit-identical to ddlo_gicp_align on an ordinary engine.
+ *   DDLO_BATCH_LANES: every unit's align is the single-registration kernel on its lane's stream, limited to
+ *     align_blocks_per_lane SMs; results are bit-identical to ddlo_gicp_align with that block limit. */
+enum { DDLO_BATCH_LANES = 0, DDLO_BATCH_WAVES = 1 };
+int ddlo_batch_set_mode(ddlo_batch* b, int mode, int wave_units);
+/* LM rounds launched and completion polls made by the WAVES driver since creation */
+int ddlo_batch_stats(ddlo_batch* b, long long* wave_rounds, long long* wave_polls);
 /* Stage an input cloud in HBM (as ddlo_cloud_create; SURVEY.md §8d: inputs are pre-staged per GPU before timing). */
 int ddlo_batch_stage_cloud(ddlo_batch* b, const float* xyz, int n, int stride_bytes, int* id);
 int ddlo_batch_staged_count(const ddlo_batch* b, int* count);
 /* One target for all units with target == -1 (a keyframe submap): index and covariances are prepared once
  * (covs_mat4x4 == NULL: computed with the batch's k and regularisation) and shared by the lanes. */
 int ddlo_batch_set_shared_target(ddlo_batch* b, int cloud_id, const double* covs_mat4x4);
-/* Enqueue m units; returns once everything is enqueued.  results[i] (HOST, m entries) is valid after
- * ddlo_batch_wait, which synchronises all lanes and returns the first error.  _run = submit + wait. */
+/* Start m units; returns without waiting for the device.  jobs and results (HOST, m entries each) must stay valid
+ * until ddlo_batch_wait, which synchronises everything, fills results and returns the first error.
+ * _run = submit + wait. */
 int ddlo_batch_submit(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_result* results);
 int ddlo_batch_wait(ddlo_batch* b);
 int ddlo_batch_run(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_result* results);

@@ -33,11 +33,13 @@ def single_align(device, blocks, src, tgt, guess=None, shared=None):
     return r
 
 
-def test_batch_s2s_bit_identical_to_single_align(scans):
-    """every unit of a batch returns the pose, Hessian and iteration counts a single ddlo_gicp_align gives with the
-    same align-block limit - bit for bit, whatever lane it ran on"""
-    b = ng.Batch(0, lanes=3, host_threads=2)
+@pytest.mark.parametrize("mode", ["waves", "lanes"])
+def test_batch_s2s_bit_identical_to_single_align(scans, mode):
+    """every unit of a batch returns the pose, Hessian and iteration counts a single ddlo_gicp_align gives (waves: an
+    ordinary engine; lanes: one with the same align-block limit) - bit for bit, whatever lane or wave it ran in"""
+    b = ng.Batch(0, lanes=3, host_threads=2, mode=mode, wave_units=4)
     ids = [b.stage(s) for s in scans]
+    scans_by_id = dict(zip(ids, scans))
     rng = np.random.default_rng(3)
     units = []
     for u in range(11):
@@ -48,20 +50,24 @@ def test_batch_s2s_bit_identical_to_single_align(scans):
     res = b.run(units)
     res2 = b.run(units)  # lanes are reused: nothing of the first run may leak into the second
     for (s, t, guess), r, r2 in zip(units, res, res2):
-        ref = single_align(0, b.align_blocks, scans[s], scans[t], guess)
+        ref = single_align(0, b.align_blocks if mode == "lanes" else 0, scans_by_id[s], scans_by_id[t], guess)
         assert r.converged and ref.converged
         assert (r.iterations, r.n_linearize, r.n_compute_error) == (ref.iterations, ref.n_linearize, ref.n_compute_error)
         assert np.array_equal(r.T, ref.T) and np.array_equal(r.hessian, ref.hessian) and r.final_error == ref.final_error
         assert r.covs_computed
         assert np.array_equal(r.T, r2.T) and np.array_equal(r.hessian, r2.hessian)
     assert b.launch_count() > 0
+    if mode == "waves":
+        rounds, polls = b.stats()
+        assert rounds >= 2 * 3 * 4 and polls >= 6  # 11 units in waves of 4, twice
     b.close()
 
 
-def test_batch_shared_target_matches_single_engine(scans):
+@pytest.mark.parametrize("mode", ["waves", "lanes"])
+def test_batch_shared_target_matches_single_engine(scans, mode):
     """scan-to-map units (target = -1) against one submap whose index and covariances are shared by all lanes"""
     submap = np.concatenate([synth.transform(scans[f], synth.pose(f)) for f in (0, 2, 4)])
-    b = ng.Batch(0, lanes=4, host_threads=1)
+    b = ng.Batch(0, lanes=4, host_threads=1, mode=mode, wave_units=5)
     sub_id = b.stage(submap)
     ids = [b.stage(scans[f]) for f in (1, 3, 5)]
     b.set_shared_target(sub_id)
@@ -73,7 +79,7 @@ def test_batch_shared_target_matches_single_engine(scans):
     tgt = ng.PointCloud(rt, submap).share()
     cov = ng.Covariances.compute(tgt, 20).share(tgt)
     for i, r in enumerate(res):
-        ref = single_align(0, b.align_blocks, scans[(1, 3, 5)[i % 3]], None, guesses[i % 3], shared=(tgt, cov))
+        ref = single_align(0, b.align_blocks if mode == "lanes" else 0, scans[(1, 3, 5)[i % 3]], None, guesses[i % 3], shared=(tgt, cov))
         assert r.converged == ref.converged and r.iterations == ref.iterations
         assert np.array_equal(r.T, ref.T) and np.array_equal(r.hessian, ref.hessian)
         assert r.covs_computed  # source covariances are computed inside the unit
@@ -86,8 +92,9 @@ def test_batch_shared_target_matches_single_engine(scans):
     b.close()
 
 
-def test_batch_errors(scans):
-    b = ng.Batch(0, lanes=2)
+@pytest.mark.parametrize("mode", ["waves", "lanes"])
+def test_batch_errors(scans, mode):
+    b = ng.Batch(0, lanes=2, mode=mode)
     i0 = b.stage(scans[0])
     with pytest.raises(ng.DdloError) as e:
         b.run([(i0, -1, None)])  # no shared target
@@ -147,3 +154,42 @@ def test_new_input_invalidates_stored_correspondences(rt, scans):
     g.clearTarget()
     with pytest.raises(ng.DdloError):
         g.getResiduals()
+
+
+def test_cpp_batch_program_shards_over_devices(scans, tmp_path):
+    """tests/cpp/batch_protocol.cpp: the batched path driven from C++ only (one batch + one host thread per visible
+    device, contiguous shards); it checks every unit against a single engine itself, and its poses must equal the ones
+    the Python mirror of the same ABI gets"""
+    import subprocess
+    from pathlib import Path
+
+    exe = Path(__file__).resolve().parent / "cpp" / "_build" / "batch_protocol"
+    if not exe.exists():
+        import __graft_entry__ as ge
+
+        ge.build_cpp_tests()
+    path = tmp_path / "scans.bin"
+    with open(path, "wb") as fh:
+        fh.write(np.int32(len(scans)).tobytes())
+        for s in scans:
+            fh.write(np.int32(len(s)).tobytes())
+            fh.write(np.ascontiguousarray(s, dtype=np.float32).tobytes())
+    units, lanes = 13, 3
+    for mode in ("lanes", "waves"):
+        out = subprocess.run([str(exe), str(path), str(units), str(lanes), "2", "8", mode, "5"], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr
+    got = {}
+    for line in out.stdout.splitlines():
+        f = line.split()
+        if f[0] == "unit":
+            got[int(f[1])] = (int(f[3]), int(f[4]), np.array(f[5:], dtype=np.float32).reshape(4, 4))
+        elif f[0] == "summary":
+            assert int(f[-1]) == 0
+    assert len(got) == units
+    b = ng.Batch(0, lanes=lanes, mode="waves")
+    ids = [b.stage(s) for s in scans]
+    n_pairs = len(scans) - 1
+    res = b.run([(ids[u % n_pairs + 1], ids[u % n_pairs], None) for u in range(units)])
+    for u, r in enumerate(res):
+        assert got[u][0] == int(r.converged) and got[u][1] == r.iterations and np.array_equal(got[u][2], r.T)
+    b.close()
