@@ -509,7 +509,7 @@ def run_batched(ng, group, local_rank, rank, world, tgt, args):
         ids.append(batch.stage(synth.scan(f, NS_BEAMS, NS_COLS, w)))
         guesses.append(synth.perturbed_guess(synth.pose(f)))
     jobs = ng.Batch.jobs([(ids[i % n_distinct], -1, guesses[i % n_distinct]) for i in range(n_units)])
-    batch.run(ng.Batch.jobs([(ids[i % n_distinct], -1, guesses[i % n_distinct]) for i in range(8 * S)]))  # warm-up
+    batch.run(ng.Batch.jobs([(ids[i % n_distinct], -1, guesses[i % n_distinct]) for i in range(max(8 * S, 8 * args.batched_wave))]))  # warm-up (allocator pools of every lane and wave slot)
 
     def timed():
         t0 = time.perf_counter()

@@ -61,7 +61,8 @@ def main():
     ids = [batch.stage(s) for s in scans]
     units = [(ids[p % args.unique + 1], ids[p % args.unique], None) for p in range(begin, end)]  # source = frame f+1, target = frame f
     jobs = ng.Batch.jobs(units)
-    batch.run(ng.Batch.jobs(units[: 4 * args.lanes]))  # warm-up (allocator pools, first-touch)
+    warm = max(4 * args.lanes, 8 * args.wave if args.mode == "waves" else 0)
+    batch.run(ng.Batch.jobs([units[i % len(units)] for i in range(warm)]))  # warm-up (allocator pools of every lane and wave slot, first touch)
 
     if dist is not None:
         dist.barrier()

@@ -94,6 +94,24 @@ int ensure_pinned(ddlo_runtime* rt, size_t bytes) {
   return DDLO_OK;
 }
 
+static void runtime_teardown(ddlo_runtime* rt) {
+  cudaSetDevice(rt->device);
+  if (rt->stream) cudaStreamSynchronize(rt->stream);
+  if (rt->d_scratch) cudaFree(rt->d_scratch);
+  if (rt->flush_buf) cudaFree(rt->flush_buf);
+  if (rt->h_pinned) cudaFreeHost(rt->h_pinned);
+  if (rt->ev0) cudaEventDestroy(rt->ev0);
+  if (rt->ev1) cudaEventDestroy(rt->ev1);
+  for (auto& e : rt->slots)
+    if (e) cudaEventDestroy(e);
+  if (rt->stream) cudaStreamDestroy(rt->stream);
+  delete rt;
+}
+void runtime_retain(ddlo_runtime* rt) { rt->refs.fetch_add(1); }
+void runtime_release(ddlo_runtime* rt) {
+  if (rt->refs.fetch_sub(1) == 1) runtime_teardown(rt);
+}
+
 static void cloud_free(ddlo_cloud* c) {
   cudaSetDevice(c->rt->device);
   cudaStream_t st = c->rt->stream;
@@ -103,6 +121,7 @@ static void cloud_free(ddlo_cloud* c) {
   if (c->meta) cudaFreeAsync(c->meta, st);
   if (c->node_of_point) cudaFreeAsync(c->node_of_point, st);
   if (c->lattice) cudaFreeAsync(c->lattice, st);
+  runtime_release(c->rt);
   delete c;
 }
 static void covs_free(ddlo_covs* v) {
@@ -110,6 +129,7 @@ static void covs_free(ddlo_covs* v) {
   if (v->c) cudaFreeAsync(v->c, v->rt->stream);
   if (v->sorted) cudaFreeAsync(v->sorted, v->rt->stream);
   if (v->sorted_for && v->sorted_for->refs.fetch_sub(1) == 1) cloud_free(v->sorted_for);
+  runtime_release(v->rt);
   delete v;
 }
 
@@ -143,6 +163,7 @@ int cloud_new(ddlo_runtime* rt, int n, ddlo_cloud** out) {
     delete c;
     return fail(DDLO_E_CUDA, std::string("cudaMallocAsync(cloud): ") + cudaGetErrorString(e));
   }
+  runtime_retain(rt);
   *out = c;
   return DDLO_OK;
 }
@@ -157,6 +178,7 @@ int cloud_adopt(ddlo_runtime* rt, float4* pts, int n, ddlo_cloud** out) {
   c->rt = rt;
   c->n = n;
   c->pts = pts;
+  runtime_retain(rt);
   *out = c;
   return DDLO_OK;
 }
@@ -171,6 +193,7 @@ int covs_new(ddlo_runtime* rt, int n, ddlo_covs** out) {
     delete v;
     return fail(DDLO_E_CUDA, std::string("cudaMallocAsync(covs): ") + cudaGetErrorString(e));
   }
+  runtime_retain(rt);
   *out = v;
   return DDLO_OK;
 }
@@ -249,15 +272,7 @@ int ddlo_runtime_destroy(ddlo_runtime* rt) {
   if (!rt) return DDLO_OK;
   cudaSetDevice(rt->device);
   if (rt->stream) cudaStreamSynchronize(rt->stream);
-  if (rt->d_scratch) cudaFree(rt->d_scratch);
-  if (rt->flush_buf) cudaFree(rt->flush_buf);
-  if (rt->h_pinned) cudaFreeHost(rt->h_pinned);
-  if (rt->ev0) cudaEventDestroy(rt->ev0);
-  if (rt->ev1) cudaEventDestroy(rt->ev1);
-  for (auto& e : rt->slots)
-    if (e) cudaEventDestroy(e);
-  if (rt->stream) cudaStreamDestroy(rt->stream);
-  delete rt;
+  runtime_release(rt);  // the stream and the scratch buffers go with the last handle made from this runtime
   return DDLO_OK;
 }
 
@@ -680,6 +695,7 @@ int ddlo_gicp_create(ddlo_runtime* rt, ddlo_gicp** out) {
   g->partial_stride = std::max(rt->max_coop_blocks_align, 64);
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&g->partials), (size_t)2 * kNumSums * g->partial_stride * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->d_out), sizeof(AlignOut));
+  if (e == cudaSuccess) runtime_retain(rt);
   if (e != cudaSuccess) {
     if (g->partials) cudaFree(g->partials);
     if (g->d_out) cudaFree(g->d_out);
@@ -705,6 +721,7 @@ int ddlo_gicp_destroy(ddlo_gicp* g) {
   if (g->partials) cudaFree(g->partials);
   if (g->d_out) cudaFree(g->d_out);
   if (g->d_prof) cudaFree(g->d_prof);
+  runtime_release(g->rt);
   delete g;
   return DDLO_OK;
 }
@@ -816,6 +833,9 @@ static int calc_covs(ddlo_gicp* g, ddlo_cloud* c, ddlo_covs*& slot) {
   if (!c) return fail(DDLO_E_NOT_READY, "calculate covariances: no cloud set");
   ddlo_covs* v = nullptr;
   DDLO_TRY(ddlo_covs_compute(c, g->p.k_correspondences, g->p.regularization_method, &v));
+  // a shared cloud of another runtime: its covariances are computed on the owner's stream; this engine's stream must
+  // not run ahead of them (rare path: callers that share a target normally share its covariances too)
+  if (c->rt != g->rt) DDLO_CUDA(cudaStreamSynchronize(c->rt->stream));
   set_covs(slot, v);
   ddlo_covs_release(v);
   return DDLO_OK;

@@ -20,6 +20,9 @@
 // bit-identical to a single engine's (WAVES: with the default block count; LANES: with the same align-block limit),
 // because chunks, groups and summation orders are shared (gicp_dev.cuh).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -160,6 +163,18 @@ static int waves_setup(ddlo_batch* b) {
       DDLO_TRY(ddlo_gicp_set_params(w.slots[s].eng, &b->lanes[0].eng->p));
       DDLO_CUDA(cudaEventCreateWithFlags(&w.slots[s].ready, cudaEventDisableTiming));
     }
+    {
+      // Grow the device's stream-ordered pool once, here: two waves of units keep their clouds, indexes, covariances
+      // and workspaces alive at the same time (about 48 MB per 64x1024 scan-to-scan unit), and growing the pool in the
+      // middle of a run costs tens of milliseconds per wave.  DDLO_BATCH_PREWARM_MB overrides (0 disables).
+      size_t mb = (size_t)W * 48;
+      if (const char* e = std::getenv("DDLO_BATCH_PREWARM_MB")) mb = (size_t)std::max(0L, std::atol(e));
+      void* warm = nullptr;
+      if (mb > 0 && cudaMallocAsync(&warm, mb << 20, b->lanes[0].rt->stream) == cudaSuccess)
+        cudaFreeAsync(warm, b->lanes[0].rt->stream);
+      else
+        (void)cudaGetLastError();
+    }
     DDLO_CUDA(cudaMalloc(&w.d_probs, batch_prob_bytes() * W));
     DDLO_CUDA(cudaMallocHost(&w.h_probs, batch_prob_bytes() * W));
     DDLO_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.d_outs), sizeof(AlignOut) * W));
@@ -241,10 +256,24 @@ static void waves_run(ddlo_batch* b, const ddlo_batch_job* jobs, int m) {
   const int nw = (m + W - 1) / W;
   std::vector<std::string> errs(std::max(1, b->host_threads));
   int rc = DDLO_OK;
+  // DDLO_BATCH_TRACE=1: one line per wave on stderr (host time spent enqueueing the next wave's preparation, host time
+  // until this wave's aligns were done, LM rounds so far); DDLO_BATCH_SKIP_ALIGN=1 (timing experiments only): the
+  // aligns are not run at all, results are undefined
+  static const bool trace = std::getenv("DDLO_BATCH_TRACE") != nullptr;
+  static const bool skip_align = std::getenv("DDLO_BATCH_SKIP_ALIGN") != nullptr;
+  using clk = std::chrono::steady_clock;
+  auto ms = [](clk::time_point a, clk::time_point c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
   wave_prepare(b, b->wb[0], jobs, 0, std::min(m, W), errs);
   for (int w = 0; w < nw && rc == DDLO_OK; ++w) {
+    const auto t0 = clk::now();
     if (w + 1 < nw) wave_prepare(b, b->wb[(w + 1) & 1], jobs, (w + 1) * W, std::min(m, (w + 2) * W), errs);
-    rc = wave_align(b, b->wb[w & 1], w * W, std::min(m, (w + 1) * W));
+    const auto t1 = clk::now();
+    if (skip_align) {
+      for (auto& l : b->lanes) cudaStreamSynchronize(l.rt->stream);
+    } else {
+      rc = wave_align(b, b->wb[w & 1], w * W, std::min(m, (w + 1) * W));
+    }
+    if (trace) std::fprintf(stderr, "[ddlo_batch] wave %d: prepare-next %.3f ms host, align %.3f ms, rounds so far %lld, polls %lld\n", w, ms(t0, t1), ms(t1, clk::now()), b->wave_rounds, b->wave_polls);
   }
   if (rc != DDLO_OK) {
     b->driver_rc = rc;
@@ -281,9 +310,9 @@ int ddlo_batch_create(int device, int n_lanes, int align_blocks_per_lane, int ho
     }
   }
   const int sms = b->lanes[0].rt->num_sms;
-  b->align_blocks = align_blocks_per_lane > 0 ? align_blocks_per_lane : std::max(1, sms / n_lanes);
-  for (auto& l : b->lanes) ddlo_runtime_set_align_blocks(l.rt, b->align_blocks);
-  b->align_blocks = b->lanes[0].rt->align_blocks_limit;
+  b->align_blocks = std::min(align_blocks_per_lane > 0 ? align_blocks_per_lane : std::max(1, sms / n_lanes), b->lanes[0].rt->max_coop_blocks_align);
+  // the per-lane block limit belongs to LANES mode; in WAVES mode (the default) a problem is cut into as many chunks
+  // as an ordinary engine's align has blocks
   *out = b;
   return DDLO_OK;
 }
@@ -475,6 +504,7 @@ int ddlo_batch_set_mode(ddlo_batch* b, int mode, int wave_units) {
     b->wave_units = wave_units;
   }
   b->mode = mode;
+  for (auto& l : b->lanes) ddlo_runtime_set_align_blocks(l.rt, mode == DDLO_BATCH_LANES ? b->align_blocks : 0);
   return DDLO_OK;
 }
 

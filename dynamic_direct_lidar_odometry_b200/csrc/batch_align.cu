@@ -194,12 +194,12 @@ __global__ void __launch_bounds__(kBThreads, kBBlocksPerSM) k_batch_err(BatchPro
   for (int g0 = 0; g0 < ngroups; g0 += kSpan) {
     for (int g = g0 + warp; g < min(ngroups, g0 + kSpan); g += kBWarps) {
       const int slot = g * kGroup + lane;
-      double e = 0.0;
+      int i = -1;
       if (slot < dl.nslots) {
-        const int i = dl.point(slot);
-        if (i < a.ns) e = err_point(a, s_xi, i);
+        i = dl.point(slot);
+        if (i >= a.ns) i = -1;
       }
-      e = warp_sum(e);
+      const double e = err_group(a, s_xi, i);
       if (lane == 0) s_egs[g - g0] = e;
     }
     __syncthreads();

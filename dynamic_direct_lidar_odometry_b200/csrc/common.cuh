@@ -78,6 +78,10 @@ struct RuntimeImpl;
 
 // opaque handle bodies ---------------------------------------------------------------------------
 struct ddlo_runtime {
+  // Reference counted: the creator holds one reference (dropped by ddlo_runtime_destroy), every cloud, covariance
+  // vector and engine made from the runtime holds another, so a handle that outlives the destroy call - e.g. a
+  // shared cloud still set as another runtime's target - never dangles; the stream goes with the last handle.
+  std::atomic<int> refs{1};
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -113,12 +113,12 @@ __device__ __forceinline__ void error_block(const GicpArgs& a, const Iso3& T, Al
   for (int g0 = 0; g0 < ngroups; g0 += kSpan) {
     for (int g = g0 + warp; g < min(ngroups, g0 + kSpan); g += kAlignWarps) {
       const int slot = g * kGroup + lane;
-      double e = 0.0;
+      int i = -1;
       if (slot < dl.nslots) {
-        const int i = dl.point(slot);
-        if (i < a.ns) e = err_point(a, T, i);
+        i = dl.point(slot);
+        if (i >= a.ns) i = -1;
       }
-      e = warp_sum(e);
+      const double e = err_group(a, T, i);
       if (lane == 0) sm.egs[g - g0] = e;
     }
     __syncthreads();

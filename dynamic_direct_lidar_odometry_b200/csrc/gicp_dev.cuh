@@ -190,8 +190,14 @@ static __device__ __noinline__ double lin_group(const GicpArgs& a, const Iso3& x
   return mine;
 }
 
-// one source point of compute_error: stored correspondence and Mahalanobis matrix, new transform
+// compute_error for the 32 slots of one group, one slot per lane (all 32 lanes; i < 0: no point): stored
+// correspondence and Mahalanobis matrix, new transform.  Returns the group's sum in every lane.
+// Out of line for the same reason as lm_on_*: one compiled body for every kernel that uses it.
+static __device__ __noinline__ double err_group(const GicpArgs& a, const Iso3& T, int i);
+
+// one source point of compute_error
 __device__ __forceinline__ double err_point(const GicpArgs& a, const Iso3& T, int i) {
+  if (i < 0) return 0.0;
   const int j = __ldcg(a.corr + i);
   if (j < 0) return 0.0;
   const float4 pa = __ldg(a.src_pts + i);
@@ -204,6 +210,8 @@ __device__ __forceinline__ double err_point(const GicpArgs& a, const Iso3& T, in
   double mx, my, mz;
   return quad_form(M, ex, ey, ez, mx, my, mz);
 }
+
+static __device__ __noinline__ double err_group(const GicpArgs& a, const Iso3& T, int i) { return warp_sum(err_point(a, T, i)); }
 
 // Where a search round parks its matches (shared memory of the block that runs it), its queue head, and the float
 // transform of the queries.
@@ -412,7 +420,9 @@ static __device__ __noinline__ void lm_solve(LmShared& s, double lambda) {
 // computeTransformation (:96-127): x0 = guess, lm_lambda_ = -1, then up to max_iterations_ outer iterations, each
 // a linearize followed (LM) by up to lm_max_iterations_ trial errors.  Each function returns what has to be
 // evaluated next: linearize at x0 (queries use Rf/tf), compute_error at xi, or nothing (done).
-__device__ __forceinline__ int lm_start(LmShared& s, const GicpArgs& a) {
+// (Out of line on purpose: k_align and the batched kernels must run the very same instruction sequence - an inlined
+// copy may contract its multiply-adds differently in each kernel, and the results are promised to be bit-identical.)
+static __device__ __noinline__ int lm_start(LmShared& s, const GicpArgs& a) {
   iso_from_colmajor(a.guess, s.x0);
   s.lambda = -1.0;  // lm_lambda_ = -1 (:100)
   s.converged = 0;
@@ -429,7 +439,7 @@ __device__ __forceinline__ int lm_start(LmShared& s, const GicpArgs& a) {
 }
 
 // the end of one outer iteration (:113-122)
-__device__ __forceinline__ int lm_end_iteration(LmShared& s, const GicpArgs& a) {
+static __device__ __noinline__ int lm_end_iteration(LmShared& s, const GicpArgs& a) {
   if (!s.step_ok) {  // "lm not converged!!" (:115-119)
     s.lm_failed = 1;
     return kNextDone;
@@ -443,7 +453,7 @@ __device__ __forceinline__ int lm_end_iteration(LmShared& s, const GicpArgs& a) 
 }
 
 // after linearize(x0): tot = the 28 sums
-__device__ __forceinline__ int lm_on_linearized(LmShared& s, const GicpArgs& a, const double* tot) {
+static __device__ __noinline__ int lm_on_linearized(LmShared& s, const GicpArgs& a, const double* tot) {
   unpack_sums(tot, s.H, s.b, s.y0);
   s.n_lin += 1;
   s.step_ok = 0;
@@ -471,7 +481,7 @@ __device__ __forceinline__ int lm_on_linearized(LmShared& s, const GicpArgs& a, 
 }
 
 // after compute_error(xi) = yi (:199-229)
-__device__ __forceinline__ int lm_on_error(LmShared& s, const GicpArgs& a, double yi) {
+static __device__ __noinline__ int lm_on_error(LmShared& s, const GicpArgs& a, double yi) {
   s.n_err += 1;
   s.yi = yi;
   double den = 0.0;
@@ -501,7 +511,7 @@ __device__ __forceinline__ int lm_on_error(LmShared& s, const GicpArgs& a, doubl
 }
 
 // what align() leaves for the host
-__device__ __forceinline__ void write_align_out(const GicpArgs& a, const LmShared& s, AlignOut* o) {
+static __device__ __noinline__ void write_align_out(const GicpArgs& a, const LmShared& s, AlignOut* o) {
   for (int i = 0; i < 16; ++i) o->final_transformation[i] = 0.0f;
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j) o->final_transformation[4 * j + i] = (float)s.x0.r[3 * i + j];

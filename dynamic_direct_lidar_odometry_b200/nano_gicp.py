@@ -114,8 +114,12 @@ class PointCloud:
         B.check(B.load().ddlo_cloud_create(rt._h, B.ptr(p), p.shape[0], p.strides[0] if p.shape[0] else 4 * p.shape[1], C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None) and getattr(self.rt, "_h", None):
-            B.load().ddlo_cloud_release(self._h)
+        # safe in any order: the C runtime is reference counted and outlives Runtime.close() while handles exist
+        if getattr(self, "_h", None):
+            try:
+                B.load().ddlo_cloud_release(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = None
 
     def size(self) -> int:
@@ -198,8 +202,11 @@ class Covariances:
         B.check(B.load().ddlo_covs_from_host(rt._h, B.ptr(m), m.shape[0], C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None) and getattr(self.rt, "_h", None):
-            B.load().ddlo_covs_release(self._h)
+        if getattr(self, "_h", None):
+            try:
+                B.load().ddlo_covs_release(self._h)
+            except Exception:  # interpreter shutdown
+                pass
             self._h = None
 
     @staticmethod
@@ -262,8 +269,11 @@ class NanoGICP:
         self._last: Optional[AlignInfo] = None
 
     def __del__(self):
-        if getattr(self, "_g", None) and getattr(self.rt, "_h", None):
-            B.load().ddlo_gicp_destroy(self._g)
+        if getattr(self, "_g", None):
+            try:
+                B.load().ddlo_gicp_destroy(self._g)
+            except Exception:  # interpreter shutdown
+                pass
             self._g = None
 
     def _push(self):
