@@ -26,6 +26,51 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 
 
+def main_cpp(args):
+    import subprocess
+    import tempfile
+
+    from dynamic_direct_lidar_odometry_b200 import synth
+
+    exe = ROOT / "tests" / "cpp" / "_build" / "odometry_sequence"
+    if not exe.exists():
+        sys.path.insert(0, str(ROOT))
+        import __graft_entry__ as ge
+
+        ge.build_cpp_tests()
+    w = synth.make_world()
+    scans = [synth.scan(f, args.beams, args.cols, w) for f in range(args.frames)]
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / "scans.bin"
+        with open(path, "wb") as fh:
+            fh.write(np.int32(len(scans)).tobytes())
+            for s in scans:
+                fh.write(np.int32(len(s)).tobytes())
+                fh.write(np.ascontiguousarray(s, dtype=np.float32).tobytes())
+        out = subprocess.run([str(exe), str(path), str(args.k), "1.0", "15", "10", str(args.kcv), str(args.kcc), str(args.voxel), str(args.voxel), "8"],
+                             capture_output=True, text=True, timeout=1200)
+    if out.returncode != 0:
+        raise RuntimeError(out.stderr)
+    rows = [l.split() for l in out.stdout.splitlines() if l.startswith("frame")]
+    ms = np.array([float(r[9]) for r in rows])
+    inv0 = np.linalg.inv(synth.pose(0))
+    err_t = [float(np.abs(np.array(r[11:27], dtype=np.float64).reshape(4, 4)[:3, 3] - (inv0 @ synth.pose(int(r[1])))[:3, 3]).max()) for r in rows]
+    summary = [l.split() for l in out.stdout.splitlines() if l.startswith("summary")][0]
+    slow = np.argsort(-ms)[:6]
+    print(json.dumps({
+        "metric": "c3_odometry_loop_ms_per_frame", "unit": "ms", "frames": args.frames, "scan": f"{args.beams}x{args.cols}",
+        "driver": "C++ (tests/cpp/odometry_sequence.cpp: C ABI + ddlo_keyframes_*, no Python in the frame)",
+        "mean_ms": float(ms.mean()), "p50_ms": float(np.percentile(ms, 50)), "p99_ms": float(np.percentile(ms, 99)), "max_ms": float(ms.max()),
+        "frames_per_s": float(1e3 / ms.mean()), "keyframes": int(summary[4]), "submap_points_last": int(rows[-1][8]),
+        "submap_rebuilds": int(sum(int(r[7]) for r in rows)), "all_converged": bool(all(int(r[4]) and int(r[5]) for r in rows)),
+        "s2s_iterations_mean": float(np.mean([int(r[2]) + 1 for r in rows])), "s2m_iterations_mean": float(np.mean([int(r[3]) + 1 for r in rows])),
+        "final_translation_error_vs_truth_m": err_t[-1], "max_translation_error_vs_truth_m": max(err_t),
+        "k_correspondences": args.k, "voxel_leaf_m": args.voxel, "submap_selection": {"knn": 10, "kcv": args.kcv, "kcc": args.kcc},
+        "timer": "host wall clock per frame inside the C++ program, scan upload and residual read-back included",
+        "slowest_frames": [{"frame": int(rows[i][1]), "ms": float(ms[i]), "new_keyframe": bool(int(rows[i][6])), "submap_changed": bool(int(rows[i][7])),
+                            "submap_points": int(rows[i][8])} for i in slow]}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=100)
@@ -35,7 +80,13 @@ def main():
     ap.add_argument("--segmentation", action="store_true",
                     help="also run the range-image segmentation stage (OdomNode::applySegmentation, odom.cc:853-857) on every frame")
     ap.add_argument("--k", type=int, default=20, help="kCorrespondences of both engines (engine default 20; the DLO yaml uses 10)")
+    ap.add_argument("--cpp", action="store_true", help="run the frame loop in C++ (tests/cpp/odometry_sequence.cpp on the C ABI and the "
+                    "device-resident keyframe store): no Python inside a frame")
+    ap.add_argument("--kcv", type=int, default=10, help="--cpp: nearest convex-hull keyframes added to the submap (the reference's default)")
+    ap.add_argument("--kcc", type=int, default=10, help="--cpp: nearest concave-hull keyframes")
     args = ap.parse_args()
+    if args.cpp:
+        return main_cpp(args)
 
     from dynamic_direct_lidar_odometry_b200 import nano_gicp as ng
     from dynamic_direct_lidar_odometry_b200 import odometry_loop as ol

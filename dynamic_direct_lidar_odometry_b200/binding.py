@@ -87,6 +87,7 @@ SIGNATURES = {
     "ddlo_cloud_concat": [_vp, _vpp, C.c_int, _vpp],
     "ddlo_cloud_voxel_filter": [_vp, C.c_float, C.c_float, C.c_float, _vpp],
     "ddlo_cloud_crop_box": [_vp, _vp, _vp, C.c_int, C.c_int, _vpp],
+    "ddlo_cloud_extract_stride": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vpp],
     "ddlo_covs_compute": [_vp, C.c_int, C.c_int, _vpp],
     "ddlo_covs_from_host": [_vp, _vp, C.c_int, _vpp],
     "ddlo_covs_to_host": [_vp, _vp],
@@ -127,6 +128,14 @@ SIGNATURES = {
     "ddlo_segment_scan": [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _ip, _vp],
     "ddlo_gicp_segment_scan": [_vp, _vp, _vp, C.c_int, _vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, C.c_int, _ip, _vp],
     "ddlo_gicp_align_batch": [_vpp, C.c_int, _vp, C.POINTER(AlignResult)],
+    "ddlo_keyframes_create": [_vp, _vpp],
+    "ddlo_keyframes_destroy": [_vp],
+    "ddlo_keyframes_count": [_vp, _ip],
+    "ddlo_keyframes_add": [_vp, _vp, _vp, _vp, _vp],
+    "ddlo_keyframes_get": [_vp, C.c_int, _vp, _vp, _vpp, _vpp],
+    "ddlo_keyframes_is_new": [_vp, _vp, _vp, C.c_float, C.c_float, _ip, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)],
+    "ddlo_keyframes_get_submap": [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _ip, _vpp, _vpp, _vp, C.c_int, _ip],
+    "ddlo_keyframes_hulls": [_vp, _vp, _ip, _vp, _ip, C.c_int, _ip],
     "ddlo_cloud_share": [_vp],
     "ddlo_covs_share": [_vp, _vp],
     "ddlo_batch_create": [C.c_int, C.c_int, C.c_int, C.c_int, _vpp],
@@ -225,6 +234,11 @@ def load() -> C.CDLL:
     L.ddlo_gicp_debug_visits.argtypes = [_vp, _vp, C.c_int]
     L.ddlo_gicp_debug_timeline.restype = C.c_int
     L.ddlo_gicp_debug_timeline.argtypes = [_vp, _vp, C.c_int]
+    for name, args in (("ddlo_hull_convex", [_vp, C.c_int, _vp, C.c_int]), ("ddlo_hull_concave", [_vp, C.c_int, C.c_double, _vp, C.c_int]),
+                       ("ddlo_hull_dimension", [_vp, C.c_int])):
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
     L.ddlo_align_d2h_bytes.restype = C.c_int
     L.ddlo_align_d2h_bytes.argtypes = []
     L.ddlo_gicp_debug_enable.restype = C.c_int

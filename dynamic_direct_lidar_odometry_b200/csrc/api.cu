@@ -30,6 +30,7 @@ int index_nonfinite_count(ddlo_cloud* c, int* count);
 int voxel_filter_device(ddlo_runtime* rt, const float4* pts, int n, const float leaf[3], float4** d_out, int* n_out);
 int crop_box_device(ddlo_runtime* rt, const float4* pts, int n, const float lo[3], const float hi[3], int negative, int keep_organized,
                     float4** d_out, int* n_out);
+int extract_stride_device(ddlo_runtime* rt, const float4* pts, int n, int width, int height, int row_stride, int col_stride, float4** d_out);
 int residual_image_device(ddlo_runtime* rt, const float4* pts, const float* sqd, int n, int w, int h, double a_min, double a_max, float4* d_out);
 int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, const float* T16, const float* d_scan, int stride_floats,
                         const float* d_residuals, int res_stride, int* d_label, float* d_range, signed char* d_ground, double* d_avg_by_label,
@@ -513,6 +514,17 @@ int ddlo_cloud_crop_box(ddlo_cloud* c, const float* min_xyz, const float* max_xy
   int n = 0;
   DDLO_TRY(crop_box_device(c->rt, c->pts, c->n, min_xyz, max_xyz, negative, keep_organized, &d, &n));
   return cloud_adopt(c->rt, d, n, out);
+}
+
+int ddlo_cloud_extract_stride(ddlo_cloud* c, int width, int height, int row_stride, int col_stride, ddlo_cloud** out) {
+  if (!c || !out) return fail(DDLO_E_INVALID, "null argument");
+  *out = nullptr;
+  if (width < 1 || height < 1 || row_stride < 1 || col_stride < 1) return fail(DDLO_E_INVALID, "extract_stride: sizes and strides must be positive");
+  if ((long long)width * height > c->n) return fail(DDLO_E_SIZE, "extract_stride: the cloud is smaller than width x height (not an organised scan of that shape)");
+  DDLO_TRY(use_device(c->rt));
+  float4* d = nullptr;
+  DDLO_TRY(extract_stride_device(c->rt, c->pts, c->n, width, height, row_stride, col_stride, &d));
+  return cloud_adopt(c->rt, d, c->n, out);
 }
 
 int ddlo_cloud_concat(ddlo_runtime* rt, ddlo_cloud* const* parts, int m, ddlo_cloud** out) {

@@ -288,6 +288,35 @@ int crop_box_device(ddlo_runtime* rt, const float4* pts, int n, const float lo[3
   return DDLO_OK;
 }
 
+// ---- strided organised down-sample (first stage) ---------------------------------
+// OdomNode::preprocessPoints, odom.cc:445-455: pcl::ExtractIndices<PointType> with the index mask built at
+// odom.cc:124-130 (every downsample_filter_row_-th row and downsample_filter_col_-th column of the
+// cloud_height_ x cloud_width_ scan), setNegative(false), setKeepOrganized(true): the cloud keeps its size and
+// order, and every point that is NOT in the mask gets user_filter_value_ = NaN in all its fields
+// (pcl/filters/impl/extract_indices.hpp, PCL 1.10: `output = *input_`, then the removed indices are overwritten).
+__global__ void __launch_bounds__(256) k_extract_stride(const float4* __restrict__ pts, int n, int width, int height, int row_stride,
+                                                        int col_stride, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int row = i / width, col = i - row * width;
+  const bool keep = row < height && row % row_stride == 0 && col % col_stride == 0;
+  const float nan = __int_as_float(0x7fc00000);
+  const float4 p = pts[i];
+  out[i] = keep ? make_float4(p.x, p.y, p.z, 1.0f) : make_float4(nan, nan, nan, 1.0f);
+}
+
+int extract_stride_device(ddlo_runtime* rt, const float4* pts, int n, int width, int height, int row_stride, int col_stride, float4** d_out) {
+  *d_out = nullptr;
+  cudaStream_t st = rt->stream;
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(d_out), std::max<size_t>(1, (size_t)n) * sizeof(float4), st));
+  if (n > 0) {
+    k_extract_stride<<<(n + 255) / 256, 256, 0, st>>>(pts, n, width, height, row_stride, col_stride, *d_out);
+    rt->launches += 1;
+  }
+  DDLO_CUDA(cudaGetLastError());
+  return DDLO_OK;
+}
+
 // ---- residual image ------------------------------------------------------------
 // OdomNode::scanMatching, odom.cc:804-827: the registration scan is projected into a W x H angular image,
 // theta = atan2(x, z), phi = atan2(y, sqrt(x^2 + z^2)), u = int((theta - a_min) / (a_max - a_min) * W), v alike

@@ -179,6 +179,12 @@ class PointCloud:
         B.check(B.load().ddlo_cloud_crop_box(self._h, B.ptr(lo), B.ptr(hi), int(negative), int(keep_organized), C.byref(h)))
         return PointCloud(self.rt, _handle=h)
 
+    def stride_filtered(self, width: int, height: int, row_stride: int, col_stride: int) -> "PointCloud":
+        """pcl::ExtractIndices with the strided mask of odom.cc:124-130, keep-organised (odom.cc:445-455): same size, NaN elsewhere."""
+        h = C.c_void_p()
+        B.check(B.load().ddlo_cloud_extract_stride(self._h, width, height, row_stride, col_stride, C.byref(h)))
+        return PointCloud(self.rt, _handle=h)
+
     @staticmethod
     def concat(rt: Runtime, parts: Sequence["PointCloud"]) -> "PointCloud":
         arr = (C.c_void_p * len(parts))(*[p._h for p in parts])
@@ -642,3 +648,95 @@ class Batch:
         n = C.c_longlong()
         B.check(B.load().ddlo_batch_launch_count(self._b, C.byref(n)))
         return n.value
+
+
+def rotation_to_wxyz(R) -> np.ndarray:
+    """unit quaternion (w, x, y, z) of a 3x3 rotation (what OdomNode keeps as rotq_)"""
+    R = np.asarray(R, dtype=np.float64)
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = [0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s]
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(1.0 + R[i, i] - R[j, j] - R[k, k]) * 2
+        q = [0.0] * 4
+        q[0] = (R[k, j] - R[j, k]) / s
+        q[1 + i] = 0.25 * s
+        q[1 + j] = (R[j, i] + R[i, j]) / s
+        q[1 + k] = (R[k, i] + R[i, k]) / s
+    return np.asarray(q, dtype=np.float32)
+
+
+class KeyframeStore:
+    """ddlo_keyframes_*: OdomNode's keyframes_ / keyframe_normals_ on the device, the new-keyframe decision of
+    updateKeyframes and the submap selection + assembly of getSubmapKeyframes (odom.cc:1067-1150, 1215-1315)."""
+
+    def __init__(self, rt: Runtime):
+        self.rt = rt
+        self._k = C.c_void_p()
+        B.check(B.load().ddlo_keyframes_create(rt._h, C.byref(self._k)))
+
+    def __del__(self):
+        if getattr(self, "_k", None):
+            try:
+                B.load().ddlo_keyframes_destroy(self._k)
+            except Exception:
+                pass
+            self._k = None
+
+    def __len__(self) -> int:
+        n = C.c_int()
+        B.check(B.load().ddlo_keyframes_count(self._k, C.byref(n)))
+        return n.value
+
+    def add(self, position, rotation_wxyz, cloud: PointCloud, covs: Covariances):
+        p = np.ascontiguousarray(position, dtype=np.float32)
+        q = np.ascontiguousarray(rotation_wxyz, dtype=np.float32)
+        B.check(B.load().ddlo_keyframes_add(self._k, B.ptr(p), B.ptr(q), cloud._h, covs._h))
+
+    def is_new(self, position, rotation_wxyz, thresh_dist: float, thresh_rot_deg: float):
+        """(new keyframe?, closest index, distance to it, rotation against it in degrees)"""
+        p = np.ascontiguousarray(position, dtype=np.float32)
+        q = np.ascontiguousarray(rotation_wxyz, dtype=np.float32)
+        new, idx, d, th = C.c_int(), C.c_int(), C.c_float(), C.c_float()
+        B.check(B.load().ddlo_keyframes_is_new(self._k, B.ptr(p), B.ptr(q), thresh_dist, thresh_rot_deg, C.byref(new), C.byref(idx), C.byref(d), C.byref(th)))
+        return bool(new.value), idx.value, d.value, th.value
+
+    def get_submap(self, position, knn: int = 10, kcv: int = 10, kcc: int = 10, alpha: float = 1.0):
+        """(changed, indices, cloud or None, covariances or None) - the cloud and covariances are built on the device"""
+        p = np.ascontiguousarray(position, dtype=np.float32)
+        changed, n = C.c_int(), C.c_int()
+        cap = max(len(self), 1)
+        idx = np.zeros(cap, dtype=np.int32)
+        hc, hv = C.c_void_p(), C.c_void_p()
+        B.check(B.load().ddlo_keyframes_get_submap(self._k, B.ptr(p), knn, kcv, kcc, float(alpha), C.byref(changed), C.byref(hc), C.byref(hv),
+                                                   B.ptr(idx), cap, C.byref(n)))
+        cloud = PointCloud(self.rt, _handle=hc) if hc.value else None
+        covs = Covariances(self.rt, _handle=hv) if hv.value else None
+        return bool(changed.value), idx[: n.value].tolist(), cloud, covs
+
+    def hulls(self):
+        """(convex hull vertex indices, concave hull vertex indices, dimension of the concave hull) of the last get_submap"""
+        cap = max(len(self), 1)
+        cv, cc = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        ncv, ncc, dim = C.c_int(), C.c_int(), C.c_int()
+        B.check(B.load().ddlo_keyframes_hulls(self._k, B.ptr(cv), C.byref(ncv), B.ptr(cc), C.byref(ncc), cap, C.byref(dim)))
+        return cv[: ncv.value].tolist(), cc[: ncc.value].tolist(), dim.value
+
+
+def hull_convex(points) -> list:
+    """convex-hull vertex indices of (n, 3) positions as the keyframe store computes them (csrc/hull.hpp; host only)"""
+    p = np.ascontiguousarray(points, dtype=np.float64)
+    out = np.zeros(max(len(p), 1), dtype=np.int32)
+    m = B.load().ddlo_hull_convex(B.ptr(p), len(p), B.ptr(out), len(out))
+    return out[:m].tolist()
+
+
+def hull_concave(points, alpha: float):
+    """concave-hull (alpha shape) vertex indices, or None when the positions are 3-dimensional in PCL's sense"""
+    p = np.ascontiguousarray(points, dtype=np.float64)
+    out = np.zeros(max(len(p), 1), dtype=np.int32)
+    m = B.load().ddlo_hull_concave(B.ptr(p), len(p), float(alpha), B.ptr(out), len(out))
+    return None if m == -3 else out[:m].tolist()

@@ -6,7 +6,7 @@ This replays, around two NanoGICP engines, exactly the calls of
     OdomNode::scanMatching            odom.cc:745-793
     OdomNode::propagateS2S / S2M      odom.cc:921-955
     OdomNode::updateKeyframes         odom.cc:1067-1150
-    OdomNode::getSubmapKeyframes      odom.cc:1215-1315 (nearest-keyframe selection + concatenation)
+    OdomNode::getSubmapKeyframes      odom.cc:1215-1315 (nearest keyframes + nearest convex- / concave-hull keyframes, concatenation)
 so that the sequence benchmark (benchmarks/c3_sequence.py) and the sequence parity test exercise the
 engine with the reference's own protocol: S2S align, covariance hand-over to S2M, swapSourceAndTarget,
 shared source index, keyframe covariances computed through the S2S source slot, submap clouds and
@@ -15,8 +15,11 @@ only when the selection changed.
 
 It is written against a tiny backend interface (`GpuBackend`: every cloud, covariance vector and submap
 stays on the device) so that the tests can replay the very same loop on their CPU checker with a
-backend of their own (tests/oracle_backend.py); this package has no CPU path.  Out of scope here, as in SURVEY.md §8: IMU prior, voxel filters,
-convex/concave-hull keyframe selection (only the k nearest keyframes are used), ROS I/O.
+backend of their own (tests/oracle_backend.py); this package has no CPU path.  The hull part of the keyframe selection
+(submap_kcv / submap_kcc > 0) asks the backend for the hull vertices: the GPU backend uses the C++ hull code of the
+keyframe store (csrc/hull.hpp), the tests' backend uses Qhull through scipy.  The same loop written in C++ on the
+keyframe store of the C ABI (ddlo_keyframes_*) is tests/cpp/odometry_sequence.cpp.  Out of scope, as in SURVEY.md §8:
+IMU prior, ROS I/O.
 """
 from __future__ import annotations
 
@@ -67,6 +70,10 @@ class GpuBackend:
     def hand_over_source_covs(self, s2m, s2s):  # odom.cc:765
         s2m.source_covs_ = s2s.source_covs_
 
+    def hull_indices(self, positions, alpha):  # computeConvexHull / computeConcaveHull (odom.cc:993-1065) -> csrc/hull.hpp
+        cc = self.ng.hull_concave(positions, alpha)
+        return self.ng.hull_convex(positions), ([] if cc is None else cc)
+
     def sync(self):
         self.rt.synchronize()
 
@@ -81,6 +88,8 @@ class LoopConfig:
     keyframe_thresh_dist: float = 1.0   # metres (odom.cc:1169, "rebuilt every 1 m" in SURVEY.md §8d C3)
     keyframe_thresh_rot: float = 15.0   # degrees
     submap_knn: int = 10                # odomNode/submap/keyframe/knn
+    submap_kcv: int = 0                 # .../kcv: nearest keyframes among the convex-hull vertices (the reference's default is 10; 0 = off)
+    submap_kcc: int = 0                 # .../kcc: the same for the concave hull (alpha = keyframe_thresh_dist, odom.cc:1175)
     voxel_leaf_scan: Optional[float] = None    # vf_scan_ leaf size (preprocessPoints, odom.cc:469-474); None = off
     voxel_leaf_submap: Optional[float] = None  # vf_submap_ leaf size applied to every new keyframe (odom.cc:494-499, 1133-1137)
 
@@ -129,6 +138,8 @@ class OdometryLoop:
         self.keyframes: List[Keyframe] = []
         self.submap_idx_prev: List[int] = []
         self.records: List[FrameRecord] = []
+        self._convex: List[int] = []   # keyframe_convex_ / keyframe_concave_
+        self._concave: List[int] = []
         self._initialised = False
 
     # odom.cc:480-516
@@ -143,17 +154,36 @@ class OdometryLoop:
         self.keyframes.append(Keyframe(self.T[:3, 3].copy(), self.T[:3, :3].copy(), first, self.s2s.getSourceCovariances(), self.b.size(first)))
         self._initialised = True
 
-    # odom.cc:1215-1315, nearest keyframes only
+    @staticmethod
+    def _push_submap_indices(dists, k, frames, out):  # odom.cc:1178-1213: every frame at most as far as the k-th nearest
+        if not dists or k <= 0:
+            return
+        kth = sorted(dists)[min(k, len(dists)) - 1]
+        out.extend(f for f, v in zip(frames, dists) if v <= kth)
+
+    # odom.cc:1215-1315
     def _submap_selection(self, position) -> List[int]:
-        d = [float(np.sqrt(np.sum((position.astype(np.float32) - k.position) ** 2, dtype=np.float32))) for k in self.keyframes]
-        order = np.argsort(np.asarray(d), kind="stable")[: self.cfg.submap_knn]
-        kth = d[order[-1]]
-        return sorted(i for i, v in enumerate(d) if v <= kth)  # "all elements smaller or equal to the kth smallest"
+        pos = position.astype(np.float32)
+        # float differences, double squares and root, rounded to float (sqrt(pow(float, 2) + ...) assigned to a float)
+        d = [float(np.float32(np.sqrt(np.sum((pos - k.position).astype(np.float64) ** 2)))) for k in self.keyframes]
+        sel: List[int] = []
+        self._push_submap_indices(d, self.cfg.submap_knn, list(range(len(d))), sel)
+        if self.cfg.submap_kcv > 0 or self.cfg.submap_kcc > 0:
+            n = len(self.keyframes)
+            pts = np.array([k.position for k in self.keyframes], dtype=np.float64)
+            convex, concave = self.b.hull_indices(pts, self.cfg.keyframe_thresh_dist) if n >= 4 else ([], [])
+            if n >= 4:  # computeConvexHull: at least 4 keyframes, else the previous (empty) list stays
+                self._convex = convex
+            if n >= 5:  # computeConcaveHull: at least 5
+                self._concave = concave
+            self._push_submap_indices([d[i] for i in self._convex], self.cfg.submap_kcv, self._convex, sel)
+            self._push_submap_indices([d[i] for i in self._concave], self.cfg.submap_kcc, self._concave, sel)
+        return sorted(set(sel))
 
     # odom.cc:1067-1150
     def _update_keyframes(self, scan_cloud, n) -> bool:
         pos, rot = self.T[:3, 3], self.T[:3, :3]
-        d = [float(np.sqrt(np.sum((pos - k.position) ** 2, dtype=np.float32))) for k in self.keyframes]
+        d = [float(np.float32(np.sqrt(np.sum((pos - k.position).astype(np.float64) ** 2)))) for k in self.keyframes]
         closest = int(np.argmin(d))
         num_nearby = sum(1 for v in d if v <= self.cfg.keyframe_thresh_dist * 1.5)
         dd, theta = d[closest], _rot_angle_deg(rot, self.keyframes[closest].rotation)

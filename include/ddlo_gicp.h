@@ -155,6 +155,11 @@ int ddlo_covs_share(ddlo_covs* v, ddlo_cloud* target /* or NULL */);
  * ascending index order, non-finite points dropped.  DDLO_E_UNSUPPORTED when the voxel index space does not fit
  * an int (PCL prints "Leaf size is too small for the input dataset" and passes the cloud through). */
 int ddlo_cloud_voxel_filter(ddlo_cloud* c, float leaf_x, float leaf_y, float leaf_z, ddlo_cloud** out);
+/* The strided organised down-sample OdomNode::preprocessPoints runs first (odom.cc:445-455): pcl::ExtractIndices with
+ * the mask of odom.cc:124-130 - rows 0, row_stride, 2 row_stride, ... and columns 0, col_stride, ... of the
+ * height x width scan (row-major) - setNegative(false), setKeepOrganized(true): same size and order, every other
+ * point becomes NaN.  The cloud must hold at least width * height points; points behind that are removed too. */
+int ddlo_cloud_extract_stride(ddlo_cloud* c, int width, int height, int row_stride, int col_stride, ddlo_cloud** out);
 /* pcl::CropBox<PointXYZI>::filter with setMin/setMax (identity box pose): keeps the points inside the box, or
  * outside with negative != 0 (setNegative); keep_organized != 0 (setKeepOrganized) keeps the size and order and
  * overwrites removed points with NaN. */
@@ -335,6 +340,37 @@ int ddlo_batch_submit(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_ali
 int ddlo_batch_wait(ddlo_batch* b);
 int ddlo_batch_run(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_result* results);
 int ddlo_batch_launch_count(ddlo_batch* b, long long* count); /* kernels launched by all lanes since creation */
+
+/* ---- keyframe store and submap builder -------------------------------------------------------
+ * What OdomNode keeps in host vectors around the path - keyframes_ (pose + world-frame cloud, odom.h:105-106) and
+ * keyframe_normals_ (their covariances, :107-108) - lives on the device here, and getSubmapKeyframes
+ * (odom.cc:1215-1315) becomes: selection on the host (a few scalar operations per keyframe), concatenation on the
+ * device.  One store belongs to one runtime. */
+typedef struct ddlo_keyframes ddlo_keyframes;
+int ddlo_keyframes_create(ddlo_runtime* rt, ddlo_keyframes** out);
+int ddlo_keyframes_destroy(ddlo_keyframes* k);
+int ddlo_keyframes_count(const ddlo_keyframes* k, int* n);
+/* keyframes_.push_back(...) + keyframe_normals_.push_back(getSourceCovariances()) (odom.cc:502-510, 1139-1149):
+ * position = pose_, rotation = rotq_ as (w, x, y, z); the handles are shared (retained), nothing is copied. */
+int ddlo_keyframes_add(ddlo_keyframes* k, const float* position_xyz, const float* rotation_wxyz, ddlo_cloud* cloud_world, ddlo_covs* covs);
+int ddlo_keyframes_get(ddlo_keyframes* k, int index, float* position_xyz, float* rotation_wxyz, ddlo_cloud** cloud, ddlo_covs** covs); /* outputs optional; handles retained */
+/* The decision of updateKeyframes (odom.cc:1067-1126) for the current pose: distance to the closest keyframe, rotation
+ * against it, the count of keyframes within 1.5 thresh_dist.  Optional outputs may be NULL. */
+int ddlo_keyframes_is_new(const ddlo_keyframes* k, const float* position_xyz, const float* rotation_wxyz, float thresh_dist, float thresh_rot_deg,
+                          int* is_new, int* closest_index, float* closest_distance, float* rotation_deg);
+/* getSubmapKeyframes (odom.cc:1215-1315) for the pose current_xyz (the translation of T_s2s_): the submap_knn nearest
+ * keyframes, the submap_kcv nearest among the convex-hull vertices of all keyframe positions and the submap_kcc nearest
+ * among the concave-hull vertices (alpha = concave_alpha, the reference sets keyframe_thresh_dist_, odom.cc:1175), ties
+ * included as pushSubmapIndices includes them (:1178-1213), sorted and made unique.  *changed = 0: the selection equals
+ * the previous one (submap_hasChanged_ = false) and no cloud is built; *changed = 1: *cloud and *covs (new handles, the
+ * caller releases them) are the selected keyframes' clouds and covariances concatenated ON THE DEVICE in index order
+ * (:1298-1313).  indices / n_indices (optional) receive the selection.  Hulls: pcl::ConvexHull / pcl::ConcaveHull
+ * restated on the host (csrc/hull.hpp); for keyframe positions that are three-dimensional in PCL's sense (smallest /
+ * largest covariance eigenvalue >= 1e-3) the concave hull is not implemented and contributes nothing. */
+int ddlo_keyframes_get_submap(ddlo_keyframes* k, const float* current_xyz, int submap_knn, int submap_kcv, int submap_kcc, double concave_alpha,
+                              int* changed, ddlo_cloud** cloud, ddlo_covs** covs, int* indices, int capacity, int* n_indices);
+/* keyframe_convex_ / keyframe_concave_ of the last call, and the dimension (2 or 3) the concave hull was taken in */
+int ddlo_keyframes_hulls(const ddlo_keyframes* k, int* convex, int* n_convex, int* concave, int* n_concave, int capacity, int* concave_dimension);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,11 @@ void ddlo_math_ldlt6_solve(const double* A36, const double* rhs6, double* x6); /
 void ddlo_math_ldlt6_solve_fast(const double* A36, const double* rhs6, double* x6); /* register-resident SPD path of the kernel */
 void ddlo_math_so3_exp(const double* omega3, double* R9);                       /* gicp/so3.hpp:101-124 */
 void ddlo_math_sym3_inverse(const double* sym6, double* out6);
+/* the hull functions of the keyframe store (csrc/hull.hpp) on n points (x, y, z doubles): number of hull vertices,
+ * indices (sorted) written up to capacity; ddlo_hull_concave returns -3 for points that are 3-dimensional in PCL's sense */
+int ddlo_hull_convex(const double* xyz, int n, int* out_indices, int capacity);
+int ddlo_hull_concave(const double* xyz, int n, double alpha, int* out_indices, int capacity);
+int ddlo_hull_dimension(const double* xyz, int n);
 struct ddlo_gicp;
 /* bytes of the result record one align copies device -> host */
 int ddlo_align_d2h_bytes(void);

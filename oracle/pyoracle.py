@@ -228,6 +228,23 @@ def crop_box(points, box_min, box_max, negative: bool = False, keep_organized: b
     return out[:m].copy()
 
 
+def extract_stride(points, width: int, height: int, row_stride: int, col_stride: int) -> np.ndarray:
+    """OdomNode's strided organised down-sample restated (TEST INFRASTRUCTURE).  The mask is built exactly as
+    odom.cc:124-130 builds downsample_filter_indices_ (row * cloud_width_ + col for row = 0, row_stride, ... and
+    col = 0, col_stride, ...); pcl::ExtractIndices with setNegative(false) + setKeepOrganized(true) (odom.cc:445-455;
+    PCL 1.10 filters/impl/extract_indices.hpp: output = input, then every index NOT in the mask gets
+    user_filter_value_ = NaN in each field).  PCL is not under /root/reference: parity unpinned, like the other filters."""
+    p = _as_points(points)
+    keep = np.zeros(p.shape[0], dtype=bool)
+    for row in range(0, height, row_stride):
+        for col in range(0, width, col_stride):
+            keep[row * width + col] = True
+    out = np.ones((p.shape[0], 4), dtype=np.float32)
+    out[:, :3] = p[:, :3]
+    out[~keep, :3] = np.nan
+    return out
+
+
 def residual_image(points, residuals, width: int = 512, height: int = 512, angle_min: float = -np.pi / 3, angle_max: float = np.pi / 3) -> np.ndarray:
     """odom.cc:804-827 restated (oracle_gicp.cpp oracle_residual_image): (height, width, 4) float32."""
     p = _as_points(points)

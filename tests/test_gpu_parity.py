@@ -407,6 +407,35 @@ def test_c2_align_matches_oracle(rt, oracle):
 
 
 # ----------------------------------------------------------------------------- the C++ shim (host side)
+def test_cpp_shim_pcl_eigen_branch_equals_pod_branch(tmp_path):
+    """tests/cpp/shim_pcl_branch.cpp is the shim compiled the way OdomNode would compile it - pcl::PointCloud<pcl::PointXYZI>::Ptr,
+    Eigen::Matrix4f, std::vector<Eigen::Matrix4d, aligned_allocator> (stand-in headers of oracle/stub_include on a test-only
+    include path) - replaying odom.cc:480-532, 745-793, 1140-1149; every line it prints must equal what the POD branch
+    (shim_protocol.cpp) prints for the same scans."""
+    import subprocess
+    from pathlib import Path
+
+    build = Path(__file__).resolve().parent / "cpp" / "_build"
+    if not (build / "shim_pcl_branch").exists() or not (build / "shim_protocol").exists():
+        import __graft_entry__ as ge
+
+        ge.build_cpp_tests()
+    w = synth.make_world()
+    scans = [synth.scan(f, 16, 256, w) for f in range(4)]
+    path = tmp_path / "scans.bin"
+    with open(path, "wb") as fh:
+        fh.write(np.int32(len(scans)).tobytes())
+        for s in scans:
+            fh.write(np.int32(len(s)).tobytes())
+            fh.write(np.ascontiguousarray(s, dtype=np.float32).tobytes())
+    outs = []
+    for exe in ("shim_protocol", "shim_pcl_branch"):
+        out = subprocess.run([str(build / exe), str(path)], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        outs.append(out.stdout.splitlines())
+    assert len(outs[0]) == 3 * 3 + 1 and outs[0] == outs[1]
+
+
 def test_cpp_shim_replays_odomnode_protocol(rt, tmp_path):
     """tests/cpp/shim_protocol.cpp drives nano_gicp::NanoGICP (the C++ header that keeps the reference's
     class interface) through OdomNode's call sequence; the same sequence through the Python mirror of
@@ -879,3 +908,29 @@ def test_sequence_loop_with_voxel_filters_matches_oracle(rt, oracle):
             o.s2s_iterations, o.s2m_iterations, o.new_keyframe, o.submap_changed, o.submap_points)
         assert np.abs(g.T[:3, 3].astype(np.float64) - o.T[:3, 3]).max() < POSE_T
         assert rot_angle(g.T[:3, :3], o.T[:3, :3]) < POSE_R
+
+
+def test_stride_filter_matches_oracle(rt, oracle):
+    """ddlo_cloud_extract_stride = pcl::ExtractIndices with OdomNode's strided mask, keep-organised (odom.cc:124-130,
+    445-455): bit-exact kept points, NaN elsewhere; then the reference's order of stages (stride -> crop -> voxel)."""
+    w = synth.make_world()
+    org = synth.organized_scan(2, 32, 512, w, dropout=0.02).reshape(-1, 4)
+    c = ng.PointCloud(rt, org)
+    for rs, cs in ((1, 1), (2, 4), (3, 5), (32, 512), (40, 600)):
+        got = c.stride_filtered(512, 32, rs, cs).download()
+        want = oracle.extract_stride(org, 512, 32, rs, cs)
+        assert got.shape == want.shape and np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.array_equal(got[~np.isnan(got)].view(np.uint32), want[~np.isnan(want)].view(np.uint32))
+    # a shape smaller than the cloud: the points behind height * width are not in the mask either
+    got = c.stride_filtered(512, 16, 2, 2).download()
+    assert np.isnan(got[16 * 512:, :3]).all() and np.array_equal(np.isnan(got), np.isnan(oracle.extract_stride(org, 512, 16, 2, 2)))
+    with pytest.raises(B.DdloError) as e:
+        c.stride_filtered(512, 33, 1, 1)
+    assert e.value.code == -6
+    with pytest.raises(B.DdloError) as e:
+        c.stride_filtered(512, 32, 0, 1)
+    assert e.value.code == -1
+    lo, hi = np.array([-1.0, -1.0, -1.0], np.float32), np.array([1.0, 1.0, 1.0], np.float32)
+    chain = c.stride_filtered(512, 32, 2, 2).cropped(lo, hi, negative=True, keep_organized=True).voxel_filtered(0.25).download()
+    want = oracle.voxel_filter(oracle.crop_box(oracle.extract_stride(org, 512, 32, 2, 2), lo, hi, negative=True, keep_organized=True), 0.25)
+    assert np.array_equal(chain.view(np.uint32), want.view(np.uint32))

@@ -77,3 +77,13 @@ def test_residual_image_oracle(oracle):
         want[v[i], u[i]] = (scan[i, 0], scan[i, 1], scan[i, 2], np.float32(res[i]))
     assert np.array_equal(img, want)
     assert (img[..., 3] > 0).any() and (img[..., 3] == 0).any()
+
+
+def test_extract_stride_known_answer(oracle):
+    """the strided mask of odom.cc:124-130 on a 4 x 6 scan with strides (2, 3): rows 0 and 2, columns 0 and 3"""
+    pts = np.ones((24, 4), np.float32)
+    pts[:, 0] = np.arange(24)
+    out = oracle.extract_stride(pts, 6, 4, 2, 3)
+    kept = np.flatnonzero(~np.isnan(out[:, 0]))
+    assert kept.tolist() == [0, 3, 12, 15]
+    assert np.array_equal(out[kept, 0], pts[kept, 0]) and (out[:, 3] == 1.0).all()
