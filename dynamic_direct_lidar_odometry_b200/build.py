@@ -17,7 +17,7 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 OBJ_DIR = PKG / "_build"
 LIB_PATH = LIB_DIR / "libddlo_gicp_b200.so"
-SOURCES = ["api.cu", "index.cu", "knn_cov.cu", "gicp.cu", "preprocess.cu", "cluster_sort.cu", "segmentation.cu", "batch.cu", "batch_align.cu",
+SOURCES = ["api.cu", "prims.cu", "index.cu", "knn_cov.cu", "gicp.cu", "preprocess.cu", "cluster_sort.cu", "segmentation.cu", "batch.cu", "batch_align.cu",
            "keyframes.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -103,8 +103,14 @@ static void runtime_teardown(ddlo_runtime* rt) {
   if (rt->h_pinned) cudaFreeHost(rt->h_pinned);
   if (rt->ev0) cudaEventDestroy(rt->ev0);
   if (rt->ev1) cudaEventDestroy(rt->ev1);
+  if (rt->ev_fork) cudaEventDestroy(rt->ev_fork);
+  if (rt->ev_join) cudaEventDestroy(rt->ev_join);
   for (auto& e : rt->slots)
     if (e) cudaEventDestroy(e);
+  if (rt->side) {
+    cudaStreamSynchronize(rt->side);
+    cudaStreamDestroy(rt->side);
+  }
   if (rt->stream) cudaStreamDestroy(rt->stream);
   delete rt;
 }
@@ -236,6 +242,9 @@ int ddlo_runtime_create(int device, ddlo_runtime** out) {
 
 static int runtime_init(ddlo_runtime* rt, int device) {
   DDLO_CUDA(cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking));
+  DDLO_CUDA(cudaStreamCreateWithFlags(&rt->side, cudaStreamNonBlocking));
+  DDLO_CUDA(cudaEventCreateWithFlags(&rt->ev_fork, cudaEventDisableTiming));
+  DDLO_CUDA(cudaEventCreateWithFlags(&rt->ev_join, cudaEventDisableTiming));
   DDLO_CUDA(cudaEventCreate(&rt->ev0));
   DDLO_CUDA(cudaEventCreate(&rt->ev1));
   for (auto& e : rt->slots) DDLO_CUDA(cudaEventCreate(&e));
@@ -260,6 +269,7 @@ static int runtime_init(ddlo_runtime* rt, int device) {
   }
   DDLO_CUDA(cudaMalloc(&rt->d_scratch, 1u << 20));
   rt->d_scratch_bytes = 1u << 20;
+  DDLO_CUDA(cudaMemsetAsync(rt->d_scratch, 0, rt->d_scratch_bytes, rt->stream));  // the index build keeps its ticket word here
   DDLO_TRY(ensure_pinned(rt, 1u << 16));
   int per_sm = 0;
   DDLO_TRY(gicp_max_coop_blocks(device, &per_sm));

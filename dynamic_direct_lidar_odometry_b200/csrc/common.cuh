@@ -84,6 +84,8 @@ struct ddlo_runtime {
   std::atomic<int> refs{1};
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;  // short independent work inside one call (node array initialisation during the sort)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t slots[16] = {};
   int num_sms = 0;

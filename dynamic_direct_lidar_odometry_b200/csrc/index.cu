@@ -7,35 +7,37 @@
 //
 //   1. k_bounds    cloud bounding box (block reduction + ordered-int atomics) + finite check
 //   2. k_morton    30-bit Morton key of every point; thread 0 publishes the lattice {lo, scale}
-//   3. radix sort  (key, original index) pairs                         [cub::DeviceRadixSort]
+//   3. radix sort  (key, original index) pairs (prims.cu; steps 1-3 are ONE kernel of a 16-CTA cluster for
+//                  scan-sized clouds, cluster_sort.cu)
 //   4. k_cells     per point: the level L(i) of its leaf cell = 1 + the longest prefix that any
-//                  window of kLeafMax+1 consecutive sorted points containing i still shares; the
-//                  flag "i is the first point of an internal cell of level t" for t = 0..9; the
-//                  gather of the point into Morton order
-//   5. inclusive scan of the level-major flags                         [cub::DeviceScan]
-//                  -> breadth-first node ids: the level-t node holding point i is S[t][i] - 1;
-//                  the last element is the node count (stays on the device)
-//   6. k_init_nodes, k_emit: for every level, every point folds its coordinates into the slot of
+//                  window of kLeafMax+1 consecutive sorted points containing i still shares; the gather of the point
+//                  into Morton order; per block and level t = 0..9 the number of points that are the first point of
+//                  an internal cell of level t.  The LAST block to finish turns these counts into per-block
+//                  prefixes and per-level bases: the level-t node that holds point i gets the breadth-first id
+//                  level_base[t] + block_prefix[t][block of i] + (cells of level t begun in i's block up to i) - 1,
+//                  and the node count stays on the device
+//   5. k_init_nodes  empty boxes (+inf / -inf) and references for the nodes that exist (for scan-sized clouds:
+//                  for the whole node array, on a side stream, while the sort runs on its 16 SMs)
+//   6. k_emit      for every level, every point folds its coordinates into the slot of
 //                  its cell in the parent node.  Points are sorted, so the points of one cell are
-//                  consecutive lanes: a segmented warp reduction first, then ONE ordered-int atomic
+//                  consecutive lanes: a segmented warp reduction first, then ONE float atomic
 //                  per run and box component.  The first point of a cell writes the child reference
 //                  (leaf: start, the count is accumulated per run; internal: child id + meta).
-//   7. k_finalize  ordered ints -> floats
 //
 // The node array is sized by the bound "every internal cell holds more than kLeafMax points and the
 // cells of one level are disjoint": at most 10 n / 17 + 1 nodes; only the nodes that exist are touched.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "common.cuh"
+#include "prims.cuh"
 
 namespace ddlo {
 
 int morton_sort_cluster(ddlo_runtime* rt, const float4* pts, int n, unsigned* keys_out, int* vals_out, float* lattice);  // cluster_sort.cu
+constexpr int kClusterSortMax = 16 * 512 * 16;  // the largest cloud the cluster sort takes
 
 __device__ __forceinline__ unsigned f2ord(float f) {
   const unsigned u = __float_as_uint(f);
@@ -45,8 +47,6 @@ __device__ __forceinline__ float ord2f(unsigned o) {
   const unsigned u = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o;
   return __uint_as_float(u);
 }
-constexpr unsigned kOrdPosInf = 0xff800000u;  // f2ord(+inf)
-constexpr unsigned kOrdNegInf = 0x007fffffu;  // f2ord(-inf)
 
 // bounds: [0..2] ordered min, [3..5] ordered max, [6] non-finite counter
 __global__ void __launch_bounds__(256) k_bounds(const float4* __restrict__ pts, int n, unsigned* __restrict__ bounds) {
@@ -148,50 +148,146 @@ __device__ __forceinline__ int common_digits(unsigned a, unsigned b) {
   return x ? (__clz(x) - 2) / 3 : kMortonLevels;
 }
 
-__global__ void __launch_bounds__(256) k_cells(const unsigned* __restrict__ keys, const int* __restrict__ perm,
-                                               const float4* __restrict__ pts, int n, unsigned char* __restrict__ leaf_level,
-                                               int* __restrict__ flags /*[10][n]*/, float4* __restrict__ spts) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned key = keys[i];
-  // longest prefix shared by kLeafMax+1 consecutive points around i: that cell is too big for a leaf
-  int g = -1;
-  const int j0 = max(0, i - kLeafMax), j1 = min(i, n - 1 - kLeafMax);
-  for (int j = j0; j <= j1; ++j) g = max(g, common_digits(__ldg(keys + j), __ldg(keys + j + kLeafMax)));
-  const int L = min(kMortonLevels, max(1, g + 1));
-  leaf_level[i] = (unsigned char)L;
-  const int cd = i == 0 ? -1 : common_digits(key, __ldg(keys + i - 1));
-#pragma unroll
-  for (int t = 0; t < kMortonLevels; ++t) flags[(size_t)t * n + i] = (t < L && cd < t) ? 1 : 0;
-  const int o = perm[i];
-  const float4 p = pts[o];
-  spts[i] = make_float4(p.x, p.y, p.z, __int_as_float(o));
+// float min / max by integer atomics: non-negative floats order like ints, negative ones in reverse like unsigned ints.
+// Correct for any mix of signs when the cell starts at +inf (min) / -inf (max); -0 is folded into +0 first.
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  v += 0.0f;
+  if (v >= 0.0f)
+    atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  v += 0.0f;
+  if (v >= 0.0f)
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
 }
 
-// the node count is the last element of the scanned flags
-__global__ void __launch_bounds__(256) k_init_nodes(unsigned* __restrict__ words, const int* __restrict__ n_nodes_ptr, float* lattice) {
-  const size_t n_words = (size_t)(*n_nodes_ptr) * 64;
-  if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int*>(lattice)[5] = *n_nodes_ptr;
+// per-build control words (device): [0] ticket of k_cells' blocks, [1] node count, [2..11] level bases
+
+// inclusive count, over the threads of the block up to and including this one, of a per-thread flag; all threads call
+__device__ __forceinline__ int block_inclusive_count(bool flag, int* s_wtot /*[8]*/, int* block_total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned b = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) s_wtot[warp] = __popc(b);
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const int t = s_wtot[w];
+    if (w < warp) base += t;
+    tot += t;
+  }
+  __syncthreads();
+  if (block_total) *block_total = tot;
+  return base + __popc(b & (0xffffffffu >> (31 - lane)));
+}
+
+__global__ void __launch_bounds__(256) k_cells(const unsigned* __restrict__ keys, const int* __restrict__ perm,
+                                               const float4* __restrict__ pts, int n, unsigned char* __restrict__ leaf_level,
+                                               int* __restrict__ counts /*[10][gridDim.x]: in: -, out: per-block prefixes*/, int* __restrict__ ctl,
+                                               float4* __restrict__ spts, float* __restrict__ lattice) {
+  __shared__ int s_wtot[8];
+  __shared__ int s_last;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  int L = 0, cd = kMortonLevels;
+  if (live) {
+    const unsigned key = keys[i];
+    // longest prefix shared by kLeafMax+1 consecutive points around i: that cell is too big for a leaf
+    int g = -1;
+    const int j0 = max(0, i - kLeafMax), j1 = min(i, n - 1 - kLeafMax);
+    for (int j = j0; j <= j1; ++j) g = max(g, common_digits(__ldg(keys + j), __ldg(keys + j + kLeafMax)));
+    L = min(kMortonLevels, max(1, g + 1));
+    leaf_level[i] = (unsigned char)L;
+    cd = i == 0 ? -1 : common_digits(key, __ldg(keys + i - 1));
+    const int o = perm[i];
+    const float4 p = pts[o];
+    spts[i] = make_float4(p.x, p.y, p.z, __int_as_float(o));
+  }
+  // cells of level t that begin in this block
+#pragma unroll
+  for (int t = 0; t < kMortonLevels; ++t) {
+    int tot = 0;
+    block_inclusive_count(live && t < L && cd < t, s_wtot, &tot);
+    if (threadIdx.x == 0) counts[(size_t)t * gridDim.x + blockIdx.x] = tot;
+  }
+  // the last block to arrive turns the counts into exclusive prefixes over the blocks and publishes the level bases
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ctl, 1) == (int)gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int nb = (int)gridDim.x;
+  const int per = (nb + 255) / 256;  // consecutive blocks per thread
+  int level_base = 0;
+  for (int t = 0; t < kMortonLevels; ++t) {
+    int* row = counts + (size_t)t * nb;
+    const int b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
+    int sum = 0;
+    for (int b = b0; b < b1; ++b) sum += __ldcg(row + b);
+    // exclusive prefix of the per-thread sums over the block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_wtot[warp] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int v = s_wtot[w];
+      if (w < warp) base += v;
+      tot += v;
+    }
+    __syncthreads();
+    int run = base + inc - sum;
+    for (int b = b0; b < b1; ++b) {
+      const int c = __ldcg(row + b);
+      row[b] = run;
+      run += c;
+    }
+    if (threadIdx.x == 0) ctl[2 + t] = level_base;
+    level_base += tot;
+  }
+  if (threadIdx.x == 0) {
+    ctl[1] = level_base;  // node count
+    reinterpret_cast<int*>(lattice)[5] = level_base;
+    ctl[0] = 0;
+  }
+}
+
+// empty nodes: boxes lo = +inf, hi = -inf, references 0.  n_nodes_ptr == nullptr: the whole array of max_nodes nodes.
+__global__ void __launch_bounds__(256) k_init_nodes(unsigned* __restrict__ words, const int* __restrict__ n_nodes_ptr, size_t max_nodes) {
+  const size_t n_words = (n_nodes_ptr ? (size_t)(*n_nodes_ptr) : max_nodes) * 64;
   for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < n_words; w += (size_t)gridDim.x * blockDim.x) {
     const int k = (int)(w & 63);
-    words[w] = k < 24 ? kOrdPosInf : (k < 48 ? kOrdNegInf : 0u);
+    words[w] = k < 24 ? 0x7f800000u : (k < 48 ? 0xff800000u : 0u);
   }
 }
 
 // One thread per sorted point.  For every tree level t = 1..L(i) the point belongs to a cell that is
-// a child slot of the level-(t-1) node S[t-1][i]-1.  The points of that cell are consecutive, so
+// a child slot of the level-(t-1) node holding it.  The points of that cell are consecutive, so
 // inside a warp they form one run of lanes: the run's box (and, for a leaf, its size) is reduced
 // with shuffles and its first lane issues the atomics.
 __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys, const unsigned char* __restrict__ leaf_level,
-                                              const int* __restrict__ S /*[10][n] inclusive scan*/, const float4* __restrict__ spts, int n,
-                                              unsigned* __restrict__ nodes, int4* __restrict__ meta, int* __restrict__ node_of_point) {
+                                              const int* __restrict__ block_prefix /*[10][gridDim.x]*/, const int* __restrict__ ctl,
+                                              const float4* __restrict__ spts, int n, float* __restrict__ nodes, int4* __restrict__ meta,
+                                              int* __restrict__ node_of_point) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool live = i < n;
   if (i == 0) meta[0] = make_int4(-1, 0, 0, 0);  // root
   unsigned key = 0;
   int L = 0, cd = kMortonLevels;
-  unsigned o[6] = {kOrdPosInf, kOrdPosInf, kOrdPosInf, kOrdNegInf, kOrdNegInf, kOrdNegInf};
+  float lo[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+  float hi[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
   int orig = 0;
   if (live) {
     key = keys[i];
@@ -199,14 +295,15 @@ __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys,
     cd = i == 0 ? -1 : common_digits(key, __ldg(keys + i - 1));
     const float4 p = spts[i];
     orig = __float_as_int(p.w);
-    o[0] = o[3] = f2ord(p.x);
-    o[1] = o[4] = f2ord(p.y);
-    o[2] = o[5] = f2ord(p.z);
+    lo[0] = hi[0] = p.x;
+    lo[1] = hi[1] = p.y;
+    lo[2] = hi[2] = p.z;
   }
   // deepest leaf level inside the block (all warps walk the same number of levels: the loop holds block barriers)
   __shared__ int s_lmax;
   __shared__ int s_cell0;
-  __shared__ unsigned s_box[8][6];
+  __shared__ float s_box[8][6];
+  __shared__ int s_wtot[8];
   if (threadIdx.x == 0) s_lmax = 0;
   __syncthreads();
   {
@@ -215,11 +312,16 @@ __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys,
   }
   __syncthreads();
   const int Lmax = s_lmax;
-  // the node ids of the point's cells on all its levels, fetched up front (independent loads: one memory
-  // latency instead of one per level)
+  // The node ids of the point's cells on all its levels: breadth-first = level base + cells of the level begun in
+  // earlier blocks + cells begun in this block up to the point (k_cells left the first two on the device).
   int nid[kMortonLevels];
 #pragma unroll
-  for (int t = 0; t < kMortonLevels; ++t) nid[t] = (live && t < L) ? __ldg(S + (size_t)t * n + i) - 1 : -1;
+  for (int t = 0; t < kMortonLevels; ++t) {
+    nid[t] = -1;
+    if (t >= Lmax) continue;  // uniform: nobody in the block has a cell on this level
+    const int within = block_inclusive_count(live && t < L && cd < t, s_wtot, nullptr);
+    if (live && t < L) nid[t] = __ldg(ctl + 2 + t) + __ldg(block_prefix + (size_t)t * gridDim.x + blockIdx.x) + within - 1;
+  }
 #pragma unroll
   for (int t = 1; t <= kMortonLevels; ++t) {
     if (t > Lmax) break;
@@ -230,7 +332,7 @@ __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys,
     if (in && t == L) node_of_point[orig] = parent;
     // child reference, written by the first point of the cell
     if (in && cd < t) {
-      unsigned* pw = nodes + (size_t)parent * 64;
+      unsigned* pw = reinterpret_cast<unsigned*>(nodes) + (size_t)parent * 64;
       if (t < L) {
         const int child = nid[t < kMortonLevels ? t : 0];  // t < L <= 10 here
         pw[48 + 2 * slot] = (unsigned)child;
@@ -249,96 +351,86 @@ __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys,
     const bool whole_block = __syncthreads_and(in && t < L && cell == s_cell0) != 0;
     if (whole_block) {
       const int warp = threadIdx.x >> 5;
-      unsigned r[6];
+      float r[6];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        r[a] = __reduce_min_sync(0xffffffffu, o[a]);
-        r[3 + a] = __reduce_max_sync(0xffffffffu, o[3 + a]);
+        r[a] = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lo[a])));
+        r[3 + a] = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hi[a])));
       }
       if (lane < 6) s_box[warp][lane] = r[lane];
       __syncthreads();
       if (threadIdx.x < 6) {
-        unsigned acc = s_box[0][threadIdx.x];
-        for (int w = 1; w < 8; ++w) acc = threadIdx.x < 3 ? min(acc, s_box[w][threadIdx.x]) : max(acc, s_box[w][threadIdx.x]);
-        unsigned* pw = nodes + (size_t)parent * 64 + 8 * threadIdx.x + slot;
+        float acc = s_box[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) acc = threadIdx.x < 3 ? fminf(acc, s_box[w][threadIdx.x]) : fmaxf(acc, s_box[w][threadIdx.x]);
+        float* pw = nodes + (size_t)parent * 64 + 8 * threadIdx.x + slot;
         if (threadIdx.x < 3)
-          atomicMin(pw, acc);
+          atomic_min_float(pw, acc);
         else
-          atomicMax(pw, acc);
+          atomic_max_float(pw, acc);
       }
       continue;
     }
     // segmented reduction over runs of equal `cell` (runs are contiguous lanes)
-    unsigned v[6] = {o[0], o[1], o[2], o[3], o[4], o[5]};
+    float v[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
     int cnt = 1;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int oc = __shfl_down_sync(0xffffffffu, cell, d);
       const int on = __shfl_down_sync(0xffffffffu, cnt, d);
-      unsigned ov[6];
+      float ov[6];
 #pragma unroll
       for (int a = 0; a < 6; ++a) ov[a] = __shfl_down_sync(0xffffffffu, v[a], d);
       if (lane + d < 32 && oc == cell) {
         cnt += on;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          v[a] = min(v[a], ov[a]);
-          v[3 + a] = max(v[3 + a], ov[3 + a]);
+          v[a] = fminf(v[a], ov[a]);
+          v[3 + a] = fmaxf(v[3 + a], ov[3 + a]);
         }
       }
     }
     const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
     if (in && (lane == 0 || prev != cell)) {
-      unsigned* pw = nodes + (size_t)parent * 64;
-      atomicMin(pw + slot, v[0]);
-      atomicMin(pw + 8 + slot, v[1]);
-      atomicMin(pw + 16 + slot, v[2]);
-      atomicMax(pw + 24 + slot, v[3]);
-      atomicMax(pw + 32 + slot, v[4]);
-      atomicMax(pw + 40 + slot, v[5]);
-      if (t == L) atomicAdd(pw + 49 + 2 * slot, (unsigned)cnt);
+      float* pw = nodes + (size_t)parent * 64;
+      atomic_min_float(pw + slot, v[0]);
+      atomic_min_float(pw + 8 + slot, v[1]);
+      atomic_min_float(pw + 16 + slot, v[2]);
+      atomic_max_float(pw + 24 + slot, v[3]);
+      atomic_max_float(pw + 32 + slot, v[4]);
+      atomic_max_float(pw + 40 + slot, v[5]);
+      if (t == L) atomicAdd(reinterpret_cast<unsigned*>(pw) + 49 + 2 * slot, (unsigned)cnt);
     }
   }
 }
 
-__global__ void __launch_bounds__(256) k_finalize(unsigned* __restrict__ words, const int* __restrict__ n_nodes_ptr) {
-  const size_t n_words = (size_t)(*n_nodes_ptr) * 64;
-  for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < n_words; w += (size_t)gridDim.x * blockDim.x)
-    if ((w & 63) < 48) words[w] = __float_as_uint(ord2f(words[w]));
-}
-
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-int build_index(ddlo_cloud* c) {
-  if (c->has_index) return DDLO_OK;
+static int build_index_impl(ddlo_cloud* c, char** base_out) {
   ddlo_runtime* rt = c->rt;
   const int n = c->n;
-  if (n <= 0) return fail(DDLO_E_EMPTY, "build_index: empty cloud");
-  if (n > (1 << 26)) return fail(DDLO_E_UNSUPPORTED, "build_index: cloud too large");
   cudaStream_t st = rt->stream;
+  const int tb = 256;
+  const int nb = (n + tb - 1) / tb;
 
-  // temporaries: bounds (8 u32) | keys | keys_alt | vals | vals_alt | leaf_level | flags[10][n] | cub temp
-  size_t sort_bytes = 0, scan_bytes = 0;
-  cub::DoubleBuffer<unsigned> kb0(nullptr, nullptr);
-  cub::DoubleBuffer<int> vb0(nullptr, nullptr);
-  DDLO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, kb0, vb0, n, 0, 30, st));
-  const size_t n_flags = (size_t)kMortonLevels * n;
-  DDLO_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (int*)nullptr, (int*)nullptr, (long long)n_flags, st));
-  const size_t cub_bytes = std::max(sort_bytes, scan_bytes);
-  const size_t off_keys = 256, sz = align256((size_t)n * 4);
-  const size_t off_lvl = off_keys + 4 * sz, off_flags = off_lvl + align256((size_t)n);
-  const size_t off_cub = off_flags + align256(n_flags * 4);
-  // temporaries come from the stream-ordered pool (warmed at runtime creation): no cudaMalloc in a frame
+  // temporaries: keys | keys_alt | vals | vals_alt | leaf_level | counts[10][nb] | sort scratch, from the stream-ordered
+  // pool (warmed at runtime creation): no cudaMalloc in a frame
+  const size_t sz = align256((size_t)n * 4);
+  const size_t off_lvl = 4 * sz, off_counts = off_lvl + align256((size_t)n);
+  const size_t off_sort = off_counts + align256((size_t)kMortonLevels * nb * sizeof(int));
   char* base = nullptr;
-  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&base), off_cub + align256(cub_bytes), st));
-  unsigned* bounds = reinterpret_cast<unsigned*>(base);
-  unsigned* keys = reinterpret_cast<unsigned*>(base + off_keys);
-  unsigned* keys_alt = reinterpret_cast<unsigned*>(base + off_keys + sz);
-  int* vals = reinterpret_cast<int*>(base + off_keys + 2 * sz);
-  int* vals_alt = reinterpret_cast<int*>(base + off_keys + 3 * sz);
+  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&base), off_sort + radix_sort_temp_bytes(n) + 256, st));
+  *base_out = base;
+  unsigned* keys = reinterpret_cast<unsigned*>(base);
+  unsigned* keys_alt = reinterpret_cast<unsigned*>(base + sz);
+  int* vals = reinterpret_cast<int*>(base + 2 * sz);
+  int* vals_alt = reinterpret_cast<int*>(base + 3 * sz);
   unsigned char* leaf_level = reinterpret_cast<unsigned char*>(base + off_lvl);
-  int* flags = reinterpret_cast<int*>(base + off_flags);
-  void* cub_tmp = base + off_cub;
+  int* counts = reinterpret_cast<int*>(base + off_counts);
+  char* sort_tmp = base + off_sort;
+  unsigned* bounds = reinterpret_cast<unsigned*>(sort_tmp + radix_sort_temp_bytes(n));  // 8 words, generic path only
+  // control words of this build (ticket, node count, level bases): a zeroed corner of the runtime's scratch; the
+  // last block of k_cells leaves the ticket at zero again
+  int* ctl = reinterpret_cast<int*>(static_cast<char*>(rt->d_scratch) + 4096);
 
   const size_t max_nodes = (size_t)kMortonLevels * n / (kLeafMax + 1) + 1;
   DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->spts), (size_t)n * sizeof(float4), st));
@@ -346,39 +438,68 @@ int build_index(ddlo_cloud* c) {
   DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->meta), max_nodes * sizeof(int4), st));
   DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->node_of_point), (size_t)n * sizeof(int), st));
   DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->lattice), 8 * sizeof(float), st));
+  unsigned* words = reinterpret_cast<unsigned*>(c->nodes);
+  const int gb = std::min(std::max(nb, 1), rt->num_sms * 4);
 
-  const int tb = 256;
-  const int nb = (n + tb - 1) / tb;
-  // Scan-sized clouds: box, Morton keys and the sort in one kernel of a 16-CTA cluster (cluster_sort.cu).
-  // Larger clouds, or a device that refuses the cluster launch: the generic kernels + CUB's radix sort.
+  // Scan-sized clouds: box, Morton keys and the sort in one kernel of a 16-CTA cluster (cluster_sort.cu), and the
+  // node array is initialised meanwhile on the runtime's side stream (the cluster occupies 16 of the SMs).
+  // Larger clouds, or a device that refuses the cluster launch: the generic kernels + the radix sort of prims.cu.
   static const bool cluster_sort_enabled = std::getenv("DDLO_NO_CLUSTER_SORT") == nullptr;
   const unsigned* skeys = keys;
   const int* svals = vals;
+  bool nodes_ready = false;
+  if (cluster_sort_enabled && n <= kClusterSortMax && rt->side) {
+    DDLO_CUDA(cudaEventRecord(rt->ev_fork, st));  // behind the allocation of the node array
+    DDLO_CUDA(cudaStreamWaitEvent(rt->side, rt->ev_fork, 0));
+    k_init_nodes<<<gb, tb, 0, rt->side>>>(words, nullptr, max_nodes);
+    DDLO_CUDA(cudaEventRecord(rt->ev_join, rt->side));
+    rt->launches += 1;
+    nodes_ready = true;
+  }
   if (!(cluster_sort_enabled && morton_sort_cluster(rt, c->pts, n, keys, vals, c->lattice) == DDLO_OK)) {
     DDLO_CUDA(cudaMemsetAsync(bounds, 0xff, 12, st));
     DDLO_CUDA(cudaMemsetAsync(bounds + 3, 0x00, 16, st));
     k_bounds<<<std::min(nb, rt->num_sms), tb, 0, st>>>(c->pts, n, bounds);
     k_morton<<<nb, tb, 0, st>>>(c->pts, n, bounds, keys, vals, c->lattice);
-    cub::DoubleBuffer<unsigned> kb(keys, keys_alt);
-    cub::DoubleBuffer<int> vb(vals, vals_alt);
-    DDLO_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, kb, vb, n, 0, 30, st));
-    // (the radix-sort and scan passes are CUB library kernels and are not counted as ours)
-    skeys = kb.Current();
-    svals = vb.Current();
     rt->launches += 2;
+    unsigned* ks = nullptr;
+    int* vs = nullptr;
+    DDLO_TRY(radix_sort_pairs(st, keys, keys_alt, vals, vals_alt, n, 30, sort_tmp, &ks, &vs, &rt->launches));
+    skeys = ks;
+    svals = vs;
   }
-  k_cells<<<nb, tb, 0, st>>>(skeys, svals, c->pts, n, leaf_level, flags, c->spts);
-  DDLO_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_bytes, flags, flags, (long long)n_flags, st));
-  const int* n_nodes_ptr = flags + (n_flags - 1);
-  unsigned* words = reinterpret_cast<unsigned*>(c->nodes);
-  const int gb = std::min(nb, rt->num_sms * 4);
-  k_init_nodes<<<gb, tb, 0, st>>>(words, n_nodes_ptr, c->lattice);
-  k_emit<<<nb, tb, 0, st>>>(skeys, leaf_level, flags, c->spts, n, words, c->meta, c->node_of_point);
-  k_finalize<<<gb, tb, 0, st>>>(words, n_nodes_ptr);
-  rt->launches += 4;
-  DDLO_CUDA(cudaFreeAsync(base, st));
+  k_cells<<<nb, tb, 0, st>>>(skeys, svals, c->pts, n, leaf_level, counts, ctl, c->spts, c->lattice);
+  if (nodes_ready) {
+    DDLO_CUDA(cudaStreamWaitEvent(st, rt->ev_join, 0));
+  } else {
+    k_init_nodes<<<gb, tb, 0, st>>>(words, ctl + 1, 0);
+    rt->launches += 1;
+  }
+  k_emit<<<nb, tb, 0, st>>>(skeys, leaf_level, counts, ctl, c->spts, n, reinterpret_cast<float*>(c->nodes), c->meta, c->node_of_point);
+  rt->launches += 2;
   DDLO_CUDA(cudaGetLastError());
+  return DDLO_OK;
+}
 
+int build_index(ddlo_cloud* c) {
+  if (c->has_index) return DDLO_OK;
+  ddlo_runtime* rt = c->rt;
+  const int n = c->n;
+  if (n <= 0) return fail(DDLO_E_EMPTY, "build_index: empty cloud");
+  if (n > (1 << 26)) return fail(DDLO_E_UNSUPPORTED, "build_index: cloud too large");
+  if (c->shared) return fail(DDLO_E_INVALID, "build_index: the cloud is shared (immutable) and has no index");
+  char* base = nullptr;
+  const int rc = build_index_impl(c, &base);
+  if (base) cudaFreeAsync(base, rt->stream);
+  if (rc != DDLO_OK) {  // nothing half-built stays behind
+    const std::string why = ddlo_last_error();
+    for (void** p : {reinterpret_cast<void**>(&c->spts), reinterpret_cast<void**>(&c->nodes), reinterpret_cast<void**>(&c->meta),
+                     reinterpret_cast<void**>(&c->node_of_point), reinterpret_cast<void**>(&c->lattice)}) {
+      if (*p) cudaFreeAsync(*p, rt->stream);
+      *p = nullptr;
+    }
+    return fail(rc, why);
+  }
   c->view.spts = c->spts;
   c->view.nodes = c->nodes;
   c->view.meta = c->meta;

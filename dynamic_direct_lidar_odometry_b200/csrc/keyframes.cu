@@ -37,7 +37,7 @@ struct ddlo_keyframes {
 
 // OdomNode::pushSubmapIndices (odom.cc:1178-1213): every frame whose distance is <= the k-th smallest distance
 static void push_submap_indices(const std::vector<float>& dists, int k, const std::vector<int>& frames, std::vector<int>& out) {
-  if (dists.empty()) return;
+  if (dists.empty() || k <= 0) return;  // (the reference never asks for k = 0: it would read the top of an empty heap)
   std::priority_queue<float> pq;
   for (float d : dists) {
     if ((int)pq.size() >= k && pq.top() > d) {
@@ -47,7 +47,6 @@ static void push_submap_indices(const std::vector<float>& dists, int k, const st
       pq.push(d);
     }
   }
-  if (pq.empty()) return;  // k <= 0
   const float kth = pq.top();
   for (size_t i = 0; i < dists.size(); ++i)
     if (dists[i] <= kth) out.push_back(frames[i]);

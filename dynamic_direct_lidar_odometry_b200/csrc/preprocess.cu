@@ -16,8 +16,7 @@
 // added (and with it the last bits of the float centroid) is unspecified there.  Here the sort is
 // stable: the points of a voxel are added in their original order, one thread per voxel, which makes
 // the result deterministic and bit-identical to the CPU oracle's restatement.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include "prims.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -143,11 +142,7 @@ int voxel_filter_device(ddlo_runtime* rt, const float4* pts, int n, const float 
   if (!(leaf[0] > 0.0f && leaf[1] > 0.0f && leaf[2] > 0.0f)) return fail(DDLO_E_INVALID, "voxel filter: leaf size must be positive");
   cudaStream_t st = rt->stream;
   const int tb = 256, nb = std::max(1, (n + tb - 1) / tb);
-  size_t sort_bytes = 0, scan_bytes = 0;
-  cub::DoubleBuffer<unsigned> kb0(nullptr, nullptr);
-  cub::DoubleBuffer<int> vb0(nullptr, nullptr);
-  DDLO_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, kb0, vb0, std::max(n, 1), 0, 32, st));
-  DDLO_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (int*)nullptr, (int*)nullptr, std::max(n, 1), st));
+  const size_t sort_bytes = radix_sort_temp_bytes(std::max(n, 1)), scan_bytes = scan_temp_bytes((size_t)std::max(n, 1));
   const size_t sz = pp_align256((size_t)std::max(n, 1) * 4);
   const size_t total = 256 + 5 * sz + pp_align256(std::max(sort_bytes, scan_bytes));
   char* base = nullptr;
@@ -198,16 +193,28 @@ int voxel_filter_device(ddlo_runtime* rt, const float4* pts, int n, const float 
   while (bits < 32 && (1ull << bits) <= (unsigned long long)g.invalid) ++bits;
 
   k_voxel_keys<<<nb, tb, 0, st>>>(pts, n, g, keys, vals);
-  cub::DoubleBuffer<unsigned> kb(keys, keys_alt);
-  cub::DoubleBuffer<int> vb(vals, vals_alt);
-  DDLO_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, kb, vb, n, 0, bits, st));  // stable: original order inside a voxel
-  k_voxel_heads<<<nb, tb, 0, st>>>(kb.Current(), n, g.invalid, flags);
-  DDLO_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_bytes, flags, flags, n, st));
+  unsigned* skeys = nullptr;
+  int* svals = nullptr;
+  {
+    const int rc = radix_sort_pairs(st, keys, keys_alt, vals, vals_alt, n, bits, cub_tmp, &skeys, &svals, &rt->launches);  // stable: original order inside a voxel
+    if (rc != DDLO_OK) {
+      cleanup();
+      return rc;
+    }
+  }
+  k_voxel_heads<<<nb, tb, 0, st>>>(skeys, n, g.invalid, flags);
+  {
+    const int rc = scan_int(st, flags, flags, (size_t)n, true, cub_tmp, &rt->launches);
+    if (rc != DDLO_OK) {
+      cleanup();
+      return rc;
+    }
+  }
   int n_vox = 0;
   DDLO_CUDA(cudaMemcpyAsync(&n_vox, flags + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
   DDLO_CUDA(cudaStreamSynchronize(st));
   DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(d_out), std::max<size_t>(1, (size_t)n_vox) * sizeof(float4), st));
-  k_voxel_centroids<<<nb, tb, 0, st>>>(kb.Current(), vb.Current(), flags, pts, n, *d_out);
+  k_voxel_centroids<<<nb, tb, 0, st>>>(skeys, svals, flags, pts, n, *d_out);
   rt->launches += 3;
   cleanup();
   DDLO_CUDA(cudaGetLastError());
@@ -268,14 +275,13 @@ int crop_box_device(ddlo_runtime* rt, const float4* pts, int n, const float lo[3
     *n_out = n;
     return DDLO_OK;
   }
-  size_t scan_bytes = 0;
-  DDLO_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (int*)nullptr, (int*)nullptr, n, st));
+  const size_t scan_bytes = scan_temp_bytes((size_t)n);
   const size_t sz = pp_align256((size_t)n * 4);
   char* base = nullptr;
   DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&base), sz + pp_align256(scan_bytes), st));
   int* flags = reinterpret_cast<int*>(base);
   k_crop_flags<<<nb, tb, 0, st>>>(pts, n, c, flags);
-  DDLO_CUDA(cub::DeviceScan::InclusiveSum(base + sz, scan_bytes, flags, flags, n, st));
+  DDLO_TRY(scan_int(st, flags, flags, (size_t)n, true, base + sz, &rt->launches));
   int kept = 0;
   DDLO_CUDA(cudaMemcpyAsync(&kept, flags + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
   DDLO_CUDA(cudaStreamSynchronize(st));

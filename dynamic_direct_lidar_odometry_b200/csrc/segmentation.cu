@@ -25,7 +25,7 @@
 // Arithmetic: float products/sums rounded one by one as the reference's -O2 x86-64 build does; atan2 is evaluated in
 // double and rounded to float (the correctly rounded float value but for ~1e-9 of the inputs; the reference's libm
 // atan2f may differ from it in the last bit, which matters only for a slope within 1 ulp of its threshold).
-#include <cub/device/device_scan.cuh>
+#include "prims.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -586,10 +586,7 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   double *seg_avg = nullptr, *res_sum = nullptr;
   int* res_count = nullptr;
   void* tmp = nullptr;
-  size_t tmp_a = 0, tmp_b = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_a, keys, keys, HW, st);
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_b, accepted, rank, HW, st);
-  const size_t tmp_bytes = std::max(tmp_a, tmp_b);
+  const size_t tmp_bytes = scan_temp_bytes((size_t)HW);
   DDLO_TRY(pool_alloc(rt, &nib, nib_bytes));
   DDLO_TRY(pool_alloc(rt, &parent, HW));
   DDLO_TRY(pool_alloc(rt, &root, HW));
@@ -629,8 +626,7 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   k_ccl_union<<<pb, 256, 0, st>>>(p, nib, parent);
   k_ccl_flatten<<<pb, 256, 0, st>>>(p, parent, d_scan, stride_floats, d_range, nib, root, size, cstat, d_residuals, res_stride, res_sum, res_count);
   k_seg_seed_keys<<<pb, 256, 0, st>>>(p, root, size, keys);
-  size_t tb = tmp_bytes;
-  DDLO_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, keys, keys, HW, st));
+  DDLO_TRY(scan_u64(st, keys, keys, (size_t)HW, false, tmp, nullptr));
   k_seg_seeds<<<pb, 256, 0, st>>>(p, root, keys, seeds, small);
   const int per_sm = smem <= 100 * 1024 ? 2 : 1;
   int ring_size = kRing;  // testing aid: a small ring forces the queue reads through global memory
@@ -641,10 +637,9 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   const int shortcut = std::getenv("DDLO_SEG_NO_SHORTCUT") ? 0 : 1;  // testing aid: replay the queue of every segment
   k_seg_fill<<<rt->num_sms * per_sm, kFillThreads, smem, st>>>(p, nib, seeds, small, keys, d_scan, stride_floats, d_range, d_residuals, res_stride, order,
                                                               small + 1, accepted, seg_avg, ring_size, size, cstat, shortcut, res_sum, res_count);
-  tb = tmp_bytes;
-  DDLO_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, accepted, rank, HW, st));
+  DDLO_TRY(scan_int(st, accepted, rank, (size_t)HW, false, tmp, nullptr));
   k_seg_labels<<<pb, 256, 0, st>>>(p, root, keys, accepted, rank, seg_avg, small, d_label, d_avg_by_label, d_label_count);
-  rt->launches += 8 + 4;  // ours + the two scans' kernels
+  rt->launches += 8 + 6;  // + the two scans (three kernels each, prims.cu)
   DDLO_CUDA(cudaGetLastError());
   for (void* q : {(void*)nib, (void*)parent, (void*)root, (void*)size, (void*)seeds, (void*)accepted, (void*)rank, (void*)small, (void*)keys,
                   (void*)order, (void*)cstat, (void*)seg_avg, tmp, (void*)moved, (void*)res_sum, (void*)res_count})
