@@ -148,6 +148,7 @@ SIGNATURES = {
     "ddlo_batch_staged_count": [_vp, _ip],
     "ddlo_batch_set_shared_target": [_vp, C.c_int, _vp],
     "ddlo_batch_submit": [_vp, _vp, C.c_int, _vp],
+    "ddlo_batch_submit_host": [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp],
     "ddlo_batch_wait": [_vp],
     "ddlo_batch_run": [_vp, _vp, C.c_int, _vp],
     "ddlo_batch_launch_count": [_vp, C.POINTER(C.c_longlong)],

@@ -53,6 +53,31 @@ def _stamp(src: Path, flags) -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, extra_flags) -> Path:
+    """a tuning variant of the library (extra -D flags) as lib/variants/<name>.so; select it with DDLO_GICP_LIB"""
+    out_dir = LIB_DIR / "variants"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    obj_dir = OBJ_DIR / ("variant_" + name)
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    nvcc = nvcc_path()
+    flags = [*NVCC_FLAGS, *extra_flags]
+
+    def one(src_name):
+        obj = obj_dir / (Path(src_name).stem + ".o")
+        res = subprocess.run([nvcc, *flags, "-c", "-o", str(obj), str(CSRC / src_name)], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(res.stdout + res.stderr)
+        return str(obj)
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(one, SOURCES))
+    out = out_dir / f"{name}.so"
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(res.stdout + res.stderr)
+    return out
+
+
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     """force=True relinks and recompiles every object whose inputs changed (objects are content-addressed, so an
     unchanged source is never recompiled needlessly); DDLO_REBUILD_ALL=1 ignores the object cache."""

@@ -75,6 +75,10 @@ struct ddlo_batch {
   std::vector<int> unit_rc;
   ddlo_align_result* results = nullptr;
   int pending = 0;
+  // sources that come from HOST memory with the submission (ddlo_batch_submit_host), else null
+  const float* const* host_src = nullptr;
+  const int* host_n = nullptr;
+  int host_stride = 0;
 };
 
 static void waves_free(ddlo_batch* b) {
@@ -118,12 +122,16 @@ static void batch_free(ddlo_batch* b) {
 static int enqueue_unit(ddlo_batch* b, ddlo_runtime* rt, ddlo_gicp* g, bool& has_shared_target, const ddlo_batch_job& job, int slot,
                         GicpArgs* args, int* nchunks) {
   const int n_staged = (int)b->staged.size();
-  if (job.source < 0 || job.source >= n_staged) return fail(DDLO_E_INVALID, "batch job: unknown source cloud id");
+  const float* host = b->host_src ? b->host_src[slot] : nullptr;
+  if (!host && (job.source < 0 || job.source >= n_staged)) return fail(DDLO_E_INVALID, "batch job: unknown source cloud id");
   if (job.target >= n_staged) return fail(DDLO_E_INVALID, "batch job: unknown target cloud id");
   if (job.target < 0 && !b->shared_tgt) return fail(DDLO_E_NOT_READY, "batch job: target < 0 needs ddlo_batch_set_shared_target");
   ddlo_cloud *src = nullptr, *tgt = nullptr;
   // fresh handles: every unit builds its own indexes and covariances, nothing is cached from an earlier unit
-  DDLO_TRY(ddlo_cloud_create_from_device(rt, b->staged[job.source]->pts, b->staged[job.source]->n, &src));
+  if (host)  // the scan crosses PCIe inside the unit (asynchronous from page-locked memory)
+    DDLO_TRY(ddlo_cloud_create(rt, host, b->host_n[slot], b->host_stride, &src));
+  else
+    DDLO_TRY(ddlo_cloud_create_from_device(rt, b->staged[job.source]->pts, b->staged[job.source]->n, &src));
   int rc = DDLO_OK;
   if (job.target >= 0) rc = ddlo_cloud_create_from_device(rt, b->staged[job.target]->pts, b->staged[job.target]->n, &tgt);
   if (rc == DDLO_OK) rc = ddlo_gicp_clear_source(g);
@@ -395,7 +403,25 @@ int ddlo_batch_set_shared_target(ddlo_batch* b, int cloud_id, const double* covs
   return DDLO_OK;
 }
 
+static int batch_submit(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_result* results);
+
 int ddlo_batch_submit(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_result* results) {
+  if (b) b->host_src = nullptr, b->host_n = nullptr, b->host_stride = 0;
+  return batch_submit(b, jobs, m, results);
+}
+
+int ddlo_batch_submit_host(ddlo_batch* b, const ddlo_batch_job* jobs, int m, const float* const* source_xyz, const int* source_n, int stride_bytes,
+                           ddlo_align_result* results) {
+  if (!b || (m > 0 && (!source_xyz || !source_n))) return fail(DDLO_E_INVALID, "null argument");
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(DDLO_E_INVALID, "bad stride");
+  if (b->pending) return fail(DDLO_E_NOT_READY, "batch: the previous submission has not been waited for");
+  b->host_src = source_xyz;
+  b->host_n = source_n;
+  b->host_stride = stride_bytes;
+  return batch_submit(b, jobs, m, results);
+}
+
+static int batch_submit(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_result* results) {
   if (!b || m < 0 || (m > 0 && (!jobs || !results))) return fail(DDLO_E_INVALID, "null argument");
   if (b->pending) return fail(DDLO_E_NOT_READY, "batch: the previous submission has not been waited for");
   if (m == 0) return DDLO_OK;

@@ -21,7 +21,10 @@ namespace ddlo {
 constexpr int kBThreads = 256;
 constexpr int kBWarps = kBThreads / 32;
 constexpr int kBRound = 1024;  // slots of a chunk searched per queue round (parking space in shared memory)
-constexpr int kBBlocksPerSM = 4;  // 64 registers per thread, as in k_align
+#ifndef DDLO_BATCH_BLOCKS_PER_SM
+#define DDLO_BATCH_BLOCKS_PER_SM 4
+#endif
+constexpr int kBBlocksPerSM = DDLO_BATCH_BLOCKS_PER_SM;  // 4: 64 registers per thread, as in k_align
 
 struct BatchProb {
   GicpArgs a;

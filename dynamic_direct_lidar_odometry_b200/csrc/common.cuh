@@ -11,6 +11,23 @@
 
 #include "../../include/ddlo_gicp.h"
 
+// -DDDLO_BOUNDS_CHECK builds (compute-sanitizer is not available on every pool): every gather / scatter index of the
+// search, linearize, covariance and sort kernels is checked on the device; the first violation prints where and traps.
+#ifdef DDLO_BOUNDS_CHECK
+#define DDLO_CHECK_INDEX(i, n, what)                                                                                          \
+  do {                                                                                                                        \
+    if ((unsigned long long)(long long)(i) >= (unsigned long long)(long long)(n)) {                                           \
+      printf("ddlo bounds check: %s: index %lld not in [0, %lld) (block %d, thread %d)\n", what, (long long)(i), (long long)(n), \
+             (int)blockIdx.x, (int)threadIdx.x);                                                                              \
+      __trap();                                                                                                               \
+    }                                                                                                                         \
+  } while (0)
+#else
+#define DDLO_CHECK_INDEX(i, n, what) \
+  do {                               \
+  } while (0)
+#endif
+
 namespace ddlo {
 
 // ---------------------------------------------------------------------------------------------

@@ -110,8 +110,13 @@ __device__ __forceinline__ Deal make_deal(int ns, int nb, int b) {
 // What update_correspondences leaves per source point (:255-274): sq_distances_, correspondences_ and, for the next
 // search, where the match sits in the Morton order and the node above its leaf.  Returns the correspondence.
 __device__ __forceinline__ int store_match(const GicpArgs& a, int i, float nn_d, int nn_idx, int nn_pos) {
+  DDLO_CHECK_INDEX(i, a.ns, "store_match: source index");
   a.sqd[i] = nn_d;
   const bool found = nn_idx != kIdxSentinel;
+  if (found) {
+    DDLO_CHECK_INDEX(nn_idx, a.tgt.n, "store_match: matched target index");
+    DDLO_CHECK_INDEX(nn_pos, a.tgt.n, "store_match: matched Morton position");
+  }
   const int j = (found && (double)nn_d < a.thr2) ? nn_idx : -1;
   a.corr[i] = j;
   // seed of the next search (kept even beyond the distance threshold)
@@ -129,6 +134,8 @@ static __device__ __noinline__ double lin_group(const GicpArgs& a, const Iso3& x
   double x = 0.0, y = 0.0, z = 0.0, ex = 0.0, ey = 0.0, ez = 0.0;
   Sym3 M{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   if (on) {
+    DDLO_CHECK_INDEX(i, a.ns, "lin_group: source index");
+    DDLO_CHECK_INDEX(nn_pos, a.tgt.n, "lin_group: target position");
     const float4 pa = __ldg(a.src_pts + i);
     const float4 pb = __ldg(a.tgt.spts + nn_pos);
     const Sym3 CA = load_sym3(a.src_cov + (size_t)i * kCovStride);
@@ -200,6 +207,8 @@ __device__ __forceinline__ double err_point(const GicpArgs& a, const Iso3& T, in
   if (i < 0) return 0.0;
   const int j = __ldcg(a.corr + i);
   if (j < 0) return 0.0;
+  DDLO_CHECK_INDEX(i, a.ns, "err_point: source index");
+  DDLO_CHECK_INDEX(__ldcg(a.nn_seed + i).x, a.tgt.n, "err_point: stored target position");
   const float4 pa = __ldg(a.src_pts + i);
   const float4 pb = __ldg(a.tgt.spts + __ldcg(a.nn_seed + i).x);
   const Sym3 M = load_sym3_cg(a.mahal + (size_t)i * kCovStride);
@@ -292,6 +301,8 @@ __device__ __forceinline__ void search_slots(const GicpArgs& a, const SearchPark
                 // The previous iteration's match is a real point of the target: its distance bounds the
                 // answer, and the search starts at the node above its leaf and climbs only while the
                 // ball of the best distance found so far sticks out of the node's cube.
+                DDLO_CHECK_INDEX(sd.x, a.tgt.n, "search: seed position");
+                DDLO_CHECK_INDEX(sd.y, reinterpret_cast<const int*>(a.tgt.lattice)[5], "search: seed node");
                 const float4 tp = __ldg(a.tgt.spts + sd.x);
                 best.seed(sqdist3_rn(qx, qy, qz, tp.x, tp.y, tp.z), __float_as_int(tp.w), sd.x);
                 start = (unsigned)sd.y;

@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(256) k_cells(const unsigned* __restrict__ keys
     leaf_level[i] = (unsigned char)L;
     cd = i == 0 ? -1 : common_digits(key, __ldg(keys + i - 1));
     const int o = perm[i];
+    DDLO_CHECK_INDEX(o, n, "k_cells: permutation entry");
     const float4 p = pts[o];
     spts[i] = make_float4(p.x, p.y, p.z, __int_as_float(o));
   }
@@ -329,7 +330,11 @@ __global__ void __launch_bounds__(256) k_emit(const unsigned* __restrict__ keys,
     const int parent = in ? nid[t - 1] : -1;
     const int slot = (key >> (3 * (kMortonLevels - t))) & 7;
     const int cell = in ? parent * 8 + slot : -1 - lane;  // run id; dead lanes never join a run
-    if (in && t == L) node_of_point[orig] = parent;
+    if (in) DDLO_CHECK_INDEX(parent, __ldg(ctl + 1), "k_emit: parent node");
+    if (in && t == L) {
+      DDLO_CHECK_INDEX(orig, n, "k_emit: original index");
+      node_of_point[orig] = parent;
+    }
     // child reference, written by the first point of the cell
     if (in && cd < t) {
       unsigned* pw = reinterpret_cast<unsigned*>(nodes) + (size_t)parent * 64;

@@ -428,6 +428,7 @@ __device__ __forceinline__ void knn_traverse_sub(const IndexView& ix, bool activ
     float b = inf;
     int2 ref = make_int2(0, 0);
     if (run) {
+      DDLO_CHECK_INDEX(node, reinterpret_cast<const int*>(ix.lattice)[5], "knn_traverse_sub: node");
       const float* g = reinterpret_cast<const float*>(ix.nodes + (size_t)node * kNodeF4);
       const float lx = __ldg(g + sb.sl), ly = __ldg(g + 8 + sb.sl), lz = __ldg(g + 16 + sb.sl);
       const float hx = __ldg(g + 24 + sb.sl), hy = __ldg(g + 32 + sb.sl), hz = __ldg(g + 40 + sb.sl);
@@ -446,6 +447,7 @@ __device__ __forceinline__ void knn_traverse_sub(const IndexView& ix, bool activ
       ml &= ~(1u << mc);
       const int st = __shfl_sync(kFull, ref.x, sb.base + mc);
       const int cnt = __shfl_sync(kFull, ref.y, sb.base + mc);
+      if (had) DDLO_CHECK_INDEX(st + cnt - 1, ix.n, "knn_traverse_sub: leaf range");
       rs.scan(had && mb <= rs.worst(), ix.spts, st, cnt, qx, qy, qz, sb);
     }
     // ---- internal children

@@ -11,13 +11,16 @@
 namespace ddlo {
 
 constexpr int kKnnThreads = 256;
+#ifndef DDLO_KNN_MIN_BLOCKS
+#define DDLO_KNN_MIN_BLOCKS 1
+#endif
 constexpr int kKnnSubs = kKnnThreads / kSubLanes;  // queries per block
 
 // self_mode = 0: query q is queries[q], output row q
 // self_mode = 1: query q is the q-th point of the index in Morton order, output row = its original index
 // R > 0: k <= 8R, result set in registers (TopKRegSub<R>); R == 0: any k, result set in shared memory
 template <int R>
-__global__ void __launch_bounds__(kKnnThreads) k_knn(IndexView ix, const float4* __restrict__ queries, int nq, int k, int self_mode,
+__global__ void __launch_bounds__(kKnnThreads, DDLO_KNN_MIN_BLOCKS) k_knn(IndexView ix, const float4* __restrict__ queries, int nq, int k, int self_mode,
                                                       int* __restrict__ idx_out, float* __restrict__ d_out) {
   extern __shared__ unsigned long long smem_knn[];
   unsigned long long* stacks = smem_knn;  // [kKnnSubs][kStackDepth]
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(256) k_cov_from_knn(const float4* __restrict__
   const int* row = knn_idx + (size_t)i * k;
   double mx = 0.0, my = 0.0, mz = 0.0;
   for (int j = 0; j < k; ++j) {
+    DDLO_CHECK_INDEX(__ldg(row + j), n, "k_cov_from_knn: neighbour index");
     const float4 p = __ldg(pts + __ldg(row + j));
     mx += (double)p.x;
     my += (double)p.y;

@@ -46,6 +46,7 @@ struct Best1Pair {
     unsigned long long key = pack(d, idx);
     int lp = pos;
     if (doit) {
+      DDLO_CHECK_INDEX(start + count - 1, 0x7fffffff, "Best1Pair::scan: leaf range");
 #pragma unroll 4
       for (int j = h; j < count; j += 2) {
         const float4 v = __ldg(spts + start + j);
@@ -83,6 +84,7 @@ __device__ __forceinline__ void nn1_visit_pair(const IndexView& ix, bool& run, f
   float b[4] = {inf, inf, inf, inf};
   int rx[4] = {0, 0, 0, 0}, ry[4] = {0, 0, 0, 0};
   if (run) {
+    DDLO_CHECK_INDEX(node, reinterpret_cast<const int*>(ix.lattice)[5], "nn1_visit_pair: node");
     const float4* g = ix.nodes + (size_t)node * kNodeF4;
     const float4 lx = __ldg(g + h), ly = __ldg(g + 2 + h), lz = __ldg(g + 4 + h);
     const float4 hx = __ldg(g + 6 + h), hy = __ldg(g + 8 + h), hz = __ldg(g + 10 + h);

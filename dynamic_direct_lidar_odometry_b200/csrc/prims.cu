@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_scatter(const unsigned* __res
     if (live) {
       int pos = s_run[d] + lane_rank;
       for (int w = 0; w < warp; ++w) pos += s_wcount[w][d];
+      DDLO_CHECK_INDEX(pos, n, "k_rs_scatter: output position");
       keys_out[pos] = key;
       vals_out[pos] = val;
       if (hist_next) atomicAdd(hist_next + (size_t)((key >> shift_next) & (kRsBins - 1)) * n_tiles + pos / tile, 1);

@@ -628,6 +628,24 @@ class Batch:
             B.load().ddlo_batch_wait(self._b)  # whatever was enqueued completes; the batch stays usable
             raise DdloError(rc, text)
 
+    def submit_host(self, jobs, sources) -> None:
+        """ddlo_batch_submit_host: unit i uploads sources[i] ((n, 4) float32 arrays, ideally from pinned_array) as its source scan"""
+        if not isinstance(jobs, C.Array):
+            jobs = self.jobs(jobs)
+        self._m = len(jobs)
+        self._res = (B.AlignResult * max(self._m, 1))()
+        self._jobs = jobs
+        self._host = [np.ascontiguousarray(s, dtype=np.float32) for s in sources]  # kept alive until wait()
+        ptrs = (C.c_void_p * max(self._m, 1))(*[a.ctypes.data for a in self._host])
+        ns = (C.c_int * max(self._m, 1))(*[a.shape[0] for a in self._host])
+        self._host_tables = (ptrs, ns)
+        stride = self._host[0].strides[0] if self._host else 16
+        rc = B.load().ddlo_batch_submit_host(self._b, jobs, self._m, ptrs, ns, stride, self._res)
+        if rc != B.OK:
+            text = B.load().ddlo_last_error().decode(errors="replace")
+            B.load().ddlo_batch_wait(self._b)
+            raise DdloError(rc, text)
+
     def stats(self):
         """(LM rounds launched, completion polls) by the waves driver since creation"""
         r, p = C.c_longlong(), C.c_longlong()

@@ -337,6 +337,12 @@ int ddlo_batch_set_shared_target(ddlo_batch* b, int cloud_id, const double* covs
  * until ddlo_batch_wait, which synchronises everything, fills results and returns the first error.
  * _run = submit + wait. */
 int ddlo_batch_submit(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_result* results);
+/* The same with the SOURCE scans coming from host memory inside the submission: unit i uploads source_xyz[i]
+ * (source_n[i] points of stride_bytes each, as ddlo_cloud_create; page-locked memory makes the copies asynchronous)
+ * on its lane's stream instead of taking jobs[i].source; a NULL entry falls back to the staged id.  All arrays must
+ * stay valid until ddlo_batch_wait. */
+int ddlo_batch_submit_host(ddlo_batch* b, const ddlo_batch_job* jobs, int m, const float* const* source_xyz, const int* source_n, int stride_bytes,
+                           ddlo_align_result* results);
 int ddlo_batch_wait(ddlo_batch* b);
 int ddlo_batch_run(ddlo_batch* b, const ddlo_batch_job* jobs, int m, ddlo_align_result* results);
 int ddlo_batch_launch_count(ddlo_batch* b, long long* count); /* kernels launched by all lanes since creation */

@@ -193,3 +193,22 @@ def test_cpp_batch_program_shards_over_devices(scans, tmp_path):
     for u, r in enumerate(res):
         assert got[u][0] == int(r.converged) and got[u][1] == r.iterations and np.array_equal(got[u][2], r.T)
     b.close()
+
+
+def test_batch_sources_from_host_memory(scans):
+    """ddlo_batch_submit_host: units whose source scan is uploaded from (pinned) host memory inside the submission give
+    the same results as units over staged clouds"""
+    b = ng.Batch(0, lanes=2, wave_units=3)
+    ids = [b.stage(s) for s in scans]
+    units = [(ids[u % 6 + 1], ids[u % 6], None) for u in range(8)]
+    staged = b.run(units)
+    host = []
+    for u in range(8):
+        a = ng.pinned_array(scans[u % 6 + 1].shape, np.float32)
+        a[:] = scans[u % 6 + 1]
+        host.append(a)
+    b.submit_host([(-1, ids[u % 6], None) for u in range(8)], host)  # the staged source id is not needed
+    got = b.wait()
+    for s, g in zip(staged, got):
+        assert g.converged and np.array_equal(s.T, g.T) and np.array_equal(s.hessian, g.hessian)
+    b.close()
