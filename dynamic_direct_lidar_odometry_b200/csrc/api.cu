@@ -107,10 +107,13 @@ static void runtime_teardown(ddlo_runtime* rt) {
   if (rt->ev_join) cudaEventDestroy(rt->ev_join);
   for (auto& e : rt->slots)
     if (e) cudaEventDestroy(e);
-  if (rt->side) {
-    cudaStreamSynchronize(rt->side);
-    cudaStreamDestroy(rt->side);
-  }
+  if (rt->ev_fork2) cudaEventDestroy(rt->ev_fork2);
+  if (rt->ev_join2) cudaEventDestroy(rt->ev_join2);
+  for (cudaStream_t q : {rt->side, rt->side2})
+    if (q) {
+      cudaStreamSynchronize(q);
+      cudaStreamDestroy(q);
+    }
   if (rt->stream) cudaStreamDestroy(rt->stream);
   delete rt;
 }
@@ -243,6 +246,9 @@ int ddlo_runtime_create(int device, ddlo_runtime** out) {
 static int runtime_init(ddlo_runtime* rt, int device) {
   DDLO_CUDA(cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking));
   DDLO_CUDA(cudaStreamCreateWithFlags(&rt->side, cudaStreamNonBlocking));
+  DDLO_CUDA(cudaStreamCreateWithFlags(&rt->side2, cudaStreamNonBlocking));
+  DDLO_CUDA(cudaEventCreateWithFlags(&rt->ev_fork2, cudaEventDisableTiming));
+  DDLO_CUDA(cudaEventCreateWithFlags(&rt->ev_join2, cudaEventDisableTiming));
   DDLO_CUDA(cudaEventCreateWithFlags(&rt->ev_fork, cudaEventDisableTiming));
   DDLO_CUDA(cudaEventCreateWithFlags(&rt->ev_join, cudaEventDisableTiming));
   DDLO_CUDA(cudaEventCreate(&rt->ev0));
@@ -935,11 +941,41 @@ static int ensure_workspace(ddlo_gicp* g, int ns) {
 }
 
 // everything align/linearize need, or the reason they can not run
-static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, GicpArgs* a) {
+static int align_blocks(const ddlo_gicp* g);
+
+// guess16_pass0 != nullptr (align() proper, not the stepwise hooks or the batched waves): when covariances have to be
+// computed first, the correspondence search of the first linearize - it needs the guess, the source points and the
+// target index, not the covariances - runs as a kernel of its own on a side stream beside the covariance kernels.
+static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, GicpArgs* a, const float* guess16_pass0 = nullptr) {
   if (!g->src || !g->tgt) return fail(DDLO_E_NOT_READY, "input source and target must both be set");
   if (g->src->n <= 0 || g->tgt->n <= 0) return fail(DDLO_E_EMPTY, "source or target cloud is empty");
   DDLO_TRY(use_device(g->rt));
   DDLO_TRY(build_index(g->tgt));
+  DDLO_TRY(ensure_workspace(g, g->src->n));
+  const bool need_src = !g->src_cov || g->src_cov->n != g->src->n, need_tgt = !g->tgt_cov || g->tgt_cov->n != g->tgt->n;
+  bool pass0 = false;
+  // opt-in (DDLO_PASS0_OVERLAP=1): measured on B200 at -2 us of 480 for the C2 step - the covariance search is issue
+  // bound, so the early search only takes its issue slots (profiles/README.md)
+  static const bool pass0_overlap = std::getenv("DDLO_PASS0_OVERLAP") != nullptr;
+  if (guess16_pass0 && compute_missing_covs && (need_src || need_tgt) && pass0_overlap && g->rt->side2 && g->p.max_iterations > 0 &&
+      g->src->rt == g->rt && g->tgt->rt == g->rt) {
+    ddlo_runtime* rt = g->rt;
+    GicpArgs sa;
+    std::memset(&sa, 0, sizeof(sa));
+    sa.tgt = g->tgt->view;
+    sa.src_pts = g->src->pts;
+    sa.ns = g->src->n;
+    sa.corr = g->corr;
+    sa.nn_seed = g->nn_seed;
+    sa.sqd = g->sqd;
+    sa.thr2 = g->p.max_correspondence_distance * g->p.max_correspondence_distance;
+    std::memcpy(sa.guess, guess16_pass0, sizeof(sa.guess));
+    DDLO_CUDA(cudaEventRecord(rt->ev_fork2, rt->stream));  // behind the target index, the source upload and the workspace
+    DDLO_CUDA(cudaStreamWaitEvent(rt->side2, rt->ev_fork2, 0));
+    DDLO_TRY(launch_search_pass0(rt, rt->side2, sa, align_blocks(g)));
+    DDLO_CUDA(cudaEventRecord(rt->ev_join2, rt->side2));
+    pass0 = true;
+  }
   if (!g->src_cov || g->src_cov->n != g->src->n) {
     if (!compute_missing_covs) return fail(g->src_cov ? DDLO_E_SIZE : DDLO_E_NOT_READY, "source covariances missing or of the wrong size");
     DDLO_TRY(calc_covs(g, g->src, g->src_cov));
@@ -950,8 +986,9 @@ static int prepare(ddlo_gicp* g, bool compute_missing_covs, int* covs_computed, 
     DDLO_TRY(calc_covs(g, g->tgt, g->tgt_cov));
     if (covs_computed) *covs_computed = 1;
   }
-  DDLO_TRY(ensure_workspace(g, g->src->n));
   DDLO_TRY(ensure_sorted_covs(g->tgt_cov, g->tgt, g->rt->stream));
+  if (pass0) DDLO_CUDA(cudaStreamWaitEvent(g->rt->stream, g->rt->ev_join2, 0));
+  a->pass0_done = pass0 ? 1 : 0;
   a->tgt = g->tgt->view;
   a->src_pts = g->src->pts;
   a->src_lattice = g->src->has_index ? g->src->lattice : nullptr;
@@ -998,9 +1035,9 @@ static int align_blocks(const ddlo_gicp* g) { return gicp_blocks_for(g->src->n, 
 
 // the argument record of one align (missing covariances are computed first, on the engine's stream) and the number
 // of blocks / chunks it runs with
-int ddlo::prepare_align(ddlo_gicp* g, const float* guess16, int* covs_computed, GicpArgs* a, int* nblocks) {
-  DDLO_TRY(prepare(g, true, covs_computed, a));
+int ddlo::prepare_align(ddlo_gicp* g, const float* guess16, int* covs_computed, GicpArgs* a, int* nblocks, bool single_launch) {
   static const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  DDLO_TRY(prepare(g, true, covs_computed, a, single_launch ? (guess16 ? guess16 : I16) : nullptr));
   std::memcpy(a->guess, guess16 ? guess16 : I16, sizeof(a->guess));
   std::memset(a->T_step, 0, sizeof(a->T_step));
   *nblocks = align_blocks(g);
@@ -1011,7 +1048,7 @@ int ddlo::prepare_align(ddlo_gicp* g, const float* guess16, int* covs_computed, 
 int ddlo::enqueue_align(ddlo_gicp* g, const float* guess16, int* covs_computed) {
   GicpArgs a;
   int blocks = 0;
-  DDLO_TRY(prepare_align(g, guess16, covs_computed, &a, &blocks));
+  DDLO_TRY(prepare_align(g, guess16, covs_computed, &a, &blocks, true));
   DDLO_TRY(launch_align(g->rt, a, blocks));
   return DDLO_OK;
 }

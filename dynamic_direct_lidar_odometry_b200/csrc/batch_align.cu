@@ -21,6 +21,13 @@ namespace ddlo {
 constexpr int kBThreads = 256;
 constexpr int kBWarps = kBThreads / 32;
 constexpr int kBRound = 1024;  // slots of a chunk searched per queue round (parking space in shared memory)
+// threads of the linearize / error kernels (512, i.e. the 14 groups of a C2 chunk in flight at once, was measured:
+// 4 500 against 4 640 registrations/s with 256)
+#ifndef DDLO_BATCH_LIN_THREADS
+#define DDLO_BATCH_LIN_THREADS 256
+#endif
+constexpr int kLThreads = DDLO_BATCH_LIN_THREADS;
+constexpr int kLWarps = kLThreads / 32;
 #ifndef DDLO_BATCH_BLOCKS_PER_SM
 #define DDLO_BATCH_BLOCKS_PER_SM 4
 #endif
@@ -132,10 +139,10 @@ __device__ __forceinline__ void finish_problem(BatchProb& P, const GicpArgs& a, 
   }
 }
 
-__global__ void __launch_bounds__(kBThreads, kBBlocksPerSM) k_batch_lin(BatchProb* probs, int* n_active) {
+__global__ void __launch_bounds__(kLThreads, 1024 / kLThreads) k_batch_lin(BatchProb* probs, int* n_active) {
   BatchProb& P = probs[blockIdx.y];
   if ((int)blockIdx.x >= P.nchunks || P.next != kNextLinearize) return;
-  __shared__ double s_gs[kBWarps][kNumSums];
+  __shared__ double s_gs[kLWarps][kNumSums];
   __shared__ double s_tot[kNumSums];
   __shared__ Iso3 s_x0;
   __shared__ LmShared s_lm;
@@ -149,9 +156,9 @@ __global__ void __launch_bounds__(kBThreads, kBBlocksPerSM) k_batch_lin(BatchPro
   const GicpArgs& a = s_a;
   const Deal dl = make_deal(a.ns, P.nchunks, blockIdx.x);
   double acc = 0.0;  // threads < 28: the chunk's sum of component threadIdx.x
-  for (int base = 0; base < dl.nslots; base += kBThreads) {
+  for (int base = 0; base < dl.nslots; base += kLThreads) {
     const int slot = base + threadIdx.x;
-    const int ngroups = min(kBWarps, (dl.nslots - base + kGroup - 1) / kGroup);
+    const int ngroups = min(kLWarps, (dl.nslots - base + kGroup - 1) / kGroup);
     if (warp < ngroups) {
       int i = -1, j = -1, pos = -1;
       if (slot < dl.nslots) {
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(kBThreads, kBBlocksPerSM) k_batch_lin(BatchPro
   finish_problem<kNumSums>(P, a, n_active, s_tot, s_lm, &s_last);
 }
 
-__global__ void __launch_bounds__(kBThreads, kBBlocksPerSM) k_batch_err(BatchProb* probs, int* n_active) {
+__global__ void __launch_bounds__(kLThreads, 1024 / kLThreads) k_batch_err(BatchProb* probs, int* n_active) {
   BatchProb& P = probs[blockIdx.y];
   if ((int)blockIdx.x >= P.nchunks || P.next != kNextError) return;
   constexpr int kSpan = 128;  // groups per sweep (k_align's error pass sweeps 128 groups too; the order is the group order anyway)
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(kBThreads, kBBlocksPerSM) k_batch_err(BatchPro
   const int ngroups = (dl.nslots + kGroup - 1) / kGroup;
   double total = 0.0;  // thread 0 only
   for (int g0 = 0; g0 < ngroups; g0 += kSpan) {
-    for (int g = g0 + warp; g < min(ngroups, g0 + kSpan); g += kBWarps) {
+    for (int g = g0 + warp; g < min(ngroups, g0 + kSpan); g += kLWarps) {
       const int slot = g * kGroup + lane;
       int i = -1;
       if (slot < dl.nslots) {
@@ -238,8 +245,8 @@ int batch_align_round(cudaStream_t st, void* d_probs, int n, int max_chunks, int
   const dim3 grid((unsigned)max_chunks, (unsigned)n);
   BatchProb* P = static_cast<BatchProb*>(d_probs);
   k_batch_search<<<grid, kBThreads, 0, st>>>(P);
-  k_batch_lin<<<grid, kBThreads, 0, st>>>(P, d_active);
-  k_batch_err<<<grid, kBThreads, 0, st>>>(P, d_active);
+  k_batch_lin<<<grid, kLThreads, 0, st>>>(P, d_active);
+  k_batch_err<<<grid, kLThreads, 0, st>>>(P, d_active);
   *launches += 3;
   DDLO_CUDA(cudaGetLastError());
   return DDLO_OK;

@@ -103,6 +103,8 @@ struct ddlo_runtime {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;  // short independent work inside one call (node array initialisation during the sort)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side2 = nullptr;  // the first correspondence search of an align that computes covariances first
+  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t slots[16] = {};
   int num_sms = 0;

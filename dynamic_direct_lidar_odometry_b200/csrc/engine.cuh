@@ -46,7 +46,9 @@ int use_device(const ddlo_runtime* rt);
 int ensure_pinned(ddlo_runtime* rt, size_t bytes);
 // enqueue one align on the engine's stream (missing covariances are computed first); nothing is read back
 int enqueue_align(ddlo_gicp* g, const float* guess16, int* covs_computed);
-int prepare_align(ddlo_gicp* g, const float* guess16, int* covs_computed, GicpArgs* a, int* nblocks);
+// single_launch: the caller will run k_align (the first correspondence search may then be started early, beside the
+// covariance kernels); false: the caller only wants the argument record (batched waves)
+int prepare_align(ddlo_gicp* g, const float* guess16, int* covs_computed, GicpArgs* a, int* nblocks, bool single_launch = false);
 void fill_result(const AlignOut* o, int covs_computed, ddlo_align_result* r);
 // batch_align.cu: a wave of problems advanced together (device array of BatchProb records, opaque here)
 size_t batch_prob_bytes();

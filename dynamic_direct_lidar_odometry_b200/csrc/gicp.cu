@@ -49,8 +49,9 @@ struct AlignSmem {
 
 // linearize over the block's chunk; leaves the chunk's 28 sums in dst[c * stride + blockIdx.x].
 // have_prev: nn_seed holds the matches of the previous linearize of the same source cloud.
+// matches_ready: the correspondences of this transform are already in corr / nn_seed (k_search_pass0): no search.
 __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm, bool have_prev, double* dst, int stride,
-                                                unsigned long long* bt = nullptr) {
+                                                unsigned long long* bt = nullptr, bool matches_ready = false) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < kNumSums) sm.acc[threadIdx.x] = 0.0;
   if (threadIdx.x == 0) sm.t_search = 0ull;
@@ -61,7 +62,7 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
     if (threadIdx.x == 0) sm.next = 0;
     __syncthreads();  // queue reset; parked matches and group sums of the previous round consumed; acc initialised
     // ---- phase A
-    if (warp < kSearchWarps) {
+    if (warp < kSearchWarps && !matches_ready) {
       search_slots(a, pk, dl, base, nround, have_prev);
       if (bt && lane == 0) atomicMax(&sm.t_search, globaltimer_ns());  // when the block's last warp left the search
     }
@@ -73,11 +74,14 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
       int i = -1, j = -1, pos = -1;
       if (threadIdx.x < nround) {
         i = dl.point(base + threadIdx.x);
-        if (i < a.ns) {
+        if (i >= a.ns) {
+          i = -1;
+        } else if (matches_ready) {
+          j = __ldcg(a.corr + i);
+          pos = __ldcg(a.nn_seed + i).x;
+        } else {
           pos = sm.nn_pos[threadIdx.x];
           j = store_match(a, i, sm.nn_d[threadIdx.x], sm.nn_idx[threadIdx.x], pos);
-        } else {
-          i = -1;
         }
       }
       const double v = lin_group(a, sm.lm.x0, i, j, pos);
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(kAlignThreads, kAlignBlocksPerSM) k_align(cons
       const int pass = s.n_lin;
       unsigned long long* bt = (a.blk_times && pass < 8) ? a.blk_times + ((size_t)pass * nblk + blockIdx.x) * 8 : nullptr;
       if (bt && threadIdx.x == 0) bt[0] = globaltimer_ns();
-      linearize_block(a, sm, pass > 0, part, a.partial_stride, bt);
+      linearize_block(a, sm, pass > 0, part, a.partial_stride, bt, pass == 0 && a.pass0_done != 0);
       if (bt && threadIdx.x == 0) {
         bt[1] = sm.t_search;
         bt[2] = globaltimer_ns();
@@ -193,6 +197,37 @@ __global__ void __launch_bounds__(kAlignThreads, kAlignBlocksPerSM) k_align(cons
     write_align_out(a, s, a.out);
     DDLO_STAMP(kTagEnd);
     if (a.stamps) a.stamps[0] = (unsigned long long)n_stamps;
+  }
+}
+
+// update_correspondences at the guess, for all chunks of the registration, as a kernel of its own (256-thread blocks
+// that share an SM with the covariance kernels; the chunks are k_align's, the matches land where k_align's first
+// linearize would have put them)
+constexpr int kP0Threads = 256;
+constexpr int kP0Round = 1024;
+__global__ void __launch_bounds__(kP0Threads, 4) k_search_pass0(const GicpArgs a) {
+  __shared__ float s_d[kP0Round];
+  __shared__ int s_idx[kP0Round], s_pos[kP0Round];
+  __shared__ int s_next;
+  __shared__ float s_T[12];
+  if (threadIdx.x == 0) {
+    Iso3 x0;
+    iso_from_colmajor(a.guess, x0);
+    iso_to_float(x0, s_T, s_T + 9);
+  }
+  const Deal dl = make_deal(a.ns, gridDim.x, blockIdx.x);
+  SearchPark pk{s_d, s_idx, s_pos, &s_next, s_T, s_T + 9, 0};
+  for (int base = 0; base < dl.nslots; base += kP0Round) {
+    const int nround = min(kP0Round, dl.nslots - base);
+    if (threadIdx.x == 0) s_next = 0;
+    __syncthreads();
+    search_slots(a, pk, dl, base, nround, false);
+    __syncthreads();
+    for (int t = threadIdx.x; t < nround; t += kP0Threads) {
+      const int i = dl.point(base + t);
+      if (i < a.ns) store_match(a, i, s_d[t], s_idx[t], s_pos[t]);
+    }
+    __syncthreads();
   }
 }
 
@@ -291,6 +326,13 @@ int launch_align(ddlo_runtime* rt, const GicpArgs& args, int blocks) {
   void* kargs[] = {const_cast<GicpArgs*>(&args)};
   DDLO_CUDA(cudaLaunchCooperativeKernel((const void*)k_align, dim3(blocks), dim3(kAlignThreads), kargs, sizeof(AlignSmem), rt->stream));
   rt->launches += 1;
+  return DDLO_OK;
+}
+
+int launch_search_pass0(ddlo_runtime* rt, cudaStream_t st, const GicpArgs& args, int chunks) {
+  k_search_pass0<<<chunks, kP0Threads, 0, st>>>(args);
+  rt->launches += 1;
+  DDLO_CUDA(cudaGetLastError());
   return DDLO_OK;
 }
 

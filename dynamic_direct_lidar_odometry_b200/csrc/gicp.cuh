@@ -38,6 +38,7 @@ struct GicpArgs {
   int lm_max_iterations;
   double thr2;              // corr_dist_threshold_^2
   double trans_eps, rot_eps, lm_init_lambda_factor;
+  int pass0_done;           // the first linearize's correspondences are already in corr / nn_seed / sqd (k_search_pass0)
   float guess[16];          // column-major Eigen::Matrix4f
   double T_step[16];        // stepwise hooks: transform to evaluate at (column-major)
   AlignOut* out;
@@ -49,6 +50,9 @@ struct GicpArgs {
 
 int gicp_max_coop_blocks(int device, int* blocks_per_sm);
 int launch_align(ddlo_runtime* rt, const GicpArgs& args, int blocks);
+// update_correspondences of the FIRST linearize (transform = the guess) as a kernel of its own on `st`: lets the
+// search run beside the covariance kernels when align() has to compute covariances first
+int launch_search_pass0(ddlo_runtime* rt, cudaStream_t st, const GicpArgs& args, int chunks);
 int launch_linearize_step(ddlo_runtime* rt, const GicpArgs& args, int blocks);
 int launch_error_step(ddlo_runtime* rt, const GicpArgs& args, int blocks);
 int launch_residual_vectors(ddlo_runtime* rt, const float4* src, const float4* tgt, const int* corr, int n, const float* T16_host,

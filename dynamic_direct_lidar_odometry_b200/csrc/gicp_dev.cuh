@@ -205,13 +205,16 @@ static __device__ __noinline__ double err_group(const GicpArgs& a, const Iso3& T
 // one source point of compute_error
 __device__ __forceinline__ double err_point(const GicpArgs& a, const Iso3& T, int i) {
   if (i < 0) return 0.0;
-  const int j = __ldcg(a.corr + i);
-  if (j < 0) return 0.0;
   DDLO_CHECK_INDEX(i, a.ns, "err_point: source index");
-  DDLO_CHECK_INDEX(__ldcg(a.nn_seed + i).x, a.tgt.n, "err_point: stored target position");
+  // every load that depends on i alone is issued before the first use (the pass is a stream of 84 bytes per point:
+  // what it needs is loads in flight); only the matched target point waits for the stored position
+  const int j = __ldcg(a.corr + i);
+  const int2 seed = __ldcg(a.nn_seed + i);
   const float4 pa = __ldg(a.src_pts + i);
-  const float4 pb = __ldg(a.tgt.spts + __ldcg(a.nn_seed + i).x);
-  const Sym3 M = load_sym3_cg(a.mahal + (size_t)i * kCovStride);
+  const Sym3 M = load_sym3_cg(a.mahal + (size_t)i * kCovStride);  // (stale for a point without correspondence: not used then)
+  if (j < 0) return 0.0;
+  DDLO_CHECK_INDEX(seed.x, a.tgt.n, "err_point: stored target position");
+  const float4 pb = __ldg(a.tgt.spts + seed.x);
   const double x = xform_d(T.r + 0, T.t[0], (double)pa.x, (double)pa.y, (double)pa.z);
   const double y = xform_d(T.r + 3, T.t[1], (double)pa.x, (double)pa.y, (double)pa.z);
   const double z = xform_d(T.r + 6, T.t[2], (double)pa.x, (double)pa.y, (double)pa.z);

@@ -208,13 +208,20 @@ __global__ void __launch_bounds__(256) k_cells(const unsigned* __restrict__ keys
     const float4 p = pts[o];
     spts[i] = make_float4(p.x, p.y, p.z, __int_as_float(o));
   }
-  // cells of level t that begin in this block
+  // cells of level t that begin in this block: one ballot per level and warp, the warp totals added in shared memory
+  __shared__ int s_cnt[kMortonLevels];
+  if (threadIdx.x < kMortonLevels) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  {
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int t = 0; t < kMortonLevels; ++t) {
-    int tot = 0;
-    block_inclusive_count(live && t < L && cd < t, s_wtot, &tot);
-    if (threadIdx.x == 0) counts[(size_t)t * gridDim.x + blockIdx.x] = tot;
+    for (int t = 0; t < kMortonLevels; ++t) {
+      const unsigned b = __ballot_sync(0xffffffffu, live && t < L && cd < t);
+      if (lane == 0 && b) atomicAdd(&s_cnt[t], __popc(b));
+    }
   }
+  __syncthreads();
+  if (threadIdx.x < kMortonLevels) counts[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x];
   // the last block to arrive turns the counts into exclusive prefixes over the blocks and publishes the level bases
   __threadfence();
   __syncthreads();
@@ -222,42 +229,43 @@ __global__ void __launch_bounds__(256) k_cells(const unsigned* __restrict__ keys
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // one warp per level (levels warp, warp + 8): a running exclusive scan over the blocks, 32 at a time, no block barrier
   const int nb = (int)gridDim.x;
-  const int per = (nb + 255) / 256;  // consecutive blocks per thread
-  int level_base = 0;
-  for (int t = 0; t < kMortonLevels; ++t) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < kMortonLevels; t += 8) {
     int* row = counts + (size_t)t * nb;
-    const int b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
-    int sum = 0;
-    for (int b = b0; b < b1; ++b) sum += __ldcg(row + b);
-    // exclusive prefix of the per-thread sums over the block
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = sum;
+    int carry = 0;
+    for (int b0 = 0; b0 < nb; b0 += 256) {  // a lane takes 8 consecutive blocks: 8 independent loads in flight
+      const int first = b0 + lane * 8;
+      int c[8], sum = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += u;
-    }
-    if (lane == 31) s_wtot[warp] = inc;
-    __syncthreads();
-    int base = 0, tot = 0;
+      for (int k = 0; k < 8; ++k) {
+        c[k] = first + k < nb ? __ldcg(row + first + k) : 0;
+        sum += c[k];
+      }
+      int inc = sum;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const int v = s_wtot[w];
-      if (w < warp) base += v;
-      tot += v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      int run = carry + inc - sum;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (first + k < nb) row[first + k] = run;
+        run += c[k];
+      }
+      carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    __syncthreads();
-    int run = base + inc - sum;
-    for (int b = b0; b < b1; ++b) {
-      const int c = __ldcg(row + b);
-      row[b] = run;
-      run += c;
-    }
-    if (threadIdx.x == 0) ctl[2 + t] = level_base;
-    level_base += tot;
+    if (lane == 0) s_cnt[t] = carry;  // cells of the level
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    int level_base = 0;
+    for (int t = 0; t < kMortonLevels; ++t) {
+      ctl[2 + t] = level_base;
+      level_base += s_cnt[t];
+    }
     ctl[1] = level_base;  // node count
     reinterpret_cast<int*>(lattice)[5] = level_base;
     ctl[0] = 0;

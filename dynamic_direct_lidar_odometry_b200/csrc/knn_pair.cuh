@@ -24,6 +24,10 @@ namespace ddlo {
 
 constexpr int kPairStack = 40;  // <= 4 pushes per lane and level, internal children live on levels 1..9
 
+// (Measured in round 2: keeping the first 12 - 16 stack entries of every lane in shared memory instead of local memory
+// leaves the DRAM traffic of k_align unchanged - its extra write traffic is the write-back of the preceding kernels'
+// dirty lines, not the stacks - and costs 13 us of 265 for the address arithmetic on the search's critical chain.)
+
 // best candidate of a pair of lanes (uniform across the pair)
 struct Best1Pair {
   float d = FLT_MAX;

@@ -25,6 +25,8 @@
 // Arithmetic: float products/sums rounded one by one as the reference's -O2 x86-64 build does; atan2 is evaluated in
 // double and rounded to float (the correctly rounded float value but for ~1e-9 of the inputs; the reference's libm
 // atan2f may differ from it in the last bit, which matters only for a slope within 1 ulp of its threshold).
+#include <vector>
+
 #include "prims.cuh"
 
 #include <algorithm>
@@ -538,11 +540,21 @@ __global__ void __launch_bounds__(256) k_seg_labels(SegDev p, const int* __restr
   if (ok && r == i) avg_by_label[lab] = seg_avg[ordinal];
 }
 
-template <class T>
-int pool_alloc(ddlo_runtime* rt, T** ptr, size_t count) {
-  DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(ptr), std::max<size_t>(count, 1) * sizeof(T), rt->stream));
-  return DDLO_OK;
-}
+// the stage's temporaries: stream-ordered pool buffers, all returned on every exit path
+struct SegPool {
+  ddlo_runtime* rt;
+  std::vector<void*> held;
+  explicit SegPool(ddlo_runtime* r) : rt(r) {}
+  ~SegPool() {
+    for (void* q : held) cudaFreeAsync(q, rt->stream);
+  }
+  template <class T>
+  int alloc(T** ptr, size_t count) {
+    DDLO_CUDA(cudaMallocAsync(reinterpret_cast<void**>(ptr), std::max<size_t>(count, 1) * sizeof(T), rt->stream));
+    held.push_back(*ptr);
+    return DDLO_OK;
+  }
+};
 
 }  // namespace
 
@@ -587,32 +599,33 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   int* res_count = nullptr;
   void* tmp = nullptr;
   const size_t tmp_bytes = scan_temp_bytes((size_t)HW);
-  DDLO_TRY(pool_alloc(rt, &nib, nib_bytes));
-  DDLO_TRY(pool_alloc(rt, &parent, HW));
-  DDLO_TRY(pool_alloc(rt, &root, HW));
-  DDLO_TRY(pool_alloc(rt, &size, HW));
-  DDLO_TRY(pool_alloc(rt, &seeds, HW));
-  DDLO_TRY(pool_alloc(rt, &accepted, HW));
-  DDLO_TRY(pool_alloc(rt, &rank, HW));
-  DDLO_TRY(pool_alloc(rt, &small, 4));  // [0] seeds found, [1] next seed to fill
-  DDLO_TRY(pool_alloc(rt, &keys, HW));
-  DDLO_TRY(pool_alloc(rt, &order, HW));
-  DDLO_TRY(pool_alloc(rt, &cstat, (size_t)kStatCount * HW));
+  SegPool pool(rt);
+  DDLO_TRY(pool.alloc(&nib, nib_bytes));
+  DDLO_TRY(pool.alloc(&parent, HW));
+  DDLO_TRY(pool.alloc(&root, HW));
+  DDLO_TRY(pool.alloc(&size, HW));
+  DDLO_TRY(pool.alloc(&seeds, HW));
+  DDLO_TRY(pool.alloc(&accepted, HW));
+  DDLO_TRY(pool.alloc(&rank, HW));
+  DDLO_TRY(pool.alloc(&small, 4));  // [0] seeds found, [1] next seed to fill
+  DDLO_TRY(pool.alloc(&keys, HW));
+  DDLO_TRY(pool.alloc(&order, HW));
+  DDLO_TRY(pool.alloc(&cstat, (size_t)kStatCount * HW));
   if (p.unordered_sums && p.have_residuals) {
-    DDLO_TRY(pool_alloc(rt, &res_sum, HW));
-    DDLO_TRY(pool_alloc(rt, &res_count, HW));
+    DDLO_TRY(pool.alloc(&res_sum, HW));
+    DDLO_TRY(pool.alloc(&res_count, HW));
     DDLO_CUDA(cudaMemsetAsync(res_sum, 0, (size_t)HW * 8, st));
     DDLO_CUDA(cudaMemsetAsync(res_count, 0, (size_t)HW * 4, st));
   }
-  DDLO_TRY(pool_alloc(rt, &seg_avg, HW));
-  DDLO_TRY(pool_alloc(rt, reinterpret_cast<unsigned char**>(&tmp), tmp_bytes));
+  DDLO_TRY(pool.alloc(&seg_avg, HW));
+  DDLO_TRY(pool.alloc(reinterpret_cast<unsigned char**>(&tmp), tmp_bytes));
   DDLO_CUDA(cudaMemsetAsync(small, 0, 16, st));
   DDLO_CUDA(cudaMemsetAsync(nib + nib_bytes - 16, 0, 16, st));  // the padding behind the last pixel pair
 
   const int pb = (HW + 255) / 256;
   float4* moved = nullptr;
   if (prm.scan_in_sensor_frame) {
-    DDLO_TRY(pool_alloc(rt, &moved, HW));
+    DDLO_TRY(pool.alloc(&moved, HW));
     SegPose pose;
     for (int i = 0; i < 16; ++i) pose.m[i] = T16[i];
     k_seg_transform<<<pb, 256, 0, st>>>(HW, d_scan, stride_floats, pose, moved);
@@ -641,10 +654,7 @@ int segment_scan_device(ddlo_runtime* rt, const ddlo_segmentation_params& prm, c
   k_seg_labels<<<pb, 256, 0, st>>>(p, root, keys, accepted, rank, seg_avg, small, d_label, d_avg_by_label, d_label_count);
   rt->launches += 8 + 6;  // + the two scans (three kernels each, prims.cu)
   DDLO_CUDA(cudaGetLastError());
-  for (void* q : {(void*)nib, (void*)parent, (void*)root, (void*)size, (void*)seeds, (void*)accepted, (void*)rank, (void*)small, (void*)keys,
-                  (void*)order, (void*)cstat, (void*)seg_avg, tmp, (void*)moved, (void*)res_sum, (void*)res_count})
-    if (q) cudaFreeAsync(q, st);
-  return DDLO_OK;
+  return DDLO_OK;  // ~SegPool returns the temporaries
 }
 
 }  // namespace ddlo
