@@ -368,9 +368,10 @@ def run_ours(args):
     # L2 flush here: consecutive units are different scans and many of them are in flight at once.
     batched = None
     S = args.batched_streams
+    extra = {}
     if S > 0:
         try:
-            batched = run_batched(ng, group, local_rank, rank, world, tgt, args)
+            batched = run_batched(ng, group, local_rank, rank, world, tgt, args, extra)
         except Exception as exc:  # noqa: BLE001
             batched = {"error": repr(exc)}
             try:
@@ -425,6 +426,9 @@ def run_ours(args):
             line["batched"] = batched
         if c1 is not None:
             line["c1"] = c1
+        for key in ("c3", "c5"):
+            if key in extra:
+                line[key] = extra[key]
         if world == 1 and not args.no_cpu_baseline:
             use_all_host_cores()
             po, ceng, _, kind, knn = cpu_reference_setup(src, tgt)
@@ -492,7 +496,40 @@ def run_c1(ng, rt):
     return out
 
 
-def run_batched(ng, group, local_rank, rank, world, tgt, args):
+def run_c3_cpp(scans, args):
+    """BASELINE configs[2]: the 100-frame S2S -> S2M odometry loop, frame loop in C++ (tests/cpp/odometry_sequence.cpp on the C
+    ABI and the device-resident keyframe store; k nearest + convex / concave hull keyframe selection as the reference's defaults)"""
+    import tempfile
+
+    from dynamic_direct_lidar_odometry_b200 import synth
+
+    exe = ROOT / "tests" / "cpp" / "_build" / "odometry_sequence"
+    if not exe.exists():
+        import __graft_entry__ as ge
+
+        ge.build_cpp_tests()
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / "scans.bin"
+        with open(path, "wb") as fh:
+            fh.write(np.int32(len(scans)).tobytes())
+            for sc in scans:
+                fh.write(np.int32(len(sc)).tobytes())
+                fh.write(np.ascontiguousarray(sc, dtype=np.float32).tobytes())
+        out = subprocess.run([str(exe), str(path), str(K_COV), "1.0", "15", "10", "10", "10", "0", "0", "8"], capture_output=True, text=True, timeout=600)
+    if out.returncode != 0:
+        raise RuntimeError(out.stderr[-500:])
+    rows = [l.split() for l in out.stdout.splitlines() if l.startswith("frame")]
+    ms = [float(r[9]) for r in rows]
+    inv0 = np.linalg.inv(synth.pose(0))
+    err = max(float(np.abs(np.array(r[11:27], dtype=np.float64).reshape(4, 4)[:3, 3] - (inv0 @ synth.pose(int(r[1])))[:3, 3]).max()) for r in rows)
+    summary = [l.split() for l in out.stdout.splitlines() if l.startswith("summary")][0]
+    return {"workload": "C3: 100-frame synthetic 64x1024 sequence, S2S + S2M + keyframes + submaps on the device, frame loop in C++",
+            "ms_per_frame": percentiles(ms), "keyframes": int(summary[4]), "submap_rebuilds": int(sum(int(r[7]) for r in rows)),
+            "all_converged": bool(all(int(r[4]) and int(r[5]) for r in rows)), "max_translation_error_vs_truth_m": err,
+            "timer": "host wall clock per frame inside the C++ program, scan upload and residual read-back included"}
+
+
+def run_batched(ng, group, local_rank, rank, world, tgt, args, extra):
     from dynamic_direct_lidar_odometry_b200 import synth
     from dynamic_direct_lidar_odometry_b200.binding import load as B_load
 
@@ -500,14 +537,17 @@ def run_batched(ng, group, local_rank, rank, world, tgt, args):
     n_units = max(512, args.batched_units)
     n_distinct = 64
     w = synth.make_world()
-    frames = [40 + ((rank * n_distinct + i) % 160) for i in range(n_distinct)]
+    # frames 0 .. 103 of the synthetic sequence: 40 .. 103 are the scans of the batched C2 leg, 0 .. 99 the C3 sequence,
+    # 0 .. 64 the pairs of the C5 leg
+    all_frames = {f: synth.scan(f, NS_BEAMS, NS_COLS, w) for f in range(40 if args.no_extra_configs else 0, 104)}
+    frames = list(range(40, 40 + n_distinct))
     batch = ng.Batch(local_rank, lanes=S, host_threads=args.batched_host_threads, mode=args.batched_mode, wave_units=args.batched_wave)
     batch.set_params(k_correspondences=K_COV)
     sub_id = batch.stage(tgt)
     batch.set_shared_target(sub_id)
     ids, guesses, host_scans = [], [], []
     for f in frames:
-        sc = synth.scan(f, NS_BEAMS, NS_COLS, w)
+        sc = all_frames[f]
         ids.append(batch.stage(sc))
         guesses.append(synth.perturbed_guess(synth.pose(f)))
         pin = ng.pinned_array(sc.shape, np.float32)  # the same scans in page-locked host memory, for the end-to-end leg
@@ -564,6 +604,37 @@ def run_batched(ng, group, local_rank, rank, world, tgt, args):
         out["one_gpu_alone"] = n_units / solo
         out["scaling_efficiency"] = (world * n_units / dt_max) / (world * n_units / solo)
     batch.close()
+    if not args.no_extra_configs:
+        # C5 (BASELINE configs[4]) in small: independent S2S pairs (frame f+1 -> f, 64 distinct), full pipeline per pair,
+        # 1 024 per GPU through the same C++ driver; the 4 096-pair strong-scaling runs are benchmarks/c5_batch.py
+        try:
+            b5 = ng.Batch(local_rank, lanes=S, host_threads=args.batched_host_threads, mode=args.batched_mode, wave_units=args.batched_wave)
+            ids5 = [b5.stage(all_frames[f]) for f in range(65)]
+            units = [(ids5[u % 64 + 1], ids5[u % 64], None) for u in range(1024)]
+            j5 = ng.Batch.jobs(units)
+            b5.run(ng.Batch.jobs(units[: max(8 * S, 8 * args.batched_wave)]))
+            group.barrier()
+            t0 = time.perf_counter()
+            r5 = b5.run(j5, raw=True)
+            dt5 = time.perf_counter() - t0
+            group.barrier()
+            (dt5_max,) = group.reduce_max([dt5])
+            extra["c5"] = {"workload": "C5: independent S2S registrations of 64x1024 scan pairs, two index builds + two covariance passes + align each",
+                           "value": world * 1024 / dt5_max, "unit": UNIT, "pairs_per_gpu": 1024, "distinct_pairs": 64,
+                           "all_converged": bool(all(r5[i].flags & 1 for i in range(1024))), "driver": "ddlo_batch_submit / ddlo_batch_wait (C++)",
+                           "algorithmic_bytes_per_pair": 100.9e6, "hbm_fraction": 1024 / dt5 * 100.9e6 / 1e9 / 6549.4}
+            b5.close()
+        except Exception as exc:  # noqa: BLE001
+            extra["c5"] = {"error": repr(exc)}
+            try:
+                group.barrier()
+            except Exception:  # noqa: BLE001
+                pass
+        if rank == 0:
+            try:
+                extra["c3"] = run_c3_cpp([all_frames[f] for f in range(100)], args)
+            except Exception as exc:  # noqa: BLE001
+                extra["c3"] = {"error": repr(exc)}
     return out
 
 
@@ -574,12 +645,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batched-streams", type=int, default=4, help="lanes (stream + engine) per GPU of the batched-throughput leg (0 = skip)")
-    ap.add_argument("--batched-units", type=int, default=1024, help="registrations per GPU in the batched leg (at least 512)")
+    ap.add_argument("--batched-streams", type=int, default=8, help="lanes (stream + engine) per GPU of the batched-throughput leg (0 = skip)")
+    ap.add_argument("--batched-units", type=int, default=2048, help="registrations per GPU in the batched leg (at least 512)")
     ap.add_argument("--batched-host-threads", type=int, default=2, help="C++ host threads that enqueue the batched leg")
     ap.add_argument("--batched-mode", choices=["waves", "lanes"], default="waves", help="align stage of the batched leg (ddlo_batch_set_mode)")
-    ap.add_argument("--batched-wave", type=int, default=32, help="units per wave in waves mode")
+    ap.add_argument("--batched-wave", type=int, default=64, help="units per wave in waves mode")
     ap.add_argument("--no-c1", action="store_true", help="skip the C1 (S2S) leg")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the C3 (sequence, C++ loop) and C5 (S2S pairs) legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

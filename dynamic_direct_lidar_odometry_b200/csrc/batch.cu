@@ -44,7 +44,7 @@ struct ddlo_batch {
   std::vector<Lane> lanes;
   // WAVES mode: two wave buffers of W slots (engine on lane slot % S + its "prepared" event), a stream for the rounds
   int mode = DDLO_BATCH_WAVES;
-  int wave_units = 32;
+  int wave_units = 64;
   struct Slot {
     ddlo_gicp* eng = nullptr;
     cudaEvent_t ready = nullptr;

@@ -316,7 +316,7 @@ int ddlo_batch_destroy(ddlo_batch* b);
 int ddlo_batch_info(const ddlo_batch* b, int* n_lanes, int* align_blocks_per_lane, int* host_threads);
 int ddlo_batch_set_params(ddlo_batch* b, const ddlo_params* p); /* all lanes */
 /* How the align stage of the units runs.
- *   DDLO_BATCH_WAVES (default): the units are taken wave_units at a time (<= 0: keep, default 32).  While the lanes
+ *   DDLO_BATCH_WAVES (default): the units are taken wave_units at a time (<= 0: keep, default 64).  While the lanes
  *     prepare one wave (handles, indexes, covariances), the previous one is aligned by batched kernels that advance ALL
  *     its problems by one LM round per three ordinary launches (no cooperative launch, no grid barrier; problems at
  *     different iterations share the launches).  A C++ thread owned by the batch drives the rounds between
