@@ -600,6 +600,19 @@ def run_batched(ng, group, local_rank, rank, world, tgt, args, extra):
                    "d2h_bytes_per_unit": int(B_load().ddlo_align_d2h_bytes()), "same_poses_as_staged_run": bool(same),
                    "note": "ddlo_batch_submit_host: scans uploaded from page-locked host memory inside the timed region"},
            "note": "`value` at the top of the line is one stream, i.e. 1000 / ms_per_scan"}
+    # algorithmic bytes of one C2 step: index + covariances of the scan, L linearize and E error passes
+    L_mean = statistics.mean(res[i].n_linearize for i in range(n_units))
+    E_mean = statistics.mean(res[i].n_compute_error for i in range(n_units))
+    step_bytes = (B_INDEX + B_COV + B_LIN * L_mean + B_ERR * E_mean) * len(host_scans[0])
+    try:
+        peak = float(json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    per_gpu = n_units / dt_max
+    out["roofline"] = {"bound": "hbm", "achieved": per_gpu * step_bytes / 1e9, "peak": peak, "unit": "GB/s per GPU", "frac": per_gpu * step_bytes / 1e9 / peak,
+                       "algorithmic_bytes_per_registration": step_bytes,
+                       "note": "whole batched step; the binding resource is instruction issue (profiles/r02_batch_launch_summary.txt: 166 M warp "
+                               "instructions per registration), the streaming kernels of the path (k_batch_lin, k_batch_err) run at 35 % of the HBM peak"}
     if solo is not None:
         out["one_gpu_alone"] = n_units / solo
         out["scaling_efficiency"] = (world * n_units / dt_max) / (world * n_units / solo)
