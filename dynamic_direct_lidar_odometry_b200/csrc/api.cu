@@ -76,6 +76,56 @@ __global__ void __launch_bounds__(256) k_fill(float4* p, size_t n4) {
     p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Concatenation of up to kConcatParts device arrays of 16-byte words in ONE launch (a submap is 10 - 30 keyframes;
+// one cudaMemcpyAsync per part costs more in launches than the copy itself)
+constexpr int kConcatParts = 32;
+struct ConcatParts {
+  const uint4* src[kConcatParts];
+  unsigned long long begin[kConcatParts + 1];  // in 16-byte words
+  int m;
+};
+__global__ void __launch_bounds__(256) k_concat(ConcatParts p, uint4* __restrict__ dst) {
+  const unsigned long long total = p.begin[p.m];
+  for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < total; w += (unsigned long long)gridDim.x * blockDim.x) {
+    int part = 0;
+#pragma unroll 1
+    for (int lo = 0, hi = p.m; lo < hi;) {  // the part that holds word w
+      const int mid = (lo + hi) >> 1;
+      if (p.begin[mid + 1] <= w)
+        lo = mid + 1;
+      else
+        hi = mid;
+      part = lo;
+    }
+    dst[w] = p.src[part][w - p.begin[part]];
+  }
+}
+
+// parts[i]: n_words[i] 16-byte words at src[i]; empty parts are skipped
+static int concat_words(ddlo_runtime* rt, const void* const* src, const size_t* n_words, int m, void* dst) {
+  size_t off = 0;
+  int i = 0;
+  while (i < m) {
+    ConcatParts p;
+    p.m = 0;
+    p.begin[0] = 0;
+    unsigned long long words = 0;
+    for (; i < m && p.m < kConcatParts; ++i) {
+      if (n_words[i] == 0) continue;
+      p.src[p.m] = static_cast<const uint4*>(src[i]);
+      words += n_words[i];
+      p.begin[++p.m] = words;
+    }
+    if (p.m == 0) break;
+    const int blocks = (int)std::min<unsigned long long>((words + 255) / 256, (unsigned long long)rt->num_sms * 16);
+    k_concat<<<blocks, 256, 0, rt->stream>>>(p, static_cast<uint4*>(dst) + off);
+    rt->launches += 1;
+    DDLO_CUDA(cudaGetLastError());
+    off += words;
+  }
+  return DDLO_OK;
+}
+
 int use_device(const ddlo_runtime* rt) {
   DDLO_CUDA(cudaSetDevice(rt->device));
   return DDLO_OK;
@@ -555,11 +605,13 @@ int ddlo_cloud_concat(ddlo_runtime* rt, ddlo_cloud* const* parts, int m, ddlo_cl
   if (total > std::numeric_limits<int>::max()) return fail(DDLO_E_UNSUPPORTED, "concat: too many points");
   ddlo_cloud* r = nullptr;
   DDLO_TRY(cloud_new(rt, (int)total, &r));
-  size_t off = 0;
-  for (int i = 0; i < m; ++i) {
-    if (parts[i]->n == 0) continue;
-    DDLO_CUDA(cudaMemcpyAsync(r->pts + off, parts[i]->pts, (size_t)parts[i]->n * sizeof(float4), cudaMemcpyDeviceToDevice, rt->stream));
-    off += parts[i]->n;
+  std::vector<const void*> src(m);
+  std::vector<size_t> words(m);
+  for (int i = 0; i < m; ++i) src[i] = parts[i]->pts, words[i] = (size_t)parts[i]->n;  // a point is one 16-byte word
+  const int rc = concat_words(rt, src.data(), words.data(), m, r->pts);
+  if (rc != DDLO_OK) {
+    cloud_free(r);
+    return rc;
   }
   *out = r;
   return DDLO_OK;
@@ -685,12 +737,13 @@ int ddlo_covs_concat(ddlo_runtime* rt, ddlo_covs* const* parts, int m, ddlo_covs
   if (total > std::numeric_limits<int>::max()) return fail(DDLO_E_UNSUPPORTED, "concat: too many points");
   ddlo_covs* r = nullptr;
   DDLO_TRY(covs_new(rt, (int)total, &r));
-  size_t off = 0;
-  for (int i = 0; i < m; ++i) {
-    if (parts[i]->n == 0) continue;
-    DDLO_CUDA(cudaMemcpyAsync(r->c + off * kCovStride, parts[i]->c, (size_t)parts[i]->n * kCovStride * sizeof(double),
-                              cudaMemcpyDeviceToDevice, rt->stream));
-    off += parts[i]->n;
+  std::vector<const void*> src(m);
+  std::vector<size_t> words(m);
+  for (int i = 0; i < m; ++i) src[i] = parts[i]->c, words[i] = (size_t)parts[i]->n * 3;  // a covariance is 48 bytes = three words
+  const int rc = concat_words(rt, src.data(), words.data(), m, r->c);
+  if (rc != DDLO_OK) {
+    covs_free(r);
+    return rc;
   }
   *out = r;
   return DDLO_OK;

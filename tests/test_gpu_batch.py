@@ -212,3 +212,45 @@ def test_batch_sources_from_host_memory(scans):
     for s, g in zip(staged, got):
         assert g.converged and np.array_equal(s.T, g.T) and np.array_equal(s.hessian, g.hessian)
     b.close()
+
+
+def test_batch_parameter_corner_cases(scans):
+    """engine parameters reach every lane and wave slot: Gauss-Newton, an iteration limit of 0 (the guess comes back),
+    a single LM trial; every result equals the ordinary engine's"""
+    b = ng.Batch(0, lanes=2, wave_units=3)
+    ids = [b.stage(s) for s in scans]
+    rng = np.random.default_rng(9)
+    guess = np.eye(4, dtype=np.float32)
+    guess[:3, 3] = rng.normal(0, 0.03, 3)
+    units = [(ids[u % 5 + 1], ids[u % 5], guess) for u in range(5)]
+    for params in (dict(optimizer=ng.OPT_GAUSS_NEWTON), dict(max_iterations=0), dict(lm_max_iterations=1, max_iterations=3),
+                   dict(max_correspondence_distance=0.5, k_correspondences=10)):
+        b.set_params(**params)
+        got = b.run(units)
+        rt = ng.Runtime(0)
+        for (s, t, g), r in zip(units, got):
+            e = ng.NanoGICP(rt)
+            for k, v in params.items():
+                setattr(e._p, k, v)
+            e._push()
+            e.setInputSource(ng.PointCloud(rt, scans[ids.index(s)]))
+            e.setInputTarget(ng.PointCloud(rt, scans[ids.index(t)]))
+            ref = e.align(g)
+            assert (r.flags, r.iterations, r.n_linearize, r.n_compute_error) == (ref.flags, ref.iterations, ref.n_linearize, ref.n_compute_error), params
+            assert np.array_equal(r.T, ref.T) and np.array_equal(r.hessian, ref.hessian), params
+            del e
+        rt.close()
+    b.close()
+
+
+def test_batch_unit_that_cannot_run_is_reported(scans):
+    """a unit whose source has fewer points than k fails alone (TOO_FEW); the other units of the submission complete"""
+    b = ng.Batch(0, lanes=2, wave_units=4)
+    ids = [b.stage(s) for s in scans[:3]]
+    tiny = b.stage(scans[0][:7])
+    with pytest.raises(ng.DdloError) as e:
+        b.run([(ids[1], ids[0], None), (tiny, ids[0], None), (ids[2], ids[1], None)])
+    assert e.value.code == -4
+    ok = b.run([(ids[1], ids[0], None), (ids[2], ids[1], None)])
+    assert all(r.converged for r in ok)
+    b.close()

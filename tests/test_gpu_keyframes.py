@@ -142,3 +142,24 @@ def test_cpp_odometry_sequence_matches_python_loop(rt, tmp_path, voxel):
         T = np.array(row[11:27], dtype=np.float32).reshape(4, 4)
         assert np.abs(T[:3, 3] - r.T[:3, 3]).max() < POSE_T and rot_angle(T[:3, :3], r.T[:3, :3]) < 2 * POSE_R
         assert abs(float(row[10]) - r.residual_mean) <= 1e-4 * max(1.0, abs(r.residual_mean))  # the guesses differ by float rounding
+
+
+def test_keyframe_store_three_dimensional_positions(rt):
+    """positions that are three-dimensional in PCL's sense: the convex hull is the 3-D one (checked against Qhull), the
+    concave hull is reported as not computed and contributes nothing to the selection"""
+    rng = np.random.default_rng(11)
+    store = ng.KeyframeStore(rt)
+    pts = synth.scan(0, 8, 64)
+    c, v = ng.PointCloud(rt, pts), ng.Covariances.compute(ng.PointCloud(rt, pts), 5)
+    pos = rng.normal(0, 5, (30, 3)).astype(np.float32)
+    for p in pos:
+        store.add(p, ng.rotation_to_wxyz(np.eye(3)), c, v)
+    query = np.zeros(3, np.float32)
+    changed, idx, cloud, cv = store.get_submap(query, 3, 4, 4, 2.0)
+    convex, concave, dim = store.hulls()
+    assert dim == 3 and concave == [] and convex == qhull_convex(pos.astype(np.float64))
+    d = [float(np.float32(np.sqrt(np.sum((query - q).astype(np.float64) ** 2)))) for q in pos]
+    sel = []
+    ol.OdometryLoop._push_submap_indices(d, 3, list(range(30)), sel)
+    ol.OdometryLoop._push_submap_indices([d[j] for j in convex], 4, convex, sel)
+    assert changed and idx == sorted(set(sel)) and len(cloud) == len(idx) * len(pts)
