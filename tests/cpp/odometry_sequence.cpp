@@ -104,6 +104,8 @@ struct Loop {
   int knn = 10, kcv = 10, kcc = 10;
   bool initialised = false;
   int submap_points = 0;
+  double* pinned_residuals = nullptr;  // page-locked: lets the residual copy ride on the align's synchronisation
+  int pinned_capacity = 0;
 
   // the keyframe cloud of the current scan (world frame, optional voxel filter), its covariances through the S2S source slot
   void add_keyframe(ddlo_cloud* scan) {
@@ -170,21 +172,26 @@ struct Loop {
       ddlo_cloud_release(submap);
       ddlo_covs_release(submap_covs);
     }
-    CHECK(ddlo_gicp_align(s2m, T_s2s.v, &r2));
-    std::memcpy(T.v, r2.final_transformation, sizeof(T.v));
-    residuals.resize(scan.n);
+    // the S2M align and getResiduals (odom.cc:787-793) behind ONE host synchronisation: both are enqueued, align_finish waits
     int n_cur = 0;
     CHECK(ddlo_cloud_size(cur, &n_cur));
-    residuals.resize(n_cur);
-    CHECK(ddlo_gicp_get_residuals(s2m, residuals.data(), n_cur));
+    if (n_cur > pinned_capacity) {
+      if (pinned_residuals) CHECK(ddlo_host_free(pinned_residuals));
+      pinned_capacity = n_cur + n_cur / 4;
+      CHECK(ddlo_host_alloc(sizeof(double) * (size_t)pinned_capacity, reinterpret_cast<void**>(&pinned_residuals)));
+    }
+    CHECK(ddlo_gicp_align_async(s2m, T_s2s.v));
+    CHECK(ddlo_gicp_get_residuals_async(s2m, pinned_residuals, n_cur));
+    CHECK(ddlo_gicp_align_finish(s2m, &r2));
+    std::memcpy(T.v, r2.final_transformation, sizeof(T.v));
+    residuals.assign(pinned_residuals, pinned_residuals + n_cur);
     T_s2s_prev = T;
     // updateKeyframes
     const float pos[3] = {T(0, 3), T(1, 3), T(2, 3)};
     float q[4];
     quaternion(T, q);
     CHECK(ddlo_keyframes_is_new(kf, pos, q, thresh_dist, thresh_rot, &new_kf, nullptr, nullptr, nullptr));
-    if (new_kf) add_keyframe(cur);
-    CHECK(ddlo_runtime_synchronize(rt));
+    if (new_kf) add_keyframe(cur);  // enqueued; the next frame's work is ordered behind it on the same stream
     ddlo_cloud_release(cur);
     return true;
   }
@@ -211,6 +218,8 @@ static Loop make_loop(ddlo_runtime* rt, int k, char** argv, int argc) {
   return L;
 }
 static void destroy_loop(Loop& L) {
+  CHECK(ddlo_runtime_synchronize(L.rt));
+  if (L.pinned_residuals) CHECK(ddlo_host_free(L.pinned_residuals));
   CHECK(ddlo_keyframes_destroy(L.kf));
   CHECK(ddlo_gicp_destroy(L.s2s));
   CHECK(ddlo_gicp_destroy(L.s2m));
