@@ -934,3 +934,65 @@ def test_stride_filter_matches_oracle(rt, oracle):
     chain = c.stride_filtered(512, 32, 2, 2).cropped(lo, hi, negative=True, keep_organized=True).voxel_filtered(0.25).download()
     want = oracle.voxel_filter(oracle.crop_box(oracle.extract_stride(org, 512, 32, 2, 2), lo, hi, negative=True, keep_organized=True), 0.25)
     assert np.array_equal(chain.view(np.uint32), want.view(np.uint32))
+
+
+def _fuzz_case(seed):
+    """A seeded registration problem with seeded engine parameters (used by test_align_fuzz_vs_reference_engine)."""
+    rng = np.random.default_rng(4200 + seed)
+    w = synth.make_world()
+    beams, cols = int(rng.choice([8, 12, 16, 24])), int(rng.choice([128, 192, 256, 384]))
+    f0 = int(rng.integers(0, 60))
+    f1 = f0 + int(rng.integers(1, 4))
+    src, tgt = synth.scan(f1, beams, cols, w), synth.scan(f0, beams, cols, w)
+    ang = np.deg2rad(rng.uniform(-1.0, 1.0))
+    guess = np.eye(4, dtype=np.float32)
+    guess[:2, :2] = [[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]]
+    guess[:3, 3] = rng.uniform(-0.08, 0.08, 3)
+    params = dict(
+        k=int(rng.choice([5, 10, 20])),
+        method=int(rng.integers(0, 5)),
+        optimizer=int(rng.integers(0, 2)),
+        corr=float(rng.choice([0.0, 0.4, 1.0, 3.0])),  # 0: leave the default (FLT_MAX)
+        max_iter=int(rng.choice([1, 3, 64])),
+        lm_iter=int(rng.choice([1, 10])),
+        lam=float(rng.choice([1e-9, 1e-6, 1e-3])),
+        trans_eps=float(rng.choice([5e-4, 1e-3])),
+        rot_eps=float(rng.choice([2e-3, 1e-3])),
+    )
+    return src, tgt, guess, params
+
+
+def _apply_fuzz_params(e, p):
+    e.setCorrespondenceRandomness(p["k"])
+    e.setRegularizationMethod(p["method"])
+    e.setOptimizer(p["optimizer"])
+    if p["corr"] > 0.0:
+        e.setMaxCorrespondenceDistance(p["corr"])
+    e.setMaximumIterations(p["max_iter"])
+    e.setLMMaxIterations(p["lm_iter"])
+    e.setInitialLambdaFactor(p["lam"])
+    e.setTransformationEpsilon(p["trans_eps"])
+    e.setRotationEpsilon(p["rot_eps"])
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_align_fuzz_vs_reference_engine(rt, ref_engine, seed):
+    """Seeded problems and seeded knob settings (neighbour count, all five regularisations, both optimisers, correspondence
+    gate, iteration limits, lambda factor, epsilons) against nano_gicp::NanoGICP itself: same converged flag and iteration
+    count, poses within the north-star bar, the Hessian within 1e-6, the correspondences of the last linearize identical
+    (or equidistant where nanoflann's first-visited tie rule picks another index)."""
+    src, tgt, guess, p = _fuzz_case(seed)
+    g, r = ng.NanoGICP(rt), ref_engine.NanoGICP()
+    _apply_fuzz_params(g, p)
+    _apply_fuzz_params(r, p)
+    g.setInputSource(ng.PointCloud(rt, src)); g.setInputTarget(ng.PointCloud(rt, tgt))
+    r.setInputSource(ref_engine.Cloud(src)); r.setInputTarget(ref_engine.Cloud(tgt))
+    rg_, rr = g.align(guess), r.align(guess)
+    assert (rg_.converged, rg_.iterations) == (rr.converged, rr.iterations), p
+    _check_pose(rg_, rr)
+    assert rel_err(rg_.hessian, rr.hessian) < 10 * REL, p
+    gc, gd = g.correspondences()
+    rc, rd = r.correspondences()
+    assert np.abs(np.sqrt(gd.astype(np.float64)) - np.sqrt(rd.astype(np.float64))).max() < POSE_T
+    diff = np.flatnonzero(gc != rc)
+    assert len(diff) <= max(2, 2e-3 * len(gc)), (len(diff), p)
