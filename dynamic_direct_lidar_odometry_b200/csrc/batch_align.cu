@@ -18,7 +18,14 @@
 
 namespace ddlo {
 
-constexpr int kBThreads = 256;
+// threads of a search block (one block per problem and chunk).  Measured on the C2 batch, registrations/s: 512 threads
+// x 2 blocks per SM 4 490, 256 x 4 4 810, 128 x 8 4 945, 64 x 16 4 900 - smaller blocks leave fewer pairs idle while the
+// chunk's last long queries finish.  Serving 1024 or 2048 CONSECUTIVE points per block instead of a chunk (the search
+// does not depend on how the sums are chunked) was measured too: 4 890 / 4 620, no gain.
+#ifndef DDLO_BATCH_SEARCH_THREADS
+#define DDLO_BATCH_SEARCH_THREADS 128
+#endif
+constexpr int kBThreads = DDLO_BATCH_SEARCH_THREADS;
 constexpr int kBWarps = kBThreads / 32;
 constexpr int kBRound = 1024;  // slots of a chunk searched per queue round (parking space in shared memory)
 // threads of the linearize / error kernels (512, i.e. the 14 groups of a C2 chunk in flight at once, was measured:
@@ -29,9 +36,9 @@ constexpr int kBRound = 1024;  // slots of a chunk searched per queue round (par
 constexpr int kLThreads = DDLO_BATCH_LIN_THREADS;
 constexpr int kLWarps = kLThreads / 32;
 #ifndef DDLO_BATCH_BLOCKS_PER_SM
-#define DDLO_BATCH_BLOCKS_PER_SM 4
+#define DDLO_BATCH_BLOCKS_PER_SM (1024 / DDLO_BATCH_SEARCH_THREADS)
 #endif
-constexpr int kBBlocksPerSM = DDLO_BATCH_BLOCKS_PER_SM;  // 4: 64 registers per thread, as in k_align
+constexpr int kBBlocksPerSM = DDLO_BATCH_BLOCKS_PER_SM;  // 1024 threads per SM: 64 registers per thread, as in k_align
 
 struct BatchProb {
   GicpArgs a;
