@@ -662,7 +662,7 @@ def main():
     ap.add_argument("--batched-units", type=int, default=2048, help="registrations per GPU in the batched leg (at least 512)")
     ap.add_argument("--batched-host-threads", type=int, default=2, help="C++ host threads that enqueue the batched leg")
     ap.add_argument("--batched-mode", choices=["waves", "lanes"], default="waves", help="align stage of the batched leg (ddlo_batch_set_mode)")
-    ap.add_argument("--batched-wave", type=int, default=64, help="units per wave in waves mode")
+    ap.add_argument("--batched-wave", type=int, default=128, help="units per wave in waves mode")
     ap.add_argument("--no-c1", action="store_true", help="skip the C1 (S2S) leg")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the C3 (sequence, C++ loop) and C5 (S2S pairs) legs")
     args = ap.parse_args()

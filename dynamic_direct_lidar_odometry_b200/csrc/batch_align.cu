@@ -28,10 +28,11 @@ namespace ddlo {
 constexpr int kBThreads = DDLO_BATCH_SEARCH_THREADS;
 constexpr int kBWarps = kBThreads / 32;
 constexpr int kBRound = 1024;  // slots of a chunk searched per queue round (parking space in shared memory)
-// threads of the linearize / error kernels (512, i.e. the 14 groups of a C2 chunk in flight at once, was measured:
-// 4 500 against 4 640 registrations/s with 256)
+// threads of the linearize / error kernels.  Measured (registrations/s on the C2 batch, one box per line):
+// 512 threads 4 500 against 4 640 with 256; 256 / 128 / 64 threads 4 996 / 5 051 / 5 097.  The sums do not depend on it
+// (group sums are added in group order whatever the number of warps).
 #ifndef DDLO_BATCH_LIN_THREADS
-#define DDLO_BATCH_LIN_THREADS 256
+#define DDLO_BATCH_LIN_THREADS 64
 #endif
 constexpr int kLThreads = DDLO_BATCH_LIN_THREADS;
 constexpr int kLWarps = kLThreads / 32;
