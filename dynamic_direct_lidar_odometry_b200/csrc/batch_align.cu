@@ -26,7 +26,6 @@ namespace ddlo {
 #define DDLO_BATCH_SEARCH_THREADS 128
 #endif
 constexpr int kBThreads = DDLO_BATCH_SEARCH_THREADS;
-constexpr int kBWarps = kBThreads / 32;
 constexpr int kBRound = 1024;  // slots of a chunk searched per queue round (parking space in shared memory)
 // threads of the linearize / error kernels.  Measured (registrations/s on the C2 batch, one box per line):
 // 512 threads 4 500 against 4 640 with 256; 256 / 128 / 64 threads 4 996 / 5 051 / 5 097.  The sums do not depend on it
