@@ -209,3 +209,20 @@ def test_detection_module_argument_checks_need_no_gpu():
     assert det.params.scan_in_sensor_frame == 1
     det.projectScan(None, np.zeros((8, 16, 4), dtype=np.float32), np.eye(4))
     assert det.params.scan_in_sensor_frame == 0
+
+
+def test_align_traffic_capture_belongs_to_this_build():
+    """`roofline.traffic` of the bench line comes from an ncu capture stored in profiles/align_traffic.json; the file is
+    stamped with a fingerprint of the kernel's sources and bench.py reports null when it does not match.  The committed
+    capture must be the one of the committed sources."""
+    import json
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    sys.path.insert(0, str(root))
+    import bench
+
+    stored = json.loads((root / "profiles" / "align_traffic.json").read_text())
+    assert stored["kernel_source_sha16"] == bench.kernel_source_sha16()
+    assert stored["dram_bytes_per_launch"] == stored["dram_bytes_read"] + stored["dram_bytes_write"]
