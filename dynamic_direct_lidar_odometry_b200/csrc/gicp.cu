@@ -25,8 +25,16 @@ namespace cg = cooperative_groups;
 namespace ddlo {
 
 constexpr int kAlignWarps = kAlignThreads / 32;
-constexpr int kAlignPairs = kAlignThreads / 2;  // source points (slots) of one round of a block
-constexpr int kRoundGroups = kAlignPairs / kGroup;
+// Source points (slots) of one ROUND of a block: searched from one queue (phase A), then linearized (phase B).  A block
+// has 512 lane pairs; a chunk of up to 512 slots (C1, C2, C3: 443) is in flight at once, a larger one (C4: 1 771) refills
+// the pairs from the round's queue, so the round should hold the whole chunk if it can: every round ends with the tail of
+// its longest queries.
+#ifndef DDLO_ALIGN_ROUND
+#define DDLO_ALIGN_ROUND 2048
+#endif
+constexpr int kRoundSlots = DDLO_ALIGN_ROUND;
+constexpr int kRoundGroups = kRoundSlots / kGroup;
+static_assert(kRoundSlots % kGroup == 0, "a round is whole groups");
 #ifndef DDLO_SEARCH_WARPS
 #define DDLO_SEARCH_WARPS 32
 #endif
@@ -34,9 +42,9 @@ constexpr int kSearchWarps = DDLO_SEARCH_WARPS;  // warps that search (16 querie
 
 // dynamic shared memory of the align / step kernels
 struct AlignSmem {
-  float nn_d[kAlignPairs];  // matches of the current round, parked per slot
-  int nn_idx[kAlignPairs];
-  int nn_pos[kAlignPairs];
+  float nn_d[kRoundSlots];  // matches of the current round, parked per slot
+  int nn_idx[kRoundSlots];
+  int nn_pos[kRoundSlots];
   int next;                 // phase A queue head
   int next_action;          // what the LM controller wants next (kNext*)
   double gs[kRoundGroups][kNumSums];  // group sums of the current round
@@ -57,8 +65,8 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
   if (threadIdx.x == 0) sm.t_search = 0ull;
   const Deal dl = make_deal(a.ns, gridDim.x, blockIdx.x);
   SearchPark pk{sm.nn_d, sm.nn_idx, sm.nn_pos, &sm.next, sm.lm.Rf, sm.lm.tf, sm.lm.n_lin};
-  for (int base = 0; base < dl.nslots; base += kAlignPairs) {
-    const int nround = min(kAlignPairs, dl.nslots - base);  // multiple of 16
+  for (int base = 0; base < dl.nslots; base += kRoundSlots) {
+    const int nround = min(kRoundSlots, dl.nslots - base);  // multiple of 16
     if (threadIdx.x == 0) sm.next = 0;
     __syncthreads();  // queue reset; parked matches and group sums of the previous round consumed; acc initialised
     // ---- phase A
@@ -69,23 +77,24 @@ __device__ __forceinline__ void linearize_block(const GicpArgs& a, AlignSmem& sm
     __syncthreads();
     // ---- phase B: one thread per point of the round, whole warps (a group = 32 slots; the last one may be half empty)
     const int ngroups = (nround + kGroup - 1) / kGroup;
-    if (warp < ngroups) {
+    for (int g = warp; g < ngroups; g += kAlignWarps) {
       const unsigned long long t0 = bt ? globaltimer_ns() : 0ull;
+      const int slot = g * kGroup + lane;
       int i = -1, j = -1, pos = -1;
-      if (threadIdx.x < nround) {
-        i = dl.point(base + threadIdx.x);
+      if (slot < nround) {
+        i = dl.point(base + slot);
         if (i >= a.ns) {
           i = -1;
         } else if (matches_ready) {
           j = __ldcg(a.corr + i);
           pos = __ldcg(a.nn_seed + i).x;
         } else {
-          pos = sm.nn_pos[threadIdx.x];
-          j = store_match(a, i, sm.nn_d[threadIdx.x], sm.nn_idx[threadIdx.x], pos);
+          pos = sm.nn_pos[slot];
+          j = store_match(a, i, sm.nn_d[slot], sm.nn_idx[slot], pos);
         }
       }
       const double v = lin_group(a, sm.lm.x0, i, j, pos);
-      if (lane < kNumSums) sm.gs[warp][lane] = v;
+      if (lane < kNumSums) sm.gs[g][lane] = v;
       if (bt && lane == 0) {
         const unsigned long long dt = globaltimer_ns() - t0;
         atomicMax(bt + 4, dt);
