@@ -50,6 +50,15 @@ __device__ __forceinline__ float box_bound_rn(float qx, float qy, float qz, floa
 // (d, i) lexicographic order
 __device__ __forceinline__ bool lex_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
 
+// a < b for two candidate keys bits(d) << 32 | index (d a finite non-negative float, or the empty key (FLT_MAX, sentinel),
+// or 0).  Such a key is also the bit pattern of a finite non-negative DOUBLE (its exponent field is the top 11 bits of
+// bits(d) < 0x7f800000, never all ones), and finite non-negative doubles - zero and denormals included, double
+// arithmetic never flushes them - order exactly like their bit patterns.  So the comparison is one DSETP instead of an
+// ISETP pair.  NOT for the "no candidate" pattern ~0 (a NaN as a double): callers compare that one as an integer.
+__device__ __forceinline__ bool key_less(unsigned long long a, unsigned long long b) {
+  return __longlong_as_double((long long)a) < __longlong_as_double((long long)b);
+}
+
 struct Sub {
   int sl;          // lane inside the sub-warp, 0..7
   int base;        // first lane of the sub-warp inside the warp
@@ -268,15 +277,18 @@ struct TopKRegSub {
       key[r] = pack(FLT_MAX, kIdxSentinel - (sb.sl * R + r));  // (distinct dummies for idle sub-warps)
       if (active) {
         const float4 v = __ldg(spts + w0 + sb.sl * R + r);
-        key[r] = pack(sqdist3_rn(qx, qy, qz, v.x, v.y, v.z), __float_as_int(v.w));
+        // (a distance that overflowed - or is NaN, in a cloud the checked entry points reject afterwards - is entered as
+        // FLT_MAX: every key stays a finite double for key_less)
+        key[r] = pack(fminf(sqdist3_rn(qx, qy, qz, v.x, v.y, v.z), FLT_MAX), __float_as_int(v.w));
       }
     }
     int rank[R];
+    auto lt = [](unsigned long long x, unsigned long long y) { return key_less(x, y); };
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       rank[r] = 0;
 #pragma unroll
-      for (int q = 0; q < R; ++q) rank[r] += key[q] < key[r] ? 1 : 0;
+      for (int q = 0; q < R; ++q) rank[r] += lt(key[q], key[r]) ? 1 : 0;
     }
 #pragma unroll
     for (int d = 1; d < kSubLanes; ++d) {
@@ -284,7 +296,7 @@ struct TopKRegSub {
       for (int q = 0; q < R; ++q) {
         const unsigned long long o = __shfl_sync(kFull, key[q], sb.base + ((sb.sl + d) & (kSubLanes - 1)));
 #pragma unroll
-        for (int r = 0; r < R; ++r) rank[r] += o < key[r] ? 1 : 0;
+        for (int r = 0; r < R; ++r) rank[r] += lt(o, key[r]) ? 1 : 0;
       }
     }
     __syncwarp();
@@ -307,14 +319,18 @@ struct TopKRegSub {
     unsigned long long left = __shfl_up_sync(kFull, e[R - 1], 1);
     if (sb.sl == 0) left = 0ull;  // nothing to the left of position 0
     if (upd) {
-      bool gl = c < left;
+      // g[r]: the content of slot r - 1 (the left neighbour's last entry for r = 0) is greater than c.  From the tail: a
+      // slot greater than c takes its left neighbour if that one is greater too, else c itself.  The comparisons are made
+      // on the keys READ AS DOUBLES (key_less): one DSETP instead of the ISETP pair of a 64-bit integer comparison, and the
+      // selects become predicated moves.  Loop body 52 -> 30 instructions; covariances of the C2 step 0.137 -> 0.121 ms.
+      bool g[R + 1];
+      g[0] = key_less(c, left);
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const bool gr = c < e[r];
-        const unsigned long long nv = gl ? left : (gr ? c : e[r]);
-        left = e[r];
-        e[r] = nv;
-        gl = gr;
+      for (int r = 0; r < R; ++r) g[r + 1] = key_less(c, e[r]);
+#pragma unroll
+      for (int r = R - 1; r >= 0; --r) {
+        const unsigned long long lv = r == 0 ? left : e[r == 0 ? 0 : r - 1];
+        if (g[r + 1]) e[r] = g[r] ? lv : c;
       }
     }
   }
