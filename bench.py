@@ -611,7 +611,7 @@ def run_batched(ng, group, local_rank, rank, world, tgt, args, extra):
     per_gpu = n_units / dt_max
     out["roofline"] = {"bound": "hbm", "achieved": per_gpu * step_bytes / 1e9, "peak": peak, "unit": "GB/s per GPU", "frac": per_gpu * step_bytes / 1e9 / peak,
                        "algorithmic_bytes_per_registration": step_bytes,
-                       "note": "whole batched step; the binding resource is instruction issue (profiles/r02_batch_launch_summary.txt: 161 M warp "
+                       "note": "whole batched step; the binding resource is instruction issue (profiles/r02_batch_launch_summary.txt: 147 M warp "
                                "instructions per registration), the streaming kernels of the path (k_batch_lin, k_batch_err) run at 35 % of the HBM peak"}
     if solo is not None:
         out["one_gpu_alone"] = n_units / solo
