@@ -36,7 +36,7 @@ def main():
     ap.add_argument("--align-blocks", type=int, default=0, help="SMs one align may use (0 = 148 // lanes)")
     ap.add_argument("--host-threads", type=int, default=2, help="C++ threads that enqueue the units")
     ap.add_argument("--mode", choices=["waves", "lanes"], default="waves", help="align stage: batched round kernels over waves of units, or one cooperative launch per unit on its lane")
-    ap.add_argument("--wave", type=int, default=128, help="units per wave (waves mode)")
+    ap.add_argument("--wave", type=int, default=64, help="units per wave (waves mode)")
     ap.add_argument("--out", type=str, default="", help="also write the JSON line to this file (rank 0)")
     args = ap.parse_args()
 
